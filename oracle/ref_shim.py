@@ -1,0 +1,95 @@
+"""Import the UNMODIFIED reference (cwchenwang/NeRF-SR) in the build container.
+
+TEST INFRASTRUCTURE ONLY (see oracle/nerf_oracle.py header).  /root/reference
+does not exist on the GPU box, so nothing in the ``-m gpu`` tests, ``smoke()``
+or ``bench.py`` may import this module; it is used by ``oracle/make_golden.py``
+and by the CPU-only test that re-pins the oracle when the reference tree is
+present.
+
+The reference does not import as-is here: numpy 2.x
+dropped ``numpy.lib.shape_base``, ``dominate`` and ``imageio`` are absent, and
+``BaseOptions.parse`` calls ``torch.cuda.set_device``.  We pre-seed
+``sys.modules`` with inert stubs and build ``opt`` by hand from the model's own
+``modify_commandline_options`` -- the reference tree is never modified.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get("NSR_REFERENCE_ROOT", "/root/reference")
+
+
+def reference_available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "models", "nerf_downX_model.py"))
+
+
+def _install_stubs() -> None:
+    import numpy as np
+    if "numpy.lib.shape_base" not in sys.modules:
+        m = types.ModuleType("numpy.lib.shape_base")
+        m.expand_dims = np.expand_dims
+        sys.modules["numpy.lib.shape_base"] = m
+    if "dominate" not in sys.modules:
+        dom = types.ModuleType("dominate")
+        tags = types.ModuleType("dominate.tags")
+        for n in ("meta", "h3", "table", "tr", "td", "p", "a", "img", "br"):
+            setattr(tags, n, lambda *a, **k: None)
+        dom.tags = tags
+        dom.document = lambda *a, **k: None
+        sys.modules["dominate"] = dom
+        sys.modules["dominate.tags"] = tags
+    if "imageio" not in sys.modules:
+        sys.modules["imageio"] = types.ModuleType("imageio")
+
+
+def load_reference_model(model_name: str = "nerf_downX", extra_args=(), device: str = "cpu"):
+    """Return (model, opt): a reference NeRFDownXModel / NeRFModel on ``device``
+    in eval mode with kaiming-initialised nets (caller overwrites weights)."""
+    if not reference_available():
+        raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
+    _install_stubs()
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    import torch
+    if model_name == "nerf_downX":
+        from models.nerf_downX_model import NeRFDownXModel as Model
+    elif model_name == "nerf":
+        from models.nerf_model import NeRFModel as Model
+    else:
+        raise ValueError(model_name)
+
+    parser = argparse.ArgumentParser()
+    # the handful of base flags the model reads (options/base_options.py:35-74)
+    parser.add_argument("--accelerator", default="dp")
+    parser.add_argument("--name", default="oracle")
+    parser.add_argument("--checkpoints_dir", default="/tmp/nsr_oracle_ckpt")
+    parser.add_argument("--init_type", default="kaiming")
+    parser.add_argument("--init_gain", type=float, default=0.02)
+    parser.add_argument("--sisr_path", default=None)
+    parser.add_argument("--img_wh", type=int, nargs=2, default=[8, 8])
+    parser.add_argument("--patch_size", type=int, default=1)
+    parser.add_argument("--ray_chunk", type=int, default=4096)
+    parser.add_argument("--point_chunk", type=int, default=2048 * 128)
+    parser.add_argument("--lr", type=float, default=5e-4)
+    parser.add_argument("--beta1", type=float, default=0.9)
+    parser = Model.modify_commandline_options(parser)
+    opt = parser.parse_args(list(extra_args))
+    opt.isTrain, opt.isTest, opt.isInfer = False, True, False
+    opt.device = torch.device(device)
+    opt.n_gpus = 0 if device == "cpu" else 1
+    opt.gpu_ids = [] if device == "cpu" else [0]
+    opt.is_master = True
+    model = Model(opt)
+    model.eval()
+    return model, opt
+
+
+def set_weights(model, p_coarse, p_fine) -> None:
+    """Load oracle-style parameter dicts into the reference nets."""
+    import torch
+    for net, p in ((model.netCoarse, p_coarse), (model.netFine, p_fine)):
+        target = net.module if hasattr(net, "module") else net
+        target.load_state_dict({k: v.clone() for k, v in p.items()}, strict=True)
