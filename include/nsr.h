@@ -1,0 +1,249 @@
+/*
+ * nsr.h -- C ABI of libnsr_b200: the B200-native volumetric-render hot path of
+ * NeRF-SR (ray generation -> stratified / inverse-CDF sampling -> positional
+ * encoding -> coarse/fine 8+1-layer MLP on tcgen05 tensor cores -> alpha
+ * compositing -> s x s box average).
+ *
+ * The reference (cwchenwang/NeRF-SR) has no FFI layer: its boundary for this
+ * path is the Python method NeRFDownXModel.forward_rays(rays[N,8]) -> dict
+ * (models/nerf_downX_model.py:280-313, called from :318/:322/:580/:604 through
+ * utils/utils.py:130-152 chunk_batch) and the finer seams below it.  Every entry
+ * point here names the reference interface it replaces.  The ctypes binding a
+ * reference maintainer would add is shown in INTEGRATION.md and shipped as
+ * nerf_sr_b200/_lib.py.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes; no C++/torch types; no exceptions.
+ *  - All tensor pointers are DEVICE pointers (fp32, row-major, contiguous)
+ *    unless the name says host.  The caller owns every buffer, including outputs
+ *    and workspace; the library borrows them for the stream-ordered call and owns
+ *    only its packed-weight images.
+ *  - Every call is asynchronous on the given stream (no host sync) except
+ *    nsr_render_host() and nsr_create()/nsr_destroy().
+ *  - Return value: 0 = NSR_OK, otherwise an NsrStatus; the message is available
+ *    from nsr_last_error().  The library never exits or aborts.
+ *  - Re-entrant per handle+stream; no global mutable state.
+ */
+#ifndef NSR_B200_H_
+#define NSR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NSR_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define NSR_API __attribute__((visibility("default")))
+#else
+#define NSR_API
+#endif
+
+typedef struct NsrHandle_ NsrHandle;   /* opaque */
+typedef void* NsrStream;               /* cudaStream_t */
+
+typedef enum NsrStatus {
+  NSR_OK = 0,
+  NSR_ERR_INVALID_ARG = 1,     /* null pointer, bad size, bad enum              */
+  NSR_ERR_UNSUPPORTED = 2,     /* option combination this build cannot run      */
+  NSR_ERR_NOT_PACKED = 3,      /* render called before nsr_pack_weights         */
+  NSR_ERR_WORKSPACE = 4,       /* workspace too small                           */
+  NSR_ERR_CUDA = 5,            /* a CUDA runtime call failed                    */
+  NSR_ERR_NO_DEVICE = 6        /* no sm_100 device / kernel image not loadable  */
+} NsrStatus;
+
+/* Arithmetic of the MLP GEMMs (parity needs ~fp32 accuracy). */
+typedef enum NsrPrecision {
+  NSR_PREC_FP32_SIMT = 0,   /* fp32 FFMA on CUDA cores; generic D/W/skips      */
+  NSR_PREC_BF16X3_TC = 1,   /* tcgen05 kind::f16, bf16 hi/lo split, 3 MMAs     */
+  NSR_PREC_FP16X3_TC = 2,   /* tcgen05 kind::f16, fp16 hi/lo split, 3 MMAs     */
+  NSR_PREC_BF16_TC   = 3    /* single bf16 pass: fast, NOT parity grade        */
+} NsrPrecision;
+
+/*
+ * Option surface the path reads from the reference's `opt`
+ * (models/nerf_model.py:46-72, models/networks.py:124-128,
+ *  models/embedding.py:17-18, models/nerf_downX_model.py:125).
+ */
+typedef struct NsrConfig {
+  uint32_t struct_size;        /* = sizeof(NsrConfig); ABI guard               */
+  int32_t  device;             /* CUDA device ordinal                          */
+  int32_t  precision;          /* NsrPrecision                                 */
+  /* VanillaMLP (models/networks.py:121-180) */
+  int32_t  D;                  /* --D, trunk depth (8)                         */
+  int32_t  W;                  /* --W, trunk width (256)                       */
+  uint32_t skips_mask;         /* bit i set <=> i in --skips (default 1<<4)    */
+  int32_t  no_dir;             /* --no_dir                                     */
+  int32_t  color_activation;   /* 0 sigmoid, 1 none                            */
+  /* PositionalEncoding (models/embedding.py:28-42) */
+  int32_t  deg_pos;            /* --deg_pos (10)                               */
+  int32_t  deg_dir;            /* --deg_dir (4)                                */
+  int32_t  no_xyz;             /* --no_xyz                                     */
+  int32_t  no_logscale;        /* --no_logscale                                */
+  /* sampling / rendering */
+  int32_t  n_coarse;           /* --N_coarse (64)                              */
+  int32_t  n_importance;       /* --N_importance (64); 0 => coarse only        */
+  int32_t  lindisp;            /* --lindisp                                    */
+  int32_t  white_bkgd;         /* --white_bkgd                                 */
+  int32_t  sigma_activation;   /* 0 relu, 1 softplus(x-1) (rendering.py:70-73) */
+  int32_t  gamma_correct;      /* --gamma_correct (nerf_downX_model.py:271)    */
+  float    noise_std;          /* --noise_std                                  */
+  int32_t  viewdir_offset;     /* column of the view direction in a ray row:
+                                  3 = NeRFDownXModel (rays[:,3:6], :286),
+                                  8 = NeRFModel (rays[:,8:11], nerf_model.py:213) */
+  int32_t  reserved[8];
+} NsrConfig;
+
+/*
+ * Explicit random inputs for train mode, in the reference's draw order
+ * (models/utils.py:41, :210, :73, :210).  Any pointer may be null:
+ *   u_coarse null  => no stratified jitter (eval, randomized=False)
+ *   u_fine   null  => u = linspace(0,1,n_importance) (eval)
+ *   noise_*  null  => no sigma noise
+ */
+typedef struct NsrRng {
+  const float* u_coarse;       /* [N, n_coarse]   U[0,1)                       */
+  const float* noise_coarse;   /* [N, n_coarse]   N(0,1)                       */
+  const float* u_fine;         /* [N, n_importance]                            */
+  const float* noise_fine;     /* [N, n_coarse+n_importance]                   */
+} NsrRng;
+
+/*
+ * Outputs of forward_rays (models/nerf_downX_model.py:293-311), same shapes and
+ * dtypes as the reference's dict.  Null pointers are skipped (e.g. drop the
+ * per-sample weight maps for inference).  fine_* must be null or are ignored
+ * when n_importance == 0.  z_fine is an extra: the merged fine z-values
+ * (models/utils.py:93), useful for depth debugging and teacher-forced tests.
+ */
+typedef struct NsrOutputs {
+  float* coarse_comp_rgbs;     /* [N,3]                                        */
+  float* coarse_depth;         /* [N]                                          */
+  float* coarse_opacity;       /* [N]                                          */
+  float* coarse_weights;       /* [N, n_coarse]                                */
+  float* fine_comp_rgbs;       /* [N,3]                                        */
+  float* fine_depth;           /* [N]                                          */
+  float* fine_opacity;         /* [N]                                          */
+  float* fine_weights;         /* [N, n_coarse+n_importance]                   */
+  float* z_fine;               /* [N, n_coarse+n_importance] (optional)        */
+} NsrOutputs;
+
+/* One rendered pass (VolumetricRenderer.forward outputs, models/rendering.py:75-111). */
+typedef struct NsrPassOutputs {
+  float* comp_rgbs;            /* [N,3]                                        */
+  float* depth;                /* [N]                                          */
+  float* opacity;              /* [N]                                          */
+  float* weights;              /* [N,S]                                        */
+  float* raw;                  /* [N,S,4] rgb(after colour act), raw sigma
+                                  = VanillaMLP.forward output (networks.py:224);
+                                  optional                                     */
+} NsrPassOutputs;
+
+/* ---- lifecycle ----------------------------------------------------------- */
+
+/* ABI version of the loaded library (compare with NSR_ABI_VERSION). */
+NSR_API int nsr_abi_version(void);
+
+/* Replaces: NeRFDownXModel.__init__'s construction of netCoarse/netFine,
+ * embeddings and renderer from `opt` (models/nerf_downX_model.py:178-197).
+ * Validates the option combination; NSR_ERR_UNSUPPORTED for combinations this
+ * build cannot run bit-faithfully (the caller then keeps the reference path --
+ * never a silent difference). */
+NSR_API int nsr_create(const NsrConfig* cfg, NsrHandle** out_handle);
+NSR_API int nsr_destroy(NsrHandle* h);
+
+/* Last error message for this handle (or for a failed nsr_create when h==NULL;
+ * thread-local).  Never null. */
+NSR_API const char* nsr_last_error(const NsrHandle* h);
+
+/* Number of parameter tensors per MLP and their element counts, in the
+ * reference's state_dict order (models/networks.py:149-180):
+ * xyz_encoding_{1..D}.0.{weight,bias}, xyz_encoding_final.{weight,bias},
+ * dir_encoding.0.{weight,bias}, sigma.{weight,bias}, rgb.0.{weight,bias}. */
+NSR_API int nsr_param_count(const NsrHandle* h);
+NSR_API int64_t nsr_param_numel(const NsrHandle* h, int index);
+
+/* Replaces: load_networks / the implicit use of net.state_dict()
+ * (models/base_model.py:198-219).  `which`: 0 = netCoarse, 1 = netFine.
+ * param_ptrs[i] = device pointer of the i-th state_dict tensor (fp32,
+ * contiguous, [out,in] row-major for weights).  Repacks into the kernel's
+ * swizzled hi/lo images on `stream`; call again whenever parameters change
+ * (every optimiser step in training). */
+NSR_API int nsr_pack_weights(NsrHandle* h, int which, const float* const* param_ptrs,
+                     int n_params, NsrStream stream);
+
+/* ---- the hot path -------------------------------------------------------- */
+
+/* Bytes of caller-provided scratch nsr_render needs for n_rays rays. */
+NSR_API size_t nsr_workspace_bytes(const NsrHandle* h, int64_t n_rays);
+
+/* Replaces: NeRFDownXModel.forward_rays (models/nerf_downX_model.py:280-313)
+ * and NeRFModel.forward_rays (models/nerf_model.py:207-236), including the
+ * chunk_batch loops around it (utils/utils.py:130-152): n_rays is unbounded,
+ * no ray_chunk / point_chunk is needed because no [P,*] intermediate reaches HBM.
+ * rays: [n_rays, ray_stride] rows (o3, d3, near, far[, viewdir3]); ray_stride
+ * is 8 or 11.  rng may be null (eval mode). */
+NSR_API int nsr_render(NsrHandle* h, const float* rays, int64_t n_rays, int ray_stride,
+               const NsrRng* rng, const NsrOutputs* out,
+               void* workspace, size_t workspace_bytes, NsrStream stream);
+
+/* Replaces: render_rays(model, xyz, dir_embedded) + add_gaussian_noise +
+ * self.renderer(rgb, sigma, z_vals, white_bkgd) for ONE network with caller-
+ * supplied z-values (models/nerf_downX_model.py:260-278,289-291; rendering.py:
+ * 75-111).  This is the teacher-forced seam of the parity protocol.
+ * z_vals: [n_rays, n_samples]; noise: [n_rays, n_samples] or null. */
+NSR_API int nsr_render_pass(NsrHandle* h, int which, const float* rays, int64_t n_rays,
+                    int ray_stride, const float* z_vals, int n_samples,
+                    const float* noise, const NsrPassOutputs* out,
+                    void* workspace, size_t workspace_bytes, NsrStream stream);
+
+/* Replaces: sample_along_rays z-values (models/utils.py:17-44).
+ * z_out: [n_rays, n_coarse]; u may be null. */
+NSR_API int nsr_sample_coarse(NsrHandle* h, const float* rays, int64_t n_rays, int ray_stride,
+                      const float* u, float* z_out, NsrStream stream);
+
+/* Replaces: resample_along_rays z-values (models/utils.py:47-95).
+ * z_in/weights: [n_rays, n_coarse]; u: [n_rays, n_importance] or null;
+ * z_out: [n_rays, n_coarse+n_importance] sorted. */
+NSR_API int nsr_resample(NsrHandle* h, const float* z_in, const float* weights, int64_t n_rays,
+                 const float* u, float* z_out, NsrStream stream);
+
+/* Replaces: PositionalEncoding.__call__ (models/embedding.py:44-63).
+ * x: [n, 3] -> out: [n, 3*2*deg + (no_xyz?0:3)]. */
+NSR_API int nsr_posenc(NsrHandle* h, const float* x, int64_t n, int deg, float* out, NsrStream stream);
+
+/* Replaces: comp_low_res_output's box average (models/nerf_downX_model.py:337-348):
+ * in [n_lr*s*s, channels] (sub-pixels contiguous) -> out [n_lr, channels]. */
+NSR_API int nsr_box_average(NsrHandle* h, const float* in, int64_t n_lr, int s, int channels,
+                    float* out, NsrStream stream);
+
+/* Replaces: get_ray_directions + get_rays (+ get_ndc_rays) + the HR->(LR,s*s)
+ * grouping for one pose (models/utils.py:98-196; data/blender_downX_dataset.py:
+ * 207-215; data/llff_downX_dataset.py:473-490).  c2w: HOST pointer to 12 floats
+ * (3x4 row-major).  ndc != 0: project to NDC at near plane 1.0, then near=0,
+ * far=1.  rays_out: [H*W, 8] in LR-pixel-major / sub-pixel-minor order. */
+NSR_API int nsr_generate_rays(NsrHandle* h, const float* c2w_host, int H, int W, float focal,
+                      int s, int ndc, float near_plane, float far_plane,
+                      float* rays_out, NsrStream stream);
+
+/* ---- host-buffer convenience (the end-to-end call) ------------------------ */
+
+/* forward over a whole frame / batch with HOST buffers: stages rays through
+ * pinned memory in chunks, overlaps H2D / render / D2H on internal streams and
+ * (optionally) box-averages on the device so only [n_rays/s^2] rows return.
+ * rays_host: [n_rays, ray_stride].  Any output pointer may be null.
+ *   rgb_host:   [n_out, 3]   fine (or coarse if n_importance==0) composite
+ *   depth_host: [n_out]
+ * with n_out = n_rays/(s*s) if s > 1 else n_rays.  Synchronous. */
+NSR_API int nsr_render_host(NsrHandle* h, const float* rays_host, int64_t n_rays, int ray_stride,
+                    int s, float* rgb_host, float* depth_host);
+
+/* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */
+NSR_API int64_t nsr_launch_count(const NsrHandle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* NSR_B200_H_ */

@@ -1,0 +1,669 @@
+// nsr_api.cu -- C ABI of libnsr_b200 (see include/nsr.h) and the small kernels
+// either side of the MLP: coarse sampling, compositing + inverse-CDF
+// resampling (one warp per ray), positional encoding, box average, on-device
+// ray generation.
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "nsr_internal.h"
+
+using namespace nsr;
+
+// ----------------------------------------------------------------------------
+// error plumbing
+// ----------------------------------------------------------------------------
+static thread_local std::string g_create_err = "";
+
+static int fail(NsrHandle_* h, int code, const std::string& msg) {
+  if (h) h->err = msg; else g_create_err = msg;
+  return code;
+}
+#define NSR_CUDA(h, expr)                                                                     \
+  do {                                                                                        \
+    cudaError_t e__ = (expr);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      return fail(h, NSR_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));       \
+  } while (0)
+
+static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// torch.linspace for fp32 (ATen RangeFactories: step = (end-start)/(steps-1);
+// first half counts up from start, second half counts down from end).
+static void host_linspace(float start, float end, int steps, float* out) {
+  if (steps == 1) { out[0] = start; return; }
+  const float step = (end - start) / (float)(steps - 1);
+  const int half = steps / 2;
+  for (int i = 0; i < steps; ++i) {
+    volatile float prod;
+    if (i < half) { prod = step * (float)i; out[i] = start + prod; }
+    else { prod = step * (float)(steps - i - 1); out[i] = end - prod; }
+  }
+}
+
+// ----------------------------------------------------------------------------
+// kernels
+// ----------------------------------------------------------------------------
+__global__ void k_sample_coarse(RenderParams rp, const SampleTables* __restrict__ tabs,
+                                const float* __restrict__ rays, int64_t n_rays, int ray_stride,
+                                const float* __restrict__ u, float* __restrict__ z_out) {
+  const int S = rp.n_coarse;
+  const int64_t total = n_rays * S;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / S;
+    const int i = (int)(idx % S);
+    const float near = rays[r * ray_stride + 6], far = rays[r * ray_stride + 7];
+    const float zc = coarse_z(near, far, tabs->t_coarse[i], tabs->one_minus_t[i], rp.lindisp);
+    float zv = zc;
+    if (u) {
+      const float zp = i > 0 ? coarse_z(near, far, tabs->t_coarse[i - 1], tabs->one_minus_t[i - 1], rp.lindisp) : zc;
+      const float zn = i + 1 < S ? coarse_z(near, far, tabs->t_coarse[i + 1], tabs->one_minus_t[i + 1], rp.lindisp) : zc;
+      zv = jitter_z(zp, zc, zn, i == 0, i + 1 == S, u[idx]);
+    }
+    z_out[idx] = zv;
+  }
+}
+
+// One warp per ray: (raw rgb/sigma, z) -> composite (+ resample).
+__global__ void __launch_bounds__(128)
+k_composite(RenderParams rp, const SampleTables* __restrict__ tabs, const float* __restrict__ raw,
+            const float* __restrict__ z, const float* __restrict__ noise, int64_t n_rays, int S,
+            int do_resample, const float* __restrict__ u_resample, float* __restrict__ comp_rgb,
+            float* __restrict__ depth, float* __restrict__ opacity, float* __restrict__ weights,
+            float* __restrict__ z_next, int per_warp_floats) {
+  extern __shared__ float csm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* base = csm + warp * per_warp_floats;
+  float* sz = base;            // [S]
+  float* ssig = sz + S;        // [S]
+  float* srgb = ssig + S;      // [3S]
+  float* sw = srgb + 3 * S;    // [S]
+  float* scratch = sw + S;     // resample scratch [2S + n_imp] then z_out [S + n_imp]
+  const int n_imp = rp.n_importance;
+  for (int64_t ray = blockIdx.x * 4 + warp; ray < n_rays; ray += (int64_t)gridDim.x * 4) {
+    const float4* r4 = reinterpret_cast<const float4*>(raw) + ray * S;
+    for (int i = lane; i < S; i += 32) {
+      const float4 v = r4[i];
+      float cr = v.x, cg = v.y, cb = v.z;
+      if (rp.gamma_correct) { cr = powf(cr, 1.f / 2.2f); cg = powf(cg, 1.f / 2.2f); cb = powf(cb, 1.f / 2.2f); }
+      srgb[3 * i] = cr; srgb[3 * i + 1] = cg; srgb[3 * i + 2] = cb;
+      float s = v.w;
+      if (noise) s = __fadd_rn(s, __fmul_rn(noise[ray * S + i], rp.noise_std));   // utils.py:210
+      ssig[i] = s;
+      sz[i] = z[ray * S + i];
+    }
+    __syncwarp();
+    float r, g, b, d, o;
+    composite_ray_warp(sz, ssig, srgb, S, rp.white_bkgd, rp.sigma_softplus, sw, r, g, b, d, o);
+    if (lane == 0) {
+      if (comp_rgb) { comp_rgb[ray * 3] = r; comp_rgb[ray * 3 + 1] = g; comp_rgb[ray * 3 + 2] = b; }
+      if (depth) depth[ray] = d;
+      if (opacity) opacity[ray] = o;
+    }
+    if (weights) for (int i = lane; i < S; i += 32) weights[ray * S + i] = sw[i];
+    if (do_resample) {
+      float* zo = scratch + 2 * S + n_imp;
+      resample_ray_warp(sz, sw, S, n_imp, u_resample ? u_resample + ray * n_imp : nullptr, tabs->u_fine,
+                        scratch, zo);
+      for (int i = lane; i < S + n_imp; i += 32) z_next[ray * (S + n_imp) + i] = zo[i];
+    }
+    __syncwarp();
+  }
+}
+
+// One warp per ray: resampling only (nsr_resample seam).
+__global__ void __launch_bounds__(128)
+k_resample(RenderParams rp, const SampleTables* __restrict__ tabs, const float* __restrict__ z,
+           const float* __restrict__ w, int64_t n_rays, const float* __restrict__ u,
+           float* __restrict__ z_out, int per_warp_floats) {
+  extern __shared__ float csm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = rp.n_coarse, n_imp = rp.n_importance;
+  float* sz = csm + warp * per_warp_floats;
+  float* sw = sz + S;
+  float* scratch = sw + S;
+  float* zo = scratch + 2 * S + n_imp;
+  for (int64_t ray = blockIdx.x * 4 + warp; ray < n_rays; ray += (int64_t)gridDim.x * 4) {
+    for (int i = lane; i < S; i += 32) { sz[i] = z[ray * S + i]; sw[i] = w[ray * S + i]; }
+    __syncwarp();
+    resample_ray_warp(sz, sw, S, n_imp, u ? u + ray * n_imp : nullptr, tabs->u_fine, scratch, zo);
+    for (int i = lane; i < S + n_imp; i += 32) z_out[ray * (S + n_imp) + i] = zo[i];
+    __syncwarp();
+  }
+}
+
+__global__ void k_posenc(const float* __restrict__ x, int64_t n, int deg, int no_xyz,
+                         const float* __restrict__ freqs, float* __restrict__ out) {
+  const int ch = 6 * deg + (no_xyz ? 0 : 3);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float* o = out + i * ch;
+    posenc3(x[3 * i], x[3 * i + 1], x[3 * i + 2], deg, freqs, no_xyz, [&](int c, float v) { o[c] = v; });
+  }
+}
+
+__global__ void k_box_average(const float* __restrict__ in, int64_t n_lr, int ss, int channels,
+                              float* __restrict__ out) {
+  // torch.mean(reshape(x, (n_lr, s*s, -1)), dim=1)   (nerf_downX_model.py:337-348)
+  const int64_t total = n_lr * channels;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = idx / channels;
+    const int c = (int)(idx % channels);
+    float s = 0.f;
+    for (int k = 0; k < ss; ++k) s = __fadd_rn(s, in[(p * ss + k) * channels + c]);
+    out[idx] = __fdiv_rn(s, (float)ss);
+  }
+}
+
+struct Pose { float m[12]; };
+
+__global__ void k_generate_rays(Pose c2w, int H, int W, float focal, int s, int ndc, float near_plane,
+                                float far_plane, float* __restrict__ rays) {
+  // get_ray_directions + get_rays (+ get_ndc_rays) + '(h s1) (w s2) c -> (h w) (s1 s2) c'
+  // (models/utils.py:98-196; data/blender_downX_dataset.py:207-215)
+  const int64_t total = (int64_t)H * W;
+  const int w_lr = W / s;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    // idx is the OUTPUT row: lr pixel (h, w), sub-pixel (s1, s2)
+    const int sub = (int)(idx % (s * s));
+    const int64_t lr = idx / (s * s);
+    const int hh = (int)(lr / w_lr), ww = (int)(lr % w_lr);
+    const int s1 = sub / s, s2 = sub % s;
+    const int row = hh * s + s1, col = ww * s + s2;
+    const float i = (float)col + 0.5f, j = (float)row + 0.5f;
+    const float cx = __fdiv_rn(__fsub_rn(i, (float)W / 2.f), focal);
+    const float cy = -__fdiv_rn(__fsub_rn(j, (float)H / 2.f), focal);
+    const float cz = -1.f;
+    // rays_d = directions @ c2w[:, :3].T
+    float d[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      d[k] = __fadd_rn(__fadd_rn(__fmul_rn(cx, c2w.m[4 * k + 0]), __fmul_rn(cy, c2w.m[4 * k + 1])),
+                       __fmul_rn(cz, c2w.m[4 * k + 2]));
+    const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+    d[0] = __fdiv_rn(d[0], nrm); d[1] = __fdiv_rn(d[1], nrm); d[2] = __fdiv_rn(d[2], nrm);
+    float o[3] = {c2w.m[3], c2w.m[7], c2w.m[11]};
+    float nearv = near_plane, farv = far_plane;
+    if (ndc) {   // get_ndc_rays at near = 1.0 (data/llff_downX_dataset.py:476-481)
+      const float nr = 1.0f;
+      const float t = __fdiv_rn(-__fadd_rn(nr, o[2]), d[2]);
+      o[0] = __fadd_rn(o[0], __fmul_rn(t, d[0]));
+      o[1] = __fadd_rn(o[1], __fmul_rn(t, d[1]));
+      o[2] = __fadd_rn(o[2], __fmul_rn(t, d[2]));
+      const float ox_oz = __fdiv_rn(o[0], o[2]), oy_oz = __fdiv_rn(o[1], o[2]);
+      const float kx = (float)(-1.0 / ((double)W / (2.0 * (double)focal)));
+      const float ky = (float)(-1.0 / ((double)H / (2.0 * (double)focal)));
+      const float o0 = __fmul_rn(kx, ox_oz), o1 = __fmul_rn(ky, oy_oz);
+      const float o2 = __fadd_rn(1.f, __fdiv_rn(__fmul_rn(2.f, nr), o[2]));
+      const float d0 = __fmul_rn(kx, __fsub_rn(__fdiv_rn(d[0], d[2]), ox_oz));
+      const float d1 = __fmul_rn(ky, __fsub_rn(__fdiv_rn(d[1], d[2]), oy_oz));
+      const float d2 = __fsub_rn(1.f, o2);
+      o[0] = o0; o[1] = o1; o[2] = o2; d[0] = d0; d[1] = d1; d[2] = d2;
+      nearv = 0.f; farv = 1.f;
+    }
+    float* out = rays + idx * 8;
+    out[0] = o[0]; out[1] = o[1]; out[2] = o[2]; out[3] = d[0]; out[4] = d[1]; out[5] = d[2];
+    out[6] = nearv; out[7] = farv;
+  }
+}
+
+// ----------------------------------------------------------------------------
+// launch helpers
+// ----------------------------------------------------------------------------
+static int grid_for(int64_t work, int block, int cap) {
+  int64_t g = (work + block - 1) / block;
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  return (int)g;
+}
+
+namespace nsr {
+cudaError_t launch_composite(NsrHandle_* h, const float* raw, const float* z, const float* noise,
+                             int64_t n_rays, int S, int do_resample, const float* u_resample,
+                             float* comp_rgb, float* depth, float* opacity, float* weights,
+                             float* z_next, cudaStream_t st) {
+  if (n_rays == 0) return cudaSuccess;
+  const int n_imp = h->rp.n_importance;
+  const int per_warp = 6 * S + (do_resample ? (3 * S + 2 * n_imp) : 0);
+  const size_t smem = (size_t)per_warp * 4 * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k_composite, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  const int grid = grid_for(n_rays, 4, h->sm_count * 8);
+  k_composite<<<grid, 128, smem, st>>>(h->rp, h->d_tables, raw, z, noise, n_rays, S, do_resample, u_resample,
+                                       comp_rgb, depth, opacity, weights, z_next, per_warp);
+  h->launches += 1;
+  return cudaGetLastError();
+}
+}  // namespace nsr
+
+// ----------------------------------------------------------------------------
+// lifecycle
+// ----------------------------------------------------------------------------
+extern "C" int nsr_abi_version(void) { return NSR_ABI_VERSION; }
+
+extern "C" const char* nsr_last_error(const NsrHandle* h) {
+  return h ? h->err.c_str() : g_create_err.c_str();
+}
+
+static int popcount_below(uint32_t mask, int n) {
+  int c = 0;
+  for (int i = 0; i < n; ++i) c += (mask >> i) & 1u;
+  return c;
+}
+
+extern "C" int nsr_create(const NsrConfig* cfg, NsrHandle** out_handle) {
+  if (!cfg || !out_handle) return fail(nullptr, NSR_ERR_INVALID_ARG, "nsr_create: null argument");
+  *out_handle = nullptr;
+  if (cfg->struct_size != sizeof(NsrConfig))
+    return fail(nullptr, NSR_ERR_INVALID_ARG, "nsr_create: NsrConfig.struct_size mismatch (ABI skew)");
+  const NsrConfig& c = *cfg;
+  if (c.D < 1 || c.D > kMaxTrunk) return fail(nullptr, NSR_ERR_UNSUPPORTED, "D must be in [1,16]");
+  if (c.W != 64 && c.W != 128 && c.W != 256) return fail(nullptr, NSR_ERR_UNSUPPORTED, "W must be 64, 128 or 256");
+  if (c.skips_mask & 1u) return fail(nullptr, NSR_ERR_UNSUPPORTED, "skip at layer 0 is ill-formed in the reference (networks.py:150-155)");
+  if (c.skips_mask >> c.D) return fail(nullptr, NSR_ERR_INVALID_ARG, "skips_mask has bits >= D");
+  if (c.deg_pos < 0 || c.deg_pos > 10 || c.deg_dir < 0 || c.deg_dir > 4)
+    return fail(nullptr, NSR_ERR_UNSUPPORTED, "deg_pos must be <= 10 and deg_dir <= 4");
+  if (c.no_xyz && (c.deg_pos == 0 || (c.deg_dir == 0 && !c.no_dir)))
+    return fail(nullptr, NSR_ERR_INVALID_ARG, "no_xyz with zero frequencies gives an empty encoding");
+  if (c.n_coarse < 3 || c.n_coarse > kMaxSamples) return fail(nullptr, NSR_ERR_UNSUPPORTED, "n_coarse must be in [3,256]");
+  if (c.n_importance < 0 || c.n_coarse + c.n_importance > kMaxSamples)
+    return fail(nullptr, NSR_ERR_UNSUPPORTED, "n_coarse + n_importance must be <= 256");
+  if (c.precision < 0 || c.precision > 3) return fail(nullptr, NSR_ERR_INVALID_ARG, "unknown precision");
+  if (c.viewdir_offset != 3 && c.viewdir_offset != 8) return fail(nullptr, NSR_ERR_INVALID_ARG, "viewdir_offset must be 3 or 8");
+  if (c.sigma_activation < 0 || c.sigma_activation > 1 || c.color_activation < 0 || c.color_activation > 1)
+    return fail(nullptr, NSR_ERR_INVALID_ARG, "unknown activation");
+  if (c.precision != NSR_PREC_FP32_SIMT) {
+    std::string why;
+    if (!tc_supported(c, &why)) return fail(nullptr, NSR_ERR_UNSUPPORTED, "tensor-core path: " + why);
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    return fail(nullptr, NSR_ERR_NO_DEVICE, "no CUDA device visible (libnsr_b200 has no CPU fallback)");
+  }
+  if (c.device < 0 || c.device >= ndev) return fail(nullptr, NSR_ERR_INVALID_ARG, "device ordinal out of range");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, c.device) != cudaSuccess) { cudaGetLastError(); return fail(nullptr, NSR_ERR_CUDA, "cudaGetDeviceProperties failed"); }
+  if (prop.major != 10) return fail(nullptr, NSR_ERR_NO_DEVICE, "device is not sm_100 (this library is built for sm_100a only)");
+
+  NsrHandle_* h = new (std::nothrow) NsrHandle_();
+  if (!h) return fail(nullptr, NSR_ERR_CUDA, "out of host memory");
+  h->cfg = c;
+  h->sm_count = prop.multiProcessorCount;
+  RenderParams& rp = h->rp;
+  rp.n_coarse = c.n_coarse; rp.n_importance = c.n_importance;
+  rp.deg_pos = c.deg_pos; rp.deg_dir = c.deg_dir; rp.no_xyz = c.no_xyz;
+  rp.ch_pos = 6 * c.deg_pos + (c.no_xyz ? 0 : 3);
+  rp.ch_dir = 6 * c.deg_dir + (c.no_xyz ? 0 : 3);
+  rp.lindisp = c.lindisp; rp.white_bkgd = c.white_bkgd; rp.sigma_softplus = c.sigma_activation;
+  rp.color_none = c.color_activation; rp.gamma_correct = c.gamma_correct; rp.no_dir = c.no_dir;
+  rp.viewdir_offset = c.viewdir_offset; rp.noise_std = c.noise_std;
+
+  SampleTables& T = h->h_tables;
+  memset(&T, 0, sizeof(T));
+  host_linspace(0.f, 1.f, c.n_coarse, T.t_coarse);
+  for (int i = 0; i < c.n_coarse; ++i) { volatile float v = 1.f - T.t_coarse[i]; T.one_minus_t[i] = v; }
+  if (c.n_importance > 0) host_linspace(0.f, 1.f, c.n_importance, T.u_fine);
+  auto bands = [&](int deg, float* out) {
+    if (deg <= 0) return;
+    if (c.no_logscale) host_linspace(1.f, (float)(1 << (deg - 1)), deg, out);   // embedding.py:42
+    else for (int k = 0; k < deg; ++k) out[k] = (float)(1 << k);                 // embedding.py:40
+  };
+  bands(c.deg_pos, T.freq_pos);
+  bands(c.deg_dir, T.freq_dir);
+
+  // parameter table (state_dict order)
+  {
+    const int ch_pos = rp.ch_pos, ch_dir = rp.ch_dir;
+    for (int i = 0; i < c.D; ++i) {
+      const bool skip = (c.skips_mask >> i) & 1u;
+      const int k = (i == 0) ? ch_pos : (skip ? c.W + ch_pos : c.W);
+      h->param_numel.push_back((int64_t)c.W * k);
+      h->param_numel.push_back(c.W);
+    }
+    h->param_numel.push_back((int64_t)c.W * c.W); h->param_numel.push_back(c.W);
+    const int kd = c.no_dir ? c.W : c.W + ch_dir;
+    h->param_numel.push_back((int64_t)(c.W / 2) * kd); h->param_numel.push_back(c.W / 2);
+    h->param_numel.push_back(c.W); h->param_numel.push_back(1);
+    h->param_numel.push_back(3 * (c.W / 2)); h->param_numel.push_back(3);
+  }
+  (void)popcount_below;
+
+  cudaError_t e = cudaSetDevice(c.device);
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_tables, sizeof(SampleTables));
+  if (e == cudaSuccess) e = cudaMemcpy(h->d_tables, &T, sizeof(T), cudaMemcpyHostToDevice);
+  const size_t blob = simt_blob_floats(h);
+  for (int w = 0; w < 2 && e == cudaSuccess; ++w) {
+    e = cudaMalloc(&h->net[w].simt_blob, blob * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemset(h->net[w].simt_blob, 0, blob * sizeof(float));
+    if (e == cudaSuccess && c.precision != NSR_PREC_FP32_SIMT) {
+      h->net[w].tc_bytes = tc_image_bytes(h);
+      e = cudaMalloc(&h->net[w].tc_image, h->net[w].tc_bytes);
+      if (e == cudaSuccess) e = cudaMalloc(&h->net[w].tc_consts, 16384 * sizeof(float));
+    }
+  }
+  if (e != cudaSuccess) {
+    std::string msg = std::string("nsr_create: ") + cudaGetErrorString(e);
+    nsr_destroy(h);
+    cudaGetLastError();
+    return fail(nullptr, NSR_ERR_CUDA, msg);
+  }
+  *out_handle = h;
+  return NSR_OK;
+}
+
+extern "C" int nsr_destroy(NsrHandle* h) {
+  if (!h) return NSR_OK;
+  cudaSetDevice(h->cfg.device);
+  for (int w = 0; w < 2; ++w) {
+    cudaFree(h->net[w].simt_blob); cudaFree(h->net[w].tc_image); cudaFree(h->net[w].tc_consts);
+  }
+  cudaFree(h->d_tables);
+  for (int i = 0; i < 2; ++i) {
+    if (h->pin_in[i]) cudaFreeHost(h->pin_in[i]);
+    if (h->pin_out[i]) cudaFreeHost(h->pin_out[i]);
+    cudaFree(h->dev_in[i]); cudaFree(h->dev_out[i]); cudaFree(h->dev_ws[i]);
+    if (h->hev[i]) cudaEventDestroy(h->hev[i]);
+    if (h->hs[i]) cudaStreamDestroy(h->hs[i]);
+  }
+  delete h;
+  return NSR_OK;
+}
+
+extern "C" int nsr_param_count(const NsrHandle* h) { return h ? (int)h->param_numel.size() : 0; }
+extern "C" int64_t nsr_param_numel(const NsrHandle* h, int index) {
+  if (!h || index < 0 || index >= (int)h->param_numel.size()) return -1;
+  return h->param_numel[index];
+}
+extern "C" int64_t nsr_launch_count(const NsrHandle* h) { return h ? h->launches : 0; }
+
+extern "C" int nsr_pack_weights(NsrHandle* h, int which, const float* const* param_ptrs, int n_params,
+                                NsrStream stream) {
+  if (!h) return NSR_ERR_INVALID_ARG;
+  if (which < 0 || which > 1 || !param_ptrs) return fail(h, NSR_ERR_INVALID_ARG, "nsr_pack_weights: bad argument");
+  if (n_params != (int)h->param_numel.size())
+    return fail(h, NSR_ERR_INVALID_ARG, "nsr_pack_weights: expected " + std::to_string(h->param_numel.size()) +
+                                            " state_dict tensors, got " + std::to_string(n_params));
+  for (int i = 0; i < n_params; ++i)
+    if (!param_ptrs[i]) return fail(h, NSR_ERR_INVALID_ARG, "nsr_pack_weights: null parameter pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  NSR_CUDA(h, cudaSetDevice(h->cfg.device));
+  NSR_CUDA(h, simt_pack(h, which, param_ptrs, st));
+  if (h->cfg.precision != NSR_PREC_FP32_SIMT) NSR_CUDA(h, tc_pack(h, which, param_ptrs, st));
+  h->net[which].packed = true;
+  return NSR_OK;
+}
+
+// ----------------------------------------------------------------------------
+// hot path
+// ----------------------------------------------------------------------------
+struct WsLayout { size_t z_c, z_f, raw, total; };
+
+static WsLayout ws_layout(const NsrHandle_* h, int64_t n) {
+  const int Sc = h->cfg.n_coarse, Sf = Sc + h->cfg.n_importance;
+  WsLayout L{};
+  size_t off = 0;
+  L.z_f = off; off += align_up((size_t)n * Sf * sizeof(float));
+  if (h->cfg.precision == NSR_PREC_FP32_SIMT) {
+    L.z_c = off; off += align_up((size_t)n * Sc * sizeof(float));
+    L.raw = off; off += align_up((size_t)n * Sf * 4 * sizeof(float));
+  }
+  L.total = off + 256;
+  return L;
+}
+
+extern "C" size_t nsr_workspace_bytes(const NsrHandle* h, int64_t n_rays) {
+  if (!h || n_rays < 0) return 0;
+  return ws_layout(h, n_rays).total;
+}
+
+static int check_render_args(NsrHandle_* h, const float* rays, int64_t n_rays, int ray_stride) {
+  if (!rays && n_rays > 0) return fail(h, NSR_ERR_INVALID_ARG, "rays is null");
+  if (n_rays < 0) return fail(h, NSR_ERR_INVALID_ARG, "n_rays < 0");
+  if (ray_stride < 8 || ray_stride < h->cfg.viewdir_offset + 3)
+    return fail(h, NSR_ERR_INVALID_ARG, "ray_stride too small for (o,d,near,far[,viewdir])");
+  return NSR_OK;
+}
+
+static int run_pass(NsrHandle_* h, int which, const float* rays, int64_t n, int stride, const float* z_in,
+                    int S, const float* u_jitter, const float* noise, int do_resample, const float* u_res,
+                    float* comp, float* depth, float* opa, float* wts, float* raw_out, float* z_next,
+                    float* ws_z, float* ws_raw, cudaStream_t st) {
+  if (!h->net[which].packed) return fail(h, NSR_ERR_NOT_PACKED, "weights of net " + std::to_string(which) + " not packed");
+  if (h->cfg.precision == NSR_PREC_FP32_SIMT) {
+    const float* z = z_in;
+    if (!z) {   // coarse pass: sample z on device
+      const int64_t total = n * S;
+      k_sample_coarse<<<grid_for(total, 256, h->sm_count * 16), 256, 0, st>>>(h->rp, h->d_tables, rays, n, stride, u_jitter, ws_z);
+      h->launches += 1;
+      z = ws_z;
+    }
+    float* raw = raw_out ? raw_out : ws_raw;
+    NSR_CUDA(h, simt_mlp(h, which, rays, n, stride, z, S, raw, st));
+    NSR_CUDA(h, launch_composite(h, raw, z, noise, n, S, do_resample, u_res, comp, depth, opa, wts, z_next, st));
+    return NSR_OK;
+  }
+  TcPassArgs a{};
+  a.rays = rays; a.n_rays = n; a.ray_stride = stride; a.z_in = z_in; a.S = S;
+  a.u_jitter = u_jitter; a.noise = noise; a.u_resample = u_res; a.do_resample = do_resample;
+  a.comp_rgb = comp; a.depth = depth; a.opacity = opa; a.weights = wts; a.raw = raw_out; a.z_next = z_next;
+  NSR_CUDA(h, tc_pass(h, which, a, st));
+  return NSR_OK;
+}
+
+extern "C" int nsr_render(NsrHandle* h, const float* rays, int64_t n_rays, int ray_stride, const NsrRng* rng,
+                          const NsrOutputs* out, void* workspace, size_t workspace_bytes, NsrStream stream) {
+  if (!h) return NSR_ERR_INVALID_ARG;
+  if (!out) return fail(h, NSR_ERR_INVALID_ARG, "nsr_render: out is null");
+  int rc = check_render_args(h, rays, n_rays, ray_stride);
+  if (rc) return rc;
+  if (n_rays == 0) return NSR_OK;
+  const WsLayout L = ws_layout(h, n_rays);
+  if (!workspace || workspace_bytes < L.total) return fail(h, NSR_ERR_WORKSPACE, "workspace too small: need " + std::to_string(L.total));
+  NSR_CUDA(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  const int Sc = h->cfg.n_coarse, Ni = h->cfg.n_importance;
+  float* z_f = out->z_fine ? out->z_fine : (float*)(ws + L.z_f);
+  float* ws_zc = (float*)(ws + L.z_c);
+  float* ws_raw = (float*)(ws + L.raw);
+  const NsrRng none{};
+  const NsrRng& R = rng ? *rng : none;
+  const float* noise_c = (h->cfg.noise_std > 0.f) ? R.noise_coarse : nullptr;
+  const float* noise_f = (h->cfg.noise_std > 0.f) ? R.noise_fine : nullptr;
+  rc = run_pass(h, 0, rays, n_rays, ray_stride, nullptr, Sc, R.u_coarse, noise_c, Ni > 0, R.u_fine,
+                out->coarse_comp_rgbs, out->coarse_depth, out->coarse_opacity, out->coarse_weights, nullptr,
+                Ni > 0 ? z_f : nullptr, ws_zc, ws_raw, st);
+  if (rc) return rc;
+  if (Ni > 0) {
+    rc = run_pass(h, 1, rays, n_rays, ray_stride, z_f, Sc + Ni, nullptr, noise_f, 0, nullptr, out->fine_comp_rgbs,
+                  out->fine_depth, out->fine_opacity, out->fine_weights, nullptr, nullptr, ws_zc, ws_raw, st);
+    if (rc) return rc;
+  }
+  return NSR_OK;
+}
+
+extern "C" int nsr_render_pass(NsrHandle* h, int which, const float* rays, int64_t n_rays, int ray_stride,
+                               const float* z_vals, int n_samples, const float* noise,
+                               const NsrPassOutputs* out, void* workspace, size_t workspace_bytes,
+                               NsrStream stream) {
+  if (!h) return NSR_ERR_INVALID_ARG;
+  if (!out || !z_vals || which < 0 || which > 1) return fail(h, NSR_ERR_INVALID_ARG, "nsr_render_pass: bad argument");
+  int rc = check_render_args(h, rays, n_rays, ray_stride);
+  if (rc) return rc;
+  if (n_samples != h->cfg.n_coarse && n_samples != h->cfg.n_coarse + h->cfg.n_importance)
+    return fail(h, NSR_ERR_UNSUPPORTED, "n_samples must be n_coarse or n_coarse+n_importance");
+  if (n_rays == 0) return NSR_OK;
+  const WsLayout L = ws_layout(h, n_rays);
+  if (!workspace || workspace_bytes < L.total) return fail(h, NSR_ERR_WORKSPACE, "workspace too small: need " + std::to_string(L.total));
+  NSR_CUDA(h, cudaSetDevice(h->cfg.device));
+  char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  return run_pass(h, which, rays, n_rays, ray_stride, z_vals, n_samples, nullptr,
+                  (h->cfg.noise_std > 0.f) ? noise : nullptr, 0, nullptr, out->comp_rgbs, out->depth,
+                  out->opacity, out->weights, out->raw, nullptr, (float*)(ws + L.z_c), (float*)(ws + L.raw),
+                  (cudaStream_t)stream);
+}
+
+extern "C" int nsr_sample_coarse(NsrHandle* h, const float* rays, int64_t n_rays, int ray_stride,
+                                 const float* u, float* z_out, NsrStream stream) {
+  if (!h) return NSR_ERR_INVALID_ARG;
+  int rc = check_render_args(h, rays, n_rays, ray_stride);
+  if (rc) return rc;
+  if (!z_out) return fail(h, NSR_ERR_INVALID_ARG, "z_out is null");
+  if (n_rays == 0) return NSR_OK;
+  NSR_CUDA(h, cudaSetDevice(h->cfg.device));
+  const int64_t total = n_rays * h->cfg.n_coarse;
+  k_sample_coarse<<<grid_for(total, 256, h->sm_count * 16), 256, 0, (cudaStream_t)stream>>>(
+      h->rp, h->d_tables, rays, n_rays, ray_stride, u, z_out);
+  h->launches += 1;
+  NSR_CUDA(h, cudaGetLastError());
+  return NSR_OK;
+}
+
+extern "C" int nsr_resample(NsrHandle* h, const float* z_in, const float* weights, int64_t n_rays,
+                            const float* u, float* z_out, NsrStream stream) {
+  if (!h) return NSR_ERR_INVALID_ARG;
+  if (!z_in || !weights || !z_out || n_rays < 0) return fail(h, NSR_ERR_INVALID_ARG, "nsr_resample: bad argument");
+  if (h->cfg.n_importance <= 0) return fail(h, NSR_ERR_UNSUPPORTED, "n_importance == 0");
+  if (n_rays == 0) return NSR_OK;
+  NSR_CUDA(h, cudaSetDevice(h->cfg.device));
+  const int S = h->cfg.n_coarse, n_imp = h->cfg.n_importance;
+  const int per_warp = 2 * S + (3 * S + 2 * n_imp);
+  const size_t smem = (size_t)per_warp * 4 * sizeof(float);
+  k_resample<<<grid_for(n_rays, 4, h->sm_count * 8), 128, smem, (cudaStream_t)stream>>>(
+      h->rp, h->d_tables, z_in, weights, n_rays, u, z_out, per_warp);
+  h->launches += 1;
+  NSR_CUDA(h, cudaGetLastError());
+  return NSR_OK;
+}
+
+extern "C" int nsr_posenc(NsrHandle* h, const float* x, int64_t n, int deg, float* out, NsrStream stream) {
+  if (!h) return NSR_ERR_INVALID_ARG;
+  if (!x || !out || n < 0) return fail(h, NSR_ERR_INVALID_ARG, "nsr_posenc: bad argument");
+  const float* freqs = nullptr;
+  if (deg == h->cfg.deg_pos) freqs = h->d_tables->freq_pos;
+  else if (deg == h->cfg.deg_dir) freqs = h->d_tables->freq_dir;
+  else return fail(h, NSR_ERR_UNSUPPORTED, "nsr_posenc: deg must be the handle's deg_pos or deg_dir");
+  if (n == 0) return NSR_OK;
+  NSR_CUDA(h, cudaSetDevice(h->cfg.device));
+  k_posenc<<<grid_for(n, 256, h->sm_count * 16), 256, 0, (cudaStream_t)stream>>>(x, n, deg, h->cfg.no_xyz, freqs, out);
+  h->launches += 1;
+  NSR_CUDA(h, cudaGetLastError());
+  return NSR_OK;
+}
+
+extern "C" int nsr_box_average(NsrHandle* h, const float* in, int64_t n_lr, int s, int channels, float* out,
+                               NsrStream stream) {
+  if (!h) return NSR_ERR_INVALID_ARG;
+  if (!in || !out || n_lr < 0 || s < 1 || channels < 1) return fail(h, NSR_ERR_INVALID_ARG, "nsr_box_average: bad argument");
+  if (n_lr == 0) return NSR_OK;
+  NSR_CUDA(h, cudaSetDevice(h->cfg.device));
+  k_box_average<<<grid_for(n_lr * channels, 256, h->sm_count * 16), 256, 0, (cudaStream_t)stream>>>(
+      in, n_lr, s * s, channels, out);
+  h->launches += 1;
+  NSR_CUDA(h, cudaGetLastError());
+  return NSR_OK;
+}
+
+extern "C" int nsr_generate_rays(NsrHandle* h, const float* c2w_host, int H, int W, float focal, int s, int ndc,
+                                 float near_plane, float far_plane, float* rays_out, NsrStream stream) {
+  if (!h) return NSR_ERR_INVALID_ARG;
+  if (!c2w_host || !rays_out || H <= 0 || W <= 0 || s < 1 || !(focal > 0.f))
+    return fail(h, NSR_ERR_INVALID_ARG, "nsr_generate_rays: bad argument");
+  if (H % s || W % s) return fail(h, NSR_ERR_INVALID_ARG, "H and W must be multiples of the supersampling factor");
+  NSR_CUDA(h, cudaSetDevice(h->cfg.device));
+  Pose p;
+  memcpy(p.m, c2w_host, sizeof(p.m));
+  k_generate_rays<<<grid_for((int64_t)H * W, 256, h->sm_count * 16), 256, 0, (cudaStream_t)stream>>>(
+      p, H, W, focal, s, ndc, near_plane, far_plane, rays_out);
+  h->launches += 1;
+  NSR_CUDA(h, cudaGetLastError());
+  return NSR_OK;
+}
+
+// ----------------------------------------------------------------------------
+// host-buffer pipeline
+// ----------------------------------------------------------------------------
+static int ensure_host_state(NsrHandle_* h, int64_t chunk, int stride) {
+  const size_t ws_bytes = ws_layout(h, chunk).total;
+  if (h->host_chunk >= (size_t)chunk * stride && h->host_ws_bytes >= ws_bytes && h->hs[0]) return NSR_OK;
+  for (int i = 0; i < 2; ++i) {
+    if (h->pin_in[i]) cudaFreeHost(h->pin_in[i]);
+    if (h->pin_out[i]) cudaFreeHost(h->pin_out[i]);
+    cudaFree(h->dev_in[i]); cudaFree(h->dev_out[i]); cudaFree(h->dev_ws[i]);
+    h->pin_in[i] = h->pin_out[i] = h->dev_in[i] = h->dev_out[i] = nullptr; h->dev_ws[i] = nullptr;
+    if (!h->hs[i]) NSR_CUDA(h, cudaStreamCreateWithFlags(&h->hs[i], cudaStreamNonBlocking));
+    if (!h->hev[i]) NSR_CUDA(h, cudaEventCreateWithFlags(&h->hev[i], cudaEventDisableTiming));
+    NSR_CUDA(h, cudaMallocHost(&h->pin_in[i], (size_t)chunk * stride * sizeof(float)));
+    NSR_CUDA(h, cudaMallocHost(&h->pin_out[i], (size_t)chunk * 4 * sizeof(float)));
+    NSR_CUDA(h, cudaMalloc(&h->dev_in[i], (size_t)chunk * stride * sizeof(float)));
+    NSR_CUDA(h, cudaMalloc(&h->dev_out[i], (size_t)chunk * 8 * sizeof(float)));   // rgb[3]+depth[1] HR, then LR copies
+    NSR_CUDA(h, cudaMalloc(&h->dev_ws[i], ws_bytes));
+  }
+  h->host_chunk = (size_t)chunk * stride;
+  h->host_ws_bytes = ws_bytes;
+  return NSR_OK;
+}
+
+extern "C" int nsr_render_host(NsrHandle* h, const float* rays_host, int64_t n_rays, int ray_stride, int s,
+                               float* rgb_host, float* depth_host) {
+  if (!h) return NSR_ERR_INVALID_ARG;
+  int rc = check_render_args(h, rays_host, n_rays, ray_stride);
+  if (rc) return rc;
+  if (s < 1 || n_rays % ((int64_t)s * s)) return fail(h, NSR_ERR_INVALID_ARG, "n_rays must be a multiple of s*s");
+  if (n_rays == 0) return NSR_OK;
+  NSR_CUDA(h, cudaSetDevice(h->cfg.device));
+  const int ss = s * s;
+  int64_t chunk = 65536;
+  chunk -= chunk % ss;
+  if (chunk > n_rays) chunk = n_rays;
+  rc = ensure_host_state(h, chunk, ray_stride);
+  if (rc) return rc;
+  const bool fine = h->cfg.n_importance > 0;
+  const int64_t n_chunks = (n_rays + chunk - 1) / chunk;
+  // software pipeline over two slots: stage(k) | H2D+render+D2H(k) async | drain(k-1)
+  auto drain = [&](int64_t k) {
+    const int slot = (int)(k & 1);
+    cudaEventSynchronize(h->hev[slot]);
+    const int64_t r0 = k * chunk, nr = (r0 + chunk <= n_rays) ? chunk : n_rays - r0;
+    const int64_t o0 = r0 / ss, no = nr / ss;
+    if (rgb_host) memcpy(rgb_host + o0 * 3, h->pin_out[slot], (size_t)no * 3 * sizeof(float));
+    if (depth_host) memcpy(depth_host + o0, h->pin_out[slot] + (size_t)chunk * 3, (size_t)no * sizeof(float));
+  };
+  for (int64_t k = 0; k < n_chunks; ++k) {
+    const int slot = (int)(k & 1);
+    if (k >= 2) drain(k - 2);
+    const int64_t r0 = k * chunk, nr = (r0 + chunk <= n_rays) ? chunk : n_rays - r0;
+    cudaStream_t st = h->hs[slot];
+    memcpy(h->pin_in[slot], rays_host + r0 * ray_stride, (size_t)nr * ray_stride * sizeof(float));
+    NSR_CUDA(h, cudaMemcpyAsync(h->dev_in[slot], h->pin_in[slot], (size_t)nr * ray_stride * sizeof(float),
+                                cudaMemcpyHostToDevice, st));
+    float* d_rgb = h->dev_out[slot];
+    float* d_dep = d_rgb + (size_t)chunk * 3;
+    float* d_rgb_lr = d_dep + (size_t)chunk;
+    float* d_dep_lr = d_rgb_lr + (size_t)chunk * 3;
+    NsrOutputs o{};
+    if (fine) { o.fine_comp_rgbs = d_rgb; o.fine_depth = d_dep; }
+    else { o.coarse_comp_rgbs = d_rgb; o.coarse_depth = d_dep; }
+    rc = nsr_render(h, h->dev_in[slot], nr, ray_stride, nullptr, &o, h->dev_ws[slot], h->host_ws_bytes, st);
+    if (rc) return rc;
+    const float* src_rgb = d_rgb;
+    const float* src_dep = d_dep;
+    const int64_t no = nr / ss;
+    if (s > 1) {
+      rc = nsr_box_average(h, d_rgb, no, s, 3, d_rgb_lr, st); if (rc) return rc;
+      rc = nsr_box_average(h, d_dep, no, s, 1, d_dep_lr, st); if (rc) return rc;
+      src_rgb = d_rgb_lr; src_dep = d_dep_lr;
+    }
+    if (rgb_host) NSR_CUDA(h, cudaMemcpyAsync(h->pin_out[slot], src_rgb, (size_t)no * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (depth_host) NSR_CUDA(h, cudaMemcpyAsync(h->pin_out[slot] + (size_t)chunk * 3, src_dep, (size_t)no * sizeof(float), cudaMemcpyDeviceToHost, st));
+    NSR_CUDA(h, cudaEventRecord(h->hev[slot], st));
+  }
+  for (int64_t k = (n_chunks >= 2 ? n_chunks - 2 : 0); k < n_chunks; ++k) drain(k);
+  NSR_CUDA(h, cudaGetLastError());
+  return NSR_OK;
+}

@@ -1,0 +1,211 @@
+// nsr_device.cuh -- device functions shared by the SIMT and the tcgen05 paths:
+// coarse sampling, point casting, positional encoding, alpha compositing and
+// inverse-CDF resampling.  Scalar fp32 math follows the reference's operation
+// ORDER (separate multiply / add roundings where PyTorch issues separate
+// elementwise kernels), because the positional encoding amplifies 1-ulp
+// differences in z by up to 2^9 (hard part 5).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nsr {
+
+constexpr int kMaxSamples = 256;     // per-ray samples the fused paths support
+constexpr int kMaxFreqs = 16;
+
+// ----------------------------------------------------------------------------
+// Small per-handle tables passed by value in kernel parameters (no global state)
+// ----------------------------------------------------------------------------
+struct SampleTables {
+  float t_coarse[kMaxSamples];       // torch.linspace(0,1,n_coarse)    (models/utils.py:31)
+  float one_minus_t[kMaxSamples];    // 1 - t, rounded once like the reference's (1 - t_vals)
+  float u_fine[kMaxSamples];         // torch.linspace(0,1,n_importance) (models/utils.py:75)
+  float freq_pos[kMaxFreqs];         // frequency bands (models/embedding.py:39-42)
+  float freq_dir[kMaxFreqs];
+};
+
+struct RenderParams {
+  int n_coarse, n_importance;
+  int deg_pos, deg_dir, no_xyz;
+  int ch_pos, ch_dir;
+  int lindisp, white_bkgd, sigma_softplus, color_none, gamma_correct, no_dir;
+  int viewdir_offset;
+  float noise_std;
+};
+
+// ----------------------------------------------------------------------------
+// a6: coarse z for sample i of a ray (models/utils.py:31-35)
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ float coarse_z(float near, float far, float t, float omt, int lindisp) {
+  if (lindisp) {
+    // 1. / (1. / near * (1 - t) + 1. / far * t)
+    float a = __fmul_rn(__fdiv_rn(1.f, near), omt);
+    float b = __fmul_rn(__fdiv_rn(1.f, far), t);
+    return __fdiv_rn(1.f, __fadd_rn(a, b));
+  }
+  // near * (1 - t) + far * t
+  return __fadd_rn(__fmul_rn(near, omt), __fmul_rn(far, t));
+}
+
+// stratified jitter (models/utils.py:37-41): z = lower + u * (upper - lower)
+__device__ __forceinline__ float jitter_z(float z_prev, float z_cur, float z_next, bool first,
+                                          bool last, float u) {
+  float lower = first ? z_cur : __fmul_rn(0.5f, __fadd_rn(z_prev, z_cur));
+  float upper = last ? z_cur : __fmul_rn(0.5f, __fadd_rn(z_cur, z_next));
+  return __fadd_rn(lower, __fmul_rn(u, __fsub_rn(upper, lower)));
+}
+
+// cast_rays (models/utils.py:14): o + z * d, multiply then add (no FMA)
+__device__ __forceinline__ float cast_point(float o, float d, float z) {
+  return __fadd_rn(o, __fmul_rn(z, d));
+}
+
+// ----------------------------------------------------------------------------
+// a5: positional encoding of one 3-vector (models/embedding.py:57-63).
+// Calls emit(channel, value) for channels in the reference's concatenation
+// order: [x] + [sin(f0 x), cos(f0 x), sin(f1 x), ...], each a 3-vector.
+// ----------------------------------------------------------------------------
+template <typename Emit>
+__device__ __forceinline__ void posenc3(float x, float y, float z, int n_freqs, const float* freqs,
+                                        int no_xyz, Emit emit) {
+  int c = 0;
+  if (!no_xyz) {
+    emit(0, x); emit(1, y); emit(2, z);
+    c = 3;
+  }
+  for (int k = 0; k < n_freqs; ++k) {
+    const float f = freqs[k];
+    const float ax = __fmul_rn(f, x), ay = __fmul_rn(f, y), az = __fmul_rn(f, z);
+    emit(c + 0, sinf(ax)); emit(c + 1, sinf(ay)); emit(c + 2, sinf(az));
+    emit(c + 3, cosf(ax)); emit(c + 4, cosf(ay)); emit(c + 5, cosf(az));
+    c += 6;
+  }
+}
+
+// ----------------------------------------------------------------------------
+// warp helpers
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float sigma_act(float s, int softplus) {
+  // rendering.py:70-73: relu, or log(1 + exp(x - 1))
+  return softplus ? logf(__fadd_rn(1.f, expf(__fsub_rn(s, 1.f)))) : fmaxf(s, 0.f);
+}
+
+// ----------------------------------------------------------------------------
+// a10: alpha compositing of ONE ray by ONE warp (models/rendering.py:89-111).
+//   z[S], sigma[S] (raw, noise already added), rgb[S*3] : shared memory
+//   w_out[S] : shared memory (weights kept for resampling)
+// Results (comp rgb, depth, opacity) are returned in every lane.
+// The transmittance product is evaluated sequentially (like torch.cumprod on
+// CPU) by lane 0 over alpha values staged in w_out.
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void composite_ray_warp(const float* z, const float* sigma, const float* rgb,
+                                                   int S, int white_bkgd, int softplus, float* w_out,
+                                                   float& r, float& g, float& b, float& depth,
+                                                   float& opacity) {
+  const int lane = threadIdx.x & 31;
+  // alpha_i = 1 - exp(-delta_i * act(sigma_i)); delta_last = 1e10
+  for (int i = lane; i < S; i += 32) {
+    const float delta = (i + 1 < S) ? __fsub_rn(z[i + 1], z[i]) : 1e10f;
+    const float a = __fsub_rn(1.f, expf(__fmul_rn(-delta, sigma_act(sigma[i], softplus))));
+    w_out[i] = a;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    // T_0 = 1, T_i = prod_{j<i} (1 - alpha_j + 1e-10)  (rendering.py:99-102)
+    float T = 1.f;
+    for (int i = 0; i < S; ++i) {
+      const float a = w_out[i];
+      w_out[i] = __fmul_rn(a, T);
+      T = __fmul_rn(T, __fadd_rn(__fsub_rn(1.f, a), 1e-10f));
+    }
+  }
+  __syncwarp();
+  float sr = 0.f, sg = 0.f, sb = 0.f, sd = 0.f, so = 0.f;
+  for (int i = lane; i < S; i += 32) {
+    const float w = w_out[i];
+    sr += w * rgb[3 * i + 0];
+    sg += w * rgb[3 * i + 1];
+    sb += w * rgb[3 * i + 2];
+    sd += w * z[i];
+    so += w;
+  }
+  sr = warp_sum(sr); sg = warp_sum(sg); sb = warp_sum(sb); sd = warp_sum(sd); so = warp_sum(so);
+  if (white_bkgd) {
+    const float bg = __fsub_rn(1.f, so);
+    sr = __fadd_rn(sr, bg); sg = __fadd_rn(sg, bg); sb = __fadd_rn(sb, bg);
+  }
+  r = sr; g = sg; b = sb; depth = sd; opacity = so;
+}
+
+// ----------------------------------------------------------------------------
+// a11: inverse-CDF resampling + sort-merge of ONE ray by ONE warp
+// (models/utils.py:61-93).
+//   z[Sc], w[Sc]      : shared memory (coarse z-values and weights)
+//   u                 : pointer to this ray's n_imp uniforms (global) or null
+//   u_table           : linspace(0,1,n_imp) when u == null
+//   scratch           : shared memory, >= 2*Sc + n_imp floats
+//   z_out[Sc + n_imp] : shared or global memory; sorted ascending
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void resample_ray_warp(const float* z, const float* w, int Sc, int n_imp,
+                                                  const float* u, const float* u_table, float* scratch,
+                                                  float* z_out) {
+  const int lane = threadIdx.x & 31;
+  const float eps = 1e-5f;
+  const int nb = Sc - 1;         // bins (mid-points) and cdf entries
+  const int nw = Sc - 2;         // interior weights
+  float* bins = scratch;         // [Sc-1]
+  float* cdf = scratch + Sc;     // [Sc-1]
+  float* znew = scratch + 2 * Sc;  // [n_imp]
+  float part = 0.f;
+  for (int i = lane; i < nb; i += 32) bins[i] = __fmul_rn(0.5f, __fadd_rn(z[i], z[i + 1]));
+  for (int i = lane; i < nw; i += 32) part += __fadd_rn(w[i + 1], eps);
+  const float total = warp_sum(part);
+  __syncwarp();
+  if (lane == 0) {   // cdf = cat(0, cumsum(pdf)) evaluated sequentially like torch.cumsum on CPU
+    float c = 0.f;
+    cdf[0] = 0.f;
+    for (int i = 0; i < nw; ++i) {
+      c = __fadd_rn(c, __fdiv_rn(__fadd_rn(w[i + 1], eps), total));
+      cdf[i + 1] = c;
+    }
+  }
+  __syncwarp();
+  for (int j = lane; j < n_imp; j += 32) {
+    const float uj = u ? u[j] : u_table[j];
+    int inds = 0;                                   // searchsorted(cdf, u, right=True)
+    for (int i = 0; i < nb; ++i) inds += (cdf[i] <= uj) ? 1 : 0;
+    const int below = max(inds - 1, 0);
+    const int above = min(inds, nw);
+    const float c0 = cdf[below], c1 = cdf[above];
+    const float b0 = bins[below], b1 = bins[above];
+    float denom = __fsub_rn(c1, c0);
+    if (denom < eps) denom = 1.f;
+    znew[j] = __fadd_rn(b0, __fmul_rn(__fdiv_rn(__fsub_rn(uj, c0), denom), __fsub_rn(b1, b0)));
+  }
+  __syncwarp();
+  // sort(cat(z, z_new)) by rank: stable w.r.t. concatenation order, handles the
+  // unsorted u of train mode as well as the two pre-sorted lists of eval mode.
+  const int n_all = Sc + n_imp;
+  for (int e = lane; e < n_all; e += 32) {
+    const float v = (e < Sc) ? z[e] : znew[e - Sc];
+    int rank = 0;
+    for (int i = 0; i < Sc; ++i) {
+      const float o = z[i];
+      rank += (o < v || (o == v && i < e)) ? 1 : 0;
+    }
+    for (int i = 0; i < n_imp; ++i) {
+      const float o = znew[i];
+      rank += (o < v || (o == v && (Sc + i) < e)) ? 1 : 0;
+    }
+    z_out[rank] = v;
+  }
+  __syncwarp();
+}
+
+}  // namespace nsr

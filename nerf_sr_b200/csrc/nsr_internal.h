@@ -1,0 +1,98 @@
+// nsr_internal.h -- host-side handle and cross-file declarations (not installed).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/nsr.h"
+#include "nsr_device.cuh"
+
+namespace nsr {
+
+constexpr int kMaxTrunk = 16;
+
+// One Linear layer of VanillaMLP as the SIMT path executes it.
+struct SimtLayer {
+  int K0, K1;          // input segments: K0 rows from src0 then K1 rows from src1 (cat order)
+  int src0, src1;      // buffer ids: 0 enc_xyz, 1 enc_dir, 2 bufA, 3 bufB
+  int dst;             // output buffer id (2|3), or -1 for a head
+  int N;               // outputs
+  int relu;            // 1: ReLU
+  int64_t w_off;       // offset (floats) of the permuted W^T image in the SIMT weight blob
+  int64_t b_off;       // offset (floats) of the bias
+};
+
+struct SimtProgram {
+  int n_layers;        // trunk + final + dir (tiled GEMM layers)
+  SimtLayer layers[kMaxTrunk + 2];
+  int sigma_src;       // buffer holding h_D (input of the sigma head)
+  int rgb_src;         // buffer holding the dir layer's output
+  int64_t w_sigma, b_sigma, w_rgb, b_rgb;   // offsets into the blob (plain [N][K] row-major)
+  int W, ch_pos, ch_dir;
+};
+
+struct NetImages {
+  bool packed = false;
+  float* simt_blob = nullptr;      // device: permuted fp32 weights for the SIMT path
+  size_t simt_floats = 0;
+  uint8_t* tc_image = nullptr;     // device: swizzled hi/lo stage images for the tcgen05 path
+  size_t tc_bytes = 0;
+  float* tc_consts = nullptr;      // device: biases, head weights, dir-part weights (fp32)
+};
+
+}  // namespace nsr
+
+struct NsrHandle_ {
+  NsrConfig cfg;
+  nsr::RenderParams rp;
+  nsr::SimtProgram prog;
+  nsr::SampleTables* d_tables = nullptr;
+  nsr::SampleTables h_tables;
+  nsr::NetImages net[2];
+  std::vector<int64_t> param_numel;
+  int sm_count = 0;
+  int64_t launches = 0;
+  std::string err;
+  // nsr_render_host state (library-owned staging)
+  cudaStream_t hs[2] = {nullptr, nullptr};
+  cudaEvent_t hev[2] = {nullptr, nullptr};
+  float* pin_in[2] = {nullptr, nullptr};
+  float* pin_out[2] = {nullptr, nullptr};
+  float* dev_in[2] = {nullptr, nullptr};
+  float* dev_out[2] = {nullptr, nullptr};
+  void* dev_ws[2] = {nullptr, nullptr};
+  size_t host_chunk = 0, host_ws_bytes = 0;
+};
+
+namespace nsr {
+
+// ---- SIMT path (nsr_simt.cu) ----
+size_t simt_blob_floats(const NsrHandle_* h);
+cudaError_t simt_pack(NsrHandle_* h, int which, const float* const* params, cudaStream_t st);
+cudaError_t simt_mlp(NsrHandle_* h, int which, const float* rays, int64_t n_rays, int ray_stride,
+                     const float* z, int S, float* raw, cudaStream_t st);
+
+// ---- tcgen05 path (nsr_tc.cu) ----
+bool tc_supported(const NsrConfig& cfg, std::string* why);
+size_t tc_image_bytes(const NsrHandle_* h);
+cudaError_t tc_pack(NsrHandle_* h, int which, const float* const* params, cudaStream_t st);
+// Fused pass: sampling/encoding -> MLP -> compositing (-> resampling).
+//   z_in   : [N,S] or null (coarse pass computes z itself; u_jitter optional)
+//   z_next : [N, S+n_imp] or null; written when do_resample
+struct TcPassArgs {
+  const float* rays; int64_t n_rays; int ray_stride;
+  const float* z_in; int S;
+  const float* u_jitter; const float* noise; const float* u_resample;
+  int do_resample;
+  float* comp_rgb; float* depth; float* opacity; float* weights; float* raw; float* z_next;
+};
+cudaError_t tc_pass(NsrHandle_* h, int which, const TcPassArgs& a, cudaStream_t st);
+
+// ---- shared small kernels (nsr_api.cu) ----
+cudaError_t launch_composite(NsrHandle_* h, const float* raw, const float* z, const float* noise,
+                             int64_t n_rays, int S, int do_resample, const float* u_resample,
+                             float* comp_rgb, float* depth, float* opacity, float* weights,
+                             float* z_next, cudaStream_t st);
+
+}  // namespace nsr

@@ -1,0 +1,762 @@
+// nsr_tc.cu -- the tcgen05 fused render pass (NSR_PREC_*_TC), sm_100a only.
+//
+// One persistent CTA per SM; a tile is 128 sampled points (2 coarse rays x 64
+// samples, or 1 fine ray x 128).  Per tile, entirely on-chip:
+//   front-end warps : z sampling / jitter, o + z*d, sin/cos positional encoding,
+//                     hi/lo 16-bit split, written as a K-major SWIZZLE_128B UMMA
+//                     operand in shared memory; per-ray view-direction bias.
+//   producer thread : streams the net's pre-swizzled weight image (72 stages x
+//                     32 KB: 128 rows x 64 k, hi | lo) L2 -> smem ring with
+//                     cp.async.bulk + mbarrier complete_tx.
+//   MMA thread      : tcgen05.mma kind::f16, M=128 N=128 K=16, fp32 accumulate in
+//                     TMEM.  Activations live in TMEM as the A operand (hi and lo
+//                     planes), weights are the smem B operand; each product is
+//                     evaluated as hi*hi + lo*hi + hi*lo (split precision, ~fp32
+//                     accuracy -- SURVEY.md section 0.6).
+//   epilogue warps  : tcgen05.ld accumulator -> +bias, ReLU, hi/lo split ->
+//                     tcgen05.st next layer's A operand; sigma / rgb heads on CUDA
+//                     cores; then alpha compositing (one warp per ray), inverse-CDF
+//                     resampling + sort-merge for the fine pass, output stores.
+// Encoded features, activations and per-sample (rgb, sigma) never reach HBM.
+//
+// TMEM map (512 columns x 128 lanes x 32 bit):
+//   [  0,256) fp32 accumulator, two N-halves of 128 columns
+//   [256,384) A operand, hi plane (256 k-values, 2 per column)
+//   [384,512) A operand, lo plane
+// The two accumulator halves let the epilogue of layer L overlap the MMAs of
+// layers L and L+1 (see the schedule in mma_role()).
+//
+// Replaces (reference): sample_along_rays + cast_rays (models/utils.py:5-44),
+// PositionalEncoding (models/embedding.py:44-63), render_rays' [P,90] concat
+// (models/nerf_downX_model.py:260-278), VanillaMLP.forward (models/networks.py:
+// 199-224), add_gaussian_noise (models/utils.py:199-212), VolumetricRenderer.forward
+// (models/rendering.py:89-111) and resample_along_rays (models/utils.py:47-95).
+#include <cstdio>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "nsr_internal.h"
+
+namespace nsr {
+
+// ---------------------------------------------------------------------------
+// compile-time geometry
+// ---------------------------------------------------------------------------
+constexpr int kTile = 128;                  // points per tile (UMMA M)
+constexpr int kStageBytes = 32768;          // 128 rows x 64 k x 2 B, hi then lo
+constexpr int kPlaneBytes = 16384;
+constexpr int kRing = 4;
+constexpr int kStagesPerTile = 72;
+constexpr int kWarpsFront = 4, kWarpsEpi = 8;
+constexpr int kThreadsTc = 32 * (2 + kWarpsFront + kWarpsEpi);   // 448
+constexpr int kFrontWarp0 = 2, kEpiWarp0 = 2 + kWarpsFront;      // warps 2-5, 6-13
+
+// consts blob (floats)
+constexpr int kcBias = 0;        // 8 x 256 trunk, then final 256, then dir 128
+constexpr int kcBiasFinal = 2048;
+constexpr int kcBiasDir = 2304;
+constexpr int kcWsig = 2432;     // 256
+constexpr int kcWrgb = 2688;     // 3 x 128
+constexpr int kcMisc = 3072;     // b_sigma, b_rgb[3]
+constexpr int kcSmemFloats = 3080;
+constexpr int kcWdd = 3080;      // dir-part of dir_encoding weight: [128][28]
+constexpr int kcTotal = 3080 + 128 * 28;
+
+// shared memory map (bytes, relative to a 1024-aligned base)
+constexpr int kSmRing = 0;
+constexpr int kSmEnc = kSmRing + kRing * kStageBytes;            // 131072
+constexpr int kSmConst = kSmEnc + 2 * kStageBytes;               // 196608
+constexpr int kSmDirBias = kSmConst + 12544;                     // 209152
+constexpr int kSmZ = kSmDirBias + 2 * 2 * 128 * 4;               // 211200
+constexpr int kSmDenc = kSmZ + 2 * 128 * 4;                      // 212224
+constexpr int kSmSig = kSmDenc + 2 * 32 * 4;                     // 212480
+constexpr int kSmRgb = kSmSig + 128 * 4;
+constexpr int kSmW = kSmRgb + 384 * 4;
+constexpr int kSmXch = kSmW + 128 * 4;                           // 215040
+constexpr int kSmScratch = kSmXch + 4 * 128 * 4;                 // 217088
+constexpr int kSmBar = kSmScratch + 2 * 320 * 4;                 // 219648
+constexpr int kSmTmemPtr = kSmBar + 32 * 8;
+constexpr int kSmemTcBytes = kSmTmemPtr + 16 + 1024;             // + alignment slack
+
+// barrier indices
+enum {
+  B_WFULL = 0,            // [4] weights landed (tx)
+  B_WEMPTY = 4,           // [4] stage consumed (tcgen05.commit)
+  B_ACCFULL = 8,          // [2] accumulator half complete (commit)
+  B_AFREE0 = 10,          // A operand k-half 0 no longer read by this layer (commit)
+  B_AREADY = 11,          // [2] epilogue finished half h: acc half free, A k-half written
+  B_ENCFULL = 13,         // [2] front-end produced tile inputs
+  B_TILEDONE = 15,        // [2] epilogue finished the tile using buffer b
+  B_COUNT = 17
+};
+
+// ---------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok;
+}
+#ifndef NSR_TC_WATCHDOG
+#define NSR_TC_WATCHDOG 1
+#endif
+// Blocks until the phase with the given parity has completed.  With the watchdog enabled a
+// protocol deadlock becomes a trapped launch failure with a diagnostic instead of a hung GPU.
+__device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
+  printf("[nsr_tc] mbarrier wait timed out: block %d thread %d barrier-offset %u parity %u\n", (int)blockIdx.x,
+         (int)threadIdx.x, bar, parity);
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#if NSR_TC_WATCHDOG
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 22)) mbar_timeout(bar, parity);
+  }
+#else
+  while (!mbar_try_wait(bar, parity)) {}
+#endif
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]
+__device__ __forceinline__ void mma_ss(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d), "r"(a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (rows of 128 B, 8-row
+// groups 1024 B apart): start>>4 | LBO(unused)=1 | SBO=1024>>4 | version=1 | layout=2
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor: D=f32, A/B = fmt (0 f16, 1 bf16), K-major both, N, M
+__host__ __device__ constexpr uint32_t umma_idesc(int fmt, int M, int N) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+#define TMEM_LD32(taddr, r)                                                                           \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                               \
+               "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"                               \
+               "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"              \
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),    \
+                 "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), \
+                 "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),          \
+                 "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),          \
+                 "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])           \
+               : "r"(taddr) : "memory")
+
+#define TMEM_ST16(taddr, r)                                                                           \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "                                         \
+               "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"                             \
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]),          \
+                 "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]),        \
+                 "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory")
+
+// ---- hi/lo split of two fp32 values into packed 16-bit pairs (even k in the low half) ----
+template <int FMT> struct Split;
+template <> struct Split<1> {   // bf16
+  static __device__ __forceinline__ void apply(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(v1), "f"(v0));
+    const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(v1 - h1), "f"(v0 - h0));
+  }
+  static __host__ __device__ __forceinline__ void apply1(float v, uint16_t& hi, uint16_t& lo) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+    hi = *reinterpret_cast<const uint16_t*>(&h);
+    lo = *reinterpret_cast<const uint16_t*>(&l);
+  }
+};
+template <> struct Split<0> {   // fp16
+  static __device__ __forceinline__ void apply(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(v1), "f"(v0));
+    const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(v1 - h.y), "f"(v0 - h.x));
+  }
+  static __host__ __device__ __forceinline__ void apply1(float v, uint16_t& hi, uint16_t& lo) {
+    const __half h = __float2half_rn(v);
+    const __half l = __float2half_rn(v - __half2float(h));
+    hi = *reinterpret_cast<const uint16_t*>(&h);
+    lo = *reinterpret_cast<const uint16_t*>(&l);
+  }
+};
+
+// ---------------------------------------------------------------------------
+// weight image: stage table shared by the packer and (by construction) the MMA
+// issue order in mma_role().
+// ---------------------------------------------------------------------------
+struct StageDesc {
+  int16_t param;     // state_dict index of the weight tensor
+  int16_t half;      // output rows [128*half, 128*half+128)
+  int16_t col0;      // first input column of this 64-wide k chunk
+  int16_t kvalid;    // valid columns (63 for the encoding chunk, else 64)
+  int16_t ld;        // row length (in_features) of the weight tensor
+};
+struct StageTable { StageDesc s[kStagesPerTile]; };
+
+static StageTable build_stage_table(int ch_dir, bool no_dir) {
+  StageTable T{};
+  int n = 0;
+  auto push = [&](int param, int half, int col0, int kvalid, int ld) {
+    T.s[n++] = StageDesc{(int16_t)param, (int16_t)half, (int16_t)col0, (int16_t)kvalid, (int16_t)ld};
+  };
+  // L1 (xyz_encoding_1, K=63): half 1 first, then half 0 (lets the next tile start while the
+  // previous tile's last epilogue still owns accumulator half 0)
+  push(0, 1, 0, 63, 63);
+  push(0, 0, 0, 63, 63);
+  for (int L = 2; L <= 9; ++L) {
+    const int param = 2 * (L - 1);                 // L9 = xyz_encoding_final (state_dict index 16)
+    const bool skip = (L == 5);
+    const int ld = skip ? 319 : 256;
+    const int off = skip ? 63 : 0;                 // cat([input_xyz(63), h(256)])  networks.py:204
+    for (int h = 0; h < 2; ++h) {
+      if (skip) push(param, h, 0, 63, ld);
+      for (int c = 0; c < 4; ++c) push(param, h, off + 64 * c, 64, ld);
+    }
+  }
+  const int ld_dir = no_dir ? 256 : 256 + ch_dir;   // cat([feat(256), enc_dir]) networks.py:214
+  for (int c = 0; c < 4; ++c) push(18, 0, 64 * c, 64, ld_dir);
+  return T;
+}
+
+template <int FMT>
+__global__ void k_tc_pack_image(StageTable T, const float* const* __restrict__ params_dev, uint8_t* __restrict__ image) {
+  // one thread per (stage, row, 16-byte chunk)
+  const int total = kStagesPerTile * 128 * 8;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int s = idx / 1024, r = (idx / 8) % 128, j = idx % 8;
+    const StageDesc d = T.s[s];
+    const float* W = params_dev[d.param];
+    const int n = 128 * d.half + r;
+    __align__(16) uint16_t hi[8];
+    __align__(16) uint16_t lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int kl = 8 * j + e;
+      const float v = (kl < d.kvalid) ? W[(int64_t)n * d.ld + d.col0 + kl] : 0.f;
+      Split<FMT>::apply1(v, hi[e], lo[e]);
+    }
+    const size_t off = (size_t)s * kStageBytes + (size_t)r * 128 + (size_t)((j ^ (r & 7)) << 4);
+    *reinterpret_cast<uint4*>(image + off) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(image + off + kPlaneBytes) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+
+__global__ void k_tc_pack_consts(const float* const* __restrict__ p, float* __restrict__ c, int ch_dir, int no_dir) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nt = gridDim.x * blockDim.x;
+  for (int i = t; i < 8 * 256; i += nt) c[kcBias + i] = p[2 * (i / 256) + 1][i % 256];
+  for (int i = t; i < 256; i += nt) c[kcBiasFinal + i] = p[17][i];
+  for (int i = t; i < 128; i += nt) c[kcBiasDir + i] = p[19][i];
+  for (int i = t; i < 256; i += nt) c[kcWsig + i] = p[20][i];
+  for (int i = t; i < 384; i += nt) c[kcWrgb + i] = p[22][i];
+  if (t == 0) { c[kcMisc] = p[21][0]; c[kcMisc + 1] = p[23][0]; c[kcMisc + 2] = p[23][1]; c[kcMisc + 3] = p[23][2]; }
+  const int ld = no_dir ? 256 : 256 + ch_dir;
+  for (int i = t; i < 128 * 28; i += nt) {
+    const int j = i / 28, k = i % 28;
+    c[kcWdd + i] = (!no_dir && k < ch_dir) ? p[18][(int64_t)j * ld + 256 + k] : 0.f;
+  }
+}
+
+bool tc_supported(const NsrConfig& c, std::string* why) {
+  auto no = [&](const char* m) { if (why) *why = m; return false; };
+  if (c.D != 8 || c.W != 256 || c.skips_mask != (1u << 4)) return no("needs D=8, W=256, skips=[4]");
+  if (c.deg_pos != 10 || c.deg_dir != 4 || c.no_xyz) return no("needs deg_pos=10, deg_dir=4, xyz included");
+  const int sc = c.n_coarse, sf = c.n_coarse + c.n_importance;
+  if (!((sc == 64 && (sf == 64 || sf == 128)) || (sc == 128 && sf == 128)))
+    return no("needs (N_coarse, N_importance) in {(64,0), (64,64), (128,0)}");
+  return true;
+}
+
+size_t tc_image_bytes(const NsrHandle_*) { return (size_t)kStagesPerTile * kStageBytes; }
+
+cudaError_t tc_pack(NsrHandle_* h, int which, const float* const* params, cudaStream_t st) {
+  NetImages& net = h->net[which];
+  // the pointer table itself has to live on the device: stage it in the consts blob tail
+  const int np = (int)h->param_numel.size();
+  const float** d_ptrs = reinterpret_cast<const float**>(net.tc_consts + 8192);
+  cudaError_t e = cudaMemcpyAsync(d_ptrs, params, np * sizeof(float*), cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return e;
+  const StageTable T = build_stage_table(h->rp.ch_dir, h->cfg.no_dir != 0);
+  const int fmt = (h->cfg.precision == NSR_PREC_FP16X3_TC) ? 0 : 1;
+  if (fmt == 1) k_tc_pack_image<1><<<144, 256, 0, st>>>(T, d_ptrs, net.tc_image);
+  else k_tc_pack_image<0><<<144, 256, 0, st>>>(T, d_ptrs, net.tc_image);
+  k_tc_pack_consts<<<8, 256, 0, st>>>(d_ptrs, net.tc_consts, h->rp.ch_dir, h->cfg.no_dir);
+  h->launches += 2;
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// kernel arguments
+// ---------------------------------------------------------------------------
+struct TcKernelArgs {
+  const uint8_t* image;
+  const float* consts;
+  const SampleTables* tabs;
+  RenderParams rp;
+  const float* rays; long long n_rays; int ray_stride;
+  const float* z_in; int S;
+  const float* u_jitter; const float* noise; const float* u_resample;
+  int do_resample;
+  float* comp_rgb; float* depth; float* opacity; float* weights; float* raw; float* z_next;
+  long long n_tiles;
+};
+
+// ---------------------------------------------------------------------------
+// roles
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void producer_role(const TcKernelArgs& a, uint32_t sm_base, long long my_tiles) {
+  uint32_t slot = 0, par = 0;
+  for (long long it = 0; it < my_tiles; ++it) {
+    for (int s = 0; s < kStagesPerTile; ++s) {
+      mbar_wait(sm_base + kSmBar + 8 * (B_WEMPTY + slot), par ^ 1);
+      const uint32_t full = sm_base + kSmBar + 8 * (B_WFULL + slot);
+      mbar_expect_tx(full, kStageBytes);
+      bulk_copy_g2s(sm_base + kSmRing + slot * kStageBytes, a.image + (size_t)s * kStageBytes, kStageBytes, full);
+      if (++slot == kRing) { slot = 0; par ^= 1; }
+    }
+  }
+}
+
+template <int PASSES>
+struct MmaState {
+  uint32_t sm_base, tmem, idesc;
+  uint32_t slot, par;
+
+  // one weight stage: 64 k-values of one accumulator half.  A comes from TMEM
+  // (a_col >= 0: column offset of the k chunk in the hi plane) or from the
+  // encoding buffer in shared memory (a_col < 0).
+  __device__ __forceinline__ void stage(int half, int a_col, uint32_t enc_addr, bool first) {
+    mbar_wait(sm_base + kSmBar + 8 * (B_WFULL + slot), par);
+    tc_fence_after();
+    const uint32_t wb = sm_base + kSmRing + slot * kStageBytes;
+    const uint32_t d = tmem + 128u * half;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint64_t bh = umma_desc(wb + 32 * k);
+      const uint64_t bl = umma_desc(wb + kPlaneBytes + 32 * k);
+      const uint32_t acc0 = (first && k == 0) ? 0u : 1u;
+      if (a_col >= 0) {
+        const uint32_t ah = tmem + 256u + (uint32_t)a_col + 8u * k;
+        mma_ts(d, ah, bh, idesc, acc0);
+        if (PASSES == 3) { mma_ts(d, ah + 128u, bh, idesc, 1u); mma_ts(d, ah, bl, idesc, 1u); }
+      } else {
+        const uint64_t eh = umma_desc(enc_addr + 32 * k);
+        const uint64_t el = umma_desc(enc_addr + kPlaneBytes + 32 * k);
+        mma_ss(d, eh, bh, idesc, acc0);
+        if (PASSES == 3) { mma_ss(d, el, bh, idesc, 1u); mma_ss(d, eh, bl, idesc, 1u); }
+      }
+    }
+    tc_commit(sm_base + kSmBar + 8 * (B_WEMPTY + slot));
+    if (++slot == kRing) { slot = 0; par ^= 1; }
+  }
+};
+
+// Schedule per layer g (global layer counter, 10 per tile), N-halves n0/n1 and
+// k-halves kh0/kh1 of the A operand (each k-half = the previous layer's
+// accumulator half):
+//   wait A_READY[0](g-1)            -> acc half 0 drained, A[kh0] written
+//   n0: k chunks 0,1
+//   wait A_READY[1](g-1)
+//   n0: k chunks 2,3                ; commit ACC_FULL[0]
+//   n1: k chunks 0,1                ; commit A_FREE0   (A[kh0] may be overwritten)
+//   n1: k chunks 2,3                ; commit ACC_FULL[1]
+// so epilogue(g, half 0) overlaps MMA(g, n1, kh1) and epilogue(g, half 1)
+// overlaps MMA(g+1, n0, kh0).
+template <int PASSES>
+__device__ __forceinline__ void mma_role(const TcKernelArgs& a, uint32_t sm_base, uint32_t tmem, uint32_t idesc,
+                                         long long my_tiles) {
+  MmaState<PASSES> m{sm_base, tmem, idesc, 0u, 0u};
+  const uint32_t bar = sm_base + kSmBar;
+  uint32_t g = 0;   // global layer counter
+  for (long long it = 0; it < my_tiles; ++it) {
+    const uint32_t buf = (uint32_t)(it & 1);
+    const uint32_t enc = sm_base + kSmEnc + buf * kStageBytes;
+    mbar_wait(bar + 8 * (B_ENCFULL + buf), (uint32_t)((it >> 1) & 1));
+    tc_fence_after();
+    // ---- L1: A = encoding (smem); half 1 then half 0
+    if (g > 0) { mbar_wait(bar + 8 * (B_AREADY + 1), (g - 1) & 1); tc_fence_after(); }
+    m.stage(1, -1, enc, true);
+    tc_commit(bar + 8 * (B_ACCFULL + 1));
+    if (g > 0) { mbar_wait(bar + 8 * (B_AREADY + 0), (g - 1) & 1); tc_fence_after(); }
+    m.stage(0, -1, enc, true);
+    tc_commit(bar + 8 * (B_ACCFULL + 0));
+    tc_commit(bar + 8 * B_AFREE0);
+    ++g;
+    // ---- L2..L9 (L5 = skip layer with the encoding chunk first)
+    for (int L = 2; L <= 9; ++L, ++g) {
+      const bool skip = (L == 5);
+      mbar_wait(bar + 8 * (B_AREADY + 0), (g - 1) & 1); tc_fence_after();
+      if (skip) m.stage(0, -1, enc, true);
+      m.stage(0, 0, 0, !skip);
+      m.stage(0, 32, 0, false);
+      mbar_wait(bar + 8 * (B_AREADY + 1), (g - 1) & 1); tc_fence_after();
+      m.stage(0, 64, 0, false);
+      m.stage(0, 96, 0, false);
+      tc_commit(bar + 8 * (B_ACCFULL + 0));
+      if (skip) m.stage(1, -1, enc, true);
+      m.stage(1, 0, 0, !skip);
+      m.stage(1, 32, 0, false);
+      tc_commit(bar + 8 * B_AFREE0);
+      m.stage(1, 64, 0, false);
+      m.stage(1, 96, 0, false);
+      tc_commit(bar + 8 * (B_ACCFULL + 1));
+    }
+    // ---- L10 (dir_encoding feat part, N = 128: half 0 only)
+    mbar_wait(bar + 8 * (B_AREADY + 0), (g - 1) & 1); tc_fence_after();
+    m.stage(0, 0, 0, true);
+    m.stage(0, 32, 0, false);
+    mbar_wait(bar + 8 * (B_AREADY + 1), (g - 1) & 1); tc_fence_after();
+    m.stage(0, 64, 0, false);
+    m.stage(0, 96, 0, false);
+    tc_commit(bar + 8 * (B_ACCFULL + 0));
+    tc_commit(bar + 8 * B_AFREE0);
+    tc_commit(bar + 8 * (B_ACCFULL + 1));
+    ++g;
+  }
+}
+
+// ---- front-end: sample, cast, encode, split, swizzled store; per-ray dir bias ----
+template <int FMT>
+__device__ __forceinline__ void frontend_role(const TcKernelArgs& a, uint8_t* sm, uint32_t sm_base, long long my_tiles,
+                                              int first_tile, int tile_stride) {
+  const int t = threadIdx.x - 32 * kFrontWarp0;   // 0..127 = tile row
+  const int lane = threadIdx.x & 31;
+  const int S = a.S, RPT = kTile / S;
+  const RenderParams& rp = a.rp;
+  for (long long it = 0; it < my_tiles; ++it) {
+    const uint32_t buf = (uint32_t)(it & 1);
+    if (it >= 2) mbar_wait(sm_base + kSmBar + 8 * (B_TILEDONE + buf), (uint32_t)(((it >> 1) - 1) & 1));
+    const long long tile = first_tile + it * (long long)tile_stride;
+    const long long ray = tile * RPT + t / S;
+    const int i = t % S;
+    const bool valid = ray < a.n_rays;
+    float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0, near = 0, far = 0;
+    if (valid) {
+      const float* rr = a.rays + ray * a.ray_stride;
+      ox = rr[0]; oy = rr[1]; oz = rr[2]; dx = rr[3]; dy = rr[4]; dz = rr[5]; near = rr[6]; far = rr[7];
+    }
+    float zv = 0.f;
+    if (valid) {
+      if (a.z_in) {
+        zv = a.z_in[ray * S + i];
+      } else {
+        const float zc = coarse_z(near, far, a.tabs->t_coarse[i], a.tabs->one_minus_t[i], rp.lindisp);
+        zv = zc;
+        if (a.u_jitter) {
+          const float zp = i > 0 ? coarse_z(near, far, a.tabs->t_coarse[i - 1], a.tabs->one_minus_t[i - 1], rp.lindisp) : zc;
+          const float zn = i + 1 < S ? coarse_z(near, far, a.tabs->t_coarse[i + 1], a.tabs->one_minus_t[i + 1], rp.lindisp) : zc;
+          zv = jitter_z(zp, zc, zn, i == 0, i + 1 == S, a.u_jitter[ray * S + i]);
+        }
+      }
+    }
+    reinterpret_cast<float*>(sm + kSmZ)[buf * 128 + t] = zv;
+    const float px = cast_point(ox, dx, zv), py = cast_point(oy, dy, zv), pz = cast_point(oz, dz, zv);
+    // 63 encoded channels (+1 zero pad), reference channel order (embedding.py:57-63)
+    float e[64];
+    e[0] = px; e[1] = py; e[2] = pz;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+      const float f = a.tabs->freq_pos[k];
+      const float ax = __fmul_rn(f, px), ay = __fmul_rn(f, py), az = __fmul_rn(f, pz);
+      e[3 + 6 * k + 0] = sinf(ax); e[3 + 6 * k + 1] = sinf(ay); e[3 + 6 * k + 2] = sinf(az);
+      e[3 + 6 * k + 3] = cosf(ax); e[3 + 6 * k + 4] = cosf(ay); e[3 + 6 * k + 5] = cosf(az);
+    }
+    e[63] = 0.f;
+    uint8_t* row_hi = sm + kSmEnc + buf * kStageBytes + t * 128;
+    uint8_t* row_lo = row_hi + kPlaneBytes;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) Split<FMT>::apply(e[8 * j + 2 * q], e[8 * j + 2 * q + 1], hi[q], lo[q]);
+      const int sw = (j ^ (t & 7)) << 4;
+      *reinterpret_cast<uint4*>(row_hi + sw) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(row_lo + sw) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+    // view-direction encoding of the tile's rays -> smem, then the per-ray bias of the dir layer:
+    // dirbias[r][j] = b_dir[j] + sum_c Wdir[j][256+c] * enc_dir[r][c]   (networks.py:214-221)
+    float* denc = reinterpret_cast<float*>(sm + kSmDenc);
+    if (t < RPT) {
+      const long long r2 = tile * RPT + t;
+      float vx = 0, vy = 0, vz = 0;
+      if (r2 < a.n_rays) {
+        const float* rr = a.rays + r2 * a.ray_stride + rp.viewdir_offset;
+        vx = rr[0]; vy = rr[1]; vz = rr[2];
+      }
+      float* o = denc + t * 32;
+      posenc3(vx, vy, vz, 4, a.tabs->freq_dir, 0, [&](int c, float v) { o[c] = v; });
+    }
+    named_bar_sync(1, 32 * kWarpsFront);
+    float* dbias = reinterpret_cast<float*>(sm + kSmDirBias) + buf * 256;
+    for (int idx = t; idx < RPT * 128; idx += 128) {
+      const int r = idx >> 7, j = idx & 127;
+      float s = a.consts[kcBiasDir + j];
+      if (!rp.no_dir) {
+        const float* w = a.consts + kcWdd + j * 28;
+        const float* de = denc + r * 32;
+#pragma unroll
+        for (int c = 0; c < 27; ++c) s = fmaf(__ldg(w + c), de[c], s);
+      }
+      dbias[idx] = s;
+    }
+    fence_proxy_async();     // make the generic-proxy enc writes visible to the tensor core's async proxy
+    __syncwarp();
+    if (lane == 0) mbar_arrive(sm_base + kSmBar + 8 * (B_ENCFULL + buf));
+    named_bar_sync(1, 32 * kWarpsFront);   // denc is reused next tile
+  }
+}
+
+// ---- epilogue + compositing ----
+template <int FMT, int PASSES>
+__device__ __forceinline__ void epilogue_role(const TcKernelArgs& a, uint8_t* sm, uint32_t sm_base, uint32_t tmem,
+                                              long long my_tiles, int first_tile, int tile_stride) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ew = warp - kEpiWarp0;          // 0..7
+  const int q = warp & 3;                   // TMEM lane quarter this warp may access
+  const int hh = ew >> 2;                   // which 64-column half of an accumulator half
+  const int row = 32 * q + lane;            // tile row == TMEM lane
+  const uint32_t tlane = tmem + ((uint32_t)(32 * q) << 16);
+  const uint32_t bar = sm_base + kSmBar;
+  const float* cst = reinterpret_cast<const float*>(sm + kSmConst);
+  const int S = a.S, RPT = kTile / S;
+  const RenderParams& rp = a.rp;
+  uint32_t g = 0;
+  for (long long it = 0; it < my_tiles; ++it) {
+    const uint32_t buf = (uint32_t)(it & 1);
+    const long long tile = first_tile + it * (long long)tile_stride;
+    float sig_p = 0.f;
+    // ---- layers 1..9: bias (+ReLU) -> hi/lo split -> next A operand ----
+    for (int L = 1; L <= 9; ++L, ++g) {
+      const float* bias = cst + (L - 1) * 256;       // L9 -> kcBiasFinal = 2048
+      for (int h = 0; h < 2; ++h) {
+        mbar_wait(bar + 8 * (B_ACCFULL + h), g & 1);
+        if (h == 0) mbar_wait(bar + 8 * B_AFREE0, g & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int col0 = 128 * h + 64 * hh + 32 * c;
+          uint32_t r[32];
+          TMEM_LD32(tlane + (uint32_t)col0, r);
+          tc_wait_ld();
+          uint32_t whi[16], wlo[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bias + col0 + j);
+            float v0 = __uint_as_float(r[j]) + b4.x, v1 = __uint_as_float(r[j + 1]) + b4.y;
+            float v2 = __uint_as_float(r[j + 2]) + b4.z, v3 = __uint_as_float(r[j + 3]) + b4.w;
+            if (L <= 8) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+            if (L == 8) {   // sigma head on h_8 (networks.py:207)
+              const float4 w4 = *reinterpret_cast<const float4*>(cst + kcWsig + col0 + j);
+              sig_p = fmaf(v0, w4.x, sig_p); sig_p = fmaf(v1, w4.y, sig_p);
+              sig_p = fmaf(v2, w4.z, sig_p); sig_p = fmaf(v3, w4.w, sig_p);
+            }
+            Split<FMT>::apply(v0, v1, whi[j / 2], wlo[j / 2]);
+            Split<FMT>::apply(v2, v3, whi[j / 2 + 1], wlo[j / 2 + 1]);
+          }
+          TMEM_ST16(tlane + 256u + (uint32_t)(col0 / 2), whi);
+          if (PASSES == 3) TMEM_ST16(tlane + 384u + (uint32_t)(col0 / 2), wlo);
+        }
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar + 8 * (B_AREADY + h));
+      }
+    }
+    // ---- layer 10: dir layer (N=128, accumulator half 0) + rgb head ----
+    float rgb_p[3] = {0.f, 0.f, 0.f};
+    {
+      mbar_wait(bar + 8 * (B_ACCFULL + 0), g & 1);
+      mbar_wait(bar + 8 * B_AFREE0, g & 1);
+      mbar_wait(bar + 8 * (B_ACCFULL + 1), g & 1);
+      tc_fence_after();
+      const float* dbias = reinterpret_cast<const float*>(sm + kSmDirBias) + buf * 256 + (row / S) * 128;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int col0 = 64 * hh + 32 * c;
+        uint32_t r[32];
+        TMEM_LD32(tlane + (uint32_t)col0, r);
+        tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float v = fmaxf(__uint_as_float(r[j]) + dbias[col0 + j], 0.f);
+          rgb_p[0] = fmaf(v, cst[kcWrgb + col0 + j], rgb_p[0]);
+          rgb_p[1] = fmaf(v, cst[kcWrgb + 128 + col0 + j], rgb_p[1]);
+          rgb_p[2] = fmaf(v, cst[kcWrgb + 256 + col0 + j], rgb_p[2]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(bar + 8 * (B_AREADY + 0)); mbar_arrive(bar + 8 * (B_AREADY + 1)); }
+      ++g;
+    }
+    // ---- combine the two column halves, activations, stage per-point (rgb, sigma) ----
+    float* xch = reinterpret_cast<float*>(sm + kSmXch);
+    float* ssig = reinterpret_cast<float*>(sm + kSmSig);
+    float* srgb = reinterpret_cast<float*>(sm + kSmRgb);
+    float* sw = reinterpret_cast<float*>(sm + kSmW);
+    const float* zt = reinterpret_cast<const float*>(sm + kSmZ) + buf * 128;
+    if (hh == 1) { xch[row] = sig_p; xch[128 + row] = rgb_p[0]; xch[256 + row] = rgb_p[1]; xch[384 + row] = rgb_p[2]; }
+    named_bar_sync(2, 32 * kWarpsEpi);
+    if (hh == 0) {
+      const long long ray = tile * RPT + row / S;
+      const bool valid = ray < a.n_rays;
+      const float sigma = (sig_p + xch[row]) + cst[kcMisc];
+      float col[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float v = (rgb_p[c] + xch[128 * (c + 1) + row]) + cst[kcMisc + 1 + c];
+        if (!rp.color_none) v = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-v)));    // torch.sigmoid
+        col[c] = v;
+      }
+      const long long gp = tile * kTile + row;
+      if (a.raw && valid) reinterpret_cast<float4*>(a.raw)[gp] = make_float4(col[0], col[1], col[2], sigma);
+      if (rp.gamma_correct) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) col[c] = powf(col[c], 1.f / 2.2f);        // nerf_downX_model.py:271
+      }
+      float s = sigma;
+      if (a.noise && valid) s = __fadd_rn(s, __fmul_rn(a.noise[gp], rp.noise_std));   // utils.py:210
+      ssig[row] = s; srgb[3 * row] = col[0]; srgb[3 * row + 1] = col[1]; srgb[3 * row + 2] = col[2];
+    }
+    named_bar_sync(2, 32 * kWarpsEpi);
+    // ---- alpha compositing (+ resampling): warp ew owns ray ew of the tile ----
+    if (ew < RPT) {
+      const long long ray = tile * RPT + ew;
+      if (ray < a.n_rays) {
+        float r, gg, b, d, o;
+        composite_ray_warp(zt + ew * S, ssig + ew * S, srgb + 3 * ew * S, S, rp.white_bkgd, rp.sigma_softplus,
+                           sw + ew * S, r, gg, b, d, o);
+        if (lane == 0) {
+          if (a.comp_rgb) { a.comp_rgb[ray * 3] = r; a.comp_rgb[ray * 3 + 1] = gg; a.comp_rgb[ray * 3 + 2] = b; }
+          if (a.depth) a.depth[ray] = d;
+          if (a.opacity) a.opacity[ray] = o;
+        }
+        if (a.weights) for (int i = lane; i < S; i += 32) a.weights[ray * S + i] = sw[ew * S + i];
+        if (a.do_resample) {
+          const int n_imp = rp.n_importance;
+          float* scratch = reinterpret_cast<float*>(sm + kSmScratch) + ew * 320;
+          resample_ray_warp(zt + ew * S, sw + ew * S, S, n_imp, a.u_resample ? a.u_resample + ray * n_imp : nullptr,
+                            a.tabs->u_fine, scratch, a.z_next + ray * (S + n_imp));
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar + 8 * (B_TILEDONE + buf));
+  }
+}
+
+template <int FMT, int PASSES>
+__global__ void __launch_bounds__(kThreadsTc, 1) k_tc_pass(const TcKernelArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sm_base = smem_u32(sm);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long my_tiles = (a.n_tiles > blockIdx.x) ? (a.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (threadIdx.x == 0) {
+    const uint32_t bar = sm_base + kSmBar;
+    for (int i = 0; i < kRing; ++i) { mbar_init(bar + 8 * (B_WFULL + i), 1); mbar_init(bar + 8 * (B_WEMPTY + i), 1); }
+    mbar_init(bar + 8 * (B_ACCFULL + 0), 1); mbar_init(bar + 8 * (B_ACCFULL + 1), 1);
+    mbar_init(bar + 8 * B_AFREE0, 1);
+    mbar_init(bar + 8 * (B_AREADY + 0), kWarpsEpi); mbar_init(bar + 8 * (B_AREADY + 1), kWarpsEpi);
+    mbar_init(bar + 8 * (B_ENCFULL + 0), kWarpsFront); mbar_init(bar + 8 * (B_ENCFULL + 1), kWarpsFront);
+    mbar_init(bar + 8 * (B_TILEDONE + 0), kWarpsEpi); mbar_init(bar + 8 * (B_TILEDONE + 1), kWarpsEpi);
+    fence_barrier_init();
+  }
+  // fp32 constants (biases, head weights) -> smem
+  {
+    float* cst = reinterpret_cast<float*>(sm + kSmConst);
+    for (int i = threadIdx.x; i < kcSmemFloats; i += kThreadsTc) cst[i] = a.consts[i];
+  }
+  if (warp == 1) {   // TMEM: all 512 columns (one CTA per SM)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sm_base + kSmTmemPtr), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + kSmTmemPtr);
+
+  if (warp == 0) {
+    if (lane == 0) producer_role(a, sm_base, my_tiles);
+  } else if (warp == 1) {
+    if (lane == 0) mma_role<PASSES>(a, sm_base, tmem, umma_idesc(FMT, 128, 128), my_tiles);
+  } else if (warp < kEpiWarp0) {
+    frontend_role<FMT>(a, sm, sm_base, my_tiles, blockIdx.x, gridDim.x);
+  } else {
+    epilogue_role<FMT, PASSES>(a, sm, sm_base, tmem, my_tiles, blockIdx.x, gridDim.x);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+  }
+}
+
+cudaError_t tc_pass(NsrHandle_* h, int which, const TcPassArgs& p, cudaStream_t st) {
+  if (p.S != 64 && p.S != 128) return cudaErrorInvalidValue;
+  TcKernelArgs a{};
+  a.image = h->net[which].tc_image; a.consts = h->net[which].tc_consts; a.tabs = h->d_tables; a.rp = h->rp;
+  a.rays = p.rays; a.n_rays = p.n_rays; a.ray_stride = p.ray_stride; a.z_in = p.z_in; a.S = p.S;
+  a.u_jitter = p.u_jitter; a.noise = p.noise; a.u_resample = p.u_resample; a.do_resample = p.do_resample;
+  a.comp_rgb = p.comp_rgb; a.depth = p.depth; a.opacity = p.opacity; a.weights = p.weights; a.raw = p.raw;
+  a.z_next = p.z_next;
+  const int rpt = kTile / p.S;
+  a.n_tiles = (p.n_rays + rpt - 1) / rpt;
+  if (a.n_tiles == 0) return cudaSuccess;
+  const int grid = (int)(a.n_tiles < h->sm_count ? a.n_tiles : h->sm_count);
+  void (*kern)(const TcKernelArgs) = nullptr;
+  switch (h->cfg.precision) {
+    case NSR_PREC_BF16X3_TC: kern = k_tc_pass<1, 3>; break;
+    case NSR_PREC_FP16X3_TC: kern = k_tc_pass<0, 3>; break;
+    case NSR_PREC_BF16_TC: kern = k_tc_pass<1, 1>; break;
+    default: return cudaErrorInvalidValue;
+  }
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTcBytes);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, kThreadsTc, kSmemTcBytes, st>>>(a);
+  h->launches += 1;
+  return cudaGetLastError();
+}
+
+}  // namespace nsr

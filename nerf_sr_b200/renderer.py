@@ -1,0 +1,299 @@
+"""Host-side mirror of the reference's render interface for the hot path.
+
+``Renderer`` owns one libnsr_b200 handle and exposes the reference's seams with
+the same names, argument meaning and result layout:
+
+    forward_rays(rays)            NeRFDownXModel.forward_rays   models/nerf_downX_model.py:280-313
+    render_pass(which, rays, z)   render_rays + renderer        :260-278 / models/rendering.py:75-111
+    sample_along_rays / resample_along_rays (z-values only)     models/utils.py:17-95
+    posenc(x, deg)                PositionalEncoding.__call__   models/embedding.py:44-63
+    box_average(x, s)             comp_low_res_output           models/nerf_downX_model.py:337-348
+    generate_rays(c2w, ...)       get_ray_directions/get_rays/get_ndc_rays + SS grouping
+    render_frame_host(...)        set_input + forward + comp_low_res_output with host buffers
+
+PyTorch is used only for device memory, streams and (in parallel.py) NCCL.  All
+arithmetic happens inside the CUDA library; there is no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Mapping, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import NsrConfig, NsrError, NsrOutputs, NsrPassOutputs, NsrRng, PRECISIONS
+
+
+def state_dict_order(D: int = 8):
+    """Parameter names in the order nsr_pack_weights expects (models/networks.py:149-180)."""
+    names = []
+    for i in range(D):
+        names += [f"xyz_encoding_{i+1}.0.weight", f"xyz_encoding_{i+1}.0.bias"]
+    names += ["xyz_encoding_final.weight", "xyz_encoding_final.bias",
+              "dir_encoding.0.weight", "dir_encoding.0.bias",
+              "sigma.weight", "sigma.bias", "rgb.0.weight", "rgb.0.bias"]
+    return names
+
+
+def config_from_opt(opt, device_index: int, precision: str = "bf16x3", viewdir_offset: int = 3) -> NsrConfig:
+    """Translate the reference's argparse ``opt`` (or the oracle's RenderConfig) into NsrConfig."""
+    g = lambda k, d=None: getattr(opt, k, d)
+    cfg = NsrConfig()
+    cfg.struct_size = C.sizeof(NsrConfig)
+    cfg.device = device_index
+    cfg.precision = PRECISIONS[precision]
+    cfg.D, cfg.W = int(g("D", 8)), int(g("W", 256))
+    mask = 0
+    for s in (g("skips", (4,)) or ()):
+        mask |= 1 << int(s)
+    cfg.skips_mask = mask
+    cfg.no_dir = int(bool(g("no_dir", False)))
+    cfg.color_activation = {"sigmoid": 0, "none": 1}[g("color_activation", "sigmoid")]
+    cfg.deg_pos, cfg.deg_dir = int(g("deg_pos", 10)), int(g("deg_dir", 4))
+    cfg.no_xyz, cfg.no_logscale = int(bool(g("no_xyz", False))), int(bool(g("no_logscale", False)))
+    cfg.n_coarse, cfg.n_importance = int(g("N_coarse", 64)), int(g("N_importance", 64))
+    cfg.lindisp, cfg.white_bkgd = int(bool(g("lindisp", False))), int(bool(g("white_bkgd", False)))
+    cfg.sigma_activation = {"relu": 0, "softplus": 1}[g("sigma_activation", "relu")]
+    cfg.gamma_correct = int(bool(g("gamma_correct", False)))
+    cfg.noise_std = float(g("noise_std", 0.0))
+    cfg.viewdir_offset = int(g("viewdir_offset", viewdir_offset))
+    if int(g("dim_rgb", 3)) != 3 or int(g("dim_pos", 3)) != 3 or int(g("dim_dir", 3)) != 3:
+        raise NsrError(2, "dim_rgb/dim_pos/dim_dir other than 3 are not supported")
+    return cfg
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class Renderer:
+    """One handle = one (opt, device).  Thread-compatible: use one Renderer per thread/stream."""
+
+    def __init__(self, opt, device: Optional[torch.device] = None, precision: str = "bf16x3",
+                 viewdir_offset: int = 3):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise NsrError(6, "no CUDA device: nerf_sr_b200 runs only on the GPU (no CPU fallback)")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.precision = precision
+        self.cfg = config_from_opt(opt, self.device.index or 0, precision, viewdir_offset)
+        h = C.c_void_p()
+        rc = self.lib.nsr_create(C.byref(self.cfg), C.byref(h))
+        if rc != _lib.NSR_OK:
+            raise NsrError(rc, self.lib.nsr_last_error(None).decode())
+        self._h = h
+        self.n_coarse, self.n_importance = self.cfg.n_coarse, self.cfg.n_importance
+        self.n_fine = self.n_coarse + self.n_importance
+        self._ws: Optional[torch.Tensor] = None
+        self._param_versions = [None, None]
+        self._keep = [None, None]
+
+    # -- plumbing ----------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.nsr_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != _lib.NSR_OK:
+            raise NsrError(rc, self.lib.nsr_last_error(self._h).decode())
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _workspace(self, n_rays: int):
+        need = self.lib.nsr_workspace_bytes(self._h, n_rays)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws.data_ptr(), self._ws.numel()
+
+    def _f32(self, t: torch.Tensor, cols: Optional[int] = None) -> torch.Tensor:
+        if t.device != self.device:
+            raise NsrError(1, f"tensor on {t.device}, renderer on {self.device}")
+        t = t.detach()
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            t = t.float().contiguous()
+        return t
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.nsr_launch_count(self._h))
+
+    # -- weights -----------------------------------------------------------------
+    def load_state_dict(self, which: int, state_dict: Mapping[str, torch.Tensor]):
+        """which: 0 = netCoarse, 1 = netFine.  Accepts the reference's state_dict (optionally with a
+        DataParallel/DDP 'module.' prefix, models/base_model.py:193-194)."""
+        names = state_dict_order(self.cfg.D)
+        tensors = []
+        for i, n in enumerate(names):
+            t = state_dict[n] if n in state_dict else state_dict["module." + n]
+            t = t.detach().to(self.device, torch.float32).contiguous()
+            if t.numel() != self.lib.nsr_param_numel(self._h, i):
+                raise NsrError(1, f"{n}: {tuple(t.shape)} does not match the configured architecture")
+            tensors.append(t)
+        arr = (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+        self._check(self.lib.nsr_pack_weights(self._h, which, arr, len(tensors), self._stream()))
+        self._keep[which] = tensors     # keep alive until the async pack has run
+
+    def sync_from_modules(self, net_coarse, net_fine):
+        """Re-pack when parameter versions changed (after every optimiser step / load_networks)."""
+        for which, net in enumerate((net_coarse, net_fine)):
+            m = net.module if hasattr(net, "module") else net
+            ver = tuple(p._version for p in m.parameters()) + tuple(p.data_ptr() for p in m.parameters())
+            if ver != self._param_versions[which]:
+                self.load_state_dict(which, m.state_dict())
+                self._param_versions[which] = ver
+
+    # -- the hot path ------------------------------------------------------------
+    def forward_rays(self, rays: torch.Tensor, rng: Optional[Mapping[str, torch.Tensor]] = None,
+                     want_weights: bool = True, want_z_fine: bool = False) -> Dict[str, torch.Tensor]:
+        """rays [N, 8|11] fp32 on self.device -> the reference's dict of 8 tensors
+        (models/nerf_downX_model.py:293-311).  rng: optional dict with u_coarse / noise_coarse /
+        u_fine / noise_fine (train mode); None = eval mode."""
+        rays = self._f32(rays)
+        n, stride = rays.shape
+        dev, f32 = self.device, torch.float32
+        out = {"coarse_comp_rgbs": torch.empty(n, 3, device=dev, dtype=f32),
+               "coarse_depth": torch.empty(n, device=dev, dtype=f32),
+               "coarse_opacity": torch.empty(n, device=dev, dtype=f32)}
+        if want_weights:
+            out["coarse_weights"] = torch.empty(n, self.n_coarse, device=dev, dtype=f32)
+        if self.n_importance > 0:
+            out["fine_comp_rgbs"] = torch.empty(n, 3, device=dev, dtype=f32)
+            out["fine_depth"] = torch.empty(n, device=dev, dtype=f32)
+            out["fine_opacity"] = torch.empty(n, device=dev, dtype=f32)
+            if want_weights:
+                out["fine_weights"] = torch.empty(n, self.n_fine, device=dev, dtype=f32)
+            if want_z_fine:
+                out["z_fine"] = torch.empty(n, self.n_fine, device=dev, dtype=f32)
+        o = NsrOutputs()
+        for k, v in out.items():
+            setattr(o, k, v.data_ptr())
+        r = NsrRng()
+        keep = []
+        if rng is not None:
+            for k in ("u_coarse", "noise_coarse", "u_fine", "noise_fine"):
+                t = rng.get(k) if isinstance(rng, Mapping) else getattr(rng, k, None)
+                if t is not None:
+                    t = self._f32(t.to(dev))
+                    keep.append(t)
+                    setattr(r, k, t.data_ptr())
+        ws, ws_bytes = self._workspace(n)
+        self._check(self.lib.nsr_render(self._h, rays.data_ptr(), n, stride, C.byref(r) if rng is not None else None,
+                                        C.byref(o), ws, ws_bytes, self._stream()))
+        return out
+
+    def render_pass(self, which: int, rays: torch.Tensor, z_vals: torch.Tensor,
+                    noise: Optional[torch.Tensor] = None, want_raw: bool = False) -> Dict[str, torch.Tensor]:
+        """One network over caller-supplied z-values: (comp_rgbs, depth, opacity, weights[, raw])."""
+        rays, z_vals = self._f32(rays), self._f32(z_vals)
+        n, stride = rays.shape
+        s = z_vals.shape[1]
+        dev, f32 = self.device, torch.float32
+        out = {"comp_rgbs": torch.empty(n, 3, device=dev, dtype=f32), "depth": torch.empty(n, device=dev, dtype=f32),
+               "opacity": torch.empty(n, device=dev, dtype=f32), "weights": torch.empty(n, s, device=dev, dtype=f32)}
+        if want_raw:
+            out["raw"] = torch.empty(n, s, 4, device=dev, dtype=f32)
+        o = NsrPassOutputs()
+        for k, v in out.items():
+            setattr(o, k, v.data_ptr())
+        nz = self._f32(noise) if noise is not None else None
+        ws, ws_bytes = self._workspace(n)
+        self._check(self.lib.nsr_render_pass(self._h, which, rays.data_ptr(), n, stride, z_vals.data_ptr(), s,
+                                             _ptr(nz), C.byref(o), ws, ws_bytes, self._stream()))
+        return out
+
+    def sample_along_rays(self, rays: torch.Tensor, u: Optional[torch.Tensor] = None) -> torch.Tensor:
+        rays = self._f32(rays)
+        z = torch.empty(rays.shape[0], self.n_coarse, device=self.device, dtype=torch.float32)
+        uu = self._f32(u) if u is not None else None
+        self._check(self.lib.nsr_sample_coarse(self._h, rays.data_ptr(), rays.shape[0], rays.shape[1], _ptr(uu),
+                                               z.data_ptr(), self._stream()))
+        return z
+
+    def resample_along_rays(self, z: torch.Tensor, weights: torch.Tensor, u: Optional[torch.Tensor] = None):
+        z, weights = self._f32(z), self._f32(weights)
+        out = torch.empty(z.shape[0], self.n_fine, device=self.device, dtype=torch.float32)
+        uu = self._f32(u) if u is not None else None
+        self._check(self.lib.nsr_resample(self._h, z.data_ptr(), weights.data_ptr(), z.shape[0], _ptr(uu),
+                                          out.data_ptr(), self._stream()))
+        return out
+
+    def posenc(self, x: torch.Tensor, deg: int) -> torch.Tensor:
+        x = self._f32(x)
+        ch = 6 * deg + (0 if self.cfg.no_xyz else 3)
+        out = torch.empty(x.shape[0], ch, device=self.device, dtype=torch.float32)
+        self._check(self.lib.nsr_posenc(self._h, x.data_ptr(), x.shape[0], deg, out.data_ptr(), self._stream()))
+        return out
+
+    def box_average(self, x: torch.Tensor, s: int) -> torch.Tensor:
+        x = self._f32(x)
+        x2 = x.reshape(x.shape[0], -1)
+        n_lr = x2.shape[0] // (s * s)
+        out = torch.empty(n_lr, x2.shape[1], device=self.device, dtype=torch.float32)
+        self._check(self.lib.nsr_box_average(self._h, x2.data_ptr(), n_lr, s, x2.shape[1], out.data_ptr(), self._stream()))
+        return out
+
+    def generate_rays(self, c2w, H: int, W: int, focal: float, s: int = 1, ndc: bool = False,
+                      near: float = 2.0, far: float = 6.0) -> torch.Tensor:
+        c = torch.as_tensor(c2w, dtype=torch.float32).reshape(12).cpu()
+        arr = (C.c_float * 12)(*c.tolist())
+        rays = torch.empty(H * W, 8, device=self.device, dtype=torch.float32)
+        self._check(self.lib.nsr_generate_rays(self._h, arr, H, W, float(focal), s, int(ndc), float(near), float(far),
+                                               rays.data_ptr(), self._stream()))
+        return rays
+
+    def render_frame_host(self, rays_host: torch.Tensor, s: int = 1):
+        """HOST rays [N, 8|11] (CPU tensor) -> (rgb [N/s^2,3], depth [N/s^2]) CPU tensors.
+        Copies, render and box average are pipelined inside the library."""
+        rays_host = rays_host.detach().to("cpu", torch.float32).contiguous()
+        n, stride = rays_host.shape
+        n_out = n // (s * s)
+        rgb = torch.empty(n_out, 3, dtype=torch.float32)
+        depth = torch.empty(n_out, dtype=torch.float32)
+        self._check(self.lib.nsr_render_host(self._h, rays_host.data_ptr(), n, stride, s, rgb.data_ptr(), depth.data_ptr()))
+        return rgb, depth
+
+
+def patch_model(model, precision: str = "bf16x3"):
+    """Rebind ``forward_rays`` of a reference NeRFDownXModel / NeRFModel instance to the CUDA path
+    (the one-line hook of INTEGRATION.md).  Keeps self.near / self.far (consumed by depth2im,
+    models/nerf_downX_model.py:422) without the reference's per-chunk device sync: they are read
+    once per distinct ray tensor.  Training (grad enabled) stays on the reference path until the
+    backward kernel lands."""
+    import types
+    vo = 8 if type(model).__name__ == "NeRFModel" else 3
+    renderer = Renderer(model.opt, device=model.device, precision=precision, viewdir_offset=vo)
+    reference_forward_rays = model.forward_rays
+
+    def forward_rays(self, rays):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.netCoarse.parameters()):
+            return reference_forward_rays(rays)
+        renderer.sync_from_modules(self.netCoarse, self.netFine)
+        if getattr(self, "_nsr_nearfar_src", None) is not rays.untyped_storage().data_ptr():
+            nf = rays[0, 6:8].cpu().numpy()
+            self.near, self.far = nf[0:1], nf[1:2]
+            self._nsr_nearfar_src = rays.untyped_storage().data_ptr()
+        rng = None
+        if self.randomized:
+            n = rays.shape[0]
+            o = self.opt
+            rng = {"u_coarse": torch.rand(n, o.N_coarse, device=rays.device)}
+            if o.noise_std > 0:
+                rng["noise_coarse"] = torch.randn(n, o.N_coarse, device=rays.device)
+            if o.N_importance > 0:
+                rng["u_fine"] = torch.rand(n, o.N_importance, device=rays.device)
+                if o.noise_std > 0:
+                    rng["noise_fine"] = torch.randn(n, o.N_coarse + o.N_importance, device=rays.device)
+        return renderer.forward_rays(rays, rng)
+
+    model.forward_rays = types.MethodType(forward_rays, model)
+    model._nsr_renderer = renderer
+    return model
