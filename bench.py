@@ -1,0 +1,267 @@
+#!/usr/bin/env python
+"""bench.py -- rays/sec of the NeRF-SR render hot path (64 coarse + 128 fine samples, 2x2 SS).
+
+    python bench.py --gpus N --steps K --warmup W              # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...    # the reference algorithm on host cores
+
+A "step" renders one synthetic frame of BASELINE.json configs[1] (Blender-like 400x400 output
+pixels, 2x2 super-sampling -> 160 000 HR rays, random-init 256-wide coarse+fine MLPs).  One JSON
+line is printed by rank 0.  `value` times the device-resident path (rays already in HBM), `e2e`
+the host-buffer call (pinned rays in, LR rgb+depth out, copies inside the timed region),
+`roofline` the dominant kernel (fine pass) against the measured tensor peak, `cpu_baseline` the
+oracle port (the reference's algorithm, torch CPU ops) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+FLOP_PER_POINT = 1186816            # 2 x 593 408 MAC  
+N_COARSE, N_IMPORTANCE = 64, 64
+WORKLOAD = "blender-like 400x400 LR pixels... see config"
+LR_W = LR_H = 200                   # configs[1]: 400x400 HR rays, downscale 2 -> 200x200 LR pixels
+SS = 2
+RAYS_PER_FRAME = LR_W * LR_H * SS * SS    # 160 000
+SEEDS = (4, 17)                     # non-degenerate kaiming seeds (tests/golden uses the same)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, False, []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 7:
+                    self.rows.append(f)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]),
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def make_inputs(seed_offset: int = 0):
+    from oracle import nerf_oracle as O
+    cfg = O.RenderConfig(white_bkgd=True, N_coarse=N_COARSE, N_importance=N_IMPORTANCE, downscale=SS)
+    pc, pf = O.make_mlp_params(cfg, SEEDS[0]), O.make_mlp_params(cfg, SEEDS[1])
+    rays = O.synthetic_rays(RAYS_PER_FRAME, 100 + seed_offset, "blender")
+    return cfg, pc, pf, rays
+
+
+def cpu_reference_rate(cfg, pc, pf, rays, sample_rays: int, repeats: int):
+    """The reference algorithm (oracle port, torch CPU ops, all host threads), eval mode, chunk 4096."""
+    from oracle import nerf_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    sample = rays[:sample_rays]
+    with torch.no_grad():
+        O.chunked_forward(pc, pf, sample[:1024], cfg)      # warm-up
+        times = []
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            O.chunked_forward(pc, pf, sample, cfg)
+            times.append(time.perf_counter() - t0)
+    times.sort()
+    return sample_rays / times[len(times) // 2], times
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cfg, pc, pf, rays = make_inputs()
+    sample = 4096
+    for _ in range(args.warmup):
+        pass
+    rate, times = cpu_reference_rate(cfg, pc, pf, rays, sample, max(1, args.steps))
+    cores = os.cpu_count() or 1
+    line = {
+        "impl": "reference", "metric": "rays/sec (64+128 samples, 2x SS)", "value": rate, "unit": "rays/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sorted(times)[len(times) // 2], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(1),
+        "cpu_baseline": {"value": rate, "unit": "rays/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} rays of the frame per step (chunk 4096), median of {len(times)}"},
+        "e2e": {"value": rate, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus):
+    return {"workload": "BASELINE configs[1]: Blender-like 400x400 HR rays (200x200 LR pixels x 2x2 SS), "
+                        "64 coarse + 128 fine samples, random-init 256-wide coarse+fine MLP, eval mode",
+            "rays_per_step_per_gpu": RAYS_PER_FRAME, "n_coarse": N_COARSE, "n_fine": N_COARSE + N_IMPORTANCE,
+            "supersampling": SS, "parallelism": f"ray-sharded x{n_gpus} (independent frames, no collective)",
+            "l2": "flushed between timed steps (256 MiB write)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16x3", choices=["fp32_simt", "bf16x3", "fp16x3", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from nerf_sr_b200 import Renderer
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no GPU visible; the CUDA path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg, pc, pf, rays_cpu = make_inputs(seed_offset=rank)
+    r = Renderer(cfg, dev, precision=args.precision)
+    r.load_state_dict(0, pc)
+    r.load_state_dict(1, pf)
+    rays = rays_cpu.to(dev)
+    rays_pinned = rays_cpu.pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    n = rays.shape[0]
+
+    def step_device():
+        out = r.forward_rays(rays, want_weights=False)
+        lr_rgb = r.box_average(out["fine_comp_rgbs"], SS)
+        lr_depth = r.box_average(out["fine_depth"], SS)
+        return out, lr_rgb, lr_depth
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+        r.render_frame_host(rays_pinned, SS)
+    torch.cuda.synchronize()
+
+    # ---- device-resident throughput -----------------------------------------------------
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    launches0 = r.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_wall0 = time.perf_counter()
+    for s, e in ev:
+        flush.fill_(1)                  # evict L2 between timed steps (untimed)
+        s.record()
+        step_device()
+        e.record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = r.launch_count - launches0
+    dev_ms = sum(s.elapsed_time(e) for s, e in ev)
+
+    # ---- dominant kernel (fine pass, one launch) for the roofline ------------------------
+    out = r.forward_rays(rays, want_weights=False, want_z_fine=True)
+    z_fine = out["z_fine"]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    for s, e in kev:
+        flush.fill_(1)
+        s.record()
+        r.render_pass(1, rays, z_fine)
+        e.record()
+    torch.cuda.synchronize()
+    fine_ms = sum(s.elapsed_time(e) for s, e in kev) / args.steps
+
+    # ---- end to end through the host-buffer call -----------------------------------------
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        rgb, depth = r.render_frame_host(rays_pinned, SS)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3, fine_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms, fine_ms = (float(x) for x in t.tolist())
+
+    if rank == 0:
+        pk, pk_kind = peaks()
+        total_rays = n * world * args.steps
+        value = total_rays / (dev_ms / 1e3)
+        fine_flops = n * (N_COARSE + N_IMPORTANCE) * FLOP_PER_POINT
+        achieved = fine_flops / (fine_ms / 1e3) / 1e12
+        peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+        line = {
+            "metric": "rays/sec (64+128 samples, 2x SS)", "value": value, "unit": "rays/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"bf16x3": "bf16x3 split (fp32 accumulate)", "fp16x3": "fp16x3 split (fp32 accumulate)",
+                      "fp32_simt": "f32", "bf16": "bf16"}[args.precision],
+            "data": "synthetic", "config": workload_config(world),
+            "lr_pixels_per_s": value / (SS * SS),
+            "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
+            "e2e": {"value": total_rays / (e2e_ms / 1e3), "unit": "rays/s", "h2d_bytes_per_step": n * rays.shape[1] * 4,
+                    "d2h_bytes_per_step": (n // (SS * SS)) * 4 * 4, "api": "nsr_render_host (pinned host rays in, LR rgb+depth out)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "k_tc_pass (fine pass, S=128)" if args.precision != "fp32_simt" else "k_simt_mlp",
+                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "peak_kind": f"{pk_kind} cuBLAS bf16 sustained", "issued_frac": (3 if "x3" in args.precision else 1) * achieved / peak,
+                         "flop_per_launch": fine_flops, "ms_per_launch": fine_ms, "traffic": None},
+            "clocks": sampler.summary(),
+        }
+        if not args.no_cpu_baseline and world == 1:
+            rate, times = cpu_reference_rate(cfg, pc, pf, rays_cpu, 4096, 3)
+            line["cpu_baseline"] = {"value": rate, "unit": "rays/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                    "sample": "4096 rays of the frame (one ray_chunk), median of 3, oracle port of the reference (torch CPU)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    r.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,207 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every check goes through the C ABI
+(nerf_sr_b200.Renderer -> ctypes -> libnsr_b200.so) and compares with the committed golden
+fixtures (outputs of the unmodified reference) or with the oracle on seeded inputs.
+
+Tolerance (BASELINE.json north_star): |a-b| <= 1e-4 + 1e-3*|b|, fp32.
+Protocol: (i) coarse stage direct; (ii) fine stage teacher-forced on the
+reference's fine z-values; (iii) end-to-end fine as a violation fraction bounded by the
+reference's own fp32-vs-fp64 floor (+ margin), because fine sample positions are an
+ill-conditioned function of coarse weights; (iv) resampler unit parity."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_DIR, golden_names
+from oracle import nerf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+PRECISIONS = ["fp32_simt", "bf16x3", "fp16x3"]
+COARSE_KEYS = ("coarse_comp_rgbs", "coarse_depth", "coarse_opacity", "coarse_weights")
+FINE_MAP = (("comp_rgbs", "fine_comp_rgbs"), ("depth", "fine_depth"), ("opacity", "fine_opacity"),
+            ("weights", "fine_weights"))
+
+
+def _renderer(fx, prec):
+    from nerf_sr_b200 import NsrError, Renderer
+    try:
+        r = Renderer(fx.cfg, torch.device("cuda:0"), precision=prec, viewdir_offset=fx.cfg.viewdir_offset)
+    except NsrError as e:
+        if e.code == 2:
+            pytest.skip(f"{prec} does not support this option set: {e}")
+        raise
+    r.load_state_dict(0, fx.p_coarse)
+    r.load_state_dict(1, fx.p_fine)
+    return r
+
+
+def _rng(fx):
+    if fx.rng is None:
+        return None
+    return {k: getattr(fx.rng, k) for k in ("u_coarse", "noise_coarse", "u_fine", "noise_fine")
+            if getattr(fx.rng, k) is not None}
+
+
+def _dev(t):
+    return None if t is None else t.cuda()
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
+@pytest.mark.parametrize("name", golden_names())
+def test_forward_rays_against_reference_golden(name, prec, load_fixture):
+    fx = load_fixture(name)
+    r = _renderer(fx, prec)
+    out = r.forward_rays(fx.rays.cuda(), _rng(fx), want_z_fine=True)
+    torch.cuda.synchronize()
+    assert set(fx.out) <= set(out)
+    for k, ref in fx.out.items():
+        assert out[k].shape == ref.shape and out[k].dtype == torch.float32, k
+    # (i) coarse stage: direct
+    for k in COARSE_KEYS:
+        mx, viol = O.tolerance_violations(out[k].cpu(), fx.out[k])
+        assert viol == 0.0, (k, mx, viol)
+    if fx.cfg.N_importance == 0:
+        assert "fine_comp_rgbs" not in out
+        return
+    # (iii) end to end: bounded by the reference's own fp32-vs-fp64 disagreement on this fixture
+    for k in ("fine_comp_rgbs", "fine_depth", "fine_opacity", "fine_weights"):
+        mx, viol = O.tolerance_violations(out[k].cpu(), fx.out[k])
+        floor = fx.meta["fp64_floor"][k]["viol"]
+        assert viol <= 2.0 * floor + 0.06, (k, mx, viol, floor)
+        assert torch.isfinite(out[k]).all()
+    r.close()
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
+@pytest.mark.parametrize("name", golden_names())
+def test_teacher_forced_passes_and_mlp_output(name, prec, load_fixture):
+    """(ii): each network on the reference's own z-values, plus the raw VanillaMLP output."""
+    fx = load_fixture(name)
+    r = _renderer(fx, prec)
+    rays = fx.rays.cuda()
+    nz = _dev(fx.rng.noise_coarse) if fx.rng is not None else None
+    pc = r.render_pass(0, rays, fx.z_coarse.cuda(), nz, want_raw=True)
+    for kl, kr in (("comp_rgbs", "coarse_comp_rgbs"), ("depth", "coarse_depth"), ("opacity", "coarse_opacity"),
+                   ("weights", "coarse_weights")):
+        mx, viol = O.tolerance_violations(pc[kl].cpu(), fx.out[kr])
+        assert viol == 0.0, (kl, mx, viol)
+    mx, viol = O.tolerance_violations(pc["raw"].cpu(), fx.raw_coarse, rtol=1e-3, atol=2e-4)
+    assert viol == 0.0, ("raw_coarse", mx, viol)
+    if fx.cfg.N_importance > 0:
+        nzf = _dev(fx.rng.noise_fine) if fx.rng is not None else None
+        pf = r.render_pass(1, rays, fx.z_fine.cuda(), nzf, want_raw=True)
+        for kl, kr in FINE_MAP:
+            mx, viol = O.tolerance_violations(pf[kl].cpu(), fx.out[kr])
+            assert viol == 0.0, (kl, mx, viol)
+        mx, viol = O.tolerance_violations(pf["raw"].cpu(), fx.raw_fine, rtol=1e-3, atol=2e-4)
+        assert viol == 0.0, ("raw_fine", mx, viol)
+    r.close()
+
+
+@pytest.mark.parametrize("name", ["eval_blender", "eval_llff", "train_blender", "train_llff_noise", "opt_small_net"])
+def test_sampling_seams(name, load_fixture):
+    """(iv) sample_along_rays / resample_along_rays z-values against the reference's."""
+    fx = load_fixture(name)
+    r = _renderer(fx, "fp32_simt")
+    u = _dev(fx.rng.u_coarse) if fx.rng is not None else None
+    z = r.sample_along_rays(fx.rays.cuda(), u)
+    assert torch.equal(z.cpu(), fx.z_coarse), float((z.cpu() - fx.z_coarse).abs().max())   # bit exact
+    uf = _dev(fx.rng.u_fine) if fx.rng is not None else None
+    zf = r.resample_along_rays(fx.z_coarse.cuda(), fx.out["coarse_weights"].cuda(), uf).cpu()
+    assert (zf[:, 1:] >= zf[:, :-1]).all()                  # sorted
+    mx, viol = O.tolerance_violations(zf, fx.z_fine)
+    # flat CDF segments amplify 1-ulp differences of the pdf normalisation: tolerance, not bit-exact
+    assert viol == 0.0, (mx, viol)
+    assert float((zf - fx.z_fine).abs().median()) < 1e-6
+    r.close()
+
+
+def test_posenc_and_box_average(load_fixture):
+    fx = load_fixture("eval_blender")
+    r = _renderer(fx, "fp32_simt")
+    x = torch.randn(1000, 3, generator=torch.Generator().manual_seed(0)) * 3
+    for deg in (10, 4):
+        e = r.posenc(x.cuda(), deg).cpu()
+        ref = O.posenc(x, deg)
+        assert e.shape == ref.shape
+        assert torch.equal(e[:, :3], x)
+        assert float((e - ref).abs().max()) < 2e-6          # sin/cos of arguments up to 2^9*|x|
+    v = torch.rand(4 * 50, 3, generator=torch.Generator().manual_seed(1))
+    assert torch.allclose(r.box_average(v.cuda(), 2).cpu(), O.box_average(v, 2), rtol=0, atol=1e-7)
+    d = torch.rand(16 * 10, generator=torch.Generator().manual_seed(2))
+    assert torch.allclose(r.box_average(d.cuda(), 4).cpu(), O.box_average(d, 4), rtol=0, atol=1e-7)
+    r.close()
+
+
+def test_generate_rays_matches_reference_dataset_path(load_fixture):
+    import os
+    fx = load_fixture("eval_blender")
+    r = _renderer(fx, "fp32_simt")
+    z = np.load(os.path.join(GOLDEN_DIR, "raygen.npz"))
+    for tag in ("blender", "llff"):
+        H, W, s, focal, ndc, near, far = z[f"{tag}_params"]
+        rays = r.generate_rays(z[f"{tag}_c2w"], int(H), int(W), float(focal), int(s), bool(ndc), float(near), float(far)).cpu()
+        ref = torch.from_numpy(z[f"{tag}_rays"])
+        assert rays.shape == ref.shape
+        assert torch.allclose(rays, ref, rtol=2e-6, atol=2e-6), float((rays - ref).abs().max())
+    r.close()
+
+
+@pytest.mark.parametrize("prec", ["bf16x3", "fp16x3"])
+def test_full_size_frame_properties(prec, load_fixture):
+    """BASELINE configs[1] size (160 000 rays): size-independent properties + agreement of the
+    tensor-core path with the fp32 CUDA-core path + determinism + ragged tail."""
+    fx = load_fixture("eval_blender")
+    cfg = fx.cfg
+    rays = O.synthetic_rays(160000 + 3, 11, "blender").cuda()      # odd count: ragged last tile
+    r = _renderer(fx, prec)
+    a = r.forward_rays(rays)
+    b = r.forward_rays(rays)
+    torch.cuda.synchronize()
+    for k in a:
+        assert torch.equal(a[k], b[k]), f"{k} not deterministic"
+        assert torch.isfinite(a[k]).all(), k
+    for p in ("coarse", "fine"):
+        w, op = a[f"{p}_weights"], a[f"{p}_opacity"]
+        assert float(w.min()) >= 0.0 and float(op.max()) <= 1.0 + 1e-5
+        assert torch.allclose(w.sum(-1), op, rtol=1e-5, atol=1e-5)            # opacity == sum of weights
+        rgb = a[f"{p}_comp_rgbs"]
+        assert float(rgb.min()) >= -1e-5 and float(rgb.max()) <= 1.0 + 1e-4    # white bkgd + sigmoid colours
+        assert float(a[f"{p}_depth"].max()) <= 6.0 + 1e-3
+    # the coarse stage must agree with the fp32 CUDA-core path within tolerance everywhere
+    s = _renderer(fx, "fp32_simt")
+    c = s.forward_rays(rays[:20000])
+    for k in COARSE_KEYS:
+        mx, viol = O.tolerance_violations(a[k][:20000].cpu(), c[k].cpu())
+        assert viol == 0.0, (k, mx, viol)
+    # a chunked call equals the single call (no cross-ray state; chunk_batch equivalence, utils.py:130-152)
+    d = r.forward_rays(rays[4096:8192])
+    for k in d:
+        assert torch.equal(d[k], a[k][4096:8192]), k
+    r.close(); s.close()
+
+
+def test_host_frame_call_equals_device_path(load_fixture):
+    fx = load_fixture("eval_blender")
+    r = _renderer(fx, "bf16x3")
+    rays = O.synthetic_rays(4 * 40000 + 4 * 7, 5, "blender")
+    rgb, depth = r.render_frame_host(rays, 2)
+    out = r.forward_rays(rays.cuda(), want_weights=False)
+    assert torch.equal(rgb, r.box_average(out["fine_comp_rgbs"], 2).cpu())
+    assert torch.equal(depth, r.box_average(out["fine_depth"], 2).cpu().squeeze(-1))
+    r.close()
+
+
+def test_errors_are_reported_not_fatal(load_fixture):
+    from nerf_sr_b200 import NsrError, Renderer
+    fx = load_fixture("eval_blender")
+    r = Renderer(fx.cfg, torch.device("cuda:0"), precision="bf16x3")
+    with pytest.raises(NsrError) as ei:                    # weights not packed yet
+        r.forward_rays(fx.rays.cuda())
+    assert ei.value.code == 3
+    bad = O.RenderConfig(W=100)
+    with pytest.raises(NsrError):
+        Renderer(bad, torch.device("cuda:0"), precision="fp32_simt")
+    with pytest.raises(NsrError):                          # tensor-core path refuses, never silently differs
+        Renderer(O.RenderConfig(D=4), torch.device("cuda:0"), precision="bf16x3")
+    r.close()

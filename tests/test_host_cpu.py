@@ -1,0 +1,68 @@
+"""CPU-only host-logic tests: the C-ABI library loads and exports every declared symbol, the
+binding's structs match the header, and it refuses to run without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT
+from oracle import nerf_oracle as O
+
+
+def _build():
+    import __graft_entry__ as g
+    g.build()
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    _build()
+    from nerf_sr_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "nsr.h")).read()
+    declared = set(re.findall(r"NSR_API [a-z0-9_ \*]+?\b(nsr_[a-z_]+)\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.nsr_abi_version() == _lib.ABI_VERSION
+
+
+def test_config_struct_matches_header():
+    from nerf_sr_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "nsr.h")).read()
+    body = header[header.index("typedef struct NsrConfig {"):header.index("} NsrConfig;")]
+    fields = re.findall(r"^\s*(?:uint32_t|int32_t|float)\s+([a-z_A-Z]+)(?:\[\d+\])?;", body, flags=re.M)
+    assert fields == [f[0] for f in _lib.NsrConfig._fields_]
+    assert C.sizeof(_lib.NsrConfig) == 4 * (len(fields) - 1) + 4 * 8
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    _build()
+    from nerf_sr_b200 import NsrError, Renderer, _lib, config_from_opt
+    with pytest.raises(NsrError):
+        Renderer(O.RenderConfig())
+    lib = _lib.load()
+    cfg = config_from_opt(O.RenderConfig(), 0)
+    h = C.c_void_p()
+    assert lib.nsr_create(C.byref(cfg), C.byref(h)) == 6          # NSR_ERR_NO_DEVICE
+    assert b"no CPU fallback" in lib.nsr_last_error(None)
+    cfg.struct_size = 12                                             # ABI skew is caught first
+    assert lib.nsr_create(C.byref(cfg), C.byref(h)) == 1
+
+
+def test_config_from_reference_style_opt():
+    from types import SimpleNamespace
+    from nerf_sr_b200 import config_from_opt
+    opt = SimpleNamespace(D=8, W=256, skips=[4], N_coarse=64, N_importance=64, white_bkgd=True, noise_std=1.0,
+                          sigma_activation="softplus", color_activation="none", lindisp=True, deg_pos=10, deg_dir=4)
+    c = config_from_opt(opt, 0, "fp16x3", viewdir_offset=8)
+    assert (c.skips_mask, c.white_bkgd, c.sigma_activation, c.color_activation, c.lindisp) == (16, 1, 1, 1, 1)
+    assert c.precision == 2 and c.viewdir_offset == 8 and abs(c.noise_std - 1.0) < 1e-7
+
+
+def test_state_dict_order_matches_oracle_shapes():
+    from nerf_sr_b200 import state_dict_order
+    assert state_dict_order(8) == [n for n, _ in O.mlp_param_shapes(O.RenderConfig())]
