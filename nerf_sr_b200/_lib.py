@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnsr_b200.so")
+LIB_PATH = os.environ.get("NSR_LIB_PATH") or os.path.join(_HERE, "libnsr_b200.so")
 ABI_VERSION = 1
 
 NSR_OK = 0
@@ -62,6 +62,7 @@ SIGNATURES = {
     "nsr_generate_rays": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_float, C.c_int,
                                     C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     "nsr_render_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "nsr_debug_set_trace": (C.c_int, [C.c_void_p, C.c_void_p]),
     "nsr_launch_count": (C.c_int64, [C.c_void_p]),
 }
 

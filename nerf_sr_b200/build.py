@@ -35,14 +35,17 @@ def _digest() -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every CUDA source and link the shared library.  Returns its path."""
+def build(force: bool = False, verbose: bool = False, extra_flags=(), lib_path: str = LIB) -> str:
+    """Compile every CUDA source and link the shared library.  Returns its path.
+    extra_flags/lib_path build a variant (e.g. the trace build: -DNSR_TC_TRACE=1)."""
+    LIB = lib_path
+    NVCC_FLAGS = [*globals()["NVCC_FLAGS"], *extra_flags]
     stamp = LIB + ".stamp"
-    dig = _digest()
+    dig = _digest() + "|" + " ".join(extra_flags)
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
         return LIB
     nvcc = _nvcc()
-    objdir = os.path.join(ROOT, "build")
+    objdir = os.path.join(ROOT, "build", os.path.basename(LIB).replace(".so", ""))
     os.makedirs(objdir, exist_ok=True)
     procs = []
     objs = []
@@ -69,4 +72,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    if "--trace" in sys.argv:
+        print(build(force=True, verbose=True, extra_flags=["-DNSR_TC_TRACE=1"],
+                    lib_path=os.path.join(PKG, "libnsr_b200_trace.so")))
+    else:
+        print(build(force="--force" in sys.argv, verbose=True))

@@ -53,6 +53,7 @@ struct NsrHandle_ {
   std::vector<int64_t> param_numel;
   int sm_count = 0;
   int64_t launches = 0;
+  long long* trace_buf = nullptr;
   std::string err;
   // nsr_render_host state (library-owned staging)
   cudaStream_t hs[2] = {nullptr, nullptr};
@@ -86,6 +87,7 @@ struct TcPassArgs {
   const float* u_jitter; const float* noise; const float* u_resample;
   int do_resample;
   float* comp_rgb; float* depth; float* opacity; float* weights; float* raw; float* z_next;
+  long long* trace;   // debug timeline buffer (NSR_TC_TRACE builds), else null
 };
 cudaError_t tc_pass(NsrHandle_* h, int which, const TcPassArgs& a, cudaStream_t st);
 

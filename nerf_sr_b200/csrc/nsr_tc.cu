@@ -76,7 +76,7 @@ constexpr int kSmXch = kSmW + 128 * 4;                           // 215040
 constexpr int kSmScratch = kSmXch + 4 * 128 * 4;                 // 217088
 constexpr int kSmBar = kSmScratch + 2 * 320 * 4;                 // 219648
 constexpr int kSmTmemPtr = kSmBar + 32 * 8;
-constexpr int kSmemTcBytes = kSmTmemPtr + 16 + 1024;             // + alignment slack
+constexpr int kSmemTcBytes = kSmTmemPtr + 16;
 
 // barrier indices
 enum {
@@ -146,6 +146,12 @@ __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 
 // D[tmem] (+)= A[smem] * B[smem]
 __device__ __forceinline__ void mma_ss(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
@@ -325,6 +331,26 @@ cudaError_t tc_pack(NsrHandle_* h, int which, const float* const* params, cudaSt
 }
 
 // ---------------------------------------------------------------------------
+// optional timeline trace (tools/tc_trace.py): -DNSR_TC_TRACE=1 stamps clock64() at protocol
+// points of CTA 0, tile iteration 3 into a global buffer: 512 slots per warp.
+// ---------------------------------------------------------------------------
+#ifndef NSR_TC_TRACE
+#define NSR_TC_TRACE 0
+#endif
+#if NSR_TC_TRACE
+#define TR_DECL(args, it) long long* tr_ = ((args).trace && blockIdx.x == 0 && (it) == 3 && (threadIdx.x & 31) == 0) \
+                                             ? (args).trace + (threadIdx.x >> 5) * 512 : nullptr; int trn_ = 0; (void)trn_
+#define TR(tag) do { if (tr_ && trn_ < 255) { tr_[2 * trn_] = (tag); tr_[2 * trn_ + 1] = clock64(); ++trn_; } } while (0)
+#define TR_PARAMS , long long* tr_, int& trn_
+#define TR_ARGS , tr_, trn_
+#else
+#define TR_DECL(args, it)
+#define TR(tag)
+#define TR_PARAMS
+#define TR_ARGS
+#endif
+
+// ---------------------------------------------------------------------------
 // kernel arguments
 // ---------------------------------------------------------------------------
 struct TcKernelArgs {
@@ -338,6 +364,7 @@ struct TcKernelArgs {
   int do_resample;
   float* comp_rgb; float* depth; float* opacity; float* weights; float* raw; float* z_next;
   long long n_tiles;
+  long long* trace;
 };
 
 // ---------------------------------------------------------------------------
@@ -410,8 +437,11 @@ __device__ __forceinline__ void mma_role(const TcKernelArgs& a, uint32_t sm_base
   for (long long it = 0; it < my_tiles; ++it) {
     const uint32_t buf = (uint32_t)(it & 1);
     const uint32_t enc = sm_base + kSmEnc + buf * kStageBytes;
+    TR_DECL(a, it);
+    TR(1000);
     mbar_wait(bar + 8 * (B_ENCFULL + buf), (uint32_t)((it >> 1) & 1));
     tc_fence_after();
+    TR(1001);
     // ---- L1: A = encoding (smem); half 1 then half 0
     if (g > 0) { mbar_wait(bar + 8 * (B_AREADY + 1), (g - 1) & 1); tc_fence_after(); }
     m.stage(1, -1, enc, true);
@@ -424,11 +454,15 @@ __device__ __forceinline__ void mma_role(const TcKernelArgs& a, uint32_t sm_base
     // ---- L2..L9 (L5 = skip layer with the encoding chunk first)
     for (int L = 2; L <= 9; ++L, ++g) {
       const bool skip = (L == 5);
+      TR(1100 + L);
       mbar_wait(bar + 8 * (B_AREADY + 0), (g - 1) & 1); tc_fence_after();
+      TR(1200 + L);
       if (skip) m.stage(0, -1, enc, true);
       m.stage(0, 0, 0, !skip);
       m.stage(0, 32, 0, false);
+      TR(1300 + L);
       mbar_wait(bar + 8 * (B_AREADY + 1), (g - 1) & 1); tc_fence_after();
+      TR(1400 + L);
       m.stage(0, 64, 0, false);
       m.stage(0, 96, 0, false);
       tc_commit(bar + 8 * (B_ACCFULL + 0));
@@ -439,6 +473,7 @@ __device__ __forceinline__ void mma_role(const TcKernelArgs& a, uint32_t sm_base
       m.stage(1, 64, 0, false);
       m.stage(1, 96, 0, false);
       tc_commit(bar + 8 * (B_ACCFULL + 1));
+      TR(1500 + L);
     }
     // ---- L10 (dir_encoding feat part, N = 128: half 0 only)
     mbar_wait(bar + 8 * (B_AREADY + 0), (g - 1) & 1); tc_fence_after();
@@ -545,6 +580,54 @@ __device__ __forceinline__ void frontend_role(const TcKernelArgs& a, uint8_t* sm
   }
 }
 
+// One trunk layer's epilogue for this warp: both accumulator halves, 64 columns of each.
+//   acc + bias (+ReLU) (-> sigma-head partial) -> hi/lo split -> A operand planes in TMEM.
+template <int FMT, int PASSES, bool RELU, bool SIGMA>
+__device__ __forceinline__ void epi_layer(int L, uint32_t g, uint32_t bar, uint32_t tlane, uint32_t cst_addr, int hh,
+                                          int lane, float& sig_p TR_PARAMS) {
+  const uint32_t bias_addr = cst_addr + 4u * (uint32_t)((L - 1) * 256);   // L9 -> kcBiasFinal
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    TR(100 * L + 10 * h + 0);
+    mbar_wait(bar + 8 * (B_ACCFULL + h), g & 1);
+    if (h == 0) mbar_wait(bar + 8 * B_AFREE0, g & 1);
+    tc_fence_after();
+    TR(100 * L + 10 * h + 1);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int col0 = 128 * h + 64 * hh + 32 * c;
+      uint32_t r[32];
+      TMEM_LD32(tlane + (uint32_t)col0, r);
+      tc_wait_ld();
+      TR(100 * L + 10 * h + 2 + 2 * c);
+      uint32_t whi[16], wlo[16];
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b4 = lds128(bias_addr + 4u * (uint32_t)(col0 + j));
+        float v0 = __uint_as_float(r[j]) + b4.x, v1 = __uint_as_float(r[j + 1]) + b4.y;
+        float v2 = __uint_as_float(r[j + 2]) + b4.z, v3 = __uint_as_float(r[j + 3]) + b4.w;
+        if (RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+        if (SIGMA) {   // sigma head on h_8 (networks.py:207)
+          const float4 w4 = lds128(cst_addr + 4u * (uint32_t)(kcWsig + col0 + j));
+          sig_p = fmaf(v0, w4.x, sig_p); sig_p = fmaf(v1, w4.y, sig_p);
+          sig_p = fmaf(v2, w4.z, sig_p); sig_p = fmaf(v3, w4.w, sig_p);
+        }
+        Split<FMT>::apply(v0, v1, whi[j / 2], wlo[j / 2]);
+        Split<FMT>::apply(v2, v3, whi[j / 2 + 1], wlo[j / 2 + 1]);
+      }
+      TMEM_ST16(tlane + 256u + (uint32_t)(col0 / 2), whi);
+      if (PASSES == 3) TMEM_ST16(tlane + 384u + (uint32_t)(col0 / 2), wlo);
+      TR(100 * L + 10 * h + 3 + 2 * c);
+    }
+    tc_wait_st();
+    TR(100 * L + 10 * h + 6);
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar + 8 * (B_AREADY + h));
+    TR(100 * L + 10 * h + 7);
+  }
+}
+
 // ---- epilogue + compositing ----
 template <int FMT, int PASSES>
 __device__ __forceinline__ void epilogue_role(const TcKernelArgs& a, uint8_t* sm, uint32_t sm_base, uint32_t tmem,
@@ -564,43 +647,12 @@ __device__ __forceinline__ void epilogue_role(const TcKernelArgs& a, uint8_t* sm
     const uint32_t buf = (uint32_t)(it & 1);
     const long long tile = first_tile + it * (long long)tile_stride;
     float sig_p = 0.f;
+    TR_DECL(a, it);
     // ---- layers 1..9: bias (+ReLU) -> hi/lo split -> next A operand ----
-    for (int L = 1; L <= 9; ++L, ++g) {
-      const float* bias = cst + (L - 1) * 256;       // L9 -> kcBiasFinal = 2048
-      for (int h = 0; h < 2; ++h) {
-        mbar_wait(bar + 8 * (B_ACCFULL + h), g & 1);
-        if (h == 0) mbar_wait(bar + 8 * B_AFREE0, g & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const int col0 = 128 * h + 64 * hh + 32 * c;
-          uint32_t r[32];
-          TMEM_LD32(tlane + (uint32_t)col0, r);
-          tc_wait_ld();
-          uint32_t whi[16], wlo[16];
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(bias + col0 + j);
-            float v0 = __uint_as_float(r[j]) + b4.x, v1 = __uint_as_float(r[j + 1]) + b4.y;
-            float v2 = __uint_as_float(r[j + 2]) + b4.z, v3 = __uint_as_float(r[j + 3]) + b4.w;
-            if (L <= 8) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
-            if (L == 8) {   // sigma head on h_8 (networks.py:207)
-              const float4 w4 = *reinterpret_cast<const float4*>(cst + kcWsig + col0 + j);
-              sig_p = fmaf(v0, w4.x, sig_p); sig_p = fmaf(v1, w4.y, sig_p);
-              sig_p = fmaf(v2, w4.z, sig_p); sig_p = fmaf(v3, w4.w, sig_p);
-            }
-            Split<FMT>::apply(v0, v1, whi[j / 2], wlo[j / 2]);
-            Split<FMT>::apply(v2, v3, whi[j / 2 + 1], wlo[j / 2 + 1]);
-          }
-          TMEM_ST16(tlane + 256u + (uint32_t)(col0 / 2), whi);
-          if (PASSES == 3) TMEM_ST16(tlane + 384u + (uint32_t)(col0 / 2), wlo);
-        }
-        tc_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar + 8 * (B_AREADY + h));
-      }
-    }
+    for (int L = 1; L <= 7; ++L, ++g)
+      epi_layer<FMT, PASSES, true, false>(L, g, bar, tlane, sm_base + kSmConst, hh, lane, sig_p TR_ARGS);
+    epi_layer<FMT, PASSES, true, true>(8, g, bar, tlane, sm_base + kSmConst, hh, lane, sig_p TR_ARGS); ++g;    // + sigma head
+    epi_layer<FMT, PASSES, false, false>(9, g, bar, tlane, sm_base + kSmConst, hh, lane, sig_p TR_ARGS); ++g;  // final: no act
     // ---- layer 10: dir layer (N=128, accumulator half 0) + rgb head ----
     float rgb_p[3] = {0.f, 0.f, 0.f};
     {
@@ -608,7 +660,8 @@ __device__ __forceinline__ void epilogue_role(const TcKernelArgs& a, uint8_t* sm
       mbar_wait(bar + 8 * B_AFREE0, g & 1);
       mbar_wait(bar + 8 * (B_ACCFULL + 1), g & 1);
       tc_fence_after();
-      const float* dbias = reinterpret_cast<const float*>(sm + kSmDirBias) + buf * 256 + (row / S) * 128;
+      const uint32_t dbias_addr = sm_base + kSmDirBias + 4u * (uint32_t)(buf * 256 + (row / S) * 128);
+      const uint32_t wrgb_addr = sm_base + kSmConst + 4u * kcWrgb;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const int col0 = 64 * hh + 32 * c;
@@ -616,11 +669,16 @@ __device__ __forceinline__ void epilogue_role(const TcKernelArgs& a, uint8_t* sm
         TMEM_LD32(tlane + (uint32_t)col0, r);
         tc_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float v = fmaxf(__uint_as_float(r[j]) + dbias[col0 + j], 0.f);
-          rgb_p[0] = fmaf(v, cst[kcWrgb + col0 + j], rgb_p[0]);
-          rgb_p[1] = fmaf(v, cst[kcWrgb + 128 + col0 + j], rgb_p[1]);
-          rgb_p[2] = fmaf(v, cst[kcWrgb + 256 + col0 + j], rgb_p[2]);
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = lds128(dbias_addr + 4u * (uint32_t)(col0 + j));
+          const float4 w0 = lds128(wrgb_addr + 4u * (uint32_t)(col0 + j));
+          const float4 w1 = lds128(wrgb_addr + 4u * (uint32_t)(128 + col0 + j));
+          const float4 w2 = lds128(wrgb_addr + 4u * (uint32_t)(256 + col0 + j));
+          const float v0 = fmaxf(__uint_as_float(r[j]) + b4.x, 0.f), v1 = fmaxf(__uint_as_float(r[j + 1]) + b4.y, 0.f);
+          const float v2 = fmaxf(__uint_as_float(r[j + 2]) + b4.z, 0.f), v3 = fmaxf(__uint_as_float(r[j + 3]) + b4.w, 0.f);
+          rgb_p[0] = fmaf(v0, w0.x, rgb_p[0]); rgb_p[0] = fmaf(v1, w0.y, rgb_p[0]); rgb_p[0] = fmaf(v2, w0.z, rgb_p[0]); rgb_p[0] = fmaf(v3, w0.w, rgb_p[0]);
+          rgb_p[1] = fmaf(v0, w1.x, rgb_p[1]); rgb_p[1] = fmaf(v1, w1.y, rgb_p[1]); rgb_p[1] = fmaf(v2, w1.z, rgb_p[1]); rgb_p[1] = fmaf(v3, w1.w, rgb_p[1]);
+          rgb_p[2] = fmaf(v0, w2.x, rgb_p[2]); rgb_p[2] = fmaf(v1, w2.y, rgb_p[2]); rgb_p[2] = fmaf(v2, w2.z, rgb_p[2]); rgb_p[2] = fmaf(v3, w2.w, rgb_p[2]);
         }
       }
       tc_fence_before();
@@ -686,9 +744,10 @@ __device__ __forceinline__ void epilogue_role(const TcKernelArgs& a, uint8_t* sm
 
 template <int FMT, int PASSES>
 __global__ void __launch_bounds__(kThreadsTc, 1) k_tc_pass(const TcKernelArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];   // SWIZZLE_128B operands need 1024-B alignment
+  uint8_t* sm = smem_raw;                                 // (keeps the __shared__ address space: LDS/STS)
   const uint32_t sm_base = smem_u32(sm);
+  if (sm_base & 1023u) { if (threadIdx.x == 0) printf("[nsr_tc] dynamic smem base %u not 1024-aligned\n", sm_base); __trap(); }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long my_tiles = (a.n_tiles > blockIdx.x) ? (a.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
@@ -741,6 +800,7 @@ cudaError_t tc_pass(NsrHandle_* h, int which, const TcPassArgs& p, cudaStream_t 
   a.u_jitter = p.u_jitter; a.noise = p.noise; a.u_resample = p.u_resample; a.do_resample = p.do_resample;
   a.comp_rgb = p.comp_rgb; a.depth = p.depth; a.opacity = p.opacity; a.weights = p.weights; a.raw = p.raw;
   a.z_next = p.z_next;
+  a.trace = p.trace;
   const int rpt = kTile / p.S;
   a.n_tiles = (p.n_rays + rpt - 1) / rpt;
   if (a.n_tiles == 0) return cudaSuccess;

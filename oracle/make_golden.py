@@ -139,8 +139,12 @@ def build_raygen_fixture() -> dict:
     rng = np.random.default_rng(7)
     for tag, (H, W, s, focal, ndc) in {"blender": (24, 32, 2, 41.7, False),
                                         "llff": (36, 24, 4, 29.3, True)}.items():
-        a = rng.standard_normal((3, 3))
+        if ndc:   # forward-facing (LLFF) pose: small rotation about identity so d_z stays away from 0
+            a = np.eye(3) + 0.15 * rng.standard_normal((3, 3))
+        else:
+            a = rng.standard_normal((3, 3))
         q, _ = np.linalg.qr(a)
+        q = q * np.sign(np.diag(q))[None, :] if ndc else q
         c2w = np.concatenate([q, rng.standard_normal((3, 1)) * 0.5 + np.array([[0.], [0.], [2.5]])], 1)
         c2w = torch.from_numpy(c2w.astype(np.float32))
         dirs = get_ray_directions(H, W, focal)
