@@ -243,6 +243,8 @@ NSR_API int nsr_render_host(NsrHandle* h, const float* rays_host, int64_t n_rays
 /* Debug: device buffer (>= 16*512 int64) that trace builds (-DNSR_TC_TRACE=1) fill with
  * (tag, clock64) pairs for one tile of CTA 0; ignored by normal builds.  tools/tc_trace.py. */
 NSR_API int nsr_debug_set_trace(NsrHandle* h, long long* device_buffer);
+/* Debug: timing-experiment switches (bit 0: weight producer skips its bulk copies -> WRONG results). */
+NSR_API int nsr_debug_set_flags(NsrHandle* h, int flags);
 
 /* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 NSR_API int64_t nsr_launch_count(const NsrHandle* h);

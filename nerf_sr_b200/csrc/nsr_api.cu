@@ -81,7 +81,8 @@ k_composite(RenderParams rp, const SampleTables* __restrict__ tabs, const float*
   float* ssig = sz + S;        // [S]
   float* srgb = ssig + S;      // [3S]
   float* sw = srgb + 3 * S;    // [S]
-  float* scratch = sw + S;     // resample scratch [2S + n_imp] then z_out [S + n_imp]
+  float* stmp = sw + S;        // [S]
+  float* scratch = stmp + S;   // resample scratch [2S + n_imp] then z_out [S + n_imp]
   const int n_imp = rp.n_importance;
   for (int64_t ray = blockIdx.x * 4 + warp; ray < n_rays; ray += (int64_t)gridDim.x * 4) {
     const float4* r4 = reinterpret_cast<const float4*>(raw) + ray * S;
@@ -97,7 +98,7 @@ k_composite(RenderParams rp, const SampleTables* __restrict__ tabs, const float*
     }
     __syncwarp();
     float r, g, b, d, o;
-    composite_ray_warp(sz, ssig, srgb, S, rp.white_bkgd, rp.sigma_softplus, sw, r, g, b, d, o);
+    composite_ray_warp(sz, ssig, srgb, S, rp.white_bkgd, rp.sigma_softplus, sw, stmp, r, g, b, d, o);
     if (lane == 0) {
       if (comp_rgb) { comp_rgb[ray * 3] = r; comp_rgb[ray * 3 + 1] = g; comp_rgb[ray * 3 + 2] = b; }
       if (depth) depth[ray] = d;
@@ -228,7 +229,7 @@ cudaError_t launch_composite(NsrHandle_* h, const float* raw, const float* z, co
                              float* z_next, cudaStream_t st) {
   if (n_rays == 0) return cudaSuccess;
   const int n_imp = h->rp.n_importance;
-  const int per_warp = 6 * S + (do_resample ? (3 * S + 2 * n_imp) : 0);
+  const int per_warp = 7 * S + (do_resample ? (3 * S + 2 * n_imp) : 0);
   const size_t smem = (size_t)per_warp * 4 * sizeof(float);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k_composite, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -386,6 +387,11 @@ extern "C" int nsr_debug_set_trace(NsrHandle* h, long long* device_buffer) {
   h->trace_buf = device_buffer;
   return NSR_OK;
 }
+extern "C" int nsr_debug_set_flags(NsrHandle* h, int flags) {
+  if (!h) return NSR_ERR_INVALID_ARG;
+  h->debug_flags = flags;
+  return NSR_OK;
+}
 extern "C" int64_t nsr_launch_count(const NsrHandle* h) { return h ? h->launches : 0; }
 
 extern "C" int nsr_pack_weights(NsrHandle* h, int which, const float* const* param_ptrs, int n_params,
@@ -458,6 +464,7 @@ static int run_pass(NsrHandle_* h, int which, const float* rays, int64_t n, int 
   a.rays = rays; a.n_rays = n; a.ray_stride = stride; a.z_in = z_in; a.S = S;
   a.u_jitter = u_jitter; a.noise = noise; a.u_resample = u_res; a.do_resample = do_resample;
   a.trace = h->trace_buf;
+  a.debug_flags = h->debug_flags;
   a.comp_rgb = comp; a.depth = depth; a.opacity = opa; a.weights = wts; a.raw = raw_out; a.z_next = z_next;
   NSR_CUDA(h, tc_pass(h, which, a, st));
   return NSR_OK;

@@ -76,8 +76,10 @@ __device__ __forceinline__ void posenc3(float x, float y, float z, int n_freqs, 
   for (int k = 0; k < n_freqs; ++k) {
     const float f = freqs[k];
     const float ax = __fmul_rn(f, x), ay = __fmul_rn(f, y), az = __fmul_rn(f, z);
-    emit(c + 0, sinf(ax)); emit(c + 1, sinf(ay)); emit(c + 2, sinf(az));
-    emit(c + 3, cosf(ax)); emit(c + 4, cosf(ay)); emit(c + 5, cosf(az));
+    float sx, cx, sy, cy, sz, cz;     // one range reduction per argument (same results as sinf/cosf)
+    sincosf(ax, &sx, &cx); sincosf(ay, &sy, &cy); sincosf(az, &sz, &cz);
+    emit(c + 0, sx); emit(c + 1, sy); emit(c + 2, sz);
+    emit(c + 3, cx); emit(c + 4, cy); emit(c + 5, cz);
     c += 6;
   }
 }
@@ -97,16 +99,46 @@ __device__ __forceinline__ float sigma_act(float s, int softplus) {
 }
 
 // ----------------------------------------------------------------------------
+// Sequential scan of x[0..n) in shared memory by ONE lane, in index order (the
+// rounding order of torch.cumsum / torch.cumprod on CPU).  Loads are batched 8
+// ahead of the dependent chain, so the cost is ~4 cycles per element.
+//   MUL = true : x[i] <- init * prod_{j<i} x[j]   (exclusive product)
+//   MUL = false: x[i] <- init + sum_{j<=i} x[j]   (inclusive sum)
+// ----------------------------------------------------------------------------
+template <bool MUL>
+__device__ __forceinline__ void seq_scan_one_lane(float* x, int n, float init) {
+  float acc = init;
+  int base = 0;
+  for (; base + 8 <= n; base += 8) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = x[base + j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (MUL) { const float t = acc; acc = __fmul_rn(acc, v[j]); v[j] = t; }
+      else { acc = __fadd_rn(acc, v[j]); v[j] = acc; }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[base + j] = v[j];
+  }
+  for (; base < n; ++base) {
+    const float v = x[base];
+    if (MUL) { x[base] = acc; acc = __fmul_rn(acc, v); }
+    else { acc = __fadd_rn(acc, v); x[base] = acc; }
+  }
+}
+
+// ----------------------------------------------------------------------------
 // a10: alpha compositing of ONE ray by ONE warp (models/rendering.py:89-111).
 //   z[S], sigma[S] (raw, noise already added), rgb[S*3] : shared memory
-//   w_out[S] : shared memory (weights kept for resampling)
+//   w_out[S] : shared memory (weights kept for resampling); tmp[S] : scratch
 // Results (comp rgb, depth, opacity) are returned in every lane.
-// The transmittance product is evaluated sequentially (like torch.cumprod on
-// CPU) by lane 0 over alpha values staged in w_out.
+// alpha and (1 - alpha + 1e-10) are evaluated in parallel; the transmittance
+// product itself is accumulated in sample order like torch.cumprod on CPU.
 // ----------------------------------------------------------------------------
 __device__ __forceinline__ void composite_ray_warp(const float* z, const float* sigma, const float* rgb,
                                                    int S, int white_bkgd, int softplus, float* w_out,
-                                                   float& r, float& g, float& b, float& depth,
+                                                   float* tmp, float& r, float& g, float& b, float& depth,
                                                    float& opacity) {
   const int lane = threadIdx.x & 31;
   // alpha_i = 1 - exp(-delta_i * act(sigma_i)); delta_last = 1e10
@@ -114,21 +146,15 @@ __device__ __forceinline__ void composite_ray_warp(const float* z, const float* 
     const float delta = (i + 1 < S) ? __fsub_rn(z[i + 1], z[i]) : 1e10f;
     const float a = __fsub_rn(1.f, expf(__fmul_rn(-delta, sigma_act(sigma[i], softplus))));
     w_out[i] = a;
+    tmp[i] = __fadd_rn(__fsub_rn(1.f, a), 1e-10f);     // 1 - alpha + eps   (rendering.py:101)
   }
   __syncwarp();
-  if (lane == 0) {
-    // T_0 = 1, T_i = prod_{j<i} (1 - alpha_j + 1e-10)  (rendering.py:99-102)
-    float T = 1.f;
-    for (int i = 0; i < S; ++i) {
-      const float a = w_out[i];
-      w_out[i] = __fmul_rn(a, T);
-      T = __fmul_rn(T, __fadd_rn(__fsub_rn(1.f, a), 1e-10f));
-    }
-  }
+  if (lane == 0) seq_scan_one_lane<true>(tmp, S, 1.f);   // T_i = prod_{j<i}(1 - alpha_j + eps), T_0 = 1
   __syncwarp();
   float sr = 0.f, sg = 0.f, sb = 0.f, sd = 0.f, so = 0.f;
   for (int i = lane; i < S; i += 32) {
-    const float w = w_out[i];
+    const float w = __fmul_rn(w_out[i], tmp[i]);
+    w_out[i] = w;
     sr += w * rgb[3 * i + 0];
     sg += w * rgb[3 * i + 1];
     sb += w * rgb[3 * i + 2];
@@ -141,6 +167,7 @@ __device__ __forceinline__ void composite_ray_warp(const float* z, const float* 
     sr = __fadd_rn(sr, bg); sg = __fadd_rn(sg, bg); sb = __fadd_rn(sb, bg);
   }
   r = sr; g = sg; b = sb; depth = sd; opacity = so;
+  __syncwarp();
 }
 
 // ----------------------------------------------------------------------------
@@ -166,15 +193,11 @@ __device__ __forceinline__ void resample_ray_warp(const float* z, const float* w
   for (int i = lane; i < nb; i += 32) bins[i] = __fmul_rn(0.5f, __fadd_rn(z[i], z[i + 1]));
   for (int i = lane; i < nw; i += 32) part += __fadd_rn(w[i + 1], eps);
   const float total = warp_sum(part);
+  // pdf in parallel, then cdf = cat(0, cumsum(pdf)) accumulated in order like torch.cumsum on CPU
+  for (int i = lane; i < nw; i += 32) cdf[i + 1] = __fdiv_rn(__fadd_rn(w[i + 1], eps), total);
+  if (lane == 0) cdf[0] = 0.f;
   __syncwarp();
-  if (lane == 0) {   // cdf = cat(0, cumsum(pdf)) evaluated sequentially like torch.cumsum on CPU
-    float c = 0.f;
-    cdf[0] = 0.f;
-    for (int i = 0; i < nw; ++i) {
-      c = __fadd_rn(c, __fdiv_rn(__fadd_rn(w[i + 1], eps), total));
-      cdf[i + 1] = c;
-    }
-  }
+  if (lane == 0) seq_scan_one_lane<false>(cdf + 1, nw, 0.f);
   __syncwarp();
   for (int j = lane; j < n_imp; j += 32) {
     const float uj = u ? u[j] : u_table[j];

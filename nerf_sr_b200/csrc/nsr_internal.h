@@ -54,6 +54,7 @@ struct NsrHandle_ {
   int sm_count = 0;
   int64_t launches = 0;
   long long* trace_buf = nullptr;
+  int debug_flags = 0;
   std::string err;
   // nsr_render_host state (library-owned staging)
   cudaStream_t hs[2] = {nullptr, nullptr};
@@ -88,6 +89,7 @@ struct TcPassArgs {
   int do_resample;
   float* comp_rgb; float* depth; float* opacity; float* weights; float* raw; float* z_next;
   long long* trace;   // debug timeline buffer (NSR_TC_TRACE builds), else null
+  int debug_flags;
 };
 cudaError_t tc_pass(NsrHandle_* h, int which, const TcPassArgs& a, cudaStream_t st);
 

@@ -18,14 +18,14 @@ r.load_state_dict(0, pc)
 r.load_state_dict(1, pf)
 rays = rays.cuda()
 out = r.forward_rays(rays, want_weights=False, want_z_fine=True)
-buf = torch.zeros(16 * 512, dtype=torch.int64, device="cuda")
+buf = torch.zeros(16 * 2048, dtype=torch.int64, device="cuda")
 r.lib.nsr_debug_set_trace(r._h, buf.data_ptr())
 r.render_pass(1, rays, out["z_fine"])
 torch.cuda.synchronize()
-b = buf.cpu().view(16, 256, 2)
+b = buf.cpu().view(16, 1024, 2)
 t0 = min(int(b[w, 0, 1]) for w in range(16) if int(b[w, 0, 0]) != 0)
 for w in range(16):
-    ev = [(int(b[w, i, 0]), int(b[w, i, 1]) - t0) for i in range(256) if int(b[w, i, 0]) != 0]
+    ev = [(int(b[w, i, 0]), int(b[w, i, 1]) - t0) for i in range(1024) if int(b[w, i, 0]) != 0]
     if not ev:
         continue
     print(f"--- warp {w}: {len(ev)} events")
