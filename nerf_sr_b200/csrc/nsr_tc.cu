@@ -774,9 +774,46 @@ __device__ __forceinline__ void epilogue_role(const TcKernelArgs& a, uint8_t* sm
   const int S = a.S, RPT = kTile / S;
   const RenderParams& rp = a.rp;
   uint32_t g = 0;
+  float* xch = reinterpret_cast<float*>(sm + kSmXch);
+  float* ssig = reinterpret_cast<float*>(sm + kSmSig);
+  float* srgb = reinterpret_cast<float*>(sm + kSmRgb);
+  // Tail of tile j: combine the two column halves of the head partial sums, activations, stage the
+  // per-point (rgb, sigma) for the compositing done by the front-end warps.  It is NOT on the MMA
+  // critical path, so it runs after the NEXT tile's first-layer epilogue (see the loop below).
+  auto tile_tail = [&](long long j, float sig_p, float r0, float r1, float r2) {
+    const long long tile = first_tile + j * (long long)tile_stride;
+    if (hh == 1) { xch[row] = sig_p; xch[128 + row] = r0; xch[256 + row] = r1; xch[384 + row] = r2; }
+    named_bar_sync(2, 32 * kWarpsEpi);
+    if (hh == 0) {
+      const long long ray = tile * RPT + row / S;
+      const bool valid = ray < a.n_rays;
+      const float sigma = (sig_p + xch[row]) + cst[kcMisc];
+      float col[3] = {r0 + xch[128 + row], r1 + xch[256 + row], r2 + xch[384 + row]};
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float v = col[c] + cst[kcMisc + 1 + c];
+        if (!rp.color_none) v = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-v)));    // torch.sigmoid
+        col[c] = v;
+      }
+      const long long gp = tile * kTile + row;
+      if (a.raw && valid) reinterpret_cast<float4*>(a.raw)[gp] = make_float4(col[0], col[1], col[2], sigma);
+      if (rp.gamma_correct) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) col[c] = powf(col[c], 1.f / 2.2f);        // nerf_downX_model.py:271
+      }
+      float sg = sigma;
+      if (a.noise && valid) sg = __fadd_rn(sg, __fmul_rn(a.noise[gp], rp.noise_std));   // utils.py:210
+      // the staging buffers are single: wait until the previous tile has been composited
+      if (j >= 1) mbar_wait(bar + 8 * B_COMPDONE, (uint32_t)((j - 1) & 1));
+      ssig[row] = sg; srgb[3 * row] = col[0]; srgb[3 * row + 1] = col[1]; srgb[3 * row + 2] = col[2];
+    }
+    named_bar_sync(2, 32 * kWarpsEpi);      // xch reads done before the next tail's writes
+    if (lane == 0) mbar_arrive(bar + 8 * B_COMPREADY);
+  };
+  float sig_prev = 0.f, rgb_prev[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
   for (long long it = 0; it < my_tiles; ++it) {
     const uint32_t buf = (uint32_t)(it & 1);
-    const long long tile = first_tile + it * (long long)tile_stride;
     float sig_p = 0.f;
     TR_DECL(a, it);
     // ---- layers 1..9: bias (+ReLU) -> hi/lo split -> next A operand ----
@@ -784,6 +821,9 @@ __device__ __forceinline__ void epilogue_role(const TcKernelArgs& a, uint8_t* sm
     //  value: 0 for the trunk, -inf for the activation-free xyz_encoding_final, networks.py:158)
 #pragma unroll 1
     for (int L = 1; L <= 9; ++L, ++g) {
+      // the previous tile's tail goes here, behind this tile's first layer: the MMA lane is already
+      // busy with L2 while the heads' activations are finished and staged
+      if (L == 2 && it >= 1) tile_tail(it - 1, sig_prev, rgb_prev[0], rgb_prev[1], rgb_prev[2]);
       if (L == 8) epi_layer<FMT, PASSES, true>(L, 0.f, g, bar, tlane, sm_base + kSmConst, hh, lane, sig_p TR_ARGS);   // + sigma head
       else epi_layer<FMT, PASSES, false>(L, L <= 8 ? 0.f : -INFINITY, g, bar, tlane, sm_base + kSmConst, hh, lane, sig_p TR_ARGS);
     }
@@ -798,7 +838,7 @@ __device__ __forceinline__ void epilogue_role(const TcKernelArgs& a, uint8_t* sm
       tc_fence_after();
       const uint32_t dbias_addr = sm_base + kSmDirBias + 4u * (uint32_t)(buf * 256 + (row / S) * 128);
       const uint32_t wrgb_addr = sm_base + kSmConst + 4u * kcWrgb;
-#pragma unroll
+#pragma unroll 1
       for (int c = 0; c < 2; ++c) {
         const int col0 = 64 * hh + 32 * c;
         uint32_t r[32];
@@ -825,42 +865,10 @@ __device__ __forceinline__ void epilogue_role(const TcKernelArgs& a, uint8_t* sm
       }
       ++g;
     }
-    // ---- combine the two column halves, activations, stage per-point (rgb, sigma) for the
-    //      compositing done by the front-end warps ----
-    float* xch = reinterpret_cast<float*>(sm + kSmXch);
-    float* ssig = reinterpret_cast<float*>(sm + kSmSig);
-    float* srgb = reinterpret_cast<float*>(sm + kSmRgb);
-    if (hh == 1) { xch[row] = sig_p; xch[128 + row] = rgb_p[0]; xch[256 + row] = rgb_p[1]; xch[384 + row] = rgb_p[2]; }
-    named_bar_sync(2, 32 * kWarpsEpi);
-    if (hh == 0) {
-      const long long ray = tile * RPT + row / S;
-      const bool valid = ray < a.n_rays;
-      const float sigma = (sig_p + xch[row]) + cst[kcMisc];
-      float col[3];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        float v = (rgb_p[c] + xch[128 * (c + 1) + row]) + cst[kcMisc + 1 + c];
-        if (!rp.color_none) v = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-v)));    // torch.sigmoid
-        col[c] = v;
-      }
-      const long long gp = tile * kTile + row;
-      if (a.raw && valid) reinterpret_cast<float4*>(a.raw)[gp] = make_float4(col[0], col[1], col[2], sigma);
-      if (rp.gamma_correct) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) col[c] = powf(col[c], 1.f / 2.2f);        // nerf_downX_model.py:271
-      }
-      float sg = sigma;
-      if (a.noise && valid) sg = __fadd_rn(sg, __fmul_rn(a.noise[gp], rp.noise_std));   // utils.py:210
-      // the staging buffers are single: wait until the previous tile has been composited
-      if (it >= 1) mbar_wait(bar + 8 * B_COMPDONE, (uint32_t)((it - 1) & 1));
-      ssig[row] = sg; srgb[3 * row] = col[0]; srgb[3 * row + 1] = col[1]; srgb[3 * row + 2] = col[2];
-    }
-    named_bar_sync(2, 32 * kWarpsEpi);      // xch reads done before the next tile's writes
-    if (lane == 0) mbar_arrive(bar + 8 * B_COMPREADY);
-    (void)buf;
+    sig_prev = sig_p; rgb_prev[0] = rgb_p[0]; rgb_prev[1] = rgb_p[1]; rgb_prev[2] = rgb_p[2];
   }
+  if (my_tiles > 0) tile_tail(my_tiles - 1, sig_prev, rgb_prev[0], rgb_prev[1], rgb_prev[2]);
 }
-
 template <int FMT, int PASSES>
 __global__ void __launch_bounds__(kThreadsTc, 1) k_tc_pass(const TcKernelArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];   // SWIZZLE_128B operands need 1024-B alignment
