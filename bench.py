@@ -84,12 +84,24 @@ def make_inputs(seed_offset: int = 0):
 
 
 def cpu_reference_rate(cfg, pc, pf, rays, sample_rays: int, repeats: int):
-    """The reference algorithm (oracle port, torch CPU ops, all host threads), eval mode, chunk 4096."""
+    """The reference algorithm (oracle port, torch CPU ops), eval mode, chunk 4096, on the host's
+    cores.  The thread count is calibrated (all cores vs fewer: small GEMMs oversubscribe badly on
+    100+ core hosts) so the baseline is the best the reference's code path does on this box."""
     from oracle import nerf_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
+    ncpu = os.cpu_count() or 1
     sample = rays[:sample_rays]
     with torch.no_grad():
-        O.chunked_forward(pc, pf, sample[:1024], cfg)      # warm-up
+        best = None
+        for nt in sorted({ncpu, max(1, ncpu // 2), min(ncpu, 32), min(ncpu, 16)}, reverse=True):
+            torch.set_num_threads(nt)
+            O.chunked_forward(pc, pf, sample[:512], cfg)   # warm-up
+            t0 = time.perf_counter()
+            O.chunked_forward(pc, pf, sample[:1024], cfg)
+            dt = time.perf_counter() - t0
+            if best is None or dt < best[0]:
+                best = (dt, nt)
+        torch.set_num_threads(best[1])
+        cpu_reference_rate.threads = best[1]
         times = []
         for _ in range(repeats):
             t0 = time.perf_counter()
@@ -114,8 +126,10 @@ def run_reference(args, rank, world):
         "ms_per_step": 1e3 * sorted(times)[len(times) // 2], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(1),
-        "cpu_baseline": {"value": rate, "unit": "rays/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} rays of the frame per step (chunk 4096), median of {len(times)}"},
+        "cpu_baseline": {"value": rate, "unit": "rays/s", "cores": getattr(cpu_reference_rate, "threads", cores), "kind": "port",
+                         "host_cores": cores,
+                         "sample": f"{sample} rays of the frame per step (chunk 4096), median of {len(times)}; "
+                                   "thread count calibrated over {all, 1/2, 32, 16}"},
         "e2e": {"value": rate, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -250,13 +264,19 @@ def main():
             "roofline": {"bound": "tensor", "kernel": "k_tc_pass (fine pass, S=128)" if args.precision != "fp32_simt" else "k_simt_mlp",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "peak_kind": f"{pk_kind} cuBLAS bf16 sustained", "issued_frac": (3 if "x3" in args.precision else 1) * achieved / peak,
-                         "flop_per_launch": fine_flops, "ms_per_launch": fine_ms, "traffic": None},
+                         "flop_per_launch": fine_flops, "ms_per_launch": fine_ms,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu --set full capture
+                         # (profiles/r01_k_tc_pass_ncu_full.md); not re-measured per run
+                         "traffic": 93537024 if args.precision != "fp32_simt" else None,
+                         "algorithmic_bytes_per_launch": n * (32 + 4 * (N_COARSE + N_IMPORTANCE) + 20)},
             "clocks": sampler.summary(),
         }
         if not args.no_cpu_baseline and world == 1:
             rate, times = cpu_reference_rate(cfg, pc, pf, rays_cpu, 4096, 3)
-            line["cpu_baseline"] = {"value": rate, "unit": "rays/s", "cores": os.cpu_count() or 1, "kind": "port",
-                                    "sample": "4096 rays of the frame (one ray_chunk), median of 3, oracle port of the reference (torch CPU)"}
+            line["cpu_baseline"] = {"value": rate, "unit": "rays/s", "cores": getattr(cpu_reference_rate, "threads", os.cpu_count() or 1),
+                                    "host_cores": os.cpu_count() or 1, "kind": "port",
+                                    "sample": "4096 rays of the frame (one ray_chunk), median of 3, oracle port of the reference "
+                                              "(torch CPU), thread count calibrated over {all, 1/2, 32, 16}"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

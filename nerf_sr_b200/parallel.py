@@ -1,0 +1,70 @@
+"""Ray sharding across the GPUs of one node.
+
+Every ray is independent (the s x s box average couples only the s*s consecutive rows of one LR
+pixel), so inference needs NO data-path collective: rank g renders rows [lo_g, hi_g) with shard
+boundaries at multiples of s*s, weights are replicated, results stay rank-local or are gathered once
+(16 B per LR pixel).  The reference instead wraps each MLP in nn.DataParallel and scatters/gathers
+the [P,90] point tensor around every call (models/networks.py:54-69) -- not reproduced.
+Training's only collective is the gradient all-reduce of DDP (models/networks.py:72-86): one flat
+4.77 MB fp32 bucket, mean over ranks -- `allreduce_mean_` below (NCCL on GPUs, gloo in the CPU tests).
+One process per GPU; torch.distributed is used for plumbing only."""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_rays: int, world_size: int, group_rows: int = 1) -> List[Tuple[int, int]]:
+    """Contiguous [lo, hi) row ranges, one per rank, with boundaries at multiples of `group_rows`
+    (= s*s sub-pixel rays of one LR pixel).  Earlier ranks get the remainder groups."""
+    if n_rays % group_rows:
+        raise ValueError(f"n_rays={n_rays} is not a multiple of the sub-pixel group {group_rows}")
+    groups = n_rays // group_rows
+    base, rem = divmod(groups, world_size)
+    out, lo = [], 0
+    for r in range(world_size):
+        hi = lo + (base + (1 if r < rem else 0)) * group_rows
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+def render_sharded(render_fn: Callable[[torch.Tensor], Sequence[torch.Tensor]], rays: torch.Tensor, s: int = 1,
+                   group: Optional[dist.ProcessGroup] = None, gather: bool = True):
+    """Render this rank's shard of `rays` with `render_fn(rays_shard) -> (rgb[n/s^2,3], depth[n/s^2])`
+    and (optionally) all-gather the LR results so every rank holds the full frame, in row order.
+    Works with any backend (NCCL for CUDA tensors, gloo for the CPU tests)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    bounds = shard_bounds(rays.shape[0], world, s * s)
+    lo, hi = bounds[rank]
+    outs = [o.reshape(o.shape[0], -1) for o in render_fn(rays[lo:hi])]
+    if not gather or world == 1:
+        return outs, bounds
+    full = []
+    for o in outs:
+        sizes = [(b[1] - b[0]) // (s * s) for b in bounds]
+        mx = max(sizes)
+        pad = torch.zeros(mx, o.shape[1], dtype=o.dtype, device=o.device)
+        pad[: o.shape[0]] = o
+        parts = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad, group=group)
+        full.append(torch.cat([p[:n] for p, n in zip(parts, sizes)], 0))
+    return full, bounds
+
+
+def allreduce_mean_(tensors: Sequence[torch.Tensor], group: Optional[dist.ProcessGroup] = None) -> None:
+    """DDP-equivalent gradient averaging: flatten into ONE bucket (2 x 595 844 fp32 = 4.77 MB for the
+    coarse+fine nets), one all-reduce, scatter back in place."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    flat = torch.cat([t.reshape(-1) for t in tensors])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat /= dist.get_world_size(group)
+    off = 0
+    for t in tensors:
+        n = t.numel()
+        t.copy_(flat[off:off + n].view_as(t))
+        off += n

@@ -205,3 +205,48 @@ def test_errors_are_reported_not_fatal(load_fixture):
     with pytest.raises(NsrError):                          # tensor-core path refuses, never silently differs
         Renderer(O.RenderConfig(D=4), torch.device("cuda:0"), precision="bf16x3")
     r.close()
+
+
+def test_patch_model_rebinds_forward_rays_on_a_reference_lookalike(load_fixture):
+    """INTEGRATION.md step 3 on an object with the reference model's attribute surface
+    (opt, device, netCoarse/netFine with the reference's state_dict names, randomized)."""
+    import torch.nn as nn
+    from types import SimpleNamespace
+    from nerf_sr_b200 import patch_model
+    fx = load_fixture("eval_blender")
+
+    class Net(nn.Module):      # parameter names = models/networks.py:149-180
+        def __init__(self, p):
+            super().__init__()
+            for i in range(8):
+                w = p[f"xyz_encoding_{i+1}.0.weight"]
+                setattr(self, f"xyz_encoding_{i+1}", nn.Sequential(nn.Linear(w.shape[1], w.shape[0]), nn.ReLU(True)))
+            self.xyz_encoding_final = nn.Linear(256, 256)
+            self.dir_encoding = nn.Sequential(nn.Linear(283, 128), nn.ReLU(True))
+            self.sigma = nn.Linear(256, 1)
+            self.rgb = nn.Sequential(nn.Linear(128, 3), nn.Sigmoid())
+            self.load_state_dict(p)
+
+    class NeRFDownXModel:      # name matters: viewdir column 3
+        pass
+
+    m = NeRFDownXModel()
+    m.opt = SimpleNamespace(**{**fx.cfg.__dict__, "skips": list(fx.cfg.skips)})
+    m.device = torch.device("cuda:0")
+    m.netCoarse = nn.DataParallel(Net(fx.p_coarse).cuda())     # 'module.' unwrap path (base_model.py:193-194)
+    m.netFine = nn.DataParallel(Net(fx.p_fine).cuda())
+    m.randomized = False
+    m.forward_rays = lambda rays: (_ for _ in ()).throw(AssertionError("reference path must not run in no_grad"))
+    patch_model(m, "bf16x3")
+    with torch.no_grad():
+        out = m.forward_rays(fx.rays.cuda())
+    for k in COARSE_KEYS:
+        mx, viol = O.tolerance_violations(out[k].cpu(), fx.out[k])
+        assert viol == 0.0, (k, mx)
+    assert float(m.near[0]) == 2.0 and float(m.far[0]) == 6.0
+    # weights are re-packed when parameters change (optimizer step / load_networks)
+    with torch.no_grad():
+        m.netCoarse.module.sigma.bias.add_(0.25)
+        out2 = m.forward_rays(fx.rays.cuda())
+    assert not torch.equal(out2["coarse_opacity"], out["coarse_opacity"])
+    m._nsr_renderer.close()
