@@ -228,6 +228,14 @@ NSR_API int nsr_generate_rays(NsrHandle* h, const float* c2w_host, int H, int W,
                       int s, int ndc, float near_plane, float far_plane,
                       float* rays_out, NsrStream stream);
 
+/* Replaces (scope row f-2, the LR-image + loss epilogue): comp_low_res_output's box average followed by
+ * ColorMSELoss and PSNR against the LR targets (models/nerf_downX_model.py:337-340,357,380;
+ * models/criterions.py:7-15,27-36).  hr_rgb: [n_lr*s*s, 3] composite colours (sub-pixels contiguous);
+ * target_lr: [n_lr, 3]; lr_rgb_out: [n_lr, 3] or null; metrics_out: device float[2] = {mse, psnr} with
+ * mse = mean((lr - target)^2) over n_lr*3 elements, psnr = -10*log10(mse).  No host sync. */
+NSR_API int nsr_lr_metrics(NsrHandle* h, const float* hr_rgb, const float* target_lr, int64_t n_lr, int s,
+                           float* lr_rgb_out, float* metrics_out, NsrStream stream);
+
 /* ---- host-buffer convenience (the end-to-end call) ------------------------ */
 
 /* forward over a whole frame / batch with HOST buffers: stages rays through

@@ -159,6 +159,44 @@ __global__ void k_box_average(const float* __restrict__ in, int64_t n_lr, int ss
   }
 }
 
+// box average + squared error against the LR target; one partial sum (double) per block
+__global__ void __launch_bounds__(256)
+k_lr_metrics_partial(const float* __restrict__ hr, const float* __restrict__ target, int64_t n_lr, int ss,
+                     float* __restrict__ lr_out, double* __restrict__ partials) {
+  const int64_t total = n_lr * 3;
+  double acc = 0.0;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = idx / 3;
+    const int c = (int)(idx % 3);
+    float sum = 0.f;
+    for (int k = 0; k < ss; ++k) sum = __fadd_rn(sum, hr[(p * ss + k) * 3 + c]);
+    const float lr = __fdiv_rn(sum, (float)ss);
+    if (lr_out) lr_out[idx] = lr;
+    const float d = __fsub_rn(lr, target[idx]);
+    acc += (double)__fmul_rn(d, d);
+  }
+  __shared__ double sh[256];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partials[blockIdx.x] = sh[0];
+}
+
+__global__ void k_lr_metrics_final(const double* __restrict__ partials, int n_blocks, int64_t n_elems,
+                                   float* __restrict__ metrics) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < n_blocks; ++i) s += partials[i];
+    const float mse = (float)(s / (double)n_elems);
+    metrics[0] = mse;
+    metrics[1] = -10.f * log10f(mse);        // criterions.py:36
+  }
+}
+
 struct Pose { float m[12]; };
 
 __global__ void k_generate_rays(Pose c2w, int H, int W, float focal, int s, int ndc, float near_plane,
@@ -338,6 +376,7 @@ extern "C" int nsr_create(const NsrConfig* cfg, NsrHandle** out_handle) {
 
   cudaError_t e = cudaSetDevice(c.device);
   if (e == cudaSuccess) e = cudaMalloc(&h->d_tables, sizeof(SampleTables));
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_partials, 1024 * sizeof(double));
   if (e == cudaSuccess) e = cudaMemcpy(h->d_tables, &T, sizeof(T), cudaMemcpyHostToDevice);
   const size_t blob = simt_blob_floats(h);
   for (int w = 0; w < 2 && e == cudaSuccess; ++w) {
@@ -366,6 +405,7 @@ extern "C" int nsr_destroy(NsrHandle* h) {
     cudaFree(h->net[w].simt_blob); cudaFree(h->net[w].tc_image); cudaFree(h->net[w].tc_consts);
   }
   cudaFree(h->d_tables);
+  cudaFree(h->d_partials);
   for (int i = 0; i < 2; ++i) {
     if (h->pin_in[i]) cudaFreeHost(h->pin_in[i]);
     if (h->pin_out[i]) cudaFreeHost(h->pin_out[i]);
@@ -596,6 +636,20 @@ extern "C" int nsr_generate_rays(NsrHandle* h, const float* c2w_host, int H, int
   k_generate_rays<<<grid_for((int64_t)H * W, 256, h->sm_count * 16), 256, 0, (cudaStream_t)stream>>>(
       p, H, W, focal, s, ndc, near_plane, far_plane, rays_out);
   h->launches += 1;
+  NSR_CUDA(h, cudaGetLastError());
+  return NSR_OK;
+}
+
+extern "C" int nsr_lr_metrics(NsrHandle* h, const float* hr_rgb, const float* target_lr, int64_t n_lr, int s,
+                              float* lr_rgb_out, float* metrics_out, NsrStream stream) {
+  if (!h) return NSR_ERR_INVALID_ARG;
+  if (!hr_rgb || !target_lr || !metrics_out || n_lr <= 0 || s < 1)
+    return fail(h, NSR_ERR_INVALID_ARG, "nsr_lr_metrics: bad argument");
+  NSR_CUDA(h, cudaSetDevice(h->cfg.device));
+  const int blocks = grid_for(n_lr * 3, 256, 1024);
+  k_lr_metrics_partial<<<blocks, 256, 0, (cudaStream_t)stream>>>(hr_rgb, target_lr, n_lr, s * s, lr_rgb_out, h->d_partials);
+  k_lr_metrics_final<<<1, 32, 0, (cudaStream_t)stream>>>(h->d_partials, blocks, n_lr * 3, metrics_out);
+  h->launches += 2;
   NSR_CUDA(h, cudaGetLastError());
   return NSR_OK;
 }

@@ -49,6 +49,7 @@ struct NsrHandle_ {
   nsr::SimtProgram prog;
   nsr::SampleTables* d_tables = nullptr;
   nsr::SampleTables h_tables;
+  double* d_partials = nullptr;     // [1024] block partial sums for nsr_lr_metrics
   nsr::NetImages net[2];
   std::vector<int64_t> param_numel;
   int sm_count = 0;

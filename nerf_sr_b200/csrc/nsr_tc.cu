@@ -83,8 +83,7 @@ constexpr int kSmXch = kSmTmp + 128 * 4;
 constexpr int kSmScratch = kSmXch + 4 * 128 * 4;
 constexpr int kSmBar = kSmScratch + 2 * 320 * 4;
 constexpr int kSmTmemPtr = kSmBar + 32 * 8;
-constexpr int kSmOps = kSmTmemPtr + 16;                           // 72 stage-op words
-constexpr int kSmemTcBytes = kSmOps + kStagesPerTile * 4;
+constexpr int kSmemTcBytes = kSmTmemPtr + 16;
 
 // barrier indices
 enum {

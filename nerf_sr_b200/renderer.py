@@ -241,6 +241,19 @@ class Renderer:
         self._check(self.lib.nsr_box_average(self._h, x2.data_ptr(), n_lr, s, x2.shape[1], out.data_ptr(), self._stream()))
         return out
 
+    def lr_metrics(self, hr_rgb: torch.Tensor, target_lr: torch.Tensor, s: int):
+        """comp_low_res_output + ColorMSELoss + PSNR (models/nerf_downX_model.py:337-340,357,380):
+        returns (lr_rgb [n_lr,3], metrics [2] = (mse, psnr)) as device tensors, no host sync."""
+        hr_rgb, target_lr = self._f32(hr_rgb), self._f32(target_lr)
+        n_lr = target_lr.shape[0]
+        if hr_rgb.shape[0] != n_lr * s * s:
+            raise NsrError(1, f"hr_rgb has {hr_rgb.shape[0]} rows, expected {n_lr}*{s}*{s}")
+        lr = torch.empty(n_lr, 3, device=self.device, dtype=torch.float32)
+        m = torch.empty(2, device=self.device, dtype=torch.float32)
+        self._check(self.lib.nsr_lr_metrics(self._h, hr_rgb.data_ptr(), target_lr.data_ptr(), n_lr, s, lr.data_ptr(),
+                                            m.data_ptr(), self._stream()))
+        return lr, m
+
     def generate_rays(self, c2w, H: int, W: int, focal: float, s: int = 1, ndc: bool = False,
                       near: float = 2.0, far: float = 6.0) -> torch.Tensor:
         c = torch.as_tensor(c2w, dtype=torch.float32).reshape(12).cpu()

@@ -348,6 +348,15 @@ def box_average(x: Tensor, s: int) -> Tensor:
     return torch.mean(torch.reshape(x, (n_lr, s * s, -1)), dim=1)
 
 
+def lr_metrics(hr_rgb: Tensor, target_lr: Tensor, s: int):
+    """Scope row f-2: box average (models/nerf_downX_model.py:337-340), ColorMSELoss
+    (models/criterions.py:7-15, nn.MSELoss mean) and PSNR (models/criterions.py:27-36)."""
+    lr = box_average(hr_rgb, s)
+    mse = torch.nn.functional.mse_loss(lr, target_lr, reduction="mean")
+    psnr = -10 * torch.log10(torch.mean((lr - target_lr) ** 2))
+    return lr, mse, psnr
+
+
 # --------------------------------------------------------------------------
 # a1-a4: ray generation   (models/utils.py:98-196, data/*_downX_dataset.py)
 # --------------------------------------------------------------------------

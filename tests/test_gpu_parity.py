@@ -250,3 +250,57 @@ def test_patch_model_rebinds_forward_rays_on_a_reference_lookalike(load_fixture)
         out2 = m.forward_rays(fx.rays.cuda())
     assert not torch.equal(out2["coarse_opacity"], out["coarse_opacity"])
     m._nsr_renderer.close()
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
+@pytest.mark.parametrize("n", [1, 2, 3, 129])
+def test_tiny_and_ragged_batches(n, prec, load_fixture):
+    """Edge sizes: a single ray, an odd count (half-filled coarse tile), more tiles than one."""
+    fx = load_fixture("eval_blender")
+    r = _renderer(fx, prec)
+    full = r.forward_rays(fx.rays.cuda())
+    part = r.forward_rays(fx.rays[:n].cuda())
+    torch.cuda.synchronize()
+    for k in part:
+        assert part[k].shape[0] == n
+        assert torch.equal(part[k], full[k][:n]), k
+    empty = r.forward_rays(fx.rays[:0].cuda())
+    assert all(v.shape[0] == 0 for v in empty.values())
+    r.close()
+
+
+def test_lr_metrics_match_reference_losses(load_fixture):
+    """Row f-2: box average + ColorMSELoss + PSNR (models/criterions.py) in one call."""
+    fx = load_fixture("eval_blender")
+    r = _renderer(fx, "fp32_simt")
+    g = torch.Generator().manual_seed(3)
+    for s, n_lr in ((2, 5000), (4, 777), (1, 333)):
+        hr = torch.rand(n_lr * s * s, 3, generator=g)
+        tgt = torch.rand(n_lr, 3, generator=g)
+        lr, m = r.lr_metrics(hr.cuda(), tgt.cuda(), s)
+        ref_lr, ref_mse, ref_psnr = O.lr_metrics(hr, tgt, s)
+        assert torch.allclose(lr.cpu(), ref_lr, rtol=0, atol=5e-7)     # fp32 summation order of the 16-term mean
+        assert abs(float(m[0]) - float(ref_mse)) <= 1e-6 * float(ref_mse)
+        assert abs(float(m[1]) - float(ref_psnr)) <= 1e-5 * abs(float(ref_psnr)) + 1e-5
+    r.close()
+
+
+@pytest.mark.parametrize("prec", ["bf16x3", "fp32_simt"])
+def test_single_pass_128_samples_against_oracle(prec):
+    """(N_coarse, N_importance) = (128, 0): the other tile shape of the tensor-core path (1 ray / tile
+    with on-the-fly z sampling).  No golden fixture: compared with the pinned oracle on seeded inputs."""
+    from nerf_sr_b200 import Renderer
+    cfg = O.RenderConfig(N_coarse=128, N_importance=0, white_bkgd=True)
+    pc = O.make_mlp_params(cfg, 4)
+    rays = O.synthetic_rays(96, 9, "blender")
+    with torch.no_grad():
+        ref = O.forward_rays(pc, pc, rays, cfg)
+    r = Renderer(cfg, torch.device("cuda:0"), precision=prec)
+    r.load_state_dict(0, pc)
+    r.load_state_dict(1, pc)
+    out = r.forward_rays(rays.cuda())
+    assert set(out) == set(ref)
+    for k in ref:
+        mx, viol = O.tolerance_violations(out[k].cpu(), ref[k])
+        assert viol == 0.0, (k, mx)
+    r.close()
