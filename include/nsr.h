@@ -248,6 +248,13 @@ NSR_API int nsr_lr_metrics(NsrHandle* h, const float* hr_rgb, const float* targe
 NSR_API int nsr_render_host(NsrHandle* h, const float* rays_host, int64_t n_rays, int ray_stride,
                     int s, float* rgb_host, float* depth_host);
 
+/* Same pipeline for one camera pose (scope row f-4: dataset-side ray construction on the device, so a
+ * test sweep uploads 48 bytes per frame instead of 32 bytes per ray): nsr_generate_rays for the whole
+ * H x W raster (data/blender_downX_dataset.py:207-215, data/llff_downX_dataset.py:473-490), render, box
+ * average, D2H.  rgb_host: [H*W/s^2, 3], depth_host: [H*W/s^2] (either may be null).  Synchronous. */
+NSR_API int nsr_render_pose_host(NsrHandle* h, const float* c2w_host, int H, int W, float focal, int s, int ndc,
+                                 float near_plane, float far_plane, float* rgb_host, float* depth_host);
+
 /* Debug: device buffer (>= 16*512 int64) that trace builds (-DNSR_TC_TRACE=1) fill with
  * (tag, clock64) pairs for one tile of CTA 0; ignored by normal builds.  tools/tc_trace.py. */
 NSR_API int nsr_debug_set_trace(NsrHandle* h, long long* device_buffer);

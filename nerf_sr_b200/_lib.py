@@ -63,6 +63,8 @@ SIGNATURES = {
                                     C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     "nsr_lr_metrics": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nsr_render_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "nsr_render_pose_host": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_float, C.c_int, C.c_int,
+                                       C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     "nsr_debug_set_trace": (C.c_int, [C.c_void_p, C.c_void_p]),
     "nsr_debug_set_flags": (C.c_int, [C.c_void_p, C.c_int]),
     "nsr_launch_count": (C.c_int64, [C.c_void_p]),

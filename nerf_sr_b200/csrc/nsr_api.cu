@@ -406,6 +406,8 @@ extern "C" int nsr_destroy(NsrHandle* h) {
   }
   cudaFree(h->d_tables);
   cudaFree(h->d_partials);
+  cudaFree(h->frame_rays);
+  if (h->frame_ev) cudaEventDestroy(h->frame_ev);
   for (int i = 0; i < 2; ++i) {
     if (h->pin_in[i]) cudaFreeHost(h->pin_in[i]);
     if (h->pin_out[i]) cudaFreeHost(h->pin_out[i]);
@@ -678,14 +680,12 @@ static int ensure_host_state(NsrHandle_* h, int64_t chunk, int stride) {
   return NSR_OK;
 }
 
-extern "C" int nsr_render_host(NsrHandle* h, const float* rays_host, int64_t n_rays, int ray_stride, int s,
-                               float* rgb_host, float* depth_host) {
-  if (!h) return NSR_ERR_INVALID_ARG;
-  int rc = check_render_args(h, rays_host, n_rays, ray_stride);
-  if (rc) return rc;
-  if (s < 1 || n_rays % ((int64_t)s * s)) return fail(h, NSR_ERR_INVALID_ARG, "n_rays must be a multiple of s*s");
-  if (n_rays == 0) return NSR_OK;
-  NSR_CUDA(h, cudaSetDevice(h->cfg.device));
+// Chunked, double-buffered frame render.  Rays come either from host memory (staged through pinned
+// buffers, H2D inside the pipeline) or from a device buffer the caller filled on stream hs[0]
+// (rays_dev != null: nsr_render_pose_host generates them on the device).
+static int render_frame_pipeline(NsrHandle* h, const float* rays_host, const float* rays_dev, int64_t n_rays,
+                                 int ray_stride, int s, float* rgb_host, float* depth_host) {
+  int rc = NSR_OK;
   const int ss = s * s;
   int64_t chunk = 65536;
   chunk -= chunk % ss;
@@ -708,9 +708,14 @@ extern "C" int nsr_render_host(NsrHandle* h, const float* rays_host, int64_t n_r
     if (k >= 2) drain(k - 2);
     const int64_t r0 = k * chunk, nr = (r0 + chunk <= n_rays) ? chunk : n_rays - r0;
     cudaStream_t st = h->hs[slot];
-    memcpy(h->pin_in[slot], rays_host + r0 * ray_stride, (size_t)nr * ray_stride * sizeof(float));
-    NSR_CUDA(h, cudaMemcpyAsync(h->dev_in[slot], h->pin_in[slot], (size_t)nr * ray_stride * sizeof(float),
-                                cudaMemcpyHostToDevice, st));
+    const float* d_rays = h->dev_in[slot];
+    if (rays_dev) {
+      d_rays = rays_dev + r0 * ray_stride;
+    } else {
+      memcpy(h->pin_in[slot], rays_host + r0 * ray_stride, (size_t)nr * ray_stride * sizeof(float));
+      NSR_CUDA(h, cudaMemcpyAsync(h->dev_in[slot], h->pin_in[slot], (size_t)nr * ray_stride * sizeof(float),
+                                  cudaMemcpyHostToDevice, st));
+    }
     float* d_rgb = h->dev_out[slot];
     float* d_dep = d_rgb + (size_t)chunk * 3;
     float* d_rgb_lr = d_dep + (size_t)chunk;
@@ -718,7 +723,7 @@ extern "C" int nsr_render_host(NsrHandle* h, const float* rays_host, int64_t n_r
     NsrOutputs o{};
     if (fine) { o.fine_comp_rgbs = d_rgb; o.fine_depth = d_dep; }
     else { o.coarse_comp_rgbs = d_rgb; o.coarse_depth = d_dep; }
-    rc = nsr_render(h, h->dev_in[slot], nr, ray_stride, nullptr, &o, h->dev_ws[slot], h->host_ws_bytes, st);
+    rc = nsr_render(h, d_rays, nr, ray_stride, nullptr, &o, h->dev_ws[slot], h->host_ws_bytes, st);
     if (rc) return rc;
     const float* src_rgb = d_rgb;
     const float* src_dep = d_dep;
@@ -735,4 +740,42 @@ extern "C" int nsr_render_host(NsrHandle* h, const float* rays_host, int64_t n_r
   for (int64_t k = (n_chunks >= 2 ? n_chunks - 2 : 0); k < n_chunks; ++k) drain(k);
   NSR_CUDA(h, cudaGetLastError());
   return NSR_OK;
+}
+
+extern "C" int nsr_render_host(NsrHandle* h, const float* rays_host, int64_t n_rays, int ray_stride, int s,
+                               float* rgb_host, float* depth_host) {
+  if (!h) return NSR_ERR_INVALID_ARG;
+  int rc = check_render_args(h, rays_host, n_rays, ray_stride);
+  if (rc) return rc;
+  if (s < 1 || n_rays % ((int64_t)s * s)) return fail(h, NSR_ERR_INVALID_ARG, "n_rays must be a multiple of s*s");
+  if (n_rays == 0) return NSR_OK;
+  NSR_CUDA(h, cudaSetDevice(h->cfg.device));
+  return render_frame_pipeline(h, rays_host, nullptr, n_rays, ray_stride, s, rgb_host, depth_host);
+}
+
+extern "C" int nsr_render_pose_host(NsrHandle* h, const float* c2w_host, int H, int W, float focal, int s, int ndc,
+                                    float near_plane, float far_plane, float* rgb_host, float* depth_host) {
+  if (!h) return NSR_ERR_INVALID_ARG;
+  if (!c2w_host || H <= 0 || W <= 0 || s < 1 || !(focal > 0.f)) return fail(h, NSR_ERR_INVALID_ARG, "nsr_render_pose_host: bad argument");
+  if (H % s || W % s) return fail(h, NSR_ERR_INVALID_ARG, "H and W must be multiples of the supersampling factor");
+  if (h->cfg.viewdir_offset != 3) return fail(h, NSR_ERR_UNSUPPORTED, "pose rendering produces 8-column rays (NeRFDownXModel layout)");
+  NSR_CUDA(h, cudaSetDevice(h->cfg.device));
+  const int64_t n_rays = (int64_t)H * W;
+  int64_t chunk = 65536;
+  chunk -= chunk % (s * s);
+  if (chunk > n_rays) chunk = n_rays;
+  int rc = ensure_host_state(h, chunk, 8);      // creates the streams / events / staging
+  if (rc) return rc;
+  if (h->frame_rays_cap < (size_t)n_rays * 8) {
+    cudaFree(h->frame_rays);
+    h->frame_rays = nullptr; h->frame_rays_cap = 0;
+    NSR_CUDA(h, cudaMalloc(&h->frame_rays, (size_t)n_rays * 8 * sizeof(float)));
+    h->frame_rays_cap = (size_t)n_rays * 8;
+  }
+  rc = nsr_generate_rays(h, c2w_host, H, W, focal, s, ndc, near_plane, far_plane, h->frame_rays, h->hs[0]);
+  if (rc) return rc;
+  if (!h->frame_ev) NSR_CUDA(h, cudaEventCreateWithFlags(&h->frame_ev, cudaEventDisableTiming));
+  NSR_CUDA(h, cudaEventRecord(h->frame_ev, h->hs[0]));
+  NSR_CUDA(h, cudaStreamWaitEvent(h->hs[1], h->frame_ev, 0));
+  return render_frame_pipeline(h, nullptr, h->frame_rays, n_rays, 8, s, rgb_host, depth_host);
 }

@@ -66,6 +66,9 @@ struct NsrHandle_ {
   float* dev_out[2] = {nullptr, nullptr};
   void* dev_ws[2] = {nullptr, nullptr};
   size_t host_chunk = 0, host_ws_bytes = 0;
+  float* frame_rays = nullptr;      // nsr_render_pose_host: device rays of one frame
+  size_t frame_rays_cap = 0;
+  cudaEvent_t frame_ev = nullptr;
 };
 
 namespace nsr {

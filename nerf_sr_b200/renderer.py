@@ -275,6 +275,23 @@ class Renderer:
         return rgb, depth
 
 
+def _render_pose_host(self, c2w, H: int, W: int, focal: float, s: int = 1, ndc: bool = False,
+                      near: float = 2.0, far: float = 6.0):
+    """One camera pose -> (rgb [H*W/s^2,3], depth [H*W/s^2]) CPU tensors; rays are generated on the
+    device (48 bytes of pose go up instead of 32 bytes per ray)."""
+    c = torch.as_tensor(c2w, dtype=torch.float32).reshape(12).cpu()
+    arr = (C.c_float * 12)(*c.tolist())
+    n_out = (H // s) * (W // s)
+    rgb = torch.empty(n_out, 3, dtype=torch.float32)
+    depth = torch.empty(n_out, dtype=torch.float32)
+    self._check(self.lib.nsr_render_pose_host(self._h, arr, H, W, float(focal), s, int(ndc), float(near), float(far),
+                                              rgb.data_ptr(), depth.data_ptr()))
+    return rgb, depth
+
+
+Renderer.render_pose_host = _render_pose_host
+
+
 def patch_model(model, precision: str = "bf16x3"):
     """Rebind ``forward_rays`` of a reference NeRFDownXModel / NeRFModel instance to the CUDA path
     (the one-line hook of INTEGRATION.md).  Keeps self.near / self.far (consumed by depth2im,

@@ -304,3 +304,20 @@ def test_single_pass_128_samples_against_oracle(prec):
         mx, viol = O.tolerance_violations(out[k].cpu(), ref[k])
         assert viol == 0.0, (k, mx)
     r.close()
+
+
+def test_render_pose_host_equals_rays_path(load_fixture):
+    """Row f-4 core: pose -> device ray generation -> render -> box average -> host, against the
+    explicit path (generate_rays + forward_rays + box_average)."""
+    fx = load_fixture("eval_blender")
+    r = _renderer(fx, "bf16x3")
+    z = np.load(__import__("os").path.join(GOLDEN_DIR, "raygen.npz"))
+    c2w = z["blender_c2w"]
+    H, W, s, focal = 96, 128, 2, 150.0
+    rgb, depth = r.render_pose_host(c2w, H, W, focal, s, False, 2.0, 6.0)
+    rays = r.generate_rays(c2w, H, W, focal, s, False, 2.0, 6.0)
+    out = r.forward_rays(rays, want_weights=False)
+    assert torch.equal(rgb, r.box_average(out["fine_comp_rgbs"], s).cpu())
+    assert torch.equal(depth, r.box_average(out["fine_depth"], s).cpu().squeeze(-1))
+    assert rgb.shape == ((H // s) * (W // s), 3) and torch.isfinite(rgb).all()
+    r.close()
