@@ -170,7 +170,21 @@ def main():
     dev = torch.device(f"cuda:{local}")
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # rank 0 must print exactly ONE line on stdout, but NCCL / c10d write a version banner there when
+        # the communicator is created: send fd 1 to stderr while the group and its first collective
+        # are set up
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     cfg, pc, pf, rays_cpu = make_inputs(seed_offset=rank)
     r = Renderer(cfg, dev, precision=args.precision)
