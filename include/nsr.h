@@ -22,7 +22,9 @@
  *    nsr_render_host() and nsr_create()/nsr_destroy().
  *  - Return value: 0 = NSR_OK, otherwise an NsrStatus; the message is available
  *    from nsr_last_error().  The library never exits or aborts.
- *  - Re-entrant per handle+stream; no global mutable state.
+ *  - No global mutable state: distinct handles are fully independent (one per thread / per GPU).  A
+ *    single handle may be used by one thread at a time (it carries the last-error string and the
+ *    nsr_render_host staging buffers); calls on it are ordered by the streams the caller passes.
  */
 #ifndef NSR_B200_H_
 #define NSR_B200_H_

@@ -434,7 +434,7 @@ extern "C" int nsr_debug_set_flags(NsrHandle* h, int flags) {
   h->debug_flags = flags;
   return NSR_OK;
 }
-extern "C" int64_t nsr_launch_count(const NsrHandle* h) { return h ? h->launches : 0; }
+extern "C" int64_t nsr_launch_count(const NsrHandle* h) { return h ? h->launches.load() : 0; }
 
 extern "C" int nsr_pack_weights(NsrHandle* h, int which, const float* const* param_ptrs, int n_params,
                                 NsrStream stream) {

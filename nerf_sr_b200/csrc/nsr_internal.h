@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -53,7 +54,7 @@ struct NsrHandle_ {
   nsr::NetImages net[2];
   std::vector<int64_t> param_numel;
   int sm_count = 0;
-  int64_t launches = 0;
+  std::atomic<int64_t> launches{0};
   long long* trace_buf = nullptr;
   int debug_flags = 0;
   std::string err;

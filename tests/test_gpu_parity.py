@@ -321,3 +321,31 @@ def test_render_pose_host_equals_rays_path(load_fixture):
     assert torch.equal(depth, r.box_average(out["fine_depth"], s).cpu().squeeze(-1))
     assert rgb.shape == ((H // s) * (W // s), 3) and torch.isfinite(rgb).all()
     r.close()
+
+
+@pytest.mark.parametrize("prec", ["bf16x3"])
+def test_tile_count_stress_no_deadlock_and_chunk_invariance(prec, load_fixture):
+    """The tcgen05 kernel is a persistent, barrier-driven pipeline: sweep ray counts so that CTAs get
+    0, 1, 2, 3, ... tiles each (148 SMs; 2 rays per coarse tile, 1 per fine tile), in eval and train
+    mode.  A protocol error shows up as a trapped launch (in-kernel mbarrier watchdog), a wrong tail
+    as a mismatch with the corresponding slice of one big batch."""
+    fx = load_fixture("eval_blender")
+    r = _renderer(fx, prec)
+    n_max = 148 * 7 + 5
+    rays = O.synthetic_rays(n_max, 21, "blender").cuda()
+    g = torch.Generator().manual_seed(5)
+    rng = {"u_coarse": torch.rand(n_max, 64, generator=g).cuda(), "u_fine": torch.rand(n_max, 64, generator=g).cuda()}
+    full = r.forward_rays(rays)
+    full_t = r.forward_rays(rays, rng)
+    sizes = sorted({1, 2, 3, 5, 64, 127, 128, 129, 147, 148, 149, 150, 295, 296, 297, 298, 443, 444, 445, 591, 592, 593,
+                    148 * 4 - 1, 148 * 4, 148 * 4 + 1, 148 * 6 + 1, 148 * 7 + 5})
+    for n in sizes:
+        out = r.forward_rays(rays[:n])
+        for k in out:
+            assert torch.equal(out[k], full[k][:n]), (n, k)
+        sub = {k: v[:n] for k, v in rng.items()}
+        out_t = r.forward_rays(rays[:n], sub)
+        for k in out_t:
+            assert torch.equal(out_t[k], full_t[k][:n]), (n, k, "train")
+    torch.cuda.synchronize()
+    r.close()
