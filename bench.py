@@ -111,6 +111,27 @@ def cpu_reference_rate(cfg, pc, pf, rays, sample_rays: int, repeats: int):
     return sample_rays / times[len(times) // 2], times
 
 
+def torch_gpu_reference_rate(cfg, pc, pf, rays_dev, n_chunks: int = 4, chunk: int = 4096):
+    """the reference's PyTorch path on the SAME GPU (oracle port = the reference's
+    ATen op sequence, fp32, allow_tf32 off, ray_chunk 4096) -- the like-for-like 'before' number."""
+    from oracle import nerf_oracle as O
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    dev = rays_dev.device
+    pcd = {k: v.to(dev) for k, v in pc.items()}
+    pfd = {k: v.to(dev) for k, v in pf.items()}
+    sample = rays_dev[: n_chunks * chunk]
+    with torch.no_grad():
+        O.chunked_forward(pcd, pfd, sample[:chunk], cfg, chunk)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        O.chunked_forward(pcd, pfd, sample, cfg, chunk)
+        b.record()
+        torch.cuda.synchronize()
+    return sample.shape[0] / (a.elapsed_time(b) * 1e-3)
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -285,6 +306,14 @@ def main():
                          "algorithmic_bytes_per_launch": n * (32 + 4 * (N_COARSE + N_IMPORTANCE) + 20)},
             "clocks": sampler.summary(),
         }
+        if world == 1:
+            try:
+                line["torch_gpu_reference_port"] = {
+                    "value": torch_gpu_reference_rate(cfg, pc, pf, rays), "unit": "rays/s",
+                    "what": "oracle port (the reference's PyTorch op sequence) on this GPU, fp32, allow_tf32 off, "
+                            "ray_chunk 4096, 4 chunks; not the product path"}
+            except Exception as e:      # never let the informational arm break the bench line
+                line["torch_gpu_reference_port"] = {"unavailable": str(e)[:200]}
         if not args.no_cpu_baseline and world == 1:
             rate, times = cpu_reference_rate(cfg, pc, pf, rays_cpu, 4096, 3)
             line["cpu_baseline"] = {"value": rate, "unit": "rays/s", "cores": getattr(cpu_reference_rate, "threads", os.cpu_count() or 1),

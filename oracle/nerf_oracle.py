@@ -88,7 +88,7 @@ def posenc(x: Tensor, n_freqs: int, no_xyz: bool = False,
     """[B,C] -> [B, C*(2L)+C]; channel order x, sin f0, cos f0, sin f1, ...
     (models/embedding.py:57-63)."""
     parts: List[Tensor] = [] if no_xyz else [x]
-    for f in frequency_bands(n_freqs, no_logscale).to(x.dtype):
+    for f in frequency_bands(n_freqs, no_logscale).to(device=x.device, dtype=x.dtype):
         parts.append(torch.sin(f * x))
         parts.append(torch.cos(f * x))
     return torch.cat(parts, -1)
@@ -178,7 +178,7 @@ def sample_along_rays(o: Tensor, d: Tensor, near: Tensor, far: Tensor, n: int,
     """near/far are [N,1].  ``u`` ([N,n] uniform draws) stands in for the
     reference's ``torch.rand_like`` (models/utils.py:41); ``None`` means the
     deterministic eval path."""
-    t = torch.linspace(0, 1, n)                                      # :31
+    t = torch.linspace(0, 1, n, device=o.device)                     # :31
     if lindisp:
         z = 1. / (1. / near * (1 - t) + 1. / far * t)                # :33
     else:
@@ -231,7 +231,7 @@ def resample_along_rays(o: Tensor, d: Tensor, z: Tensor, weights: Tensor,
     cdf = torch.cumsum(pdf, -1)                                      # :69
     cdf = torch.cat([torch.zeros_like(cdf[:, :1]), cdf], -1)         # :70
     if u is None:
-        u = torch.linspace(0, 1, n).expand(n_rays, n)                # :75-76
+        u = torch.linspace(0, 1, n, device=z.device).expand(n_rays, n)   # :75-76
     u = u.contiguous()
     inds = torch.searchsorted(cdf, u, right=True)                    # :79
     below = torch.clamp_min(inds - 1, 0)                             # :80
