@@ -76,10 +76,11 @@ class ClockSampler(threading.Thread):
 
 
 def make_inputs(seed_offset: int = 0):
-    from oracle import nerf_oracle as O
-    cfg = O.RenderConfig(white_bkgd=True, N_coarse=N_COARSE, N_importance=N_IMPORTANCE, downscale=SS)
-    pc, pf = O.make_mlp_params(cfg, SEEDS[0]), O.make_mlp_params(cfg, SEEDS[1])
-    rays = O.synthetic_rays(RAYS_PER_FRAME, 100 + seed_offset, "blender")
+    # input generation only (seeded rays + kaiming weights); no oracle code on the GPU arm
+    from nerf_sr_b200 import synthetic as S
+    cfg = S.RenderConfig(white_bkgd=True, N_coarse=N_COARSE, N_importance=N_IMPORTANCE, downscale=SS)
+    pc, pf = S.make_mlp_params(cfg, SEEDS[0]), S.make_mlp_params(cfg, SEEDS[1])
+    rays = S.synthetic_rays(RAYS_PER_FRAME, 100 + seed_offset, "blender")
     return cfg, pc, pf, rays
 
 
