@@ -257,6 +257,69 @@ NSR_API int nsr_render_host(NsrHandle* h, const float* rays_host, int64_t n_rays
 NSR_API int nsr_render_pose_host(NsrHandle* h, const float* c2w_host, int H, int W, float focal, int s, int ndc,
                                  float near_plane, float far_plane, float* rgb_host, float* depth_host);
 
+/* ---- training (scope row f-1: backward + fused optimiser) ------------------ */
+
+/* dL/d(outputs of forward_rays).  Null = that output does not enter the loss.  Per-sample weight maps
+ * are not differentiable through this interface (the reference's losses never use them). */
+typedef struct NsrOutGrads {
+  const float* coarse_comp_rgbs;   /* [N,3] */
+  const float* coarse_depth;       /* [N]   */
+  const float* coarse_opacity;     /* [N]   */
+  const float* fine_comp_rgbs;     /* [N,3] */
+  const float* fine_depth;         /* [N]   */
+  const float* fine_opacity;       /* [N]   */
+} NsrOutGrads;
+
+/* Elements of one net's flat gradient (= sum of nsr_param_numel): tensors in state_dict order. */
+NSR_API int64_t nsr_grad_numel(const NsrHandle* h);
+
+/* Bytes of caller-provided scratch that nsr_render_train fills (activation stash) and nsr_backward
+ * consumes; the SAME buffer must be passed to both. */
+NSR_API size_t nsr_train_workspace_bytes(const NsrHandle* h, int64_t n_rays);
+
+/* Replaces: forward_rays in train mode with autograd recording (models/nerf_downX_model.py:280-313 under
+ * torch.enable_grad()): same outputs as nsr_render, and every tile's MLP inputs / activations are kept in
+ * train_ws for the backward.  rng as in nsr_render (train mode draws). */
+NSR_API int nsr_render_train(NsrHandle* h, const float* rays, int64_t n_rays, int ray_stride, const NsrRng* rng,
+                             const NsrOutputs* out, void* train_ws, size_t train_ws_bytes, NsrStream stream);
+
+/* Replaces: loss_tot.backward() through forward_rays (models/nerf_downX_model.py:390-396): given
+ * dL/d(outputs), writes dL/d(parameters) of netCoarse / netFine as flat fp32 buffers (state_dict order,
+ * nsr_grad_numel elements each; overwritten, not accumulated).  rays / rng: the ones passed to
+ * nsr_render_train (only the sigma noise is read). */
+NSR_API int nsr_backward(NsrHandle* h, const float* rays, int64_t n_rays, int ray_stride, const NsrRng* rng,
+                         const NsrOutGrads* g, float* grad_coarse, float* grad_fine, void* train_ws,
+                         size_t train_ws_bytes, NsrStream stream);
+
+/* Replaces: comp_low_res_output + ColorMSELoss * lambda + PSNR + the loss's backward down to the HR composite
+ * colours (models/nerf_downX_model.py:337-340,357-359,380-382).  metrics_out: device float[2] =
+ * {lambda * mse, psnr}; g_hr_out: [n_lr*s*s, 3] = d(lambda * mse)/d(hr_rgb) (or null). */
+NSR_API int nsr_lr_loss_grad(NsrHandle* h, const float* hr_rgb, const float* target_lr, int64_t n_lr, int s, float lambda,
+                             float* lr_rgb_out, float* metrics_out, float* g_hr_out, NsrStream stream);
+
+/* Replaces: nn.utils.clip_grad_norm_ over chain(netCoarse, netFine) (models/nerf_downX_model.py:404-405).
+ * coef_out: device float[2] = {min(1, max_norm / (total_norm + 1e-6)), total_norm}; grad_b may be null. */
+NSR_API int nsr_clip_coef(NsrHandle* h, const float* grad_a, const float* grad_b, int64_t numel, float max_norm,
+                          float* coef_out, NsrStream stream);
+
+/* Replaces: torch.optim.Adam.step for one net (models/nerf_downX_model.py:201-204,408), in place on the
+ * caller's parameter tensors (param_ptrs as in nsr_pack_weights).  exp_avg / exp_avg_sq: flat state
+ * buffers (caller-owned, zero-initialised); step: 1-based count after the increment.  clip_coef_dev (or
+ * null) multiplies the gradient (norm clipping); clip_value > 0 clamps it (clip_grad_value_).  Call
+ * nsr_pack_weights afterwards. */
+NSR_API int nsr_adam_step(NsrHandle* h, float* const* param_ptrs, int n_params, const float* grad_flat, float* exp_avg,
+                          float* exp_avg_sq, int64_t step, float lr, float beta1, float beta2, float eps,
+                          const float* clip_coef_dev, float clip_value, NsrStream stream);
+
+/* Test seams of the backward GEMMs ("tile image" = [ceil(rows/128)][cols/64][hi 16 KB | lo 16 KB], 128-B rows,
+ * XOR-swizzled 16-B chunks; see nsr_train.cu). */
+NSR_API int nsr_debug_pack_image(NsrHandle* h, const float* src, int64_t n_rows, int n_cols, int ld, void* image, NsrStream stream);
+NSR_API int nsr_debug_unpack_image(NsrHandle* h, const void* image, int64_t n_rows, int n_cols, int ld, float* dst, NsrStream stream);
+NSR_API int nsr_debug_dx(NsrHandle* h, int which, int layer_idx, const void* a_img, void* out_img, const void* mask_img,
+                         const float* dsig, const float* wsig, int64_t n_rows, NsrStream stream);
+NSR_API int nsr_debug_dw(NsrHandle* h, const void* a_img, int a_cols, int blk0, int blk1, const void* b_img, int b_cols,
+                         float* out, float* bias_out, int64_t n_rows, void* scratch, size_t scratch_bytes, NsrStream stream);
+
 /* Debug: device buffer (>= 16*512 int64) that trace builds (-DNSR_TC_TRACE=1) fill with
  * (tag, clock64) pairs for one tile of CTA 0; ignored by normal builds.  tools/tc_trace.py. */
 NSR_API int nsr_debug_set_trace(NsrHandle* h, long long* device_buffer);

@@ -12,8 +12,8 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libnsr_b200.so")
-SOURCES = ["nsr_api.cu", "nsr_simt.cu", "nsr_tc.cu"]
-HEADERS = ["nsr_internal.h", "nsr_device.cuh", os.path.join(ROOT, "include", "nsr.h")]
+SOURCES = ["nsr_api.cu", "nsr_simt.cu", "nsr_tc.cu", "nsr_train.cu"]
+HEADERS = ["nsr_internal.h", "nsr_device.cuh", "nsr_tc_ptx.cuh", os.path.join(ROOT, "include", "nsr.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-diag-suppress", "177"]
 

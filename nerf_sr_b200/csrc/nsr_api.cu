@@ -386,6 +386,7 @@ extern "C" int nsr_create(const NsrConfig* cfg, NsrHandle** out_handle) {
       h->net[w].tc_bytes = tc_image_bytes(h);
       e = cudaMalloc(&h->net[w].tc_image, h->net[w].tc_bytes);
       if (e == cudaSuccess) e = cudaMalloc(&h->net[w].tc_consts, 16384 * sizeof(float));
+      if (e == cudaSuccess) e = cudaMalloc(&h->net[w].wt_image, train_wt_bytes());
     }
   }
   if (e != cudaSuccess) {
@@ -402,7 +403,7 @@ extern "C" int nsr_destroy(NsrHandle* h) {
   if (!h) return NSR_OK;
   cudaSetDevice(h->cfg.device);
   for (int w = 0; w < 2; ++w) {
-    cudaFree(h->net[w].simt_blob); cudaFree(h->net[w].tc_image); cudaFree(h->net[w].tc_consts);
+    cudaFree(h->net[w].simt_blob); cudaFree(h->net[w].tc_image); cudaFree(h->net[w].tc_consts); cudaFree(h->net[w].wt_image);
   }
   cudaFree(h->d_tables);
   cudaFree(h->d_partials);
@@ -448,7 +449,11 @@ extern "C" int nsr_pack_weights(NsrHandle* h, int which, const float* const* par
   cudaStream_t st = (cudaStream_t)stream;
   NSR_CUDA(h, cudaSetDevice(h->cfg.device));
   NSR_CUDA(h, simt_pack(h, which, param_ptrs, st));
-  if (h->cfg.precision != NSR_PREC_FP32_SIMT) NSR_CUDA(h, tc_pack(h, which, param_ptrs, st));
+  if (h->cfg.precision != NSR_PREC_FP32_SIMT) {
+    NSR_CUDA(h, tc_pack(h, which, param_ptrs, st));
+    // the device-side pointer table tc_pack staged behind the consts blob also feeds the backward's images
+    NSR_CUDA(h, train_pack_wt(h, which, reinterpret_cast<const float* const*>(h->net[which].tc_consts + 8192), st));
+  }
   h->net[which].packed = true;
   return NSR_OK;
 }

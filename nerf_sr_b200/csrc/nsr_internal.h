@@ -40,6 +40,7 @@ struct NetImages {
   uint8_t* tc_image = nullptr;     // device: swizzled hi/lo stage images for the tcgen05 path
   size_t tc_bytes = 0;
   float* tc_consts = nullptr;      // device: biases, head weights, dir-part weights (fp32)
+  uint8_t* wt_image = nullptr;     // device: transposed hi/lo weight images for the backward dX GEMMs
 };
 
 }  // namespace nsr
@@ -81,6 +82,16 @@ cudaError_t simt_mlp(NsrHandle_* h, int which, const float* rays, int64_t n_rays
                      const float* z, int S, float* raw, cudaStream_t st);
 
 // ---- tcgen05 path (nsr_tc.cu) ----
+// layout of NetImages::tc_consts (floats)
+constexpr int kcBias = 0;        // 8 x 256 trunk, then final 256, then dir 128
+constexpr int kcBiasFinal = 2048;
+constexpr int kcBiasDir = 2304;
+constexpr int kcWsig = 2432;     // 256
+constexpr int kcWrgb = 2688;     // 3 x 128
+constexpr int kcMisc = 3072;     // b_sigma, b_rgb[3]
+constexpr int kcSmemFloats = 3080;
+constexpr int kcWdd = 3080;      // dir-part of dir_encoding weight: [128][28]
+constexpr int kcTotal = 3080 + 128 * 28;
 bool tc_supported(const NsrConfig& cfg, std::string* why);
 size_t tc_image_bytes(const NsrHandle_* h);
 cudaError_t tc_pack(NsrHandle_* h, int which, const float* const* params, cudaStream_t st);
@@ -95,8 +106,15 @@ struct TcPassArgs {
   float* comp_rgb; float* depth; float* opacity; float* weights; float* raw; float* z_next;
   long long* trace;   // debug timeline buffer (NSR_TC_TRACE builds), else null
   int debug_flags;
+  // training stash (all three set together, or all null): see TcKernelArgs in nsr_tc.cu
+  uint8_t* stash_enc = nullptr; uint8_t* stash_h = nullptr; uint8_t* stash_dir = nullptr;
+  float* z_out = nullptr;
 };
 cudaError_t tc_pass(NsrHandle_* h, int which, const TcPassArgs& a, cudaStream_t st);
+
+// ---- training path (nsr_train.cu) ----
+size_t train_wt_bytes();
+cudaError_t train_pack_wt(NsrHandle_* h, int which, const float* const* params_dev, cudaStream_t st);
 
 // ---- shared small kernels (nsr_api.cu) ----
 cudaError_t launch_composite(NsrHandle_* h, const float* raw, const float* z, const float* noise,

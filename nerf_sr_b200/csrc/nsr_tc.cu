@@ -31,11 +31,8 @@
 // (models/nerf_downX_model.py:260-278), VanillaMLP.forward (models/networks.py:
 // 199-224), add_gaussian_noise (models/utils.py:199-212), VolumetricRenderer.forward
 // (models/rendering.py:89-111) and resample_along_rays (models/utils.py:47-95).
-#include <cstdio>
-#include <cuda_bf16.h>
-#include <cuda_fp16.h>
-
 #include "nsr_internal.h"
+#include "nsr_tc_ptx.cuh"
 
 namespace nsr {
 
@@ -57,16 +54,7 @@ constexpr int kEpiWarp0 = kWarpsFront;                           // warps 4-11 (
 constexpr int kProducerWarp = kWarpsFront + kWarpsEpi;           // warp 12
 constexpr int kMmaWarp = kProducerWarp + 1;                      // warp 13
 
-// consts blob (floats)
-constexpr int kcBias = 0;        // 8 x 256 trunk, then final 256, then dir 128
-constexpr int kcBiasFinal = 2048;
-constexpr int kcBiasDir = 2304;
-constexpr int kcWsig = 2432;     // 256
-constexpr int kcWrgb = 2688;     // 3 x 128
-constexpr int kcMisc = 3072;     // b_sigma, b_rgb[3]
-constexpr int kcSmemFloats = 3080;
-constexpr int kcWdd = 3080;      // dir-part of dir_encoding weight: [128][28]
-constexpr int kcTotal = 3080 + 128 * 28;
+// (layout of the fp32 consts blob: kc* in nsr_internal.h)
 
 // shared memory map (bytes, relative to a 1024-aligned base)
 constexpr int kSmRing = 0;
@@ -96,154 +84,6 @@ enum {
   B_COMPREADY = 18,       // epilogue staged the tile's per-sample (rgb, sigma) for compositing
   B_COMPDONE = 19,        // front-end finished compositing the staged tile
   B_COUNT = 20
-};
-
-// ---------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok;
-}
-#ifndef NSR_TC_WATCHDOG
-#define NSR_TC_WATCHDOG 1
-#endif
-// Blocks until the phase with the given parity has completed.  With the watchdog enabled a
-// protocol deadlock becomes a trapped launch failure with a diagnostic instead of a hung GPU.
-__device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
-  printf("[nsr_tc] mbarrier wait timed out: block %d thread %d barrier-offset %u parity %u\n", (int)blockIdx.x,
-         (int)threadIdx.x, bar, parity);
-  __trap();
-}
-__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
-#if NSR_TC_WATCHDOG
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 22)) mbar_timeout(bar, parity);
-  }
-#else
-  while (!mbar_try_wait(bar, parity)) {}
-#endif
-}
-// One inline probe (the common case in the issue loops: already complete), slow path out of line
-// so the single-lane MMA / producer loops stay short.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
-}
-__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-
-// One lane of a converged warp (the pattern ptxas recognises for single-thread tcgen05/TMA issue:
-// operands stay in uniform registers instead of a per-lane R2UR waterfall loop).
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-  float4 v;
-  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
-}
-
-// D[tmem] (+)= A[smem] * B[smem]
-__device__ __forceinline__ void mma_ss(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
-}
-// D[tmem] (+)= A[tmem] * B[smem]
-__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(d), "r"(a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
-}
-
-// K-major SWIZZLE_128B shared-memory matrix descriptor (rows of 128 B, 8-row
-// groups 1024 B apart): start>>4 | LBO(unused)=1 | SBO=1024>>4 | version=1 | layout=2
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-// kind::f16 instruction descriptor: D=f32, A/B = fmt (0 f16, 1 bf16), K-major both, N, M
-__host__ __device__ constexpr uint32_t umma_idesc(int fmt, int M, int N) {
-  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-#define TMEM_LD32(taddr, r)                                                                           \
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                               \
-               "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"                               \
-               "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"              \
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),    \
-                 "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), \
-                 "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),          \
-                 "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),          \
-                 "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])           \
-               : "r"(taddr) : "memory")
-
-#define TMEM_ST16(taddr, r)                                                                           \
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "                                         \
-               "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"                             \
-               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]),          \
-                 "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]),        \
-                 "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory")
-
-// ---- hi/lo split of two fp32 values into packed 16-bit pairs (even k in the low half) ----
-template <int FMT> struct Split;
-template <> struct Split<1> {   // bf16
-  static __device__ __forceinline__ void apply(float v0, float v1, uint32_t& hi, uint32_t& lo) {
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(v1), "f"(v0));
-    const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(v1 - h1), "f"(v0 - h0));
-  }
-  static __host__ __device__ __forceinline__ void apply1(float v, uint16_t& hi, uint16_t& lo) {
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
-    hi = *reinterpret_cast<const uint16_t*>(&h);
-    lo = *reinterpret_cast<const uint16_t*>(&l);
-  }
-};
-template <> struct Split<0> {   // fp16
-  static __device__ __forceinline__ void apply(float v0, float v1, uint32_t& hi, uint32_t& lo) {
-    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(v1), "f"(v0));
-    const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));
-    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(v1 - h.y), "f"(v0 - h.x));
-  }
-  static __host__ __device__ __forceinline__ void apply1(float v, uint16_t& hi, uint16_t& lo) {
-    const __half h = __float2half_rn(v);
-    const __half l = __float2half_rn(v - __half2float(h));
-    hi = *reinterpret_cast<const uint16_t*>(&h);
-    lo = *reinterpret_cast<const uint16_t*>(&l);
-  }
 };
 
 // ---------------------------------------------------------------------------
@@ -387,6 +227,13 @@ struct TcKernelArgs {
   long long n_tiles;
   long long* trace;
   int debug_flags;   // bit0: producer skips the bulk copies (timing experiment: stale weights)
+  // training stash (STASH kernels only; scope row f-1): every tile's MLP inputs and activations in the
+  // exact shared-memory operand format (tile image: hi plane 16 KB | lo plane 16 KB per 64-feature chunk,
+  // 128-B rows, 16-B chunks XOR-swizzled), so the backward GEMMs load them with plain bulk copies.
+  uint8_t* stash_enc;   // [n_tiles][32 KB]            encoded xyz (63 + zero pad)
+  uint8_t* stash_h;     // [9][n_tiles][4][32 KB]      h_1..h_8 (post-ReLU) and feat = xyz_encoding_final(h_8)
+  uint8_t* stash_dir;   // [n_tiles][2][32 KB]         dir layer output (post-ReLU, 128 wide)
+  float* z_out;         // [N,S] z-values actually used (coarse pass computes them on the fly), or null
 };
 
 // ---------------------------------------------------------------------------
@@ -562,7 +409,7 @@ __device__ __forceinline__ void mma_role(const TcKernelArgs& a, uint8_t* sm, uin
 __device__ __noinline__ void sincos_shared(float x, float* s, float* c) { sincosf(x, s, c); }
 
 // ---- front-end: sample, cast, encode, split, swizzled store; per-ray dir bias ----
-template <int FMT>
+template <int FMT, bool STASH>
 __device__ __forceinline__ void frontend_role(const TcKernelArgs& a, uint8_t* sm, uint32_t sm_base, long long my_tiles,
                                               int first_tile, int tile_stride) {
   const int t = threadIdx.x - 32 * kFrontWarp0;   // 0..127 = tile row
@@ -637,6 +484,7 @@ __device__ __forceinline__ void frontend_role(const TcKernelArgs& a, uint8_t* sm
       }
     }
     reinterpret_cast<float*>(sm + kSmZ)[buf * 128 + t] = zv;
+    if (STASH && a.z_out && valid) a.z_out[ray * S + i] = zv;
     const float px = cast_point(ox, dx, zv), py = cast_point(oy, dy, zv), pz = cast_point(oz, dz, zv);
     // 63 encoded channels (+1 zero pad), reference channel order (embedding.py:57-63)
     float e[64];
@@ -662,6 +510,11 @@ __device__ __forceinline__ void frontend_role(const TcKernelArgs& a, uint8_t* sm
       const int sw = (j ^ (t & 7)) << 4;
       *reinterpret_cast<uint4*>(row_hi + sw) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
       *reinterpret_cast<uint4*>(row_lo + sw) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      if (STASH) {
+        uint8_t* g = a.stash_enc + (size_t)tile * kStageBytes + t * 128 + sw;
+        *reinterpret_cast<uint4*>(g) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(g + kPlaneBytes) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
     }
     TR(5002);
     // view-direction encoding of the tile's rays -> smem, then the per-ray bias of the dir layer:
@@ -715,9 +568,10 @@ __device__ __forceinline__ void frontend_role(const TcKernelArgs& a, uint8_t* sm
 
 // One trunk layer's epilogue for this warp: the four 64-column accumulator quarters in order,
 // 32 columns of each:  acc + bias (+ReLU) (-> sigma-head partial) -> hi/lo split -> A operand planes.
-template <int FMT, int PASSES, bool SIGMA>
+template <int FMT, int PASSES, bool SIGMA, bool STASH>
 __device__ __forceinline__ void epi_layer(int L, float relu_floor, uint32_t g, uint32_t bar, uint32_t tlane,
-                                          uint32_t cst_addr, int hh, int lane, float& sig_p TR_PARAMS) {
+                                          uint32_t cst_addr, int hh, int lane, float& sig_p,
+                                          uint8_t* stash_row TR_PARAMS) {
   const uint32_t bias_addr = cst_addr + 4u * (uint32_t)((L - 1) * 256);   // L9 -> kcBiasFinal
 #pragma unroll 1
   for (int q4 = 0; q4 < 4; ++q4) {
@@ -749,6 +603,16 @@ __device__ __forceinline__ void epi_layer(int L, float relu_floor, uint32_t g, u
     }
     TMEM_ST16(tlane + 256u + (uint32_t)(col0 / 2), whi);
     if (PASSES == 3) TMEM_ST16(tlane + 384u + (uint32_t)(col0 / 2), wlo);
+    if (STASH) {   // this thread's 32 activations of layer L -> the layer's tile image (row = tile row)
+      uint8_t* gp = stash_row + (size_t)q4 * kStageBytes;        // k chunk = 64-column quarter
+      const int r7 = lane & 7;                                   // tile row = 32*quarter + lane
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int sw = ((4 * hh + jj) ^ r7) << 4;
+        *reinterpret_cast<uint4*>(gp + sw) = make_uint4(whi[4 * jj], whi[4 * jj + 1], whi[4 * jj + 2], whi[4 * jj + 3]);
+        *reinterpret_cast<uint4*>(gp + kPlaneBytes + sw) = make_uint4(wlo[4 * jj], wlo[4 * jj + 1], wlo[4 * jj + 2], wlo[4 * jj + 3]);
+      }
+    }
     TR(100 * L + 10 * q4 + 3);
     tc_wait_st();
     tc_fence_before();
@@ -759,7 +623,7 @@ __device__ __forceinline__ void epi_layer(int L, float relu_floor, uint32_t g, u
 }
 
 // ---- epilogue + compositing ----
-template <int FMT, int PASSES>
+template <int FMT, int PASSES, bool STASH>
 __device__ __forceinline__ void epilogue_role(const TcKernelArgs& a, uint8_t* sm, uint32_t sm_base, uint32_t tmem,
                                               long long my_tiles, int first_tile, int tile_stride) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -823,8 +687,10 @@ __device__ __forceinline__ void epilogue_role(const TcKernelArgs& a, uint8_t* sm
       // the previous tile's tail goes here, behind this tile's first layer: the MMA lane is already
       // busy with L2 while the heads' activations are finished and staged
       if (L == 2 && it >= 1) tile_tail(it - 1, sig_prev, rgb_prev[0], rgb_prev[1], rgb_prev[2]);
-      if (L == 8) epi_layer<FMT, PASSES, true>(L, 0.f, g, bar, tlane, sm_base + kSmConst, hh, lane, sig_p TR_ARGS);   // + sigma head
-      else epi_layer<FMT, PASSES, false>(L, L <= 8 ? 0.f : -INFINITY, g, bar, tlane, sm_base + kSmConst, hh, lane, sig_p TR_ARGS);
+      uint8_t* stash_row = nullptr;
+      if (STASH) stash_row = a.stash_h + ((size_t)(L - 1) * (size_t)a.n_tiles + (size_t)(first_tile + it * (long long)tile_stride)) * (size_t)(4 * kStageBytes) + (size_t)row * 128;
+      if (L == 8) epi_layer<FMT, PASSES, true, STASH>(L, 0.f, g, bar, tlane, sm_base + kSmConst, hh, lane, sig_p, stash_row TR_ARGS);   // + sigma head
+      else epi_layer<FMT, PASSES, false, STASH>(L, L <= 8 ? 0.f : -INFINITY, g, bar, tlane, sm_base + kSmConst, hh, lane, sig_p, stash_row TR_ARGS);
     }
     // ---- layer 10: dir layer (N=128, accumulator half 0) + rgb head ----
     float rgb_p[3] = {0.f, 0.f, 0.f};
@@ -854,6 +720,15 @@ __device__ __forceinline__ void epilogue_role(const TcKernelArgs& a, uint8_t* sm
           rgb_p[0] = fmaf(v0, w0.x, rgb_p[0]); rgb_p[0] = fmaf(v1, w0.y, rgb_p[0]); rgb_p[0] = fmaf(v2, w0.z, rgb_p[0]); rgb_p[0] = fmaf(v3, w0.w, rgb_p[0]);
           rgb_p[1] = fmaf(v0, w1.x, rgb_p[1]); rgb_p[1] = fmaf(v1, w1.y, rgb_p[1]); rgb_p[1] = fmaf(v2, w1.z, rgb_p[1]); rgb_p[1] = fmaf(v3, w1.w, rgb_p[1]);
           rgb_p[2] = fmaf(v0, w2.x, rgb_p[2]); rgb_p[2] = fmaf(v1, w2.y, rgb_p[2]); rgb_p[2] = fmaf(v2, w2.z, rgb_p[2]); rgb_p[2] = fmaf(v3, w2.w, rgb_p[2]);
+          if (STASH) {   // dir layer activations (post-ReLU) -> tile image, chunk hh, 16-B chunk 4c + j/8
+            uint32_t dh0, dl0, dh1, dl1;
+            Split<FMT>::apply(v0, v1, dh0, dl0);
+            Split<FMT>::apply(v2, v3, dh1, dl1);
+            uint8_t* gp = a.stash_dir + ((size_t)(first_tile + it * (long long)tile_stride) * 2 + (size_t)hh) * (size_t)kStageBytes +
+                          (size_t)row * 128 + (size_t)((((4 * c + (j >> 3)) ^ (row & 7)) << 4) + ((j & 4) << 1));
+            *reinterpret_cast<uint2*>(gp) = make_uint2(dh0, dh1);
+            *reinterpret_cast<uint2*>(gp + kPlaneBytes) = make_uint2(dl0, dl1);
+          }
         }
       }
       tc_fence_before();
@@ -868,7 +743,7 @@ __device__ __forceinline__ void epilogue_role(const TcKernelArgs& a, uint8_t* sm
   }
   if (my_tiles > 0) tile_tail(my_tiles - 1, sig_prev, rgb_prev[0], rgb_prev[1], rgb_prev[2]);
 }
-template <int FMT, int PASSES>
+template <int FMT, int PASSES, bool STASH>
 __global__ void __launch_bounds__(kThreadsTc, 1) k_tc_pass(const TcKernelArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];   // SWIZZLE_128B operands need 1024-B alignment
   uint8_t* sm = smem_raw;                                 // (keeps the __shared__ address space: LDS/STS)
@@ -914,9 +789,9 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_tc_pass(const TcKernelArgs a)
     mma_role<PASSES>(a, sm, sm_base, tmem, umma_idesc(FMT, 128, 128), my_tiles);
     __syncwarp();
   } else if (warp < kEpiWarp0) {
-    frontend_role<FMT>(a, sm, sm_base, my_tiles, blockIdx.x, gridDim.x);
+    frontend_role<FMT, STASH>(a, sm, sm_base, my_tiles, blockIdx.x, gridDim.x);
   } else {
-    epilogue_role<FMT, PASSES>(a, sm, sm_base, tmem, my_tiles, blockIdx.x, gridDim.x);
+    epilogue_role<FMT, PASSES, STASH>(a, sm, sm_base, tmem, my_tiles, blockIdx.x, gridDim.x);
   }
 
   tc_fence_before();
@@ -941,10 +816,12 @@ cudaError_t tc_pass(NsrHandle_* h, int which, const TcPassArgs& p, cudaStream_t 
   if (a.n_tiles == 0) return cudaSuccess;
   const int grid = (int)(a.n_tiles < h->sm_count ? a.n_tiles : h->sm_count);
   void (*kern)(const TcKernelArgs) = nullptr;
+  const bool stash = p.stash_enc != nullptr;
+  a.stash_enc = p.stash_enc; a.stash_h = p.stash_h; a.stash_dir = p.stash_dir; a.z_out = p.z_out;
   switch (h->cfg.precision) {
-    case NSR_PREC_BF16X3_TC: kern = k_tc_pass<1, 3>; break;
-    case NSR_PREC_FP16X3_TC: kern = k_tc_pass<0, 3>; break;
-    case NSR_PREC_BF16_TC: kern = k_tc_pass<1, 1>; break;
+    case NSR_PREC_BF16X3_TC: kern = stash ? k_tc_pass<1, 3, true> : k_tc_pass<1, 3, false>; break;
+    case NSR_PREC_FP16X3_TC: kern = stash ? k_tc_pass<0, 3, true> : k_tc_pass<0, 3, false>; break;
+    case NSR_PREC_BF16_TC: if (stash) return cudaErrorInvalidValue; kern = k_tc_pass<1, 1, false>; break;
     default: return cudaErrorInvalidValue;
   }
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTcBytes);

@@ -1,0 +1,1225 @@
+// nsr_train.cu -- backward of the fused render pass + fused optimiser (scope row f-1), sm_100a only.
+//
+// Replaces (reference): loss_tot.backward() through forward_rays (models/nerf_downX_model.py:280-313,
+// 390-396: autograd over VolumetricRenderer.forward, VanillaMLP.forward and the colour/sigma
+// activations), nn.utils.clip_grad_norm_/clip_grad_value_ (:403-407) and torch.optim.Adam.step (:408,
+// :201-204).  Sample positions carry no gradient (weights and rays only; coarse_weights.detach(), :302).
+//
+// Data flow of one net's backward (all device-resident, stream-ordered, no host sync):
+//   the STASH variant of k_tc_pass (nsr_tc.cu) has saved every tile's MLP inputs and activations as
+//   "tile images": per 128-point tile and 64-feature chunk, a bf16/fp16 hi plane (16 KB) and lo plane
+//   (16 KB) of 128-B rows with XOR-swizzled 16-B chunks -- the exact SWIZZLE_128B shared-memory operand
+//   layout, so every GEMM operand below is fetched with plain cp.async.bulk copies and no conversion.
+//   The same image is a K-major operand (rows = points = M, K = features) for the dX GEMMs and an
+//   MN-major operand (rows = points = K, features = M/N) for the dW GEMMs.
+//
+//   k_render_bwd   one warp per ray: alpha-compositing backward (reverse scan), colour / sigma
+//                  activation backward, rgb-head backward -> images dHead (d sigma, d rgb_pre),
+//                  dZ_dir (masked by the stashed dir activations), encdir (per-point copy of the ray's
+//                  view-direction encoding), and the fp32 d sigma vector.
+//   k_tg_dx        dH_{l-1} = dZ_l . W_l  (M = 128 points, N = 256, K = 64 per chunk), tcgen05.mma
+//                  kind::f16 with hi/lo split operands (3 MMAs per product), fp32 accumulate in a
+//                  double-buffered TMEM accumulator; epilogue: (+ d sigma x w_sigma) . ReLU mask from
+//                  the stashed activation -> hi/lo split -> next dZ image.
+//   k_tg_dw        dW_l = dZ_l^T . X_l over all points (K = points, split across CTAs), both operands
+//                  MN-major views of the tile images; the bias gradient is one more N=16 MMA against a
+//                  tile of ones; fp32 partials per CTA, summed in a fixed order by k_grad_reduce
+//                  (deterministic).
+//   k_adam         torch.optim.Adam single-tensor semantics on the caller's parameter tensors, with
+//                  the clip coefficient / clip value folded in.
+#include <cmath>
+#include <string>
+
+#include "nsr_internal.h"
+#include "nsr_tc_ptx.cuh"
+
+namespace nsr {
+
+constexpr int kT = 128;               // points per tile
+constexpr int kChunk = 32768;         // one 64-feature chunk of a tile image: hi plane | lo plane
+constexpr int kPlane = 16384;
+constexpr int kNumDxLayers = 9;       // dir, final, L8..L2
+constexpr int kWtChunkBytes = 65536;  // transposed-weight chunk: 256 rows x 64 k, hi 32 KB | lo 32 KB
+constexpr int kWtChunks = 2 + 8 * 4;
+constexpr int kMaxSplit = 148;
+
+__host__ __device__ inline size_t img_off(int row, int j) { return (size_t)row * 128 + (size_t)((j ^ (row & 7)) << 4); }
+
+// ---------------------------------------------------------------------------
+// transposed weight images for the dX GEMMs (B operand: rows = input feature n, K = output feature)
+// ---------------------------------------------------------------------------
+struct WtLayer { int param, n_out, ld, col0, chunk0; };
+struct WtTable { WtLayer l[kNumDxLayers]; };
+
+static WtTable build_wt_table(int ch_dir, bool no_dir) {
+  WtTable T{};
+  int c = 0;
+  T.l[0] = WtLayer{18, 128, no_dir ? 256 : 256 + ch_dir, 0, c}; c += 2;     // dir_encoding.0 (feat part)
+  T.l[1] = WtLayer{16, 256, 256, 0, c}; c += 4;                              // xyz_encoding_final
+  for (int i = 0; i < 7; ++i) {                                              // L8 .. L2
+    const int L = 8 - i;
+    const bool skip = (L == 5);
+    T.l[2 + i] = WtLayer{2 * (L - 1), 256, skip ? 319 : 256, skip ? 63 : 0, c}; c += 4;
+  }
+  return T;
+}
+
+template <int FMT>
+__global__ void k_pack_wt(WtTable T, const float* const* __restrict__ params, uint8_t* __restrict__ image) {
+  // one thread per (chunk, row n, 16-byte chunk j)
+  const int total = kWtChunks * 256 * 8;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int cg = idx / 2048, n = (idx / 8) % 256, j = idx % 8;
+    int li = 0;
+#pragma unroll
+    for (int t = 1; t < kNumDxLayers; ++t) if (cg >= T.l[t].chunk0) li = t;
+    const WtLayer L = T.l[li];
+    const int c = cg - L.chunk0;
+    const float* W = params[L.param];
+    __align__(16) uint16_t hi[8];
+    __align__(16) uint16_t lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int o = 64 * c + 8 * j + e;
+      const float v = W[(int64_t)o * L.ld + L.col0 + n];
+      Split<FMT>::apply1(v, hi[e], lo[e]);
+    }
+    uint8_t* dst = image + (size_t)cg * kWtChunkBytes + img_off(n, j);
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(dst + 32768) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+
+size_t train_wt_bytes() { return (size_t)kWtChunks * kWtChunkBytes; }
+
+cudaError_t train_pack_wt(NsrHandle_* h, int which, const float* const* params_dev, cudaStream_t st) {
+  const WtTable T = build_wt_table(h->rp.ch_dir, h->cfg.no_dir != 0);
+  if (h->cfg.precision == NSR_PREC_FP16X3_TC) k_pack_wt<0><<<136, 256, 0, st>>>(T, params_dev, h->net[which].wt_image);
+  else k_pack_wt<1><<<136, 256, 0, st>>>(T, params_dev, h->net[which].wt_image);
+  h->launches += 1;
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// generic image pack / unpack (test seams and small producers)
+// ---------------------------------------------------------------------------
+template <int FMT>
+__global__ void k_pack_image(const float* __restrict__ src, long long n_rows, int n_cols, int ld, uint8_t* __restrict__ image) {
+  // image [tiles][n_cols/64][32 KB]; rows past n_rows and columns past ld are zero
+  const int cpt = n_cols / 64;
+  const long long tiles = (n_rows + kT - 1) / kT;
+  const long long total = tiles * cpt * kT * 8;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % 8), row = (int)((idx / 8) % kT);
+    const long long tc = idx / (8 * kT);
+    const int c = (int)(tc % cpt);
+    const long long tile = tc / cpt, p = tile * kT + row;
+    __align__(16) uint16_t hi[8];
+    __align__(16) uint16_t lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = 64 * c + 8 * j + e;
+      const float v = (p < n_rows && k < ld) ? src[p * ld + k] : 0.f;
+      Split<FMT>::apply1(v, hi[e], lo[e]);
+    }
+    uint8_t* dst = image + (size_t)tc * kChunk + img_off(row, j);
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(dst + kPlane) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+
+template <int FMT> __device__ __forceinline__ float half_to_float(uint16_t x);
+template <> __device__ __forceinline__ float half_to_float<1>(uint16_t x) { return __uint_as_float((uint32_t)x << 16); }
+template <> __device__ __forceinline__ float half_to_float<0>(uint16_t x) { return __half2float(*reinterpret_cast<const __half*>(&x)); }
+
+template <int FMT>
+__global__ void k_unpack_image(const uint8_t* __restrict__ image, long long n_rows, int n_cols, int ld, float* __restrict__ dst) {
+  const int cpt = n_cols / 64;
+  const long long total = n_rows * ld;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long p = idx / ld;
+    const int k = (int)(idx % ld);
+    const long long tile = p / kT;
+    const int row = (int)(p % kT), c = k / 64, j = (k % 64) / 8, e = k % 8;
+    const uint8_t* s = image + (size_t)(tile * cpt + c) * kChunk + img_off(row, j) + 2 * e;
+    const uint16_t hi = *reinterpret_cast<const uint16_t*>(s), lo = *reinterpret_cast<const uint16_t*>(s + kPlane);
+    dst[idx] = half_to_float<FMT>(hi) + half_to_float<FMT>(lo);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// k_render_bwd: compositing + activation + rgb-head backward, one warp per ray
+// ---------------------------------------------------------------------------
+struct RenderBwdArgs {
+  RenderParams rp;
+  const SampleTables* tabs;
+  const float* rays; long long n_rays; int ray_stride;
+  const float* z;        // [N,S]
+  const float* raw;      // [N,S,4]  rgb after the colour activation, raw sigma (VanillaMLP output)
+  const float* noise;    // [N,S] or null
+  int S;
+  const float* g_rgb;    // [N,3] dL/d comp_rgb (required)
+  const float* g_depth;  // [N] or null
+  const float* g_opacity;// [N] or null
+  const float* w_rgb;    // [3][128] fp32
+  const uint8_t* stash_dir;   // [tiles][2][32 KB] (ReLU mask of the dir layer)
+  uint8_t* dhead;        // [tiles][32 KB]    columns: 0 d sigma, 1..3 d rgb_pre
+  uint8_t* dzdir;        // [tiles][2][32 KB]
+  uint8_t* encdir;       // [tiles][32 KB]    27 valid columns
+  float* dsig;           // [tiles*128]
+  long long n_tiles;
+};
+
+template <int FMT>
+__global__ void __launch_bounds__(128)
+k_render_bwd(const RenderBwdArgs a) {
+  extern __shared__ float bsm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = a.S, RPT = kT / S;
+  const RenderParams& rp = a.rp;
+  float* swr = bsm;                               // [384] rgb head weights
+  float* base = bsm + 384 + warp * (10 * S + 32);
+  float* sz = base;                               // z
+  float* ssg = sz + S;                            // sigma (+ noise)
+  float* sal = ssg + S;                           // alpha
+  float* sT = sal + S;                            // 1 - alpha + eps  ->  transmittance (exclusive product)
+  float* sG = sT + S;                             // dL/dw
+  float* sR = sG + S;                             // G*w -> suffix sums
+  float* sex = sR + S;                            // exp(-delta * act)
+  float* srgb = sex + S;                          // [3S] colours entering the compositing sum
+  float* senc = srgb + 3 * S;                     // [32] view-direction encoding of the ray
+  for (int i = threadIdx.x; i < 384; i += blockDim.x) swr[i] = a.w_rgb[i];
+  __syncthreads();
+  const float eps = 1e-10f;
+  const long long ray_slots = a.n_tiles * RPT;
+  for (long long ray = blockIdx.x * 4ll + warp; ray < ray_slots; ray += (long long)gridDim.x * 4) {
+    const bool valid = ray < a.n_rays;
+    float gr = 0.f, gg = 0.f, gb = 0.f, gd = 0.f, go = 0.f;
+    if (valid) {
+      gr = a.g_rgb[ray * 3]; gg = a.g_rgb[ray * 3 + 1]; gb = a.g_rgb[ray * 3 + 2];
+      if (a.g_depth) gd = a.g_depth[ray];
+      if (a.g_opacity) go = a.g_opacity[ray];
+      const float4* r4 = reinterpret_cast<const float4*>(a.raw) + ray * S;
+      for (int i = lane; i < S; i += 32) {
+        const float4 v = r4[i];
+        float cr = v.x, cg = v.y, cb = v.z;
+        if (rp.gamma_correct) { cr = powf(cr, 1.f / 2.2f); cg = powf(cg, 1.f / 2.2f); cb = powf(cb, 1.f / 2.2f); }
+        srgb[3 * i] = cr; srgb[3 * i + 1] = cg; srgb[3 * i + 2] = cb;
+        float s = v.w;
+        if (a.noise) s = __fadd_rn(s, __fmul_rn(a.noise[ray * S + i], rp.noise_std));
+        ssg[i] = s;
+        sz[i] = a.z[ray * S + i];
+      }
+      // view-direction encoding (same channel order as the forward's per-ray dir bias)
+      {
+        const float* vd = a.rays + ray * a.ray_stride + rp.viewdir_offset;
+        float val = 0.f;
+        if (lane < 3) val = vd[lane];
+        else if (lane < 27) {
+          const int idx = lane - 3, k = idx / 6, r = idx % 6, comp = r % 3;
+          const float arg = __fmul_rn(a.tabs->freq_dir[k], vd[comp]);
+          val = (r >= 3) ? cosf(arg) : sinf(arg);
+        }
+        senc[lane] = val;
+      }
+      __syncwarp();
+      // forward recompute (models/rendering.py:89-103), same roundings as composite_ray_warp
+      for (int i = lane; i < S; i += 32) {
+        const float delta = (i + 1 < S) ? __fsub_rn(sz[i + 1], sz[i]) : 1e10f;
+        const float e = expf(__fmul_rn(-delta, sigma_act(ssg[i], rp.sigma_softplus)));
+        const float al = __fsub_rn(1.f, e);
+        sex[i] = e; sal[i] = al;
+        sT[i] = __fadd_rn(__fsub_rn(1.f, al), eps);
+      }
+      __syncwarp();
+      if (lane == 0) seq_scan_one_lane<true>(sT, S, 1.f);
+      __syncwarp();
+      const float white = rp.white_bkgd ? 1.f : 0.f;
+      for (int i = lane; i < S; i += 32) {
+        const float w = __fmul_rn(sal[i], sT[i]);
+        // comp = sum w*c (+ 1 - sum w), depth = sum w*z, opacity = sum w
+        const float G = gr * (srgb[3 * i] - white) + gg * (srgb[3 * i + 1] - white) + gb * (srgb[3 * i + 2] - white) +
+                        gd * sz[i] + go;
+        sG[i] = G;
+        sR[i] = G * w;
+      }
+      __syncwarp();
+      if (lane == 0) {          // R_i = sum_{k>i} G_k w_k  (reverse exclusive scan)
+        float acc = 0.f;
+        for (int i = S - 1; i >= 0; --i) { const float t = sR[i]; sR[i] = acc; acc += t; }
+      }
+      __syncwarp();
+    }
+    // per sample: gradients of the MLP outputs, then the three image rows of this point
+    for (int i = lane; i < S; i += 32) {
+      float dsg = 0.f, drgb[3] = {0.f, 0.f, 0.f};
+      const long long p = ray * S + i;
+      if (valid) {
+        const float delta = (i + 1 < S) ? __fsub_rn(sz[i + 1], sz[i]) : 1e10f;
+        const float x = __fadd_rn(__fsub_rn(1.f, sal[i]), eps);
+        const float w = __fmul_rn(sal[i], sT[i]);
+        const float dalpha = sG[i] * sT[i] - sR[i] / x;           // d w_i/d alpha_i = T_i ; d T_k/d alpha_i = -T_k / x_i
+        const float dact = dalpha * delta * sex[i];               // alpha = 1 - exp(-delta * act)
+        const float s = ssg[i];
+        if (rp.sigma_softplus) {
+          const float t = expf(__fsub_rn(s, 1.f));
+          dsg = dact * (t / (1.f + t));
+        } else {
+          dsg = (s > 0.f) ? dact : 0.f;                           // relu backward: select, never 0 * inf
+        }
+        const float4 v = reinterpret_cast<const float4*>(a.raw)[p];
+        const float c[3] = {v.x, v.y, v.z};
+        const float g3[3] = {gr, gg, gb};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          float d = g3[k] * w;
+          if (rp.gamma_correct) d *= (1.f / 2.2f) * powf(c[k], 1.f / 2.2f - 1.f);
+          if (!rp.color_none) d *= (1.f - c[k]) * c[k];           // sigmoid backward
+          drgb[k] = d;
+        }
+      }
+      const long long tile = p >> 7;
+      const int row = (int)(p & 127);
+      a.dsig[p] = dsg;
+      const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+      {   // dHead: (d sigma, d r, d g, d b, 0...) in the first 16-byte chunk
+        uint32_t h0, l0, h1, l1;
+        Split<FMT>::apply(dsg, drgb[0], h0, l0);
+        Split<FMT>::apply(drgb[1], drgb[2], h1, l1);
+        uint8_t* g = a.dhead + (size_t)tile * kChunk;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint8_t* q = g + img_off(row, j);
+          *reinterpret_cast<uint4*>(q) = (j == 0) ? make_uint4(h0, h1, 0u, 0u) : zero4;
+          *reinterpret_cast<uint4*>(q + kPlane) = (j == 0) ? make_uint4(l0, l1, 0u, 0u) : zero4;
+        }
+      }
+      {   // encdir: the ray's 27 encoded view-direction channels (+ zero pad to 64)
+        uint8_t* g = a.encdir + (size_t)tile * kChunk;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint32_t hi[4] = {0u, 0u, 0u, 0u}, lo[4] = {0u, 0u, 0u, 0u};
+          if (j < 4 && valid) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) Split<FMT>::apply(senc[8 * j + 2 * q], senc[8 * j + 2 * q + 1], hi[q], lo[q]);
+          }
+          uint8_t* q = g + img_off(row, j);
+          *reinterpret_cast<uint4*>(q) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(q + kPlane) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      }
+      // dZ_dir = (d rgb_pre . W_rgb) masked by the dir layer's ReLU (networks.py:221-222)
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint8_t* g = a.dzdir + (size_t)(tile * 2 + c) * kChunk;
+        const uint8_t* m = a.stash_dir + (size_t)(tile * 2 + c) * kChunk;
+#pragma unroll 2
+        for (int j = 0; j < 8; ++j) {
+          const size_t off = img_off(row, j);
+          const uint4 mk = *reinterpret_cast<const uint4*>(m + off);
+          const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int n = 64 * c + 8 * j + 2 * q;
+            float d0 = drgb[0] * swr[n] + drgb[1] * swr[128 + n] + drgb[2] * swr[256 + n];
+            float d1 = drgb[0] * swr[n + 1] + drgb[1] * swr[128 + n + 1] + drgb[2] * swr[256 + n + 1];
+            if ((mw[q] & 0x7fffu) == 0u) d0 = 0.f;
+            if ((mw[q] & 0x7fff0000u) == 0u) d1 = 0.f;
+            Split<FMT>::apply(d0, d1, hi[q], lo[q]);
+          }
+          *reinterpret_cast<uint4*>(g + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(g + off + kPlane) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// shared pieces of the two GEMM kernels
+// ---------------------------------------------------------------------------
+constexpr int kGemmThreads = 192;     // warp 0 producer, warp 1 MMA issue, warps 2-5 epilogue
+constexpr int kSlotBytes = 98304;
+constexpr int kSmSlots = 0;
+constexpr int kSmAux = 2 * kSlotBytes;            // 196608: w_sigma (dx) / tile of ones (dw), 2 KB
+constexpr int kSmGBar = kSmAux + 2048;
+constexpr int kSmGTmem = kSmGBar + 16 * 8;
+constexpr int kSmemGemmBytes = kSmGTmem + 16;
+enum { G_FULL = 0, G_EMPTY = 2, G_ACCFULL = 4, G_ACCEMPTY = 6 };
+
+// K-major SWIZZLE_128B descriptor (rows of 128 B, 8-row groups 1024 B apart)
+__device__ __forceinline__ uint64_t kmajor_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// MN-major SWIZZLE_128B descriptor over the same rows: a row is one k (point), its 128 B hold 64
+// consecutive M/N indices (features); 8-k groups are 1024 B apart (SBO), 64-feature blocks `lbo` bytes
+// apart (LBO).  Canonical form ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units.
+__device__ __forceinline__ uint64_t mnmajor_desc(uint32_t saddr, uint32_t lbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) | (64ull << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+__host__ __device__ constexpr uint32_t gemm_idesc(int fmt, int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t gemm_prologue(uint8_t* sm, uint32_t sm_base, int accempty_count) {
+  if (sm_base & 1023u) { if (threadIdx.x == 0) printf("[nsr_train] dynamic smem base %u not 1024-aligned\n", sm_base); __trap(); }
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    const uint32_t bar = sm_base + kSmGBar;
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar + 8 * (G_FULL + i), 1); mbar_init(bar + 8 * (G_EMPTY + i), 1);
+      mbar_init(bar + 8 * (G_ACCFULL + i), 1); mbar_init(bar + 8 * (G_ACCEMPTY + i), accempty_count);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sm_base + kSmGTmem), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  return *reinterpret_cast<volatile uint32_t*>(sm + kSmGTmem);
+}
+__device__ __forceinline__ void gemm_epilogue_free(uint32_t tmem) {
+  tc_fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+// ---------------------------------------------------------------------------
+// k_tg_dx: out = mask . (A . Wt^T [+ dsig x wsig])   per 128-point tile
+// ---------------------------------------------------------------------------
+struct DxArgs {
+  const uint8_t* a_img; int nkc;        // [n_tiles][nkc][32 KB]   dZ of this layer (K = its output features)
+  const uint8_t* wt_img;                // [nkc][64 KB]            transposed weights (rows = input features)
+  uint8_t* out_img;                     // [n_tiles][4][32 KB]     dZ of the previous layer
+  const uint8_t* mask_img;              // [n_tiles][4][32 KB]     stashed activation whose ReLU gates the output, or null
+  const float* dsig; const float* wsig; // rank-1 term of the sigma head (final layer only), or null
+  long long n_tiles;
+};
+
+template <int FMT>
+__global__ void __launch_bounds__(kGemmThreads, 1) k_tg_dx(const DxArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* sm = smem_raw;
+  const uint32_t sm_base = smem_u32(sm);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long my_tiles = (a.n_tiles > blockIdx.x) ? (a.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  if (a.wsig) for (int i = threadIdx.x; i < 256; i += kGemmThreads) reinterpret_cast<float*>(sm + kSmAux)[i] = a.wsig[i];
+  const uint32_t tmem = gemm_prologue(sm, sm_base, 4);
+  const uint32_t bar = sm_base + kSmGBar;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      uint32_t n = 0;
+      for (long long it = 0; it < my_tiles; ++it) {
+        const long long tile = blockIdx.x + it * (long long)gridDim.x;
+        for (int c = 0; c < a.nkc; ++c, ++n) {
+          const uint32_t slot = n & 1u, par = (n >> 1) & 1u;
+          mbar_wait(bar + 8 * (G_EMPTY + slot), par ^ 1u);
+          const uint32_t full = bar + 8 * (G_FULL + slot);
+          const uint32_t dst = sm_base + kSmSlots + slot * kSlotBytes;
+          mbar_expect_tx(full, kSlotBytes);
+          bulk_copy_g2s(dst, a.a_img + ((size_t)tile * a.nkc + c) * kChunk, kChunk, full);
+          bulk_copy_g2s(dst + 32768, a.wt_img + (size_t)c * kWtChunkBytes, 32768, full);
+          bulk_copy_g2s(dst + 65536, a.wt_img + (size_t)c * kWtChunkBytes + 32768, 32768, full);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc = gemm_idesc(FMT, 128, 256, 0, 0);
+      uint32_t n = 0;
+      for (long long it = 0; it < my_tiles; ++it) {
+        const uint32_t buf = (uint32_t)(it & 1);
+        mbar_wait(bar + 8 * (G_ACCEMPTY + buf), (uint32_t)(((it >> 1) & 1) ^ 1));
+        tc_fence_after();
+        const uint32_t d = tmem + 256u * buf;
+        for (int c = 0; c < a.nkc; ++c, ++n) {
+          const uint32_t slot = n & 1u, par = (n >> 1) & 1u;
+          mbar_wait(bar + 8 * (G_FULL + slot), par);
+          tc_fence_after();
+          const uint32_t sa = sm_base + kSmSlots + slot * kSlotBytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ah = kmajor_desc(sa + 32 * k), al = kmajor_desc(sa + kPlane + 32 * k);
+            const uint64_t bh = kmajor_desc(sa + 32768 + 32 * k), bl = kmajor_desc(sa + 65536 + 32 * k);
+            mma_ss(d, ah, bh, idesc, (c | k) ? 1u : 0u);
+            mma_ss(d, al, bh, idesc, 1u);
+            mma_ss(d, ah, bl, idesc, 1u);
+          }
+          tc_commit(bar + 8 * (G_EMPTY + slot));
+        }
+        tc_commit(bar + 8 * (G_ACCFULL + buf));
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int row = 32 * q + lane, r7 = lane & 7;
+    const uint32_t tlane = tmem + ((uint32_t)(32 * q) << 16);
+    const float* wsig = reinterpret_cast<const float*>(sm + kSmAux);
+    for (long long it = 0; it < my_tiles; ++it) {
+      const uint32_t buf = (uint32_t)(it & 1);
+      const long long tile = blockIdx.x + it * (long long)gridDim.x;
+      mbar_wait(bar + 8 * (G_ACCFULL + buf), (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      const float ds = a.dsig ? a.dsig[tile * kT + row] : 0.f;
+#pragma unroll 1
+      for (int cc = 0; cc < 8; ++cc) {
+        uint32_t r[32];
+        TMEM_LD32(tlane + 256u * buf + 32u * (uint32_t)cc, r);
+        tc_wait_ld();
+        const size_t cbase = ((size_t)tile * 4 + (size_t)(cc >> 1)) * kChunk + (size_t)row * 128;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const size_t off = cbase + (size_t)((((cc & 1) * 4 + jj) ^ r7) << 4);
+          uint32_t mw[4] = {0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u};
+          if (a.mask_img) { const uint4 mk = *reinterpret_cast<const uint4*>(a.mask_img + off); mw[0] = mk.x; mw[1] = mk.y; mw[2] = mk.z; mw[3] = mk.w; }
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float v0 = __uint_as_float(r[8 * jj + 2 * e]), v1 = __uint_as_float(r[8 * jj + 2 * e + 1]);
+            if (a.wsig) { v0 = fmaf(ds, wsig[32 * cc + 8 * jj + 2 * e], v0); v1 = fmaf(ds, wsig[32 * cc + 8 * jj + 2 * e + 1], v1); }
+            if ((mw[e] & 0x7fffu) == 0u) v0 = 0.f;
+            if ((mw[e] & 0x7fff0000u) == 0u) v1 = 0.f;
+            Split<FMT>::apply(v0, v1, hi[e], lo[e]);
+          }
+          *reinterpret_cast<uint4*>(a.out_img + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(a.out_img + off + kPlane) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar + 8 * (G_ACCEMPTY + buf));
+    }
+  }
+  gemm_epilogue_free(tmem);
+}
+
+// ---------------------------------------------------------------------------
+// k_tg_dw: partial[split][m][n] = sum over this CTA's tiles of A[p][m] * B[p][n]; bias partial = sum A[p][m]
+// ---------------------------------------------------------------------------
+struct DwJob {
+  const uint8_t* a_img; int a_cpt;      // A image and its chunks per tile
+  int a_blk0, a_blk1;                   // chunk indices giving output rows 0..63 and 64..127
+  float* part;                          // [n_split][128][N]
+  float* part_bias;                     // [n_split][128]
+};
+struct DwArgs {
+  DwJob job[4];
+  const uint8_t* b_img; int b_cpt; int b_chunk0; int nB;    // N = 64 * nB
+  long long n_tiles; int n_split;
+};
+
+template <int FMT>
+__global__ void __launch_bounds__(kGemmThreads, 1) k_tg_dw(const DwArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* sm = smem_raw;
+  const uint32_t sm_base = smem_u32(sm);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const DwJob& J = a.job[blockIdx.y];
+  const int split = blockIdx.x;
+  const long long my_tiles = (a.n_tiles > split) ? (a.n_tiles - split + a.n_split - 1) / a.n_split : 0;
+  const int N = 64 * a.nB;
+  {   // a 16-row K-major tile of ones for the bias-gradient MMA
+    const uint32_t one2 = (FMT == 1) ? 0x3f803f80u : 0x3c003c00u;
+    for (int i = threadIdx.x; i < 512; i += kGemmThreads) reinterpret_cast<uint32_t*>(sm + kSmAux)[i] = one2;
+    fence_proxy_async();
+  }
+  const uint32_t tmem = gemm_prologue(sm, sm_base, 4);
+  const uint32_t bar = sm_base + kSmGBar;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      uint32_t n = 0;
+      const uint32_t bytes = (uint32_t)(4 + 2 * a.nB) * 8192u;
+      for (long long it = 0; it < my_tiles; ++it) {
+        const long long tile = split + it * (long long)a.n_split;
+        for (int half = 0; half < 2; ++half, ++n) {
+          const uint32_t slot = n & 1u, par = (n >> 1) & 1u;
+          mbar_wait(bar + 8 * (G_EMPTY + slot), par ^ 1u);
+          const uint32_t full = bar + 8 * (G_FULL + slot);
+          const uint32_t dst = sm_base + kSmSlots + slot * kSlotBytes;
+          mbar_expect_tx(full, bytes);
+          for (int b = 0; b < 2; ++b) {
+            const uint8_t* src = J.a_img + ((size_t)tile * J.a_cpt + (b ? J.a_blk1 : J.a_blk0)) * kChunk + (size_t)half * 8192;
+            bulk_copy_g2s(dst + b * 8192, src, 8192, full);
+            bulk_copy_g2s(dst + 16384 + b * 8192, src + kPlane, 8192, full);
+          }
+          for (int b = 0; b < a.nB; ++b) {
+            const uint8_t* src = a.b_img + ((size_t)tile * a.b_cpt + a.b_chunk0 + b) * kChunk + (size_t)half * 8192;
+            bulk_copy_g2s(dst + 32768 + b * 8192, src, 8192, full);
+            bulk_copy_g2s(dst + 65536 + b * 8192, src + kPlane, 8192, full);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc = gemm_idesc(FMT, 128, N, 1, 1);
+      const uint32_t idesc_b = gemm_idesc(FMT, 128, 16, 1, 0);
+      const uint64_t ones = kmajor_desc(sm_base + kSmAux);
+      uint32_t n = 0;
+      for (long long it = 0; it < my_tiles; ++it) {
+        for (int half = 0; half < 2; ++half, ++n) {
+          const uint32_t slot = n & 1u, par = (n >> 1) & 1u;
+          mbar_wait(bar + 8 * (G_FULL + slot), par);
+          tc_fence_after();
+          const uint32_t sa = sm_base + kSmSlots + slot * kSlotBytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t first = (n | (uint32_t)k) ? 1u : 0u;
+            const uint64_t ah = mnmajor_desc(sa + 2048 * k, 8192), al = mnmajor_desc(sa + 16384 + 2048 * k, 8192);
+            const uint64_t bh = mnmajor_desc(sa + 32768 + 2048 * k, 8192), bl = mnmajor_desc(sa + 65536 + 2048 * k, 8192);
+            mma_ss(tmem, ah, bh, idesc, first);
+            mma_ss(tmem, al, bh, idesc, 1u);
+            mma_ss(tmem, ah, bl, idesc, 1u);
+            mma_ss(tmem + 256u, ah, ones, idesc_b, first);
+            mma_ss(tmem + 256u, al, ones, idesc_b, 1u);
+          }
+          tc_commit(bar + 8 * (G_EMPTY + slot));
+        }
+      }
+      tc_commit(bar + 8 * (G_ACCFULL + 0));
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int row = 32 * q + lane;
+    const uint32_t tlane = tmem + ((uint32_t)(32 * q) << 16);
+    float* dst = J.part + ((size_t)split * 128 + row) * N;
+    if (my_tiles > 0) {
+      mbar_wait(bar + 8 * (G_ACCFULL + 0), 0u);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int cc = 0; cc < 2 * a.nB; ++cc) {
+      uint32_t r[32];
+      if (my_tiles > 0) { TMEM_LD32(tlane + 32u * (uint32_t)cc, r); tc_wait_ld(); }
+      else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) r[i] = 0u;
+      }
+#pragma unroll
+      for (int i = 0; i < 32; i += 4)
+        *reinterpret_cast<uint4*>(dst + 32 * cc + i) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
+    }
+    {
+      uint32_t r[32];
+      float b = 0.f;
+      if (my_tiles > 0) { TMEM_LD32(tlane + 256u, r); tc_wait_ld(); b = __uint_as_float(r[0]); }
+      J.part_bias[(size_t)split * 128 + row] = b;
+    }
+  }
+  gemm_epilogue_free(tmem);
+}
+
+// ---------------------------------------------------------------------------
+// k_grad_reduce: fixed-order sum of the per-CTA partials into the flat gradient
+// ---------------------------------------------------------------------------
+struct RedJob {
+  const float* part; const float* part_bias;
+  int n_split, N, row0, rows, cols, ld, col0;
+  long long dst, bias_dst;             // offsets into the flat gradient; bias_dst < 0: no bias
+};
+constexpr int kMaxRedJobs = 28;
+struct RedArgs { RedJob job[kMaxRedJobs]; int n_jobs; float* grad; };
+
+__global__ void __launch_bounds__(256) k_grad_reduce(const RedArgs a) {
+  const RedJob& J = a.job[blockIdx.y];
+  const int total = J.rows * J.cols;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int r = idx / J.cols, c = idx % J.cols;
+    const float* p = J.part + (size_t)(J.row0 + r) * J.N + c;
+    float s = 0.f;
+    for (int k = 0; k < J.n_split; ++k) s += p[(size_t)k * 128 * J.N];
+    a.grad[J.dst + (long long)r * J.ld + J.col0 + c] = s;
+  }
+  if (J.bias_dst >= 0) {
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < J.rows; r += gridDim.x * blockDim.x) {
+      float s = 0.f;
+      for (int k = 0; k < J.n_split; ++k) s += J.part_bias[(size_t)k * 128 + J.row0 + r];
+      a.grad[J.bias_dst + r] = s;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// loss gradient, clip coefficient, Adam
+// ---------------------------------------------------------------------------
+// box average + squared error + dL/d(hr) for lambda * mean((lr - target)^2)
+__global__ void __launch_bounds__(256)
+k_lr_loss_grad(const float* __restrict__ hr, const float* __restrict__ target, int64_t n_lr, int ss, float scale,
+               float* __restrict__ lr_out, float* __restrict__ g_hr, double* __restrict__ partials) {
+  const int64_t total = n_lr * 3;
+  double acc = 0.0;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = idx / 3;
+    const int c = (int)(idx % 3);
+    float sum = 0.f;
+    for (int k = 0; k < ss; ++k) sum = __fadd_rn(sum, hr[(p * ss + k) * 3 + c]);
+    const float lr = __fdiv_rn(sum, (float)ss);
+    if (lr_out) lr_out[idx] = lr;
+    const float d = __fsub_rn(lr, target[idx]);
+    acc += (double)__fmul_rn(d, d);
+    if (g_hr) {
+      const float g = scale * d;
+      for (int k = 0; k < ss; ++k) g_hr[(p * ss + k) * 3 + c] = g;
+    }
+  }
+  __shared__ double sh[256];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partials[blockIdx.x] = sh[0];
+}
+
+__global__ void k_loss_final(const double* __restrict__ partials, int n_blocks, int64_t n_elems, float lambda,
+                             float* __restrict__ metrics) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < n_blocks; ++i) s += partials[i];
+    const float mse = (float)(s / (double)n_elems);
+    metrics[0] = mse * lambda;                 // loss term (criterions.py:7-15 times lambda_*_mse)
+    metrics[1] = -10.f * log10f(mse);          // criterions.py:36
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_sqnorm_partial(const float* __restrict__ a, const float* __restrict__ b, int64_t n, double* __restrict__ partials) {
+  double acc = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float x = a[i];
+    acc += (double)x * (double)x;
+    if (b) { const float y = b[i]; acc += (double)y * (double)y; }
+  }
+  __shared__ double sh[256];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partials[blockIdx.x] = sh[0];
+}
+
+__global__ void k_clip_final(const double* __restrict__ partials, int n_blocks, float max_norm, float* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < n_blocks; ++i) s += partials[i];
+    const float total = (float)sqrt(s);
+    out[0] = fminf(max_norm / (total + 1e-6f), 1.f);   // nn.utils.clip_grad_norm_
+    out[1] = total;
+  }
+}
+
+constexpr int kMaxParams = 40;
+struct AdamArgs {
+  float* p[kMaxParams];
+  long long off[kMaxParams + 1];
+  int n;
+  const float* grad; float* m; float* v;
+  float step_size, bc2_sqrt, beta1, beta2, eps;
+  const float* clip_coef;   // device scalar or null
+  float clip_value;         // > 0: clamp gradients to [-v, v]
+};
+
+__global__ void __launch_bounds__(256) k_adam(const AdamArgs a) {
+  const long long total = a.off[a.n];
+  const float coef = a.clip_coef ? *a.clip_coef : 1.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int t = 0;
+    while (i >= a.off[t + 1]) ++t;
+    float g = a.grad[i];
+    if (a.clip_coef) g = __fmul_rn(g, coef);
+    if (a.clip_value > 0.f) g = fminf(fmaxf(g, -a.clip_value), a.clip_value);
+    float m = a.m[i], v = a.v[i];
+    m = __fadd_rn(m, __fmul_rn(1.f - a.beta1, __fsub_rn(g, m)));                 // exp_avg.lerp_(grad, 1 - beta1)
+    v = __fadd_rn(__fmul_rn(v, a.beta2), __fmul_rn(__fmul_rn(1.f - a.beta2, g), g));   // mul_(beta2).addcmul_(g, g, 1 - beta2)
+    a.m[i] = m; a.v[i] = v;
+    const float denom = __fadd_rn(__fdiv_rn(sqrtf(v), a.bc2_sqrt), a.eps);
+    float* p = a.p[t] + (i - a.off[t]);
+    *p = __fadd_rn(*p, __fmul_rn(-a.step_size, __fdiv_rn(m, denom)));            // addcdiv_(m, denom, -step_size)
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static int tfail(NsrHandle_* h, int code, const std::string& msg) { h->err = msg; return code; }
+#define NSR_TCUDA(h, expr)                                                                    \
+  do {                                                                                        \
+    cudaError_t e__ = (expr);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      return tfail(h, NSR_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));      \
+  } while (0)
+
+static size_t al256(size_t x) { return (x + 255) / 256 * 256; }
+static int fmt_of(const NsrHandle_* h) { return h->cfg.precision == NSR_PREC_FP16X3_TC ? 0 : 1; }
+
+struct TrainWs {
+  // per pass (0 coarse, 1 fine)
+  size_t enc[2], hh[2], dir[2], raw[2], z[2];
+  // shared by the two backward passes
+  size_t dhead, encdir, dzdir, g0, g1, dsig, part;
+  size_t part_region;       // bytes of one dW launch's partial region
+  size_t total;
+  long long tiles[2];
+  int S[2];
+};
+
+static TrainWs train_layout(const NsrHandle_* h, int64_t n) {
+  TrainWs L{};
+  L.S[0] = h->cfg.n_coarse; L.S[1] = h->cfg.n_coarse + h->cfg.n_importance;
+  size_t off = 0;
+  for (int w = 0; w < 2; ++w) {
+    const int rpt = kT / L.S[w];
+    L.tiles[w] = (n + rpt - 1) / rpt;
+    const size_t t = (size_t)L.tiles[w];
+    L.enc[w] = off; off += t * kChunk;
+    L.hh[w] = off; off += 9 * t * 4 * kChunk;
+    L.dir[w] = off; off += t * 2 * kChunk;
+    L.raw[w] = off; off += al256((size_t)n * L.S[w] * 4 * sizeof(float));
+    L.z[w] = off; off += al256((size_t)n * L.S[w] * sizeof(float));
+  }
+  const size_t T = (size_t)(L.tiles[0] > L.tiles[1] ? L.tiles[0] : L.tiles[1]);
+  L.dhead = off; off += T * kChunk;
+  L.encdir = off; off += T * kChunk;
+  L.dzdir = off; off += T * 2 * kChunk;
+  L.g0 = off; off += T * 4 * kChunk;
+  L.g1 = off; off += T * 4 * kChunk;
+  L.dsig = off; off += al256(T * kT * sizeof(float));
+  L.part_region = al256((size_t)kMaxSplit * 128 * 257 * sizeof(float));
+  L.part = off; off += 12 * L.part_region;
+  L.total = off + 1024;
+  return L;
+}
+
+static cudaError_t launch_dx(NsrHandle_* h, const DxArgs& a, cudaStream_t st) {
+  if (a.n_tiles == 0) return cudaSuccess;
+  const int grid = (int)(a.n_tiles < h->sm_count ? a.n_tiles : h->sm_count);
+  cudaError_t e;
+  if (fmt_of(h) == 1) {
+    e = cudaFuncSetAttribute(k_tg_dx<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemGemmBytes);
+    if (e != cudaSuccess) return e;
+    k_tg_dx<1><<<grid, kGemmThreads, kSmemGemmBytes, st>>>(a);
+  } else {
+    e = cudaFuncSetAttribute(k_tg_dx<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemGemmBytes);
+    if (e != cudaSuccess) return e;
+    k_tg_dx<0><<<grid, kGemmThreads, kSmemGemmBytes, st>>>(a);
+  }
+  h->launches += 1;
+  return cudaGetLastError();
+}
+
+static cudaError_t launch_dw(NsrHandle_* h, const DwArgs& a, int n_jobs, cudaStream_t st) {
+  if (a.n_tiles == 0 || n_jobs == 0) return cudaSuccess;
+  const dim3 grid((unsigned)a.n_split, (unsigned)n_jobs);
+  cudaError_t e;
+  if (fmt_of(h) == 1) {
+    e = cudaFuncSetAttribute(k_tg_dw<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemGemmBytes);
+    if (e != cudaSuccess) return e;
+    k_tg_dw<1><<<grid, kGemmThreads, kSmemGemmBytes, st>>>(a);
+  } else {
+    e = cudaFuncSetAttribute(k_tg_dw<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemGemmBytes);
+    if (e != cudaSuccess) return e;
+    k_tg_dw<0><<<grid, kGemmThreads, kSmemGemmBytes, st>>>(a);
+  }
+  h->launches += 1;
+  return cudaGetLastError();
+}
+
+// flat-gradient offsets (state_dict order)
+static std::vector<long long> grad_offsets(const NsrHandle_* h) {
+  std::vector<long long> off(h->param_numel.size() + 1, 0);
+  for (size_t i = 0; i < h->param_numel.size(); ++i) off[i + 1] = off[i] + h->param_numel[i];
+  return off;
+}
+
+// Builder for one net's dW launches: collects the reduce jobs while launching the GEMMs.
+struct DwPlanner {
+  NsrHandle_* h; cudaStream_t st; long long n_tiles; char* part_base; size_t region; int launch_idx = 0;
+  RedArgs red{};
+  cudaError_t err = cudaSuccess;
+  struct JobSpec { const uint8_t* a_img; int a_cpt, blk0, blk1; int row0, rows; long long dst; int ld, col0; long long bias_dst; };
+  void launch(const uint8_t* b_img, int b_cpt, int b_chunk0, int nB, int cols, const JobSpec* js, int n_jobs) {
+    if (err != cudaSuccess) return;
+    DwArgs a{};
+    a.b_img = b_img; a.b_cpt = b_cpt; a.b_chunk0 = b_chunk0; a.nB = nB; a.n_tiles = n_tiles;
+    int n_split = h->sm_count / n_jobs;
+    if (n_split > kMaxSplit / n_jobs) n_split = kMaxSplit / n_jobs;
+    if (n_split > n_tiles) n_split = (int)n_tiles;
+    if (n_split < 1) n_split = 1;
+    a.n_split = n_split;
+    const int N = 64 * nB;
+    char* reg = part_base + (size_t)launch_idx * region;
+    size_t off = 0;
+    for (int j = 0; j < n_jobs; ++j) {
+      a.job[j].a_img = js[j].a_img; a.job[j].a_cpt = js[j].a_cpt; a.job[j].a_blk0 = js[j].blk0; a.job[j].a_blk1 = js[j].blk1;
+      a.job[j].part = reinterpret_cast<float*>(reg + off); off += (size_t)n_split * 128 * N * sizeof(float);
+      a.job[j].part_bias = reinterpret_cast<float*>(reg + off); off += (size_t)n_split * 128 * sizeof(float);
+      RedJob& R = red.job[red.n_jobs++];
+      R.part = a.job[j].part; R.part_bias = a.job[j].part_bias; R.n_split = n_split; R.N = N;
+      R.row0 = js[j].row0; R.rows = js[j].rows; R.cols = cols; R.ld = js[j].ld; R.col0 = js[j].col0;
+      R.dst = js[j].dst; R.bias_dst = js[j].bias_dst;
+    }
+    err = launch_dw(h, a, n_jobs, st);
+    ++launch_idx;
+  }
+};
+
+// Backward of ONE net over the stash of one pass.  g_* are dL/d(outputs) of that pass.
+static int backward_net(NsrHandle_* h, int which, const float* rays, int64_t n, int stride, const float* noise,
+                        const float* g_rgb, const float* g_depth, const float* g_opa, float* grad_flat,
+                        char* ws, const TrainWs& L, cudaStream_t st) {
+  const int S = L.S[which];
+  const long long tiles = L.tiles[which];
+  const NetImages& net = h->net[which];
+  const std::vector<long long> off = grad_offsets(h);
+  uint8_t* enc = (uint8_t*)(ws + L.enc[which]);
+  uint8_t* hh = (uint8_t*)(ws + L.hh[which]);
+  uint8_t* dir = (uint8_t*)(ws + L.dir[which]);
+  uint8_t* dhead = (uint8_t*)(ws + L.dhead);
+  uint8_t* encdir = (uint8_t*)(ws + L.encdir);
+  uint8_t* dzdir = (uint8_t*)(ws + L.dzdir);
+  uint8_t* G[2] = {(uint8_t*)(ws + L.g0), (uint8_t*)(ws + L.g1)};
+  float* dsig = (float*)(ws + L.dsig);
+  auto h_layer = [&](int l) { return hh + (size_t)(l - 1) * (size_t)tiles * 4 * kChunk; };   // l = 1..8 activations, 9 = feat
+
+  // ---- compositing / activation / rgb-head backward ----
+  {
+    RenderBwdArgs a{};
+    a.rp = h->rp; a.tabs = h->d_tables; a.rays = rays; a.n_rays = n; a.ray_stride = stride;
+    a.z = (const float*)(ws + L.z[which]); a.raw = (const float*)(ws + L.raw[which]);
+    a.noise = (h->cfg.noise_std > 0.f) ? noise : nullptr; a.S = S;
+    a.g_rgb = g_rgb; a.g_depth = g_depth; a.g_opacity = g_opa;
+    a.w_rgb = net.tc_consts + kcWrgb; a.stash_dir = dir;
+    a.dhead = dhead; a.dzdir = dzdir; a.encdir = encdir; a.dsig = dsig; a.n_tiles = tiles;
+    const long long slots = tiles * (kT / S);
+    int grid = (int)((slots + 3) / 4);
+    if (grid > h->sm_count * 8) grid = h->sm_count * 8;
+    const size_t smem = (size_t)(384 + 4 * (10 * S + 32)) * sizeof(float);
+    if (fmt_of(h) == 1) k_render_bwd<1><<<grid, 128, smem, st>>>(a);
+    else k_render_bwd<0><<<grid, 128, smem, st>>>(a);
+    h->launches += 1;
+    NSR_TCUDA(h, cudaGetLastError());
+  }
+
+  DwPlanner P{h, st, tiles, ws + L.part, L.part_region};
+  P.red.grad = grad_flat;
+  const WtTable WT = build_wt_table(h->rp.ch_dir, h->cfg.no_dir != 0);
+  auto wt = [&](int idx) { return net.wt_image + (size_t)WT.l[idx].chunk0 * kWtChunkBytes; };
+  using JS = DwPlanner::JobSpec;
+  const int ld_dir = h->cfg.no_dir ? 256 : 256 + h->rp.ch_dir;
+
+  // ---- heads and dir layer ----
+  {   // rgb.0: dW = dHead[:,1:4]^T . dir_act, db
+    const JS js[1] = {{dhead, 1, 0, 0, 1, 3, off[22], 128, 0, off[23]}};
+    P.launch(dir, 2, 0, 2, 128, js, 1);
+  }
+  {   // dir_encoding.0 (feat part, bias) and its view-direction columns
+    const JS js[1] = {{dzdir, 2, 0, 1, 0, 128, off[18], ld_dir, 0, off[19]}};
+    P.launch(h_layer(9), 4, 0, 4, 256, js, 1);
+    if (!h->cfg.no_dir) {
+      const JS jd[1] = {{dzdir, 2, 0, 1, 0, 128, off[18], ld_dir, 256, -1}};
+      P.launch(encdir, 1, 0, 1, h->rp.ch_dir, jd, 1);
+    }
+  }
+  {   // d feat = dZ_dir . W_dir[:, :256]   (xyz_encoding_final has no activation: no mask)
+    DxArgs a{};
+    a.a_img = dzdir; a.nkc = 2; a.wt_img = wt(0); a.out_img = G[0]; a.mask_img = nullptr; a.n_tiles = tiles;
+    NSR_TCUDA(h, launch_dx(h, a, st));
+  }
+  {   // xyz_encoding_final: dW = d feat^T . h8 ; sigma head: dW = d sigma^T . h8, db
+    const JS js[3] = {{G[0], 4, 0, 1, 0, 128, off[16], 256, 0, off[17]},
+                      {G[0], 4, 2, 3, 0, 128, off[16] + 128 * 256, 256, 0, off[17] + 128},
+                      {dhead, 1, 0, 0, 0, 1, off[20], 256, 0, off[21]}};
+    P.launch(h_layer(8), 4, 0, 4, 256, js, 3);
+  }
+  {   // dZ_8 = (d feat . W_final + d sigma x w_sigma) . [h8 > 0]
+    DxArgs a{};
+    a.a_img = G[0]; a.nkc = 4; a.wt_img = wt(1); a.out_img = G[1]; a.mask_img = h_layer(8);
+    a.dsig = dsig; a.wsig = net.tc_consts + kcWsig; a.n_tiles = tiles;
+    NSR_TCUDA(h, launch_dx(h, a, st));
+  }
+  // ---- trunk: L = 8 .. 1 ; dZ_L lives in G[cur] ----
+  int cur = 1;
+  for (int Lyr = 8; Lyr >= 1; --Lyr) {
+    const int pw = 2 * (Lyr - 1), pb = pw + 1;
+    const uint8_t* dz = G[cur];
+    if (Lyr == 1) {          // input = enc (63 columns)
+      const JS js[2] = {{dz, 4, 0, 1, 0, 128, off[pw], 63, 0, off[pb]}, {dz, 4, 2, 3, 0, 128, off[pw] + 128 * 63, 63, 0, off[pb] + 128}};
+      P.launch(enc, 1, 0, 1, 63, js, 2);
+    } else if (Lyr == 5) {   // input = cat(enc, h4)
+      const JS js[2] = {{dz, 4, 0, 1, 0, 128, off[pw], 319, 63, off[pb]}, {dz, 4, 2, 3, 0, 128, off[pw] + 128 * 319, 319, 63, off[pb] + 128}};
+      P.launch(h_layer(4), 4, 0, 4, 256, js, 2);
+      const JS je[2] = {{dz, 4, 0, 1, 0, 128, off[pw], 319, 0, -1}, {dz, 4, 2, 3, 0, 128, off[pw] + 128 * 319, 319, 0, -1}};
+      P.launch(enc, 1, 0, 1, 63, je, 2);
+    } else {
+      const JS js[2] = {{dz, 4, 0, 1, 0, 128, off[pw], 256, 0, off[pb]}, {dz, 4, 2, 3, 0, 128, off[pw] + 128 * 256, 256, 0, off[pb] + 128}};
+      P.launch(h_layer(Lyr - 1), 4, 0, 4, 256, js, 2);
+    }
+    if (P.err != cudaSuccess) return tfail(h, NSR_ERR_CUDA, std::string("dW launch: ") + cudaGetErrorString(P.err));
+    if (Lyr >= 2) {          // dZ_{L-1} = (dZ_L . W_L[:, h part]) . [h_{L-1} > 0]
+      DxArgs a{};
+      a.a_img = dz; a.nkc = 4; a.wt_img = wt(2 + (8 - Lyr)); a.out_img = G[cur ^ 1]; a.mask_img = h_layer(Lyr - 1); a.n_tiles = tiles;
+      NSR_TCUDA(h, launch_dx(h, a, st));
+      cur ^= 1;
+    }
+  }
+  if (P.err != cudaSuccess) return tfail(h, NSR_ERR_CUDA, std::string("dW launch: ") + cudaGetErrorString(P.err));
+  {
+    const dim3 grid(32, (unsigned)P.red.n_jobs);
+    k_grad_reduce<<<grid, 256, 0, st>>>(P.red);
+    h->launches += 1;
+    NSR_TCUDA(h, cudaGetLastError());
+  }
+  return NSR_OK;
+}
+
+}  // namespace nsr
+
+using namespace nsr;
+
+// ---------------------------------------------------------------------------
+// C ABI (include/nsr.h, training section)
+// ---------------------------------------------------------------------------
+static int train_supported(NsrHandle_* h) {
+  if (h->cfg.precision != NSR_PREC_BF16X3_TC && h->cfg.precision != NSR_PREC_FP16X3_TC)
+    return tfail(h, NSR_ERR_UNSUPPORTED, "training needs the split-precision tensor-core path (bf16x3 / fp16x3)");
+  if (h->cfg.n_importance <= 0) return tfail(h, NSR_ERR_UNSUPPORTED, "training needs N_importance > 0 (coarse + fine)");
+  if (h->cfg.no_dir) return tfail(h, NSR_ERR_UNSUPPORTED, "training with --no_dir is not supported");
+  return NSR_OK;
+}
+
+extern "C" int64_t nsr_grad_numel(const NsrHandle* h) {
+  if (!h) return 0;
+  int64_t s = 0;
+  for (int64_t v : h->param_numel) s += v;
+  return s;
+}
+
+extern "C" size_t nsr_train_workspace_bytes(const NsrHandle* h, int64_t n_rays) {
+  if (!h || n_rays < 0) return 0;
+  return train_layout(h, n_rays).total;
+}
+
+extern "C" int nsr_render_train(NsrHandle* h, const float* rays, int64_t n_rays, int ray_stride, const NsrRng* rng,
+                                const NsrOutputs* out, void* train_ws, size_t train_ws_bytes, NsrStream stream) {
+  if (!h) return NSR_ERR_INVALID_ARG;
+  int rc = train_supported(h);
+  if (rc) return rc;
+  if (!rays || !out || n_rays <= 0 || ray_stride < 8 || ray_stride < h->cfg.viewdir_offset + 3)
+    return tfail(h, NSR_ERR_INVALID_ARG, "nsr_render_train: bad argument");
+  if (!h->net[0].packed || !h->net[1].packed) return tfail(h, NSR_ERR_NOT_PACKED, "weights not packed");
+  const TrainWs L = train_layout(h, n_rays);
+  if (!train_ws || train_ws_bytes < L.total) return tfail(h, NSR_ERR_WORKSPACE, "train workspace too small: need " + std::to_string(L.total));
+  NSR_TCUDA(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)(((uintptr_t)train_ws + 255) & ~(uintptr_t)255);
+  const NsrRng none{};
+  const NsrRng& R = rng ? *rng : none;
+  const bool noisy = h->cfg.noise_std > 0.f;
+  for (int w = 0; w < 2; ++w) {
+    TcPassArgs a{};
+    a.rays = rays; a.n_rays = n_rays; a.ray_stride = ray_stride; a.S = L.S[w];
+    a.z_in = w ? (const float*)(ws + L.z[1]) : nullptr;
+    a.u_jitter = w ? nullptr : R.u_coarse;
+    a.noise = noisy ? (w ? R.noise_fine : R.noise_coarse) : nullptr;
+    a.u_resample = w ? nullptr : R.u_fine;
+    a.do_resample = w ? 0 : 1;
+    a.comp_rgb = w ? out->fine_comp_rgbs : out->coarse_comp_rgbs;
+    a.depth = w ? out->fine_depth : out->coarse_depth;
+    a.opacity = w ? out->fine_opacity : out->coarse_opacity;
+    a.weights = w ? out->fine_weights : out->coarse_weights;
+    a.raw = (float*)(ws + L.raw[w]);
+    a.z_next = w ? nullptr : (float*)(ws + L.z[1]);
+    a.z_out = w ? nullptr : (float*)(ws + L.z[0]);
+    a.stash_enc = (uint8_t*)(ws + L.enc[w]); a.stash_h = (uint8_t*)(ws + L.hh[w]); a.stash_dir = (uint8_t*)(ws + L.dir[w]);
+    a.trace = nullptr; a.debug_flags = 0;
+    NSR_TCUDA(h, tc_pass(h, w, a, st));
+  }
+  if (out->z_fine)
+    NSR_TCUDA(h, cudaMemcpyAsync(out->z_fine, ws + L.z[1], (size_t)n_rays * L.S[1] * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return NSR_OK;
+}
+
+extern "C" int nsr_backward(NsrHandle* h, const float* rays, int64_t n_rays, int ray_stride, const NsrRng* rng,
+                            const NsrOutGrads* g, float* grad_coarse, float* grad_fine, void* train_ws,
+                            size_t train_ws_bytes, NsrStream stream) {
+  if (!h) return NSR_ERR_INVALID_ARG;
+  int rc = train_supported(h);
+  if (rc) return rc;
+  if (!rays || !g || !grad_coarse || !grad_fine || n_rays <= 0) return tfail(h, NSR_ERR_INVALID_ARG, "nsr_backward: bad argument");
+  const TrainWs L = train_layout(h, n_rays);
+  if (!train_ws || train_ws_bytes < L.total) return tfail(h, NSR_ERR_WORKSPACE, "train workspace too small: need " + std::to_string(L.total));
+  NSR_TCUDA(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)(((uintptr_t)train_ws + 255) & ~(uintptr_t)255);
+  const NsrRng none{};
+  const NsrRng& R = rng ? *rng : none;
+  const int64_t numel = nsr_grad_numel(h);
+  if (g->coarse_comp_rgbs) {
+    rc = backward_net(h, 0, rays, n_rays, ray_stride, R.noise_coarse, g->coarse_comp_rgbs, g->coarse_depth, g->coarse_opacity,
+                      grad_coarse, ws, L, st);
+    if (rc) return rc;
+  } else {
+    NSR_TCUDA(h, cudaMemsetAsync(grad_coarse, 0, (size_t)numel * sizeof(float), st));
+  }
+  if (g->fine_comp_rgbs) {
+    rc = backward_net(h, 1, rays, n_rays, ray_stride, R.noise_fine, g->fine_comp_rgbs, g->fine_depth, g->fine_opacity,
+                      grad_fine, ws, L, st);
+    if (rc) return rc;
+  } else {
+    NSR_TCUDA(h, cudaMemsetAsync(grad_fine, 0, (size_t)numel * sizeof(float), st));
+  }
+  return NSR_OK;
+}
+
+extern "C" int nsr_lr_loss_grad(NsrHandle* h, const float* hr_rgb, const float* target_lr, int64_t n_lr, int s, float lambda,
+                                float* lr_rgb_out, float* metrics_out, float* g_hr_out, NsrStream stream) {
+  if (!h) return NSR_ERR_INVALID_ARG;
+  if (!hr_rgb || !target_lr || !metrics_out || n_lr <= 0 || s < 1) return tfail(h, NSR_ERR_INVALID_ARG, "nsr_lr_loss_grad: bad argument");
+  NSR_TCUDA(h, cudaSetDevice(h->cfg.device));
+  int64_t blocks64 = (n_lr * 3 + 255) / 256;
+  const int blocks = (int)(blocks64 > 1024 ? 1024 : blocks64);
+  // d/d hr of lambda * mean((lr - t)^2): 2 (lr - t) lambda / (3 n_lr) / s^2
+  const float scale = (float)(2.0 * (double)lambda / ((double)n_lr * 3.0) / (double)(s * s));
+  k_lr_loss_grad<<<blocks, 256, 0, (cudaStream_t)stream>>>(hr_rgb, target_lr, n_lr, s * s, scale, lr_rgb_out, g_hr_out, h->d_partials);
+  k_loss_final<<<1, 32, 0, (cudaStream_t)stream>>>(h->d_partials, blocks, n_lr * 3, lambda, metrics_out);
+  h->launches += 2;
+  NSR_TCUDA(h, cudaGetLastError());
+  return NSR_OK;
+}
+
+extern "C" int nsr_clip_coef(NsrHandle* h, const float* grad_a, const float* grad_b, int64_t numel, float max_norm,
+                             float* coef_out, NsrStream stream) {
+  if (!h) return NSR_ERR_INVALID_ARG;
+  if (!grad_a || !coef_out || numel <= 0 || !(max_norm > 0.f)) return tfail(h, NSR_ERR_INVALID_ARG, "nsr_clip_coef: bad argument");
+  NSR_TCUDA(h, cudaSetDevice(h->cfg.device));
+  const int blocks = 592;
+  k_sqnorm_partial<<<blocks, 256, 0, (cudaStream_t)stream>>>(grad_a, grad_b, numel, h->d_partials);
+  k_clip_final<<<1, 32, 0, (cudaStream_t)stream>>>(h->d_partials, blocks, max_norm, coef_out);
+  h->launches += 2;
+  NSR_TCUDA(h, cudaGetLastError());
+  return NSR_OK;
+}
+
+extern "C" int nsr_adam_step(NsrHandle* h, float* const* param_ptrs, int n_params, const float* grad_flat, float* exp_avg,
+                             float* exp_avg_sq, int64_t step, float lr, float beta1, float beta2, float eps,
+                             const float* clip_coef_dev, float clip_value, NsrStream stream) {
+  if (!h) return NSR_ERR_INVALID_ARG;
+  if (!param_ptrs || !grad_flat || !exp_avg || !exp_avg_sq || step < 1) return tfail(h, NSR_ERR_INVALID_ARG, "nsr_adam_step: bad argument");
+  if (n_params != (int)h->param_numel.size() || n_params > kMaxParams)
+    return tfail(h, NSR_ERR_INVALID_ARG, "nsr_adam_step: expected " + std::to_string(h->param_numel.size()) + " parameter tensors");
+  NSR_TCUDA(h, cudaSetDevice(h->cfg.device));
+  AdamArgs a{};
+  a.n = n_params;
+  a.off[0] = 0;
+  for (int i = 0; i < n_params; ++i) {
+    if (!param_ptrs[i]) return tfail(h, NSR_ERR_INVALID_ARG, "nsr_adam_step: null parameter pointer");
+    a.p[i] = param_ptrs[i];
+    a.off[i + 1] = a.off[i] + h->param_numel[i];
+  }
+  a.grad = grad_flat; a.m = exp_avg; a.v = exp_avg_sq;
+  // torch.optim.Adam (_single_tensor_adam): python-float scalars, rounded to fp32 at the tensor ops
+  const double bc1 = 1.0 - std::pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - std::pow((double)beta2, (double)step);
+  a.step_size = (float)((double)lr / bc1);
+  a.bc2_sqrt = (float)std::sqrt(bc2);
+  a.beta1 = beta1; a.beta2 = beta2; a.eps = eps;
+  a.clip_coef = clip_coef_dev; a.clip_value = clip_value;
+  const long long total = a.off[n_params];
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > h->sm_count * 8) blocks = h->sm_count * 8;
+  k_adam<<<blocks, 256, 0, (cudaStream_t)stream>>>(a);
+  h->launches += 1;
+  NSR_TCUDA(h, cudaGetLastError());
+  return NSR_OK;
+}
+
+// ---- test seams ----------------------------------------------------------------
+extern "C" int nsr_debug_pack_image(NsrHandle* h, const float* src, int64_t n_rows, int n_cols, int ld, void* image, NsrStream stream) {
+  if (!h) return NSR_ERR_INVALID_ARG;
+  if (!src || !image || n_rows <= 0 || n_cols <= 0 || n_cols % 64 || ld <= 0 || ld > n_cols)
+    return tfail(h, NSR_ERR_INVALID_ARG, "nsr_debug_pack_image: bad argument");
+  NSR_TCUDA(h, cudaSetDevice(h->cfg.device));
+  if (fmt_of(h) == 1) k_pack_image<1><<<h->sm_count * 4, 256, 0, (cudaStream_t)stream>>>(src, n_rows, n_cols, ld, (uint8_t*)image);
+  else k_pack_image<0><<<h->sm_count * 4, 256, 0, (cudaStream_t)stream>>>(src, n_rows, n_cols, ld, (uint8_t*)image);
+  h->launches += 1;
+  NSR_TCUDA(h, cudaGetLastError());
+  return NSR_OK;
+}
+
+extern "C" int nsr_debug_unpack_image(NsrHandle* h, const void* image, int64_t n_rows, int n_cols, int ld, float* dst, NsrStream stream) {
+  if (!h) return NSR_ERR_INVALID_ARG;
+  if (!dst || !image || n_rows <= 0 || n_cols <= 0 || n_cols % 64 || ld <= 0 || ld > n_cols)
+    return tfail(h, NSR_ERR_INVALID_ARG, "nsr_debug_unpack_image: bad argument");
+  NSR_TCUDA(h, cudaSetDevice(h->cfg.device));
+  if (fmt_of(h) == 1) k_unpack_image<1><<<h->sm_count * 4, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)image, n_rows, n_cols, ld, dst);
+  else k_unpack_image<0><<<h->sm_count * 4, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)image, n_rows, n_cols, ld, dst);
+  h->launches += 1;
+  NSR_TCUDA(h, cudaGetLastError());
+  return NSR_OK;
+}
+
+// out_img[rows,256] = mask . (a_img[rows, k_cols] . W[k_cols, ld][:, col0:col0+256] + dsig x wsig)
+// with W given as the transposed-weight image of net `which`, dX layer `layer_idx` (0 dir, 1 final, 2.. = L8..L2).
+extern "C" int nsr_debug_dx(NsrHandle* h, int which, int layer_idx, const void* a_img, void* out_img, const void* mask_img,
+                            const float* dsig, const float* wsig, int64_t n_rows, NsrStream stream) {
+  if (!h) return NSR_ERR_INVALID_ARG;
+  int rc = train_supported(h);
+  if (rc) return rc;
+  if (which < 0 || which > 1 || layer_idx < 0 || layer_idx >= kNumDxLayers || !a_img || !out_img || n_rows <= 0)
+    return tfail(h, NSR_ERR_INVALID_ARG, "nsr_debug_dx: bad argument");
+  if (!h->net[which].packed) return tfail(h, NSR_ERR_NOT_PACKED, "weights not packed");
+  NSR_TCUDA(h, cudaSetDevice(h->cfg.device));
+  const WtTable WT = build_wt_table(h->rp.ch_dir, h->cfg.no_dir != 0);
+  DxArgs a{};
+  a.a_img = (const uint8_t*)a_img; a.nkc = WT.l[layer_idx].n_out / 64;
+  a.wt_img = h->net[which].wt_image + (size_t)WT.l[layer_idx].chunk0 * kWtChunkBytes;
+  a.out_img = (uint8_t*)out_img; a.mask_img = (const uint8_t*)mask_img; a.dsig = dsig; a.wsig = wsig;
+  a.n_tiles = (n_rows + kT - 1) / kT;
+  NSR_TCUDA(h, launch_dx(h, a, (cudaStream_t)stream));
+  return NSR_OK;
+}
+
+// out[128, b_cols] = a_img[rows, blocks blk0|blk1]^T . b_img[rows, b_cols];  bias_out[128] = column sums of A.
+// scratch: >= 148*128*(b_cols+1)*4 bytes.
+extern "C" int nsr_debug_dw(NsrHandle* h, const void* a_img, int a_cols, int blk0, int blk1, const void* b_img, int b_cols,
+                            float* out, float* bias_out, int64_t n_rows, void* scratch, size_t scratch_bytes, NsrStream stream) {
+  if (!h) return NSR_ERR_INVALID_ARG;
+  int rc = train_supported(h);
+  if (rc) return rc;
+  if (!a_img || !b_img || !out || !bias_out || !scratch || a_cols % 64 || b_cols % 64 || b_cols < 64 || b_cols > 256 || n_rows <= 0 ||
+      blk0 < 0 || blk1 < 0 || blk0 >= a_cols / 64 || blk1 >= a_cols / 64)
+    return tfail(h, NSR_ERR_INVALID_ARG, "nsr_debug_dw: bad argument");
+  if (scratch_bytes < (size_t)kMaxSplit * 128 * (b_cols + 1) * sizeof(float)) return tfail(h, NSR_ERR_WORKSPACE, "nsr_debug_dw: scratch too small");
+  NSR_TCUDA(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  DwPlanner P{h, st, (n_rows + kT - 1) / kT, (char*)scratch, 0};
+  // flat "gradient": out rows then bias
+  P.red.grad = out;
+  const DwPlanner::JobSpec js[1] = {{(const uint8_t*)a_img, a_cols / 64, blk0, blk1, 0, 128, 0, b_cols, 0, -1}};
+  P.launch((const uint8_t*)b_img, b_cols / 64, 0, b_cols / 64, b_cols, js, 1);
+  if (P.err != cudaSuccess) return tfail(h, NSR_ERR_CUDA, std::string("dW launch: ") + cudaGetErrorString(P.err));
+  k_grad_reduce<<<dim3(32, 1), 256, 0, st>>>(P.red);
+  RedArgs rb = P.red;           // second pass: the bias partials into bias_out
+  rb.grad = bias_out;
+  rb.job[0].rows = 128; rb.job[0].cols = 0; rb.job[0].bias_dst = 0;
+  k_grad_reduce<<<dim3(1, 1), 256, 0, st>>>(rb);
+  h->launches += 2;
+  NSR_TCUDA(h, cudaGetLastError());
+  return NSR_OK;
+}

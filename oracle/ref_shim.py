@@ -45,9 +45,11 @@ def _install_stubs() -> None:
         sys.modules["imageio"] = types.ModuleType("imageio")
 
 
-def load_reference_model(model_name: str = "nerf_downX", extra_args=(), device: str = "cpu"):
+def load_reference_model(model_name: str = "nerf_downX", extra_args=(), device: str = "cpu", train: bool = False):
     """Return (model, opt): a reference NeRFDownXModel / NeRFModel on ``device``
-    in eval mode with kaiming-initialised nets (caller overwrites weights)."""
+    in eval mode with kaiming-initialised nets (caller overwrites weights).
+    train=True builds it the way train.py does (isTrain: the model creates its Adam optimiser,
+    models/nerf_downX_model.py:198-204) and leaves it in train mode."""
     if not reference_available():
         raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
     _install_stubs()
@@ -75,15 +77,25 @@ def load_reference_model(model_name: str = "nerf_downX", extra_args=(), device: 
     parser.add_argument("--point_chunk", type=int, default=2048 * 128)
     parser.add_argument("--lr", type=float, default=5e-4)
     parser.add_argument("--beta1", type=float, default=0.9)
+    # train flags read by optimize_parameters / the schedulers (options/train_options.py:33-55)
+    parser.add_argument("--grad_clip_val", type=float, default=0)
+    parser.add_argument("--grad_clip_type", type=str, default="norm")
+    parser.add_argument("--lr_policy", type=str, default="exp")
+    parser.add_argument("--lr_final", type=float, default=5e-6)
+    parser.add_argument("--n_epochs", type=int, default=20)
+    parser.add_argument("--n_epochs_decay", type=int, default=10)
     parser = Model.modify_commandline_options(parser)
     opt = parser.parse_args(list(extra_args))
-    opt.isTrain, opt.isTest, opt.isInfer = False, True, False
+    opt.isTrain, opt.isTest, opt.isInfer = (True, False, False) if train else (False, True, False)
     opt.device = torch.device(device)
     opt.n_gpus = 0 if device == "cpu" else 1
     opt.gpu_ids = [] if device == "cpu" else [0]
     opt.is_master = True
     model = Model(opt)
-    model.eval()
+    if train:
+        model.train()
+    else:
+        model.eval()
     return model, opt
 
 

@@ -1,0 +1,150 @@
+"""CPU oracle for the training step around the render hot path (scope row f-1).
+
+TEST INFRASTRUCTURE ONLY (see oracle/nerf_oracle.py header): imported by tests/, smoke() and the
+baseline legs of bench.py, never by nerf_sr_b200/.
+
+Restates, with plain torch CPU ops, what the reference does in one ``optimize_parameters`` call
+(models/nerf_downX_model.py:398-408):
+
+  forward()                       :316-319  (train mode: stratified jitter, sigma noise)
+  comp_low_res_output()           :326-353  (s x s box average of the composite colours)
+  calculate_losses()              :355-388  (lambda_c * MSE(coarse_lr, target) + lambda_f * MSE(fine_lr, target),
+                                             PSNR of both; the var / sr / ref terms are out of scope)
+  loss_tot.backward()             :390-396  (torch autograd through exactly the ops nerf_oracle restates;
+                                             the fine z-values use coarse_weights.detach(), :302)
+  clip_grad_norm_/clip_grad_value_:403-407
+  optimizer.step()                :408      (torch.optim.Adam, betas=(beta1, 0.999), eps 1e-8, :201-204)
+  scheduler (per epoch)           models/networks.py:102-118  ('linear' | 'exp' LambdaLR rules)
+
+Gradients are DEFINED by autograd over ``nerf_oracle.forward_rays`` -- the same definition the
+reference uses -- so the pin (oracle/make_golden_train.py) is bit-exact on CPU.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import nerf_oracle as O
+
+Tensor = torch.Tensor
+
+
+@dataclass
+class TrainConfig:
+    """Subset of the reference's train options the step reads (options/train_options.py:33-55,
+    models/nerf_model.py lambda_* flags)."""
+    lr: float = 5e-4
+    beta1: float = 0.9
+    beta2: float = 0.999
+    eps: float = 1e-8
+    lambda_coarse_mse: float = 1.0
+    lambda_fine_mse: float = 1.0
+    grad_clip_val: float = 0.0
+    grad_clip_type: str = "norm"        # norm | value
+    lr_policy: str = "exp"              # linear | exp
+    lr_final: float = 5e-6
+    n_epochs: int = 20
+    n_epochs_decay: int = 10
+
+
+def loss_and_grads(pc: Dict[str, Tensor], pf: Dict[str, Tensor], rays: Tensor, target_lr: Tensor,
+                   cfg: O.RenderConfig, tcfg: TrainConfig, rng: Optional[O.RenderRng] = None,
+                   s: int = 2, z_fine_override: Optional[Tensor] = None, extras: Optional[dict] = None):
+    """One forward + backward.  Returns (losses dict, grads_coarse dict, grads_fine dict, outputs dict).
+    target_lr: [N/s^2, 3].  Gradients are None-free: parameters the loss does not reach get zeros
+    (the reference leaves .grad = None for them; Adam then skips the parameter)."""
+    pc_r = {k: v.detach().clone().requires_grad_(True) for k, v in pc.items()}
+    pf_r = {k: v.detach().clone().requires_grad_(True) for k, v in pf.items()}
+    out = O.forward_rays(pc_r, pf_r, rays, cfg, rng, z_fine_override=z_fine_override, extras=extras)
+    lr_c = O.box_average(out["coarse_comp_rgbs"], s)                          # :337-338
+    loss_c = torch.nn.functional.mse_loss(lr_c, target_lr) * tcfg.lambda_coarse_mse   # :357
+    losses = {"coarse_mse": loss_c}
+    tot = loss_c
+    if cfg.N_importance > 0:
+        lr_f = O.box_average(out["fine_comp_rgbs"], s)                        # :343-344
+        loss_f = torch.nn.functional.mse_loss(lr_f, target_lr) * tcfg.lambda_fine_mse  # :359
+        losses["fine_mse"] = loss_f
+        tot = tot + loss_f                                                    # :362
+    losses["tot"] = tot
+    tot.backward()                                                            # :396
+    with torch.no_grad():                                                     # :379-384
+        losses["coarse_psnr"] = -10 * torch.log10(torch.mean((lr_c - target_lr) ** 2))
+        if cfg.N_importance > 0:
+            losses["fine_psnr"] = -10 * torch.log10(torch.mean((lr_f - target_lr) ** 2))
+    gc = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in pc_r.items()}
+    gf = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in pf_r.items()}
+    return ({k: v.detach() for k, v in losses.items()}, gc, gf, {k: v.detach() for k, v in out.items()})
+
+
+def clip_grads(grads: List[Tensor], tcfg: TrainConfig) -> Optional[Tensor]:
+    """nn.utils.clip_grad_norm_ (2-norm over all tensors, coefficient clamp(max/(norm+1e-6), max=1))
+    or clip_grad_value_, in place.  Returns the total norm (norm mode)."""
+    if tcfg.grad_clip_val <= 0:
+        return None
+    if tcfg.grad_clip_type == "norm":
+        total = torch.linalg.vector_norm(torch.stack([torch.linalg.vector_norm(g, 2.0) for g in grads]), 2.0)
+        coef = torch.clamp(tcfg.grad_clip_val / (total + 1e-6), max=1.0)
+        for g in grads:
+            g.mul_(coef)
+        return total
+    for g in grads:
+        g.clamp_(min=-tcfg.grad_clip_val, max=tcfg.grad_clip_val)
+    return None
+
+
+def adam_step(params: List[Tensor], grads: List[Tensor], exp_avg: List[Tensor], exp_avg_sq: List[Tensor],
+              step: int, lr: float, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8) -> None:
+    """torch.optim.Adam (single-tensor path, no amsgrad / weight decay / maximize), in place.
+    ``step`` is the 1-based step count AFTER the increment."""
+    bc1 = 1 - beta1 ** step
+    bc2 = 1 - beta2 ** step
+    step_size = lr / bc1
+    bc2_sqrt = bc2 ** 0.5
+    for p, g, m, v in zip(params, grads, exp_avg, exp_avg_sq):
+        m.lerp_(g, 1 - beta1)
+        v.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+        denom = (v.sqrt() / bc2_sqrt).add_(eps)
+        p.addcdiv_(m, denom, value=-step_size)
+
+
+def lr_at_epoch(tcfg: TrainConfig, epoch: int) -> float:
+    """LambdaLR rules of models/networks.py:102-113 (lr after `epoch` scheduler steps)."""
+    t = max(0, epoch + 1 - tcfg.n_epochs + tcfg.n_epochs_decay) / float(tcfg.n_epochs_decay + 1)
+    if tcfg.lr_policy == "linear":
+        lr = tcfg.lr * (1 - t) + tcfg.lr_final * t
+    elif tcfg.lr_policy == "exp":
+        lr = math.exp(math.log(tcfg.lr) * (1 - t) + math.log(tcfg.lr_final) * t)
+    else:
+        raise ValueError(tcfg.lr_policy)
+    return (lr / tcfg.lr) * tcfg.lr
+
+
+class TrainState:
+    """Parameters + Adam moments of both nets, in the reference's optimiser order
+    (itertools.chain(netCoarse.parameters(), netFine.parameters()), :201-203)."""
+
+    def __init__(self, pc: Dict[str, Tensor], pf: Dict[str, Tensor]):
+        self.pc = {k: v.detach().clone() for k, v in pc.items()}
+        self.pf = {k: v.detach().clone() for k, v in pf.items()}
+        self.m = [torch.zeros_like(v) for v in self.param_list()]
+        self.v = [torch.zeros_like(v) for v in self.param_list()]
+        self.step = 0
+
+    def param_list(self) -> List[Tensor]:
+        return list(self.pc.values()) + list(self.pf.values())
+
+
+def optimize_parameters(state: TrainState, rays: Tensor, target_lr: Tensor, cfg: O.RenderConfig,
+                        tcfg: TrainConfig, rng: Optional[O.RenderRng], s: int = 2, lr: Optional[float] = None,
+                        z_fine_override: Optional[Tensor] = None):
+    """One full reference training iteration on ``state`` (in place).  Returns (losses, grads list)."""
+    losses, gc, gf, _ = loss_and_grads(state.pc, state.pf, rays, target_lr, cfg, tcfg, rng, s, z_fine_override)
+    grads = [gc[k] for k in state.pc] + [gf[k] for k in state.pf]
+    clip_grads(grads, tcfg)
+    state.step += 1
+    adam_step(state.param_list(), grads, state.m, state.v, state.step, tcfg.lr if lr is None else lr,
+              tcfg.beta1, tcfg.beta2, tcfg.eps)
+    return losses, grads
