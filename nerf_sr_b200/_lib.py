@@ -37,6 +37,11 @@ class NsrOutputs(C.Structure):
                  "fine_depth", "fine_opacity", "fine_weights", "z_fine")]
 
 
+class NsrOutGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in
+                ("coarse_comp_rgbs", "coarse_depth", "coarse_opacity", "fine_comp_rgbs", "fine_depth", "fine_opacity")]
+
+
 class NsrPassOutputs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("comp_rgbs", "depth", "opacity", "weights", "raw")]
 
@@ -65,6 +70,25 @@ SIGNATURES = {
     "nsr_render_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "nsr_render_pose_host": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_float, C.c_int, C.c_int,
                                        C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
+    # training (scope row f-1)
+    "nsr_grad_numel": (C.c_int64, [C.c_void_p]),
+    "nsr_train_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64]),
+    "nsr_render_train": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.POINTER(NsrRng), C.POINTER(NsrOutputs),
+                                   C.c_void_p, C.c_size_t, C.c_void_p]),
+    "nsr_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.POINTER(NsrRng), C.POINTER(NsrOutGrads),
+                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "nsr_lr_loss_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nsr_clip_coef": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_void_p]),
+    "nsr_adam_step": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_float, C.c_void_p]),
+    "nsr_debug_train_layout": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
+    "nsr_debug_pack_image": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "nsr_debug_unpack_image": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "nsr_debug_dx": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                               C.c_int64, C.c_void_p]),
+    "nsr_debug_dw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                               C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
     "nsr_debug_set_trace": (C.c_int, [C.c_void_p, C.c_void_p]),
     "nsr_debug_set_flags": (C.c_int, [C.c_void_p, C.c_int]),
     "nsr_launch_count": (C.c_int64, [C.c_void_p]),

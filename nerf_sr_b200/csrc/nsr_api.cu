@@ -448,7 +448,8 @@ extern "C" int nsr_pack_weights(NsrHandle* h, int which, const float* const* par
     if (!param_ptrs[i]) return fail(h, NSR_ERR_INVALID_ARG, "nsr_pack_weights: null parameter pointer");
   cudaStream_t st = (cudaStream_t)stream;
   NSR_CUDA(h, cudaSetDevice(h->cfg.device));
-  NSR_CUDA(h, simt_pack(h, which, param_ptrs, st));
+  // each precision packs only the images its kernels read (training re-packs every step)
+  if (h->cfg.precision == NSR_PREC_FP32_SIMT) NSR_CUDA(h, simt_pack(h, which, param_ptrs, st));
   if (h->cfg.precision != NSR_PREC_FP32_SIMT) {
     NSR_CUDA(h, tc_pack(h, which, param_ptrs, st));
     // the device-side pointer table tc_pack staged behind the consts blob also feeds the backward's images

@@ -1150,6 +1150,16 @@ extern "C" int nsr_adam_step(NsrHandle* h, float* const* param_ptrs, int n_param
 }
 
 // ---- test seams ----------------------------------------------------------------
+extern "C" int nsr_debug_train_layout(const NsrHandle* h, int64_t n_rays, int64_t* out16) {
+  if (!h || !out16 || n_rays <= 0) return NSR_ERR_INVALID_ARG;
+  const TrainWs L = train_layout(h, n_rays);
+  const int64_t v[16] = {(int64_t)L.enc[0], (int64_t)L.hh[0], (int64_t)L.dir[0], (int64_t)L.raw[0], (int64_t)L.z[0], L.tiles[0],
+                         (int64_t)L.enc[1], (int64_t)L.hh[1], (int64_t)L.dir[1], (int64_t)L.raw[1], (int64_t)L.z[1], L.tiles[1],
+                         (int64_t)L.dhead, (int64_t)L.dzdir, (int64_t)L.g0, (int64_t)L.g1};
+  for (int i = 0; i < 16; ++i) out16[i] = v[i];
+  return NSR_OK;
+}
+
 extern "C" int nsr_debug_pack_image(NsrHandle* h, const float* src, int64_t n_rows, int n_cols, int ld, void* image, NsrStream stream) {
   if (!h) return NSR_ERR_INVALID_ARG;
   if (!src || !image || n_rows <= 0 || n_cols <= 0 || n_cols % 64 || ld <= 0 || ld > n_cols)

@@ -296,17 +296,23 @@ def patch_model(model, precision: str = "bf16x3"):
     """Rebind ``forward_rays`` of a reference NeRFDownXModel / NeRFModel instance to the CUDA path
     (the one-line hook of INTEGRATION.md).  Keeps self.near / self.far (consumed by depth2im,
     models/nerf_downX_model.py:422) without the reference's per-chunk device sync: they are read
-    once per distinct ray tensor.  Training (grad enabled) stays on the reference path until the
-    backward kernel lands."""
+    once per distinct ray tensor.  With grad enabled the outputs are autograd-connected to the
+    parameters of netCoarse / netFine through training.RenderFunction (CUDA backward), so the
+    reference's loss_tot.backward() / optimizer.step() run unchanged; option sets the backward does
+    not cover (fp32_simt precision, N_importance == 0, --no_dir) keep the reference path in train mode."""
     import types
     vo = 8 if type(model).__name__ == "NeRFModel" else 3
     renderer = Renderer(model.opt, device=model.device, precision=precision, viewdir_offset=vo)
     reference_forward_rays = model.forward_rays
 
+    train_capable = (precision in ("bf16x3", "fp16x3") and renderer.n_importance > 0 and not renderer.cfg.no_dir)
+
     def forward_rays(self, rays):
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.netCoarse.parameters()):
+        grad_mode = torch.is_grad_enabled() and any(p.requires_grad for p in self.netCoarse.parameters())
+        if grad_mode and not train_capable:
             return reference_forward_rays(rays)
-        renderer.sync_from_modules(self.netCoarse, self.netFine)
+        if not grad_mode:
+            renderer.sync_from_modules(self.netCoarse, self.netFine)
         if getattr(self, "_nsr_nearfar_src", None) is not rays.untyped_storage().data_ptr():
             nf = rays[0, 6:8].cpu().numpy()
             self.near, self.far = nf[0:1], nf[1:2]
@@ -322,6 +328,12 @@ def patch_model(model, precision: str = "bf16x3"):
                 rng["u_fine"] = torch.rand(n, o.N_importance, device=rays.device)
                 if o.noise_std > 0:
                     rng["noise_fine"] = torch.randn(n, o.N_coarse + o.N_importance, device=rays.device)
+        if grad_mode:
+            from . import training as T
+            pcs, pfs = T.module_params_in_order(self.netCoarse), T.module_params_in_order(self.netFine)
+            outs = T.RenderFunction.apply(renderer, rays, rng, len(pcs), *pcs, *pfs)
+            renderer._param_versions = [None, None]          # the images now hold the training weights
+            return dict(zip(T.OUT_KEYS, outs))
         return renderer.forward_rays(rays, rng)
 
     model.forward_rays = types.MethodType(forward_rays, model)

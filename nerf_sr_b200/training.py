@@ -1,0 +1,353 @@
+"""Host-side mirror of the reference's training iteration around the render hot path (scope row f-1).
+
+    Renderer-level seams (thin wrappers over the C ABI, include/nsr.h "training" section):
+        render_train / backward / lr_loss_grad / clip_coef / adam_step
+    RenderFunction            torch.autograd.Function: forward_rays with autograd-connected outputs, so the
+                              reference's ``loss_tot.backward(); optimizer.step()`` run unchanged
+                              (models/nerf_downX_model.py:390-408)
+    Trainer.optimize_parameters   the whole reference iteration on the device: forward (train mode) ->
+                              box average + ColorMSELoss (+PSNR) -> backward -> [gradient all-reduce] ->
+                              clip -> Adam -> re-pack; no host sync, losses stay on the device.
+
+PyTorch provides device memory, streams, RNG draws (in the reference's order) and NCCL only; every
+arithmetic step runs in libnsr_b200.  There is no fallback path."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Mapping, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import NsrError, NsrOutGrads, NsrOutputs, NsrRng
+from .renderer import Renderer, state_dict_order
+
+OUT_KEYS = ("coarse_comp_rgbs", "coarse_depth", "coarse_opacity", "coarse_weights",
+            "fine_comp_rgbs", "fine_depth", "fine_opacity", "fine_weights")
+GRAD_KEYS = ("coarse_comp_rgbs", "coarse_depth", "coarse_opacity", "fine_comp_rgbs", "fine_depth", "fine_opacity")
+
+
+def _rng_struct(r: Renderer, rng: Optional[Mapping[str, torch.Tensor]], keep: list) -> Optional[NsrRng]:
+    if rng is None:
+        return None
+    s = NsrRng()
+    for k in ("u_coarse", "noise_coarse", "u_fine", "noise_fine"):
+        t = rng.get(k) if isinstance(rng, Mapping) else getattr(rng, k, None)
+        if t is not None:
+            t = r._f32(t.to(r.device))
+            keep.append(t)
+            setattr(s, k, t.data_ptr())
+    return s
+
+
+# ---- Renderer seams ------------------------------------------------------------------------------------
+def _train_workspace(self: Renderer, n_rays: int) -> torch.Tensor:
+    need = self.lib.nsr_train_workspace_bytes(self._h, n_rays)
+    ws = getattr(self, "_train_ws", None)
+    if ws is None or ws.numel() < need:
+        self._train_ws = None
+        ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        self._train_ws = ws
+    return ws
+
+
+def render_train(self: Renderer, rays: torch.Tensor, rng=None, want_weights: bool = True, want_z_fine: bool = False):
+    """forward_rays in train mode, keeping the activation stash for ``backward`` (same outputs as
+    forward_rays).  The stash lives in a renderer-owned buffer: one forward/backward pair at a time."""
+    rays = self._f32(rays)
+    n, stride = rays.shape
+    dev, f32 = self.device, torch.float32
+    out = {"coarse_comp_rgbs": torch.empty(n, 3, device=dev, dtype=f32), "coarse_depth": torch.empty(n, device=dev, dtype=f32),
+           "coarse_opacity": torch.empty(n, device=dev, dtype=f32),
+           "fine_comp_rgbs": torch.empty(n, 3, device=dev, dtype=f32), "fine_depth": torch.empty(n, device=dev, dtype=f32),
+           "fine_opacity": torch.empty(n, device=dev, dtype=f32)}
+    if want_weights:
+        out["coarse_weights"] = torch.empty(n, self.n_coarse, device=dev, dtype=f32)
+        out["fine_weights"] = torch.empty(n, self.n_fine, device=dev, dtype=f32)
+    if want_z_fine:
+        out["z_fine"] = torch.empty(n, self.n_fine, device=dev, dtype=f32)
+    o = NsrOutputs()
+    for k, v in out.items():
+        setattr(o, k, v.data_ptr())
+    keep: list = []
+    r = _rng_struct(self, rng, keep)
+    ws = _train_workspace(self, n)
+    self._check(self.lib.nsr_render_train(self._h, rays.data_ptr(), n, stride, C.byref(r) if r is not None else None,
+                                          C.byref(o), ws.data_ptr(), ws.numel(), self._stream()))
+    return out
+
+
+def backward(self: Renderer, rays: torch.Tensor, rng, grads: Mapping[str, Optional[torch.Tensor]]):
+    """dL/d(outputs) -> (grad_coarse_flat, grad_fine_flat): flat fp32 gradients in state_dict order."""
+    rays = self._f32(rays)
+    n, stride = rays.shape
+    g = NsrOutGrads()
+    keep: list = []
+    for k in GRAD_KEYS:
+        t = grads.get(k)
+        if t is not None:
+            t = self._f32(t).reshape(n, -1)
+            keep.append(t)
+            setattr(g, k, t.data_ptr())
+    for k in ("coarse_weights", "fine_weights"):
+        if grads.get(k) is not None:
+            raise NsrError(2, f"gradient w.r.t. {k} is not supported (the reference's losses never use it)")
+    r = _rng_struct(self, rng, keep)
+    numel = int(self.lib.nsr_grad_numel(self._h))
+    gc = torch.empty(numel, device=self.device, dtype=torch.float32)
+    gf = torch.empty(numel, device=self.device, dtype=torch.float32)
+    ws = _train_workspace(self, n)
+    self._check(self.lib.nsr_backward(self._h, rays.data_ptr(), n, stride, C.byref(r) if r is not None else None, C.byref(g),
+                                      gc.data_ptr(), gf.data_ptr(), ws.data_ptr(), ws.numel(), self._stream()))
+    return gc, gf
+
+
+def lr_loss_grad(self: Renderer, hr_rgb: torch.Tensor, target_lr: torch.Tensor, s: int, lam: float = 1.0,
+                 want_grad: bool = True):
+    """(lr_rgb [n_lr,3], metrics [2] = (lam*mse, psnr), g_hr [n_lr*s*s,3] = d(lam*mse)/d(hr_rgb))."""
+    hr_rgb, target_lr = self._f32(hr_rgb), self._f32(target_lr)
+    n_lr = target_lr.shape[0]
+    if hr_rgb.shape[0] != n_lr * s * s:
+        raise NsrError(1, f"hr_rgb has {hr_rgb.shape[0]} rows, expected {n_lr}*{s}*{s}")
+    lr = torch.empty(n_lr, 3, device=self.device, dtype=torch.float32)
+    m = torch.empty(2, device=self.device, dtype=torch.float32)
+    g = torch.empty_like(hr_rgb) if want_grad else None
+    self._check(self.lib.nsr_lr_loss_grad(self._h, hr_rgb.data_ptr(), target_lr.data_ptr(), n_lr, s, float(lam), lr.data_ptr(),
+                                          m.data_ptr(), g.data_ptr() if g is not None else None, self._stream()))
+    return lr, m, g
+
+
+def clip_coef(self: Renderer, grad_a: torch.Tensor, grad_b: Optional[torch.Tensor], max_norm: float) -> torch.Tensor:
+    out = torch.empty(2, device=self.device, dtype=torch.float32)
+    self._check(self.lib.nsr_clip_coef(self._h, grad_a.data_ptr(), grad_b.data_ptr() if grad_b is not None else None,
+                                       grad_a.numel(), float(max_norm), out.data_ptr(), self._stream()))
+    return out
+
+
+def adam_step(self: Renderer, params: Sequence[torch.Tensor], grad_flat: torch.Tensor, exp_avg: torch.Tensor,
+              exp_avg_sq: torch.Tensor, step: int, lr: float, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8,
+              clip_coef_dev: Optional[torch.Tensor] = None, clip_value: float = 0.0):
+    for p in params:
+        if p.dtype != torch.float32 or not p.is_contiguous() or p.device != self.device:
+            raise NsrError(1, "adam_step needs contiguous fp32 parameters on the renderer's device")
+    arr = (C.c_void_p * len(params))(*[p.data_ptr() for p in params])
+    self._check(self.lib.nsr_adam_step(self._h, arr, len(params), grad_flat.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
+                                       int(step), float(lr), float(beta1), float(beta2), float(eps),
+                                       clip_coef_dev.data_ptr() if clip_coef_dev is not None else None, float(clip_value),
+                                       self._stream()))
+
+
+# ---- test seams of the backward GEMMs ----
+def image_bytes(n_rows: int, n_cols: int) -> int:
+    return ((n_rows + 127) // 128) * (n_cols // 64) * 32768
+
+
+def pack_image(self: Renderer, x: torch.Tensor, n_cols: Optional[int] = None) -> torch.Tensor:
+    x = self._f32(x)
+    n_rows, ld = x.shape
+    n_cols = n_cols or ((ld + 63) // 64) * 64
+    img = torch.empty(image_bytes(n_rows, n_cols), dtype=torch.uint8, device=self.device)
+    self._check(self.lib.nsr_debug_pack_image(self._h, x.data_ptr(), n_rows, n_cols, ld, img.data_ptr(), self._stream()))
+    return img
+
+
+def unpack_image(self: Renderer, img: torch.Tensor, n_rows: int, n_cols: int, ld: Optional[int] = None) -> torch.Tensor:
+    ld = ld or n_cols
+    out = torch.empty(n_rows, ld, device=self.device, dtype=torch.float32)
+    self._check(self.lib.nsr_debug_unpack_image(self._h, img.data_ptr(), n_rows, n_cols, ld, out.data_ptr(), self._stream()))
+    return out
+
+
+def debug_dx(self: Renderer, which: int, layer_idx: int, a_img: torch.Tensor, n_rows: int, mask_img=None, dsig=None, wsig=None):
+    out = torch.empty(image_bytes(n_rows, 256), dtype=torch.uint8, device=self.device)
+    self._check(self.lib.nsr_debug_dx(self._h, which, layer_idx, a_img.data_ptr(), out.data_ptr(),
+                                      mask_img.data_ptr() if mask_img is not None else None,
+                                      dsig.data_ptr() if dsig is not None else None,
+                                      wsig.data_ptr() if wsig is not None else None, n_rows, self._stream()))
+    return out
+
+
+def debug_dw(self: Renderer, a_img: torch.Tensor, a_cols: int, blk0: int, blk1: int, b_img: torch.Tensor, b_cols: int, n_rows: int):
+    out = torch.empty(128, b_cols, device=self.device, dtype=torch.float32)
+    bias = torch.empty(128, device=self.device, dtype=torch.float32)
+    scratch = torch.empty(148 * 128 * (b_cols + 1) * 4 + 1024, dtype=torch.uint8, device=self.device)
+    self._check(self.lib.nsr_debug_dw(self._h, a_img.data_ptr(), a_cols, blk0, blk1, b_img.data_ptr(), b_cols, out.data_ptr(),
+                                      bias.data_ptr(), n_rows, scratch.data_ptr(), scratch.numel(), self._stream()))
+    return out, bias
+
+
+def train_layout(self: Renderer, n_rays: int) -> Dict[str, int]:
+    """Offsets of the stash regions inside the train workspace (test seam)."""
+    arr = (C.c_int64 * 16)()
+    self._check(self.lib.nsr_debug_train_layout(self._h, n_rays, arr))
+    keys = ["enc0", "h0", "dir0", "raw0", "z0", "tiles0", "enc1", "h1", "dir1", "raw1", "z1", "tiles1",
+            "dhead", "dzdir", "g0", "g1"]
+    return dict(zip(keys, [int(x) for x in arr]))
+
+
+def stash_activation(self: Renderer, n_rays: int, which: int, layer: int) -> torch.Tensor:
+    """Unpack one stashed tensor of pass `which` after render_train: layer 0 = encoded xyz [P,64],
+    1..8 = h_l [P,256], 9 = feat [P,256], 10 = dir activations [P,128] (test seam)."""
+    L = train_layout(self, n_rays)
+    ws = self._train_ws
+    base = (-ws.data_ptr()) % 256
+    S = self.n_fine if which else self.n_coarse
+    tiles = L[f"tiles{which}"]
+    rows = n_rays * S
+    if layer == 0:
+        off, cols = L[f"enc{which}"], 64
+    elif layer <= 9:
+        off, cols = L[f"h{which}"] + (layer - 1) * tiles * 4 * 32768, 256
+    else:
+        off, cols = L[f"dir{which}"], 128
+    img = ws[base + off: base + off + tiles * (cols // 64) * 32768]
+    return unpack_image(self, img, rows, cols)
+
+
+for _f in (train_layout, stash_activation, render_train, backward, lr_loss_grad, clip_coef, adam_step, pack_image, unpack_image, debug_dx, debug_dw):
+    setattr(Renderer, _f.__name__, _f)
+
+
+def unflatten_grads(flat: torch.Tensor, shapes: Sequence[Sequence[int]]) -> List[torch.Tensor]:
+    out, off = [], 0
+    for s in shapes:
+        n = int(math.prod(s))
+        out.append(flat[off:off + n].view(*s))
+        off += n
+    return out
+
+
+# ---- autograd bridge ---------------------------------------------------------------------------------
+class RenderFunction(torch.autograd.Function):
+    """forward_rays whose outputs are connected to the parameters of netCoarse / netFine.
+
+    apply(renderer, rays, rng_dict_or_None, n_coarse_params, *params) -> the 8 tensors of OUT_KEYS.
+    The backward hands dL/d(comp_rgbs, depth, opacity) to the CUDA library and returns per-parameter
+    gradients (views of the two flat buffers)."""
+
+    @staticmethod
+    def forward(ctx, renderer: Renderer, rays: torch.Tensor, rng, n_coarse: int, *params: torch.Tensor):
+        with torch.no_grad():
+            renderer.load_params(0, params[:n_coarse])
+            renderer.load_params(1, params[n_coarse:])
+            out = renderer.render_train(rays, rng)
+        ctx.renderer, ctx.rays, ctx.rng = renderer, rays, rng
+        ctx.shapes = [tuple(p.shape) for p in params]
+        ctx.n_coarse = n_coarse
+        ctx.set_materialize_grads(False)
+        outs = tuple(out[k] for k in OUT_KEYS)
+        ctx.mark_non_differentiable(outs[3], outs[7])
+        return outs
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        grads = dict(zip(OUT_KEYS, gouts))
+        gc, gf = ctx.renderer.backward(ctx.rays, ctx.rng, grads)
+        nc = ctx.n_coarse
+        pg = unflatten_grads(gc, ctx.shapes[:nc]) + unflatten_grads(gf, ctx.shapes[nc:])
+        return (None, None, None, None, *pg)
+
+
+def _load_params(self: Renderer, which: int, params: Sequence[torch.Tensor]):
+    """nsr_pack_weights straight from a parameter list in state_dict order (no name lookup)."""
+    ts = [p.detach() for p in params]
+    for i, t in enumerate(ts):
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.device != self.device:
+            raise NsrError(1, "parameters must be contiguous fp32 tensors on the renderer's device")
+        if t.numel() != self.lib.nsr_param_numel(self._h, i):
+            raise NsrError(1, f"parameter {i}: {tuple(t.shape)} does not match the configured architecture")
+    arr = (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+    self._check(self.lib.nsr_pack_weights(self._h, which, arr, len(ts), self._stream()))
+    self._keep[which] = ts
+
+
+Renderer.load_params = _load_params
+
+
+def module_params_in_order(net) -> List[torch.Tensor]:
+    """Parameters of a reference VanillaMLP (optionally DP/DDP-wrapped) in state_dict order."""
+    m = net.module if hasattr(net, "module") else net
+    named = dict(m.named_parameters())
+    D = sum(1 for k in named if k.startswith("xyz_encoding_") and k.endswith(".0.weight"))
+    return [named[n] for n in state_dict_order(D)]
+
+
+# ---- the fused training iteration -----------------------------------------------------------------------
+class Trainer:
+    """The reference's ``optimize_parameters`` (models/nerf_downX_model.py:398-408) on the device.
+
+    Owns fp32 master parameters of both nets (state_dict order) and the Adam moments as flat buffers;
+    ``optimize_parameters(rays, target_lr)`` runs forward (train mode), the LR loss, the backward, an
+    optional gradient all-reduce (DDP semantics: mean over ranks), clipping, Adam and the re-pack of
+    the tensor-core weight images.  Nothing synchronises with the host; ``last_metrics`` is a device
+    tensor [coarse lam*mse, coarse psnr, fine lam*mse, fine psnr]."""
+
+    def __init__(self, renderer: Renderer, params_coarse: Mapping[str, torch.Tensor], params_fine: Mapping[str, torch.Tensor],
+                 lr: float = 5e-4, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8, lambda_coarse_mse: float = 1.0,
+                 lambda_fine_mse: float = 1.0, grad_clip_val: float = 0.0, grad_clip_type: str = "norm", downscale: int = 2,
+                 group=None):
+        self.r = renderer
+        dev = renderer.device
+        names = state_dict_order(renderer.cfg.D)
+        take = lambda sd: [sd[n].detach().to(dev, torch.float32).contiguous().clone() for n in names]
+        self.names = names
+        self.params = [take(params_coarse), take(params_fine)]
+        numel = int(renderer.lib.nsr_grad_numel(renderer._h))
+        self.m = [torch.zeros(numel, device=dev), torch.zeros(numel, device=dev)]
+        self.v = [torch.zeros(numel, device=dev), torch.zeros(numel, device=dev)]
+        self.lr, self.beta1, self.beta2, self.eps = lr, beta1, beta2, eps
+        self.lam = (lambda_coarse_mse, lambda_fine_mse)
+        self.clip_val, self.clip_type = grad_clip_val, grad_clip_type
+        self.s = downscale
+        self.step = 0
+        self.group = group
+        self.last_metrics: Optional[torch.Tensor] = None
+        self.last_grads = None
+        for w in (0, 1):
+            renderer.load_params(w, self.params[w])
+
+    def state_dict(self, which: int) -> Dict[str, torch.Tensor]:
+        return dict(zip(self.names, self.params[which]))
+
+    def draw_rng(self, n_rays: int, generator: Optional[torch.Generator] = None) -> Dict[str, torch.Tensor]:
+        """The reference's train-mode draws, in its order (models/utils.py:41, :210, :73, :210)."""
+        c = self.r.cfg
+        dev = self.r.device
+        rng = {"u_coarse": torch.rand(n_rays, c.n_coarse, device=dev, generator=generator)}
+        if c.noise_std > 0:
+            rng["noise_coarse"] = torch.randn(n_rays, c.n_coarse, device=dev, generator=generator)
+        rng["u_fine"] = torch.rand(n_rays, c.n_importance, device=dev, generator=generator)
+        if c.noise_std > 0:
+            rng["noise_fine"] = torch.randn(n_rays, c.n_coarse + c.n_importance, device=dev, generator=generator)
+        return rng
+
+    def forward_backward(self, rays: torch.Tensor, target_lr: torch.Tensor, rng=None):
+        """forward + loss + backward; returns (grad_coarse_flat, grad_fine_flat), sets last_metrics."""
+        r = self.r
+        out = r.render_train(rays, rng, want_weights=False)
+        _, mc, g_c = r.lr_loss_grad(out["coarse_comp_rgbs"], target_lr, self.s, self.lam[0])
+        _, mf, g_f = r.lr_loss_grad(out["fine_comp_rgbs"], target_lr, self.s, self.lam[1])
+        self.last_metrics = torch.cat([mc, mf])
+        return r.backward(rays, rng, {"coarse_comp_rgbs": g_c, "fine_comp_rgbs": g_f})
+
+    def optimize_parameters(self, rays: torch.Tensor, target_lr: torch.Tensor, rng=None, lr: Optional[float] = None):
+        r = self.r
+        gc, gf = self.forward_backward(rays, target_lr, rng)
+        if self.group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
+                                      and torch.distributed.get_world_size() > 1):
+            from .parallel import allreduce_mean_
+            allreduce_mean_([gc, gf], self.group)       # one 4.77 MB bucket (DDP: models/networks.py:72-86)
+        coef, clip_value = None, 0.0
+        if self.clip_val > 0:
+            if self.clip_type == "norm":
+                coef = r.clip_coef(gc, gf, self.clip_val)
+            else:
+                clip_value = self.clip_val
+        self.step += 1
+        for w, g in ((0, gc), (1, gf)):
+            r.adam_step(self.params[w], g, self.m[w], self.v[w], self.step, self.lr if lr is None else lr, self.beta1,
+                        self.beta2, self.eps, coef, clip_value)
+            r.load_params(w, self.params[w])
+        self.last_grads = (gc, gf)
+        return self.last_metrics

@@ -43,15 +43,10 @@ FIXTURES = {
 }
 
 
-def sub_indices(numel: int, tag: int) -> np.ndarray:
-    g = np.random.Generator(np.random.PCG64(1000003 * tag + numel))
-    return np.sort(g.integers(0, numel, size=min(N_SUB, numel)))
-
-
 def summarize(tensors, prefix: str, arrays: dict) -> None:
     for i, t in enumerate(tensors):
         flat = t.detach().reshape(-1)
-        idx = sub_indices(flat.numel(), i)
+        idx = T.golden_sub_indices(flat.numel(), i, N_SUB)
         arrays[f"{prefix}_{i}_sub"] = flat[torch.from_numpy(idx)].numpy()
         arrays[f"{prefix}_{i}_norm"] = np.array([float(torch.linalg.vector_norm(flat.double()))])
 

@@ -66,9 +66,10 @@ def _linear(x: Tensor, p: Dict[str, Tensor], name: str) -> Tensor:
     return torch.nn.functional.linear(x, p[name + ".weight"], p[name + ".bias"])
 
 
-def mlp_forward(p: Dict[str, Tensor], x: Tensor, cfg: RenderConfig) -> Tensor:
+def mlp_forward(p: Dict[str, Tensor], x: Tensor, cfg: RenderConfig, acts: Optional[list] = None) -> Tensor:
     """[P, ch_pos+ch_dir] -> [P,4] = (rgb after colour activation, raw sigma).
-    models/networks.py:199-224."""
+    models/networks.py:199-224.  ``acts`` (a list) receives the intermediate tensors
+    [h_1, ..., h_D, feat, dir_act] for the training-stash tests."""
     ch_pos, ch_dir = cfg.ch_pos, cfg.ch_dir
     in_xyz, in_dir = torch.split(x, [ch_pos, ch_dir], dim=-1)      # :199
     h = in_xyz
@@ -76,10 +77,14 @@ def mlp_forward(p: Dict[str, Tensor], x: Tensor, cfg: RenderConfig) -> Tensor:
         if i in cfg.skips:
             h = torch.cat([in_xyz, h], -1)                           # :204
         h = torch.relu(_linear(h, p, f"xyz_encoding_{i+1}.0"))
+        if acts is not None:
+            acts.append(h)
     sigma = _linear(h, p, "sigma")                                   # :207
     feat = _linear(h, p, "xyz_encoding_final")                       # :211 (no act)
     d_in = feat if cfg.no_dir else torch.cat([feat, in_dir], -1)     # :213-216
     d = torch.relu(_linear(d_in, p, "dir_encoding.0"))               # :221
+    if acts is not None:
+        acts += [feat, d]
     rgb = _linear(d, p, "rgb.0")                                     # :222
     if cfg.color_activation == "sigmoid":
         rgb = torch.sigmoid(rgb)

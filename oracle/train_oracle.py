@@ -122,6 +122,13 @@ def lr_at_epoch(tcfg: TrainConfig, epoch: int) -> float:
     return (lr / tcfg.lr) * tcfg.lr
 
 
+def golden_sub_indices(numel: int, tag: int, n_sub: int = 256):
+    """Fixed pseudo-random subset of a tensor's entries stored in tests/golden/train_step_*.npz."""
+    import numpy as np
+    g = np.random.Generator(np.random.PCG64(1000003 * tag + numel))
+    return np.sort(g.integers(0, numel, size=min(n_sub, numel)))
+
+
 class TrainState:
     """Parameters + Adam moments of both nets, in the reference's optimiser order
     (itertools.chain(netCoarse.parameters(), netFine.parameters()), :201-203)."""

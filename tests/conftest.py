@@ -21,7 +21,44 @@ def pytest_configure(config):
 
 def golden_names():
     return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR)
-                  if f.endswith(".npz") and f != "raygen.npz")
+                  if f.endswith(".npz") and f != "raygen.npz" and not f.startswith("train_step_"))
+
+
+def train_golden_names():
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.startswith("train_step_") and f.endswith(".npz"))
+
+
+class TrainFixture:
+    """A committed training-step fixture (tests/golden/train_step_*.npz, produced by
+    oracle/make_golden_train.py from the unmodified reference's optimize_parameters)."""
+
+    def __init__(self, name):
+        from oracle import nerf_oracle as O
+        from oracle import train_oracle as T
+        z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+        self.name, self.z = name, z
+        self.meta = json.loads(bytes(z["meta_json"]).decode())
+        self.cfg = O.RenderConfig(**self.meta["cfg"])
+        self.tcfg = T.TrainConfig(**self.meta["tcfg"])
+        self.s = int(self.meta["s"])
+        self.rays = torch.from_numpy(z["rays"])
+        self.target = torch.from_numpy(z["target"])
+        self.rng = []
+        for step in range(2):
+            get = lambda f: torch.from_numpy(z[f"rng{step}_{f}"]) if f"rng{step}_{f}" in z.files else None
+            self.rng.append(O.RenderRng(get("u_coarse"), get("noise_coarse"), get("u_fine"), get("noise_fine")))
+        sd = self.meta["seeds"]
+        self.p_coarse = O.make_mlp_params(self.cfg, sd[0])
+        self.p_fine = O.make_mlp_params(self.cfg, sd[1])
+
+    def sub(self, prefix, step, i):
+        return torch.from_numpy(self.z[f"{prefix}{step}_{i}_sub"]), float(self.z[f"{prefix}{step}_{i}_norm"][0])
+
+
+def rng_dict(rng):
+    if rng is None:
+        return None
+    return {k: getattr(rng, k) for k in ("u_coarse", "noise_coarse", "u_fine", "noise_fine") if getattr(rng, k) is not None}
 
 
 class Fixture:

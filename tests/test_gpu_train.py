@@ -1,0 +1,391 @@
+"""GPU tests of the training path (scope row f-1), all through the C ABI: activation stash of the fused
+forward, the tcgen05 backward GEMMs (dX, dW) against torch fp64 matmuls, full gradients against the
+oracle's autograd (= the reference's definition, pinned in tests/golden/train_step_*.npz), the LR loss +
+its gradient, clipping, Adam against torch.optim.Adam, and the fused training iteration.
+
+Gradient parity: the fine sample positions are an ill-conditioned function of the coarse weights
+(SURVEY.md 0.6), so the oracle is teacher-forced on the z-values the CUDA forward actually used
+(protocol ii); what remains is compared as relative L2 per parameter tensor against the oracle's own
+fp32-vs-fp64 disagreement on the same inputs (ReLU / sigma-ReLU kink flips make that floor ~1e-3..1e-2)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import TrainFixture, rng_dict, train_golden_names
+from oracle import nerf_oracle as O
+from oracle import train_oracle as T
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+REPORT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "train_parity.jsonl")
+
+
+def _report(**kw):
+    try:
+        os.makedirs(os.path.dirname(REPORT), exist_ok=True)
+        with open(REPORT, "a") as fh:
+            fh.write(json.dumps(kw) + "\n")
+    except OSError:
+        pass
+
+
+def _renderer(cfg, pc, pf, prec="bf16x3"):
+    from nerf_sr_b200 import Renderer
+    r = Renderer(cfg, torch.device(DEV), precision=prec)
+    r.load_state_dict(0, pc)
+    r.load_state_dict(1, pf)
+    return r
+
+
+def _rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float(torch.linalg.vector_norm(a - b) / (torch.linalg.vector_norm(b) + 1e-30))
+
+
+def _split_eps(prec):
+    return 2.0 ** -15 if prec == "bf16x3" else 2.0 ** -20
+
+
+# ----------------------------------------------------------------------------- tile images
+@pytest.mark.parametrize("prec", ["bf16x3", "fp16x3"])
+def test_image_pack_roundtrip(prec):
+    cfg = O.RenderConfig()
+    r = _renderer(cfg, O.make_mlp_params(cfg, 4), O.make_mlp_params(cfg, 17), prec)
+    g = torch.Generator().manual_seed(0)
+    for rows, ld in ((300, 256), (128, 63), (1, 128), (1000, 27)):
+        x = torch.randn(rows, ld, generator=g).to(DEV)
+        img = r.pack_image(x)
+        n_cols = (ld + 63) // 64 * 64
+        y = r.unpack_image(img, rows, n_cols, ld)
+        assert float((x - y).abs().max()) <= _split_eps(prec) * float(x.abs().max()), (rows, ld)
+    r.close()
+
+
+# ----------------------------------------------------------------------------- activation stash
+@pytest.mark.parametrize("prec", ["bf16x3", "fp16x3"])
+def test_stash_matches_oracle_activations(prec):
+    cfg = O.RenderConfig(white_bkgd=True)
+    pc, pf = O.make_mlp_params(cfg, 4), O.make_mlp_params(cfg, 17)
+    n = 101                                         # ragged: last coarse tile half empty
+    rays = O.synthetic_rays(n, 3, "blender")
+    r = _renderer(cfg, pc, pf, prec)
+    out = r.render_train(rays.to(DEV), None, want_z_fine=True)
+    ref_eval = r.forward_rays(rays.to(DEV))          # the non-stash kernel must agree bit for bit
+    torch.cuda.synchronize()
+    for k in ("coarse_comp_rgbs", "coarse_weights", "fine_comp_rgbs", "fine_depth"):
+        assert torch.equal(out[k], ref_eval[k]), k
+    z_f = out["z_fine"].cpu()
+    extras = {}
+    with torch.no_grad():
+        O.forward_rays(pc, pf, rays, cfg, None, z_fine_override=z_f, extras=extras)
+    for which, (p, z) in enumerate(((pc, extras["z_coarse"]), (pf, z_f))):
+        xyz = O.cast_rays(rays[:, 0:3], rays[:, 3:6], z).reshape(-1, 3)
+        enc = O.posenc(xyz, cfg.deg_pos)
+        denc = O.posenc(rays[:, 3:6], cfg.deg_dir).repeat_interleave(z.shape[1], dim=0)
+        acts = []
+        with torch.no_grad():
+            O.mlp_forward(p, torch.cat([enc, denc], -1), cfg, acts=acts)
+        got = r.stash_activation(n, which, 0).cpu()
+        mx, viol = O.tolerance_violations(got[:, :63], enc)
+        assert viol == 0.0 and float(got[:, 63].abs().max()) == 0.0, ("enc", which, mx)
+        for layer, ref in enumerate(acts, start=1):       # h1..h8, feat, dir
+            got = r.stash_activation(n, which, layer).cpu()
+            mx, viol = O.tolerance_violations(got, ref)
+            _report(test="stash", prec=prec, which=which, layer=layer, max_abs=mx, viol=viol)
+            assert viol == 0.0, (which, layer, mx, viol)
+    r.close()
+
+
+# ----------------------------------------------------------------------------- dX GEMM
+@pytest.mark.parametrize("prec", ["bf16x3", "fp16x3"])
+def test_dx_gemm_against_torch(prec):
+    cfg = O.RenderConfig()
+    pc, pf = O.make_mlp_params(cfg, 4), O.make_mlp_params(cfg, 17)
+    r = _renderer(cfg, pc, pf, prec)
+    g = torch.Generator().manual_seed(1)
+    names = ["dir_encoding.0.weight", "xyz_encoding_final.weight"] + [f"xyz_encoding_{L}.0.weight" for L in range(8, 1, -1)]
+    for rows in (300, 148 * 128 + 77):
+        for idx, name in enumerate(names):
+            if rows > 1000 and idx not in (0, 1, 5):
+                continue
+            W = pf[name].double()
+            k_out = W.shape[0]
+            col0 = 63 if name == "xyz_encoding_5.0.weight" else 0
+            dz = torch.randn(rows, k_out, generator=g)
+            hmask = torch.relu(torch.randn(rows, 256, generator=g))
+            a_img = r.pack_image(dz.to(DEV))
+            m_img = r.pack_image(hmask.to(DEV))
+            dsig = wsig = None
+            ref = dz.double() @ W[:, col0:col0 + 256]
+            if idx == 1:
+                dsig = torch.randn((rows + 127) // 128 * 128, generator=g)
+                dsig[rows:] = 0
+                wsig = torch.randn(256, generator=g)
+                ref = ref + dsig[:rows, None].double() * wsig[None].double()
+                dsig, wsig = dsig.to(DEV), wsig.to(DEV)
+            use_mask = idx != 0
+            if use_mask:
+                ref = ref * (hmask > 0)
+            out_img = r.debug_dx(1, idx, a_img, rows, m_img if use_mask else None, dsig, wsig)
+            got = r.unpack_image(out_img, rows, 256).cpu().double()
+            err = float((got - ref).abs().max()) / float(ref.abs().max())
+            _report(test="dx", prec=prec, rows=rows, layer=name, rel_max_err=err)
+            assert err < (1e-4 if prec == "bf16x3" else 2e-5), (name, rows, err)
+    r.close()
+
+
+# ----------------------------------------------------------------------------- dW GEMM
+@pytest.mark.parametrize("prec", ["bf16x3", "fp16x3"])
+def test_dw_gemm_against_torch(prec):
+    cfg = O.RenderConfig()
+    r = _renderer(cfg, O.make_mlp_params(cfg, 4), O.make_mlp_params(cfg, 17), prec)
+    g = torch.Generator().manual_seed(2)
+    for rows, a_cols, blk, b_cols in ((300, 256, (0, 1), 256), (300, 256, (2, 3), 64), (1000, 128, (0, 1), 128),
+                                      (148 * 128 * 2 + 500, 256, (2, 3), 256), (5000, 64, (0, 0), 256), (40, 256, (1, 2), 192)):
+        A = torch.randn(rows, a_cols, generator=g)
+        B = torch.randn(rows, b_cols, generator=g)
+        out, bias = r.debug_dw(r.pack_image(A.to(DEV)), a_cols, blk[0], blk[1], r.pack_image(B.to(DEV)), b_cols, rows)
+        sel = torch.cat([A[:, 64 * blk[0]:64 * blk[0] + 64], A[:, 64 * blk[1]:64 * blk[1] + 64]], 1).double()
+        ref = sel.T @ B.double()
+        err = float((out.cpu().double() - ref).abs().max()) / float(ref.abs().max())
+        berr = float((bias.cpu().double() - sel.sum(0)).abs().max()) / float(sel.sum(0).abs().max())
+        _report(test="dw", prec=prec, rows=rows, a_cols=a_cols, blk=blk, b_cols=b_cols, rel_max_err=err, bias_err=berr)
+        assert err < 1e-4 and berr < 1e-4, (rows, a_cols, blk, b_cols, err, berr)
+    r.close()
+
+
+# ----------------------------------------------------------------------------- loss, clip, Adam
+@pytest.mark.parametrize("s,lam", [(2, 1.0), (4, 0.5), (1, 1.0)])
+def test_lr_loss_grad_against_autograd(s, lam):
+    cfg = O.RenderConfig()
+    r = _renderer(cfg, O.make_mlp_params(cfg, 4), O.make_mlp_params(cfg, 17))
+    g = torch.Generator().manual_seed(5)
+    n_lr = 777
+    hr = torch.rand(n_lr * s * s, 3, generator=g, requires_grad=True)
+    tgt = torch.rand(n_lr, 3, generator=g)
+    lr_ref = O.box_average(hr, s)
+    loss = torch.nn.functional.mse_loss(lr_ref, tgt) * lam
+    loss.backward()
+    psnr = -10 * torch.log10(torch.mean((lr_ref.detach() - tgt) ** 2))
+    lr, m, ghr = r.lr_loss_grad(hr.detach().to(DEV), tgt.to(DEV), s, lam)
+    assert torch.allclose(lr.cpu(), lr_ref.detach(), rtol=0, atol=1e-7)
+    assert float(m[0]) == pytest.approx(float(loss), rel=1e-5) and float(m[1]) == pytest.approx(float(psnr), rel=1e-5)
+    assert torch.allclose(ghr.cpu(), hr.grad, rtol=1e-5, atol=1e-12)
+    r.close()
+
+
+def test_clip_and_adam_against_torch():
+    cfg = O.RenderConfig()
+    pc = O.make_mlp_params(cfg, 4)
+    r = _renderer(cfg, pc, O.make_mlp_params(cfg, 17))
+    names = list(pc)
+    g = torch.Generator().manual_seed(6)
+    ref = [torch.nn.Parameter(pc[n].clone()) for n in names]
+    opt = torch.optim.Adam(ref, lr=1e-3, betas=(0.9, 0.999))
+    mine = [pc[n].clone().to(DEV) for n in names]
+    numel = sum(p.numel() for p in mine)
+    m, v = torch.zeros(numel, device=DEV), torch.zeros(numel, device=DEV)
+    for step in range(1, 4):
+        grads = [torch.randn(p.shape, generator=g) * 10 ** float(2 * torch.randn((), generator=g)) for p in ref]
+        flat = torch.cat([x.reshape(-1) for x in grads]).to(DEV)
+        for p, x in zip(ref, grads):
+            p.grad = x.clone()
+        total = torch.nn.utils.clip_grad_norm_(ref, 0.5)
+        coef = r.clip_coef(flat, None, 0.5)
+        assert float(coef[1]) == pytest.approx(float(total), rel=1e-5)
+        opt.step()
+        r.adam_step(mine, flat, m, v, step, 1e-3, clip_coef_dev=coef)
+        torch.cuda.synchronize()
+        for a, b, n in zip(mine, ref, names):
+            assert torch.allclose(a.cpu(), b.detach(), rtol=2e-6, atol=2e-9), (step, n, float((a.cpu() - b.detach()).abs().max()))
+    # value clipping
+    ref2 = [torch.nn.Parameter(pc[n].clone()) for n in names]
+    opt2 = torch.optim.Adam(ref2, lr=5e-4)
+    mine2 = [pc[n].clone().to(DEV) for n in names]
+    m.zero_(); v.zero_()
+    grads = [torch.randn(p.shape, generator=g) for p in ref2]
+    for p, x in zip(ref2, grads):
+        p.grad = x.clone()
+    torch.nn.utils.clip_grad_value_(ref2, 0.2)
+    opt2.step()
+    r.adam_step(mine2, torch.cat([x.reshape(-1) for x in grads]).to(DEV), m, v, 1, 5e-4, clip_value=0.2)
+    for a, b in zip(mine2, ref2):
+        assert torch.allclose(a.cpu(), b.detach(), rtol=2e-6, atol=2e-9)
+    r.close()
+
+
+# ----------------------------------------------------------------------------- full gradients
+def _oracle_grads(fx, z_f, rng, dtype=torch.float32):
+    cast = lambda t: None if t is None else t.to(dtype)
+    rr = None if rng is None else O.RenderRng(cast(rng.u_coarse), cast(rng.noise_coarse), cast(rng.u_fine), cast(rng.noise_fine))
+    pc = {k: v.to(dtype) for k, v in fx.p_coarse.items()}
+    pf = {k: v.to(dtype) for k, v in fx.p_fine.items()}
+    return T.loss_and_grads(pc, pf, fx.rays.to(dtype), fx.target.to(dtype), fx.cfg, fx.tcfg, rr, fx.s, z_fine_override=z_f.to(dtype))
+
+
+@pytest.mark.parametrize("prec", ["bf16x3", "fp16x3"])
+@pytest.mark.parametrize("name", train_golden_names())
+def test_gradients_against_oracle_autograd(name, prec):
+    from nerf_sr_b200 import Trainer
+    fx = TrainFixture(name)
+    r = _renderer(fx.cfg, fx.p_coarse, fx.p_fine, prec)
+    tr = Trainer(r, fx.p_coarse, fx.p_fine, lambda_coarse_mse=fx.tcfg.lambda_coarse_mse, lambda_fine_mse=fx.tcfg.lambda_fine_mse,
+                 downscale=fx.s)
+    rng = rng_dict(fx.rng[0])
+    rays = fx.rays.to(DEV)
+    out = r.render_train(rays, rng, want_z_fine=True)
+    z_f = out["z_fine"].cpu()
+    gc, gf = tr.forward_backward(rays, fx.target.to(DEV), rng)
+    torch.cuda.synchronize()
+    assert torch.isfinite(gc).all() and torch.isfinite(gf).all()
+    losses, oc, of, _ = _oracle_grads(fx, z_f, fx.rng[0])
+    _, oc64, of64, _ = _oracle_grads(fx, z_f, fx.rng[0], torch.float64)
+    m = tr.last_metrics.cpu()
+    assert float(m[0]) == pytest.approx(float(losses["coarse_mse"]), rel=2e-3)
+    assert float(m[2]) == pytest.approx(float(losses["fine_mse"]), rel=2e-3)
+    assert float(m[1]) == pytest.approx(float(losses["coarse_psnr"]), rel=2e-3)
+    worst = 0.0
+    for net, flat, ref32, ref64 in (("coarse", gc, oc, oc64), ("fine", gf, of, of64)):
+        off = 0
+        for k, ref in ref32.items():
+            n = ref.numel()
+            got = flat[off:off + n].view_as(ref).cpu()
+            off += n
+            floor = _rel(ref, ref64[k])
+            err = _rel(got, ref64[k])
+            cos = float(torch.nn.functional.cosine_similarity(got.double().reshape(1, -1), ref64[k].reshape(1, -1)))
+            _report(test="grads", fixture=name, prec=prec, net=net, param=k, rel_l2=err, fp32_floor=floor, cos=cos,
+                    ref_norm=float(torch.linalg.vector_norm(ref64[k])))
+            worst = max(worst, err / max(floor, 1e-4))
+            assert err <= 3.0 * floor + 3e-3, (net, k, err, floor)
+            assert cos > 0.9999, (net, k, cos)
+        assert off == flat.numel()
+    r.close()
+
+
+def test_autograd_function_matches_trainer_and_reference_adam():
+    """RenderFunction: loss.backward() fills p.grad with the same gradients Trainer computes, and torch's
+    own Adam on those parameters matches nsr_adam_step (the drop-in path of patch_model in train mode)."""
+    from nerf_sr_b200 import RenderFunction, Trainer
+    from nerf_sr_b200.training import OUT_KEYS
+    fx = TrainFixture("train_step_blender")
+    r = _renderer(fx.cfg, fx.p_coarse, fx.p_fine)
+    names = list(fx.p_coarse)
+    pcs = [torch.nn.Parameter(fx.p_coarse[n].clone().to(DEV)) for n in names]
+    pfs = [torch.nn.Parameter(fx.p_fine[n].clone().to(DEV)) for n in names]
+    rng = rng_dict(fx.rng[0])
+    rays, tgt = fx.rays.to(DEV), fx.target.to(DEV)
+    outs = dict(zip(OUT_KEYS, RenderFunction.apply(r, rays, rng, len(pcs), *pcs, *pfs)))
+    lr_c = O.box_average(outs["coarse_comp_rgbs"], fx.s)
+    lr_f = O.box_average(outs["fine_comp_rgbs"], fx.s)
+    loss = torch.nn.functional.mse_loss(lr_c, tgt) + torch.nn.functional.mse_loss(lr_f, tgt)
+    loss.backward()
+    tr = Trainer(r, fx.p_coarse, fx.p_fine, downscale=fx.s)
+    gc, gf = tr.forward_backward(rays, tgt, rng)
+    flat_c = torch.cat([p.grad.reshape(-1) for p in pcs])
+    flat_f = torch.cat([p.grad.reshape(-1) for p in pfs])
+    assert _rel(flat_c, gc) < 1e-5 and _rel(flat_f, gf) < 1e-5
+    assert float(loss) == pytest.approx(float(tr.last_metrics[0] + tr.last_metrics[2]), rel=1e-5)
+    opt = torch.optim.Adam(pcs + pfs, lr=5e-4, betas=(0.9, 0.999))
+    opt.step()
+    tr2 = Trainer(r, fx.p_coarse, fx.p_fine, downscale=fx.s)
+    tr2.optimize_parameters(rays, tgt, rng)
+    for a, b in zip(pcs + pfs, tr2.params[0] + tr2.params[1]):
+        assert torch.allclose(a.detach(), b, rtol=2e-6, atol=1e-8), float((a.detach() - b).abs().max())
+    r.close()
+
+
+def test_depth_and_opacity_gradients():
+    """dL/d(depth) and dL/d(opacity) (used by the reference's depth-variance term) against autograd."""
+    fx = TrainFixture("train_step_blender")
+    r = _renderer(fx.cfg, fx.p_coarse, fx.p_fine)
+    rays = fx.rays[:64].to(DEV)
+    out = r.render_train(rays, None, want_z_fine=True)
+    z_f = out["z_fine"].cpu()
+    g = torch.Generator().manual_seed(8)
+    gd_c, go_c = torch.randn(64, generator=g), torch.randn(64, generator=g)
+    gr_f, gd_f = torch.randn(64, 3, generator=g), torch.randn(64, generator=g)
+    gc, gf = r.backward(rays, None, {"coarse_comp_rgbs": torch.zeros(64, 3, device=DEV), "coarse_depth": gd_c.to(DEV),
+                                      "coarse_opacity": go_c.to(DEV), "fine_comp_rgbs": gr_f.to(DEV), "fine_depth": gd_f.to(DEV)})
+    pc = {k: v.double().requires_grad_(True) for k, v in fx.p_coarse.items()}
+    pf = {k: v.double().requires_grad_(True) for k, v in fx.p_fine.items()}
+    o = O.forward_rays(pc, pf, fx.rays[:64].double(), fx.cfg, None, z_fine_override=z_f.double())
+    L = (o["coarse_depth"] * gd_c.double()).sum() + (o["coarse_opacity"] * go_c.double()).sum() + \
+        (o["fine_comp_rgbs"] * gr_f.double()).sum() + (o["fine_depth"] * gd_f.double()).sum()
+    L.backward()
+    for flat, p in ((gc, pc), (gf, pf)):
+        ref = torch.cat([v.grad.reshape(-1) for v in p.values()])
+        err = _rel(flat, ref)
+        _report(test="depth_opacity_grads", rel_l2=err)
+        assert err < 5e-2, err
+    r.close()
+
+
+def test_trainer_trajectory_against_oracle():
+    """Five full iterations (forward, loss, backward, Adam, re-pack) on the same draws as the oracle's
+    optimize_parameters: the loss trajectories must stay together."""
+    from nerf_sr_b200 import Trainer
+    fx = TrainFixture("train_step_blender")
+    r = _renderer(fx.cfg, fx.p_coarse, fx.p_fine)
+    tr = Trainer(r, fx.p_coarse, fx.p_fine, lr=fx.tcfg.lr, downscale=fx.s)
+    state = T.TrainState(fx.p_coarse, fx.p_fine)
+    g = torch.Generator().manual_seed(123)
+    rays, tgt = fx.rays.to(DEV), fx.target.to(DEV)
+    mine, ref = [], []
+    for it in range(5):
+        rng = fx.rng[it] if it < 2 else O.RenderRng.draw(fx.rays.shape[0], fx.cfg, g)
+        m = tr.optimize_parameters(rays, tgt, rng_dict(rng))
+        losses, _ = T.optimize_parameters(state, fx.rays, fx.target, fx.cfg, fx.tcfg, rng, fx.s)
+        mine.append(float(m[0] + m[2])); ref.append(float(losses["tot"]))
+    _report(test="trajectory", mine=mine, oracle=ref)
+    assert mine[0] == pytest.approx(fx.meta["steps"][0]["tot"], rel=2e-3)
+    for a, b in zip(mine, ref):
+        assert a == pytest.approx(b, rel=0.08), (mine, ref)
+    r.close()
+
+
+def test_training_reduces_the_loss_on_a_fixed_batch():
+    from nerf_sr_b200 import Trainer
+    cfg = O.RenderConfig(white_bkgd=True)
+    pc, pf = O.make_mlp_params(cfg, 4), O.make_mlp_params(cfg, 17)
+    r = _renderer(cfg, pc, pf)
+    tr = Trainer(r, pc, pf, lr=5e-4, downscale=2)
+    n_lr = 257                                      # ragged tile counts in both passes
+    rays = O.synthetic_rays(n_lr * 4, 12, "blender").to(DEV)
+    tgt = torch.rand(n_lr, 3, generator=torch.Generator().manual_seed(3)).to(DEV)
+    gen = torch.Generator(device=DEV).manual_seed(0)
+    hist = []
+    for it in range(40):
+        m = tr.optimize_parameters(rays, tgt, tr.draw_rng(rays.shape[0], gen))
+        hist.append(float(m[0] + m[2]))
+    _report(test="fixed_batch_training", first=hist[0], last=hist[-1], hist=hist)
+    assert all(np.isfinite(hist))
+    assert min(hist[-10:]) < hist[0], hist
+    # and the oracle, started from the trained weights, sees the same loss (eval of the CUDA-trained nets)
+    sd_c = {k: v.cpu() for k, v in tr.state_dict(0).items()}
+    sd_f = {k: v.cpu() for k, v in tr.state_dict(1).items()}
+    with torch.no_grad():
+        o = O.forward_rays(sd_c, sd_f, rays.cpu(), cfg)
+    out = r.forward_rays(rays)
+    mx, viol = O.tolerance_violations(out["coarse_comp_rgbs"].cpu(), o["coarse_comp_rgbs"])
+    assert viol == 0.0, mx
+    r.close()
+
+
+def test_train_api_errors():
+    from nerf_sr_b200 import NsrError, Renderer
+    cfg = O.RenderConfig()
+    r = Renderer(cfg, torch.device(DEV), precision="fp32_simt")
+    r.load_state_dict(0, O.make_mlp_params(cfg, 4)); r.load_state_dict(1, O.make_mlp_params(cfg, 17))
+    with pytest.raises(NsrError) as e:
+        r.render_train(O.synthetic_rays(8, 1, "blender").to(DEV))
+    assert e.value.code == 2
+    r.close()
+    r = _renderer(cfg, O.make_mlp_params(cfg, 4), O.make_mlp_params(cfg, 17))
+    with pytest.raises(NsrError):
+        r.backward(O.synthetic_rays(8, 1, "blender").to(DEV), None, {"coarse_comp_rgbs": torch.zeros(8, 3, device=DEV),
+                                                                        "coarse_weights": torch.zeros(8, 64, device=DEV)})
+    r.close()
