@@ -996,8 +996,10 @@ using namespace nsr;
 // C ABI (include/nsr.h, training section)
 // ---------------------------------------------------------------------------
 static int train_supported(NsrHandle_* h) {
-  if (h->cfg.precision != NSR_PREC_BF16X3_TC && h->cfg.precision != NSR_PREC_FP16X3_TC)
-    return tfail(h, NSR_ERR_UNSUPPORTED, "training needs the split-precision tensor-core path (bf16x3 / fp16x3)");
+  // bf16 keeps fp32's exponent range, so gradients (1e-3 .. 1e-9 here) need no loss scaling; the fp16 split
+  // would (its lo plane underflows below ~6e-8), hence training is offered on the bf16x3 path only.
+  if (h->cfg.precision != NSR_PREC_BF16X3_TC)
+    return tfail(h, NSR_ERR_UNSUPPORTED, "training needs the bf16 split-precision tensor-core path (precision bf16x3)");
   if (h->cfg.n_importance <= 0) return tfail(h, NSR_ERR_UNSUPPORTED, "training needs N_importance > 0 (coarse + fine)");
   if (h->cfg.no_dir) return tfail(h, NSR_ERR_UNSUPPORTED, "training with --no_dir is not supported");
   return NSR_OK;

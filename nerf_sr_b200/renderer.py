@@ -299,13 +299,13 @@ def patch_model(model, precision: str = "bf16x3"):
     once per distinct ray tensor.  With grad enabled the outputs are autograd-connected to the
     parameters of netCoarse / netFine through training.RenderFunction (CUDA backward), so the
     reference's loss_tot.backward() / optimizer.step() run unchanged; option sets the backward does
-    not cover (fp32_simt precision, N_importance == 0, --no_dir) keep the reference path in train mode."""
+    not cover (precisions other than bf16x3, N_importance == 0, --no_dir) keep the reference path in train mode."""
     import types
     vo = 8 if type(model).__name__ == "NeRFModel" else 3
     renderer = Renderer(model.opt, device=model.device, precision=precision, viewdir_offset=vo)
     reference_forward_rays = model.forward_rays
 
-    train_capable = (precision in ("bf16x3", "fp16x3") and renderer.n_importance > 0 and not renderer.cfg.no_dir)
+    train_capable = (precision == "bf16x3" and renderer.n_importance > 0 and not renderer.cfg.no_dir)
 
     def forward_rays(self, rays):
         grad_mode = torch.is_grad_enabled() and any(p.requires_grad for p in self.netCoarse.parameters())
