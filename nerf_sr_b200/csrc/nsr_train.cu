@@ -42,6 +42,7 @@ constexpr int kNumDxLayers = 9;       // dir, final, L8..L2
 constexpr int kWtChunkBytes = 65536;  // transposed-weight chunk: 256 rows x 64 k, hi 32 KB | lo 32 KB
 constexpr int kWtChunks = 2 + 8 * 4;
 constexpr int kMaxSplit = 148;
+constexpr int kDwLaunchesPerNet = 14;   // 13 used: rgb, dir, dir-enc, final+sigma, L8..L2 (7), L5-enc, L1
 
 __host__ __device__ inline size_t img_off(int row, int j) { return (size_t)row * 128 + (size_t)((j ^ (row & 7)) << 4); }
 
@@ -801,7 +802,7 @@ static TrainWs train_layout(const NsrHandle_* h, int64_t n) {
   L.g1 = off; off += T * 4 * kChunk;
   L.dsig = off; off += al256(T * kT * sizeof(float));
   L.part_region = al256((size_t)kMaxSplit * 128 * 257 * sizeof(float));
-  L.part = off; off += 12 * L.part_region;
+  L.part = off; off += (size_t)kDwLaunchesPerNet * L.part_region;
   L.total = off + 1024;
   return L;
 }
@@ -855,6 +856,7 @@ struct DwPlanner {
   struct JobSpec { const uint8_t* a_img; int a_cpt, blk0, blk1; int row0, rows; long long dst; int ld, col0; long long bias_dst; };
   void launch(const uint8_t* b_img, int b_cpt, int b_chunk0, int nB, int cols, const JobSpec* js, int n_jobs) {
     if (err != cudaSuccess) return;
+    if (region != 0 && launch_idx >= kDwLaunchesPerNet) { err = cudaErrorInvalidValue; return; }   // partial regions exhausted
     DwArgs a{};
     a.b_img = b_img; a.b_cpt = b_cpt; a.b_chunk0 = b_chunk0; a.nB = nB; a.n_tiles = n_tiles;
     int n_split = h->sm_count / n_jobs;
