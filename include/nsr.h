@@ -314,11 +314,14 @@ NSR_API int nsr_adam_step(NsrHandle* h, float* const* param_ptrs, int n_params, 
 /* Test seams of the backward GEMMs ("tile image" = [ceil(rows/128)][cols/64][hi 16 KB | lo 16 KB], 128-B rows,
  * XOR-swizzled 16-B chunks; see nsr_train.cu). */
 /* Byte offsets (from the 256-aligned base of train_ws) of the stash regions, per pass p = 0 coarse / 1 fine:
- * out16 = {enc_p, h_p, dir_p, raw_p, z_p, n_tiles_p} x 2, then dhead, dzdir, g0, g1.  h_p = [9][n_tiles][4 chunks]. */
-NSR_API int nsr_debug_train_layout(const NsrHandle* h, int64_t n_rays, int64_t* out16);
+ * out18 = {enc_p, h_p, dir_p, raw_p, z_p, n_tiles_p} x 2, then dhead, dzdir, g0, g1, mask_0, mask_1.
+ * h_p = [9][n_tiles][4 chunks]; mask_p = [8][n_tiles][128][8] uint32 (1 bit per activation of h_1..h_8). */
+NSR_API int nsr_debug_train_layout(const NsrHandle* h, int64_t n_rays, int64_t* out18);
+/* bits_out[ceil(rows/128)*128][8] uint32: bit j of word w of a row = x[row][32 w + j] > 0  (x: [rows,256]). */
+NSR_API int nsr_debug_relu_bits(NsrHandle* h, const float* x, int64_t n_rows, void* bits_out, NsrStream stream);
 NSR_API int nsr_debug_pack_image(NsrHandle* h, const float* src, int64_t n_rows, int n_cols, int ld, void* image, NsrStream stream);
 NSR_API int nsr_debug_unpack_image(NsrHandle* h, const void* image, int64_t n_rows, int n_cols, int ld, float* dst, NsrStream stream);
-NSR_API int nsr_debug_dx(NsrHandle* h, int which, int layer_idx, const void* a_img, void* out_img, const void* mask_img,
+NSR_API int nsr_debug_dx(NsrHandle* h, int which, int layer_idx, const void* a_img, void* out_img, const void* mask_bits,
                          const float* dsig, const float* wsig, int64_t n_rows, NsrStream stream);
 NSR_API int nsr_debug_dw(NsrHandle* h, const void* a_img, int a_cols, int blk0, int blk1, const void* b_img, int b_cols,
                          float* out, float* bias_out, int64_t n_rows, void* scratch, size_t scratch_bytes, NsrStream stream);

@@ -107,7 +107,7 @@ struct TcPassArgs {
   long long* trace;   // debug timeline buffer (NSR_TC_TRACE builds), else null
   int debug_flags;
   // training stash (all three set together, or all null): see TcKernelArgs in nsr_tc.cu
-  uint8_t* stash_enc = nullptr; uint8_t* stash_h = nullptr; uint8_t* stash_dir = nullptr;
+  uint8_t* stash_enc = nullptr; uint8_t* stash_h = nullptr; uint8_t* stash_dir = nullptr; uint32_t* stash_mask = nullptr;
   float* z_out = nullptr;
 };
 cudaError_t tc_pass(NsrHandle_* h, int which, const TcPassArgs& a, cudaStream_t st);

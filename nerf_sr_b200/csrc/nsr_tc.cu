@@ -233,6 +233,7 @@ struct TcKernelArgs {
   uint8_t* stash_enc;   // [n_tiles][32 KB]            encoded xyz (63 + zero pad)
   uint8_t* stash_h;     // [9][n_tiles][4][32 KB]      h_1..h_8 (post-ReLU) and feat = xyz_encoding_final(h_8)
   uint8_t* stash_dir;   // [n_tiles][2][32 KB]         dir layer output (post-ReLU, 128 wide)
+  uint32_t* stash_mask; // [8][n_tiles][128][8]        ReLU masks of h_1..h_8, one bit per activation
   float* z_out;         // [N,S] z-values actually used (coarse pass computes them on the fly), or null
 };
 
@@ -571,7 +572,7 @@ __device__ __forceinline__ void frontend_role(const TcKernelArgs& a, uint8_t* sm
 template <int FMT, int PASSES, bool SIGMA, bool STASH>
 __device__ __forceinline__ void epi_layer(int L, float relu_floor, uint32_t g, uint32_t bar, uint32_t tlane,
                                           uint32_t cst_addr, int hh, int lane, float& sig_p,
-                                          uint8_t* stash_row TR_PARAMS) {
+                                          uint8_t* stash_row, uint32_t* mask_row TR_PARAMS) {
   const uint32_t bias_addr = cst_addr + 4u * (uint32_t)((L - 1) * 256);   // L9 -> kcBiasFinal
 #pragma unroll 1
   for (int q4 = 0; q4 < 4; ++q4) {
@@ -587,6 +588,7 @@ __device__ __forceinline__ void epi_layer(int L, float relu_floor, uint32_t g, u
     tc_wait_ld();
     TR(100 * L + 10 * q4 + 2);
     uint32_t whi[16], wlo[16];
+    uint32_t relu_bits = 0u;
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       const float4 b4 = lds128(bias_addr + 4u * (uint32_t)(col0 + j));
@@ -600,6 +602,7 @@ __device__ __forceinline__ void epi_layer(int L, float relu_floor, uint32_t g, u
       }
       Split<FMT>::apply(v0, v1, whi[j / 2], wlo[j / 2]);
       Split<FMT>::apply(v2, v3, whi[j / 2 + 1], wlo[j / 2 + 1]);
+      if (STASH) relu_bits |= ((v0 > 0.f ? 1u : 0u) | (v1 > 0.f ? 2u : 0u) | (v2 > 0.f ? 4u : 0u) | (v3 > 0.f ? 8u : 0u)) << j;
     }
     TMEM_ST16(tlane + 256u + (uint32_t)(col0 / 2), whi);
     if (PASSES == 3) TMEM_ST16(tlane + 384u + (uint32_t)(col0 / 2), wlo);
@@ -612,6 +615,7 @@ __device__ __forceinline__ void epi_layer(int L, float relu_floor, uint32_t g, u
         *reinterpret_cast<uint4*>(gp + sw) = make_uint4(whi[4 * jj], whi[4 * jj + 1], whi[4 * jj + 2], whi[4 * jj + 3]);
         *reinterpret_cast<uint4*>(gp + kPlaneBytes + sw) = make_uint4(wlo[4 * jj], wlo[4 * jj + 1], wlo[4 * jj + 2], wlo[4 * jj + 3]);
       }
+      if (mask_row) mask_row[2 * q4 + hh] = relu_bits;          // columns [64 q4 + 32 hh, +32)
     }
     TR(100 * L + 10 * q4 + 3);
     tc_wait_st();
@@ -688,9 +692,14 @@ __device__ __forceinline__ void epilogue_role(const TcKernelArgs& a, uint8_t* sm
       // busy with L2 while the heads' activations are finished and staged
       if (L == 2 && it >= 1) tile_tail(it - 1, sig_prev, rgb_prev[0], rgb_prev[1], rgb_prev[2]);
       uint8_t* stash_row = nullptr;
-      if (STASH) stash_row = a.stash_h + ((size_t)(L - 1) * (size_t)a.n_tiles + (size_t)(first_tile + it * (long long)tile_stride)) * (size_t)(4 * kStageBytes) + (size_t)row * 128;
-      if (L == 8) epi_layer<FMT, PASSES, true, STASH>(L, 0.f, g, bar, tlane, sm_base + kSmConst, hh, lane, sig_p, stash_row TR_ARGS);   // + sigma head
-      else epi_layer<FMT, PASSES, false, STASH>(L, L <= 8 ? 0.f : -INFINITY, g, bar, tlane, sm_base + kSmConst, hh, lane, sig_p, stash_row TR_ARGS);
+      uint32_t* mask_row = nullptr;
+      if (STASH) {
+        const size_t lt = (size_t)(L - 1) * (size_t)a.n_tiles + (size_t)(first_tile + it * (long long)tile_stride);
+        stash_row = a.stash_h + lt * (size_t)(4 * kStageBytes) + (size_t)row * 128;
+        if (L <= 8) mask_row = a.stash_mask + (lt * 128 + (size_t)row) * 8;
+      }
+      if (L == 8) epi_layer<FMT, PASSES, true, STASH>(L, 0.f, g, bar, tlane, sm_base + kSmConst, hh, lane, sig_p, stash_row, mask_row TR_ARGS);   // + sigma head
+      else epi_layer<FMT, PASSES, false, STASH>(L, L <= 8 ? 0.f : -INFINITY, g, bar, tlane, sm_base + kSmConst, hh, lane, sig_p, stash_row, mask_row TR_ARGS);
     }
     // ---- layer 10: dir layer (N=128, accumulator half 0) + rgb head ----
     float rgb_p[3] = {0.f, 0.f, 0.f};
@@ -817,7 +826,7 @@ cudaError_t tc_pass(NsrHandle_* h, int which, const TcPassArgs& p, cudaStream_t 
   const int grid = (int)(a.n_tiles < h->sm_count ? a.n_tiles : h->sm_count);
   void (*kern)(const TcKernelArgs) = nullptr;
   const bool stash = p.stash_enc != nullptr;
-  a.stash_enc = p.stash_enc; a.stash_h = p.stash_h; a.stash_dir = p.stash_dir; a.z_out = p.z_out;
+  a.stash_enc = p.stash_enc; a.stash_h = p.stash_h; a.stash_dir = p.stash_dir; a.stash_mask = p.stash_mask; a.z_out = p.z_out;
   switch (h->cfg.precision) {
     case NSR_PREC_BF16X3_TC: kern = stash ? k_tc_pass<1, 3, true> : k_tc_pass<1, 3, false>; break;
     case NSR_PREC_FP16X3_TC: kern = stash ? k_tc_pass<0, 3, true> : k_tc_pass<0, 3, false>; break;

@@ -393,16 +393,39 @@ __device__ __forceinline__ void gemm_epilogue_free(uint32_t tmem) {
 }
 
 // ---------------------------------------------------------------------------
-// k_tg_dx: out = mask . (A . Wt^T [+ dsig x wsig])   per 128-point tile
+// k_tg_dx: out = relu_mask . (A . Wt^T [+ dsig x wsig])   per 128-point tile
+//
+// Epilogue data path: TMEM -> registers -> (mask, hi/lo split) -> a 32 KB shared-memory staging chunk in
+// tile-image layout -> ONE cp.async.bulk store per 64-feature chunk.  (The first version stored 16-byte
+// pieces straight to global memory: 32 lanes x 128-B stride = 32 half-used sectors per instruction, and
+// read the mask from the stashed hi plane the same way; the load/store unit, not the tensor pipe or HBM,
+// bounded the kernel -- profiles/r01_train_launches.md.)  The ReLU mask is the forward's 1-bit-per-
+// activation stash: 32 B per row, read once per tile.
 // ---------------------------------------------------------------------------
 struct DxArgs {
   const uint8_t* a_img; int nkc;        // [n_tiles][nkc][32 KB]   dZ of this layer (K = its output features)
   const uint8_t* wt_img;                // [nkc][64 KB]            transposed weights (rows = input features)
   uint8_t* out_img;                     // [n_tiles][4][32 KB]     dZ of the previous layer
-  const uint8_t* mask_img;              // [n_tiles][4][32 KB]     stashed activation whose ReLU gates the output, or null
+  const uint32_t* mask_bits;            // [n_tiles][128][8]       ReLU mask gating the output, or null
   const float* dsig; const float* wsig; // rank-1 term of the sigma head (final layer only), or null
   long long n_tiles;
 };
+constexpr int kSmDxStage = 2 * kSlotBytes;            // 196608: 32 KB output staging chunk
+constexpr int kSmDxAux = kSmDxStage + kChunk;         // 229376: w_sigma (1 KB)
+constexpr int kSmDxBar = kSmDxAux + 1024;
+constexpr int kSmDxTmem = kSmDxBar + 16 * 8;
+constexpr int kSmemDxBytes = kSmDxTmem + 16;
+static_assert(kSmemDxBytes <= 227 * 1024, "dx smem budget");
+
+__device__ __forceinline__ void bulk_store_s2g(void* gdst, uint32_t ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 
 template <int FMT>
 __global__ void __launch_bounds__(kGemmThreads, 1) k_tg_dx(const DxArgs a) {
@@ -411,9 +434,24 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_tg_dx(const DxArgs a) {
   const uint32_t sm_base = smem_u32(sm);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long my_tiles = (a.n_tiles > blockIdx.x) ? (a.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  if (a.wsig) for (int i = threadIdx.x; i < 256; i += kGemmThreads) reinterpret_cast<float*>(sm + kSmAux)[i] = a.wsig[i];
-  const uint32_t tmem = gemm_prologue(sm, sm_base, 4);
-  const uint32_t bar = sm_base + kSmGBar;
+  if (a.wsig) for (int i = threadIdx.x; i < 256; i += kGemmThreads) reinterpret_cast<float*>(sm + kSmDxAux)[i] = a.wsig[i];
+  if (sm_base & 1023u) { if (threadIdx.x == 0) printf("[nsr_train] dynamic smem base %u not 1024-aligned\n", sm_base); __trap(); }
+  const uint32_t bar = sm_base + kSmDxBar;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar + 8 * (G_FULL + i), 1); mbar_init(bar + 8 * (G_EMPTY + i), 1);
+      mbar_init(bar + 8 * (G_ACCFULL + i), 1); mbar_init(bar + 8 * (G_ACCEMPTY + i), 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sm_base + kSmDxTmem), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + kSmDxTmem);
 
   if (warp == 0) {
     if (elect_one()) {
@@ -465,43 +503,65 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_tg_dx(const DxArgs a) {
     const int q = warp & 3;
     const int row = 32 * q + lane, r7 = lane & 7;
     const uint32_t tlane = tmem + ((uint32_t)(32 * q) << 16);
-    const float* wsig = reinterpret_cast<const float*>(sm + kSmAux);
+    const float* wsig = reinterpret_cast<const float*>(sm + kSmDxAux);
+    const uint32_t stage_row = sm_base + kSmDxStage + (uint32_t)row * 128u;
+    const bool issuer = (warp == 2 && lane == 0);
     for (long long it = 0; it < my_tiles; ++it) {
       const uint32_t buf = (uint32_t)(it & 1);
       const long long tile = blockIdx.x + it * (long long)gridDim.x;
+      uint32_t mbits[8];
+      if (a.mask_bits) {
+        const uint4* mp = reinterpret_cast<const uint4*>(a.mask_bits + ((size_t)tile * kT + row) * 8);
+        const uint4 m0 = mp[0], m1 = mp[1];
+        mbits[0] = m0.x; mbits[1] = m0.y; mbits[2] = m0.z; mbits[3] = m0.w; mbits[4] = m1.x; mbits[5] = m1.y; mbits[6] = m1.z; mbits[7] = m1.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mbits[i] = 0xffffffffu;
+      }
+      const float ds = a.dsig ? a.dsig[tile * kT + row] : 0.f;
       mbar_wait(bar + 8 * (G_ACCFULL + buf), (uint32_t)((it >> 1) & 1));
       tc_fence_after();
-      const float ds = a.dsig ? a.dsig[tile * kT + row] : 0.f;
-#pragma unroll 1
+#pragma unroll
       for (int cc = 0; cc < 8; ++cc) {
+        if ((cc & 1) == 0) {      // a new 64-feature chunk: the staging buffer must have been read out
+          if (issuer) bulk_store_wait_read();
+          named_bar_sync(3, 128);
+        }
         uint32_t r[32];
         TMEM_LD32(tlane + 256u * buf + 32u * (uint32_t)cc, r);
         tc_wait_ld();
-        const size_t cbase = ((size_t)tile * 4 + (size_t)(cc >> 1)) * kChunk + (size_t)row * 128;
+        const uint32_t mb = mbits[cc];
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
-          const size_t off = cbase + (size_t)((((cc & 1) * 4 + jj) ^ r7) << 4);
-          uint32_t mw[4] = {0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u};
-          if (a.mask_img) { const uint4 mk = *reinterpret_cast<const uint4*>(a.mask_img + off); mw[0] = mk.x; mw[1] = mk.y; mw[2] = mk.z; mw[3] = mk.w; }
           uint32_t hi[4], lo[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            float v0 = __uint_as_float(r[8 * jj + 2 * e]), v1 = __uint_as_float(r[8 * jj + 2 * e + 1]);
-            if (a.wsig) { v0 = fmaf(ds, wsig[32 * cc + 8 * jj + 2 * e], v0); v1 = fmaf(ds, wsig[32 * cc + 8 * jj + 2 * e + 1], v1); }
-            if ((mw[e] & 0x7fffu) == 0u) v0 = 0.f;
-            if ((mw[e] & 0x7fff0000u) == 0u) v1 = 0.f;
+            const int col = 8 * jj + 2 * e;
+            float v0 = __uint_as_float(r[col]), v1 = __uint_as_float(r[col + 1]);
+            if (a.wsig) { v0 = fmaf(ds, wsig[32 * cc + col], v0); v1 = fmaf(ds, wsig[32 * cc + col + 1], v1); }
+            if (!((mb >> col) & 1u)) v0 = 0.f;
+            if (!((mb >> (col + 1)) & 1u)) v1 = 0.f;
             Split<FMT>::apply(v0, v1, hi[e], lo[e]);
           }
-          *reinterpret_cast<uint4*>(a.out_img + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(a.out_img + off + kPlane) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          const uint32_t sw = (uint32_t)((((cc & 1) * 4 + jj) ^ r7) << 4);
+          sts128(stage_row + sw, hi[0], hi[1], hi[2], hi[3]);
+          sts128(stage_row + kPlane + sw, lo[0], lo[1], lo[2], lo[3]);
+        }
+        if (cc & 1) {             // chunk complete: hand it to the bulk-copy engine
+          fence_proxy_async();
+          named_bar_sync(3, 128);
+          if (issuer) bulk_store_s2g(a.out_img + ((size_t)tile * 4 + (size_t)(cc >> 1)) * kChunk, sm_base + kSmDxStage, kChunk);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar + 8 * (G_ACCEMPTY + buf));
     }
+    if (issuer) bulk_store_wait_all();
   }
-  gemm_epilogue_free(tmem);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
 // ---------------------------------------------------------------------------
@@ -771,7 +831,7 @@ static int fmt_of(const NsrHandle_* h) { return h->cfg.precision == NSR_PREC_FP1
 
 struct TrainWs {
   // per pass (0 coarse, 1 fine)
-  size_t enc[2], hh[2], dir[2], raw[2], z[2];
+  size_t enc[2], hh[2], dir[2], mask[2], raw[2], z[2];
   // shared by the two backward passes
   size_t dhead, encdir, dzdir, g0, g1, dsig, part;
   size_t part_region;       // bytes of one dW launch's partial region
@@ -791,6 +851,7 @@ static TrainWs train_layout(const NsrHandle_* h, int64_t n) {
     L.enc[w] = off; off += t * kChunk;
     L.hh[w] = off; off += 9 * t * 4 * kChunk;
     L.dir[w] = off; off += t * 2 * kChunk;
+    L.mask[w] = off; off += 8 * t * kT * 8 * sizeof(uint32_t);
     L.raw[w] = off; off += al256((size_t)n * L.S[w] * 4 * sizeof(float));
     L.z[w] = off; off += al256((size_t)n * L.S[w] * sizeof(float));
   }
@@ -812,13 +873,13 @@ static cudaError_t launch_dx(NsrHandle_* h, const DxArgs& a, cudaStream_t st) {
   const int grid = (int)(a.n_tiles < h->sm_count ? a.n_tiles : h->sm_count);
   cudaError_t e;
   if (fmt_of(h) == 1) {
-    e = cudaFuncSetAttribute(k_tg_dx<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemGemmBytes);
+    e = cudaFuncSetAttribute(k_tg_dx<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemDxBytes);
     if (e != cudaSuccess) return e;
-    k_tg_dx<1><<<grid, kGemmThreads, kSmemGemmBytes, st>>>(a);
+    k_tg_dx<1><<<grid, kGemmThreads, kSmemDxBytes, st>>>(a);
   } else {
-    e = cudaFuncSetAttribute(k_tg_dx<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemGemmBytes);
+    e = cudaFuncSetAttribute(k_tg_dx<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemDxBytes);
     if (e != cudaSuccess) return e;
-    k_tg_dx<0><<<grid, kGemmThreads, kSmemGemmBytes, st>>>(a);
+    k_tg_dx<0><<<grid, kGemmThreads, kSmemDxBytes, st>>>(a);
   }
   h->launches += 1;
   return cudaGetLastError();
@@ -898,6 +959,7 @@ static int backward_net(NsrHandle_* h, int which, const float* rays, int64_t n, 
   uint8_t* G[2] = {(uint8_t*)(ws + L.g0), (uint8_t*)(ws + L.g1)};
   float* dsig = (float*)(ws + L.dsig);
   auto h_layer = [&](int l) { return hh + (size_t)(l - 1) * (size_t)tiles * 4 * kChunk; };   // l = 1..8 activations, 9 = feat
+  auto m_layer = [&](int l) { return (const uint32_t*)(ws + L.mask[which]) + (size_t)(l - 1) * (size_t)tiles * kT * 8; };   // l = 1..8
 
   // ---- compositing / activation / rgb-head backward ----
   {
@@ -940,7 +1002,7 @@ static int backward_net(NsrHandle_* h, int which, const float* rays, int64_t n, 
   }
   {   // d feat = dZ_dir . W_dir[:, :256]   (xyz_encoding_final has no activation: no mask)
     DxArgs a{};
-    a.a_img = dzdir; a.nkc = 2; a.wt_img = wt(0); a.out_img = G[0]; a.mask_img = nullptr; a.n_tiles = tiles;
+    a.a_img = dzdir; a.nkc = 2; a.wt_img = wt(0); a.out_img = G[0]; a.mask_bits = nullptr; a.n_tiles = tiles;
     NSR_TCUDA(h, launch_dx(h, a, st));
   }
   {   // xyz_encoding_final: dW = d feat^T . h8 ; sigma head: dW = d sigma^T . h8, db
@@ -951,7 +1013,7 @@ static int backward_net(NsrHandle_* h, int which, const float* rays, int64_t n, 
   }
   {   // dZ_8 = (d feat . W_final + d sigma x w_sigma) . [h8 > 0]
     DxArgs a{};
-    a.a_img = G[0]; a.nkc = 4; a.wt_img = wt(1); a.out_img = G[1]; a.mask_img = h_layer(8);
+    a.a_img = G[0]; a.nkc = 4; a.wt_img = wt(1); a.out_img = G[1]; a.mask_bits = m_layer(8);
     a.dsig = dsig; a.wsig = net.tc_consts + kcWsig; a.n_tiles = tiles;
     NSR_TCUDA(h, launch_dx(h, a, st));
   }
@@ -975,7 +1037,7 @@ static int backward_net(NsrHandle_* h, int which, const float* rays, int64_t n, 
     if (P.err != cudaSuccess) return tfail(h, NSR_ERR_CUDA, std::string("dW launch: ") + cudaGetErrorString(P.err));
     if (Lyr >= 2) {          // dZ_{L-1} = (dZ_L . W_L[:, h part]) . [h_{L-1} > 0]
       DxArgs a{};
-      a.a_img = dz; a.nkc = 4; a.wt_img = wt(2 + (8 - Lyr)); a.out_img = G[cur ^ 1]; a.mask_img = h_layer(Lyr - 1); a.n_tiles = tiles;
+      a.a_img = dz; a.nkc = 4; a.wt_img = wt(2 + (8 - Lyr)); a.out_img = G[cur ^ 1]; a.mask_bits = m_layer(Lyr - 1); a.n_tiles = tiles;
       NSR_TCUDA(h, launch_dx(h, a, st));
       cur ^= 1;
     }
@@ -1051,6 +1113,7 @@ extern "C" int nsr_render_train(NsrHandle* h, const float* rays, int64_t n_rays,
     a.z_next = w ? nullptr : (float*)(ws + L.z[1]);
     a.z_out = w ? nullptr : (float*)(ws + L.z[0]);
     a.stash_enc = (uint8_t*)(ws + L.enc[w]); a.stash_h = (uint8_t*)(ws + L.hh[w]); a.stash_dir = (uint8_t*)(ws + L.dir[w]);
+    a.stash_mask = (uint32_t*)(ws + L.mask[w]);
     a.trace = nullptr; a.debug_flags = 0;
     NSR_TCUDA(h, tc_pass(h, w, a, st));
   }
@@ -1157,10 +1220,10 @@ extern "C" int nsr_adam_step(NsrHandle* h, float* const* param_ptrs, int n_param
 extern "C" int nsr_debug_train_layout(const NsrHandle* h, int64_t n_rays, int64_t* out16) {
   if (!h || !out16 || n_rays <= 0) return NSR_ERR_INVALID_ARG;
   const TrainWs L = train_layout(h, n_rays);
-  const int64_t v[16] = {(int64_t)L.enc[0], (int64_t)L.hh[0], (int64_t)L.dir[0], (int64_t)L.raw[0], (int64_t)L.z[0], L.tiles[0],
+  const int64_t v[18] = {(int64_t)L.enc[0], (int64_t)L.hh[0], (int64_t)L.dir[0], (int64_t)L.raw[0], (int64_t)L.z[0], L.tiles[0],
                          (int64_t)L.enc[1], (int64_t)L.hh[1], (int64_t)L.dir[1], (int64_t)L.raw[1], (int64_t)L.z[1], L.tiles[1],
-                         (int64_t)L.dhead, (int64_t)L.dzdir, (int64_t)L.g0, (int64_t)L.g1};
-  for (int i = 0; i < 16; ++i) out16[i] = v[i];
+                         (int64_t)L.dhead, (int64_t)L.dzdir, (int64_t)L.g0, (int64_t)L.g1, (int64_t)L.mask[0], (int64_t)L.mask[1]};
+  for (int i = 0; i < 18; ++i) out16[i] = v[i];
   return NSR_OK;
 }
 
@@ -1190,7 +1253,29 @@ extern "C" int nsr_debug_unpack_image(NsrHandle* h, const void* image, int64_t n
 
 // out_img[rows,256] = mask . (a_img[rows, k_cols] . W[k_cols, ld][:, col0:col0+256] + dsig x wsig)
 // with W given as the transposed-weight image of net `which`, dX layer `layer_idx` (0 dir, 1 final, 2.. = L8..L2).
-extern "C" int nsr_debug_dx(NsrHandle* h, int which, int layer_idx, const void* a_img, void* out_img, const void* mask_img,
+__global__ void k_relu_bits(const float* __restrict__ x, long long n_rows, uint32_t* __restrict__ bits) {
+  // bits[(row)*8 + w] bit j = x[row][32 w + j] > 0   (rows padded to a multiple of 128 with zeros)
+  const long long rows_pad = (n_rows + 127) / 128 * 128;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < rows_pad * 8; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / 8;
+    const int w = (int)(i % 8);
+    uint32_t b = 0u;
+    if (row < n_rows) for (int j = 0; j < 32; ++j) b |= (x[row * 256 + 32 * w + j] > 0.f ? 1u : 0u) << j;
+    bits[i] = b;
+  }
+}
+
+extern "C" int nsr_debug_relu_bits(NsrHandle* h, const float* x, int64_t n_rows, void* bits_out, NsrStream stream) {
+  if (!h) return NSR_ERR_INVALID_ARG;
+  if (!x || !bits_out || n_rows <= 0) return tfail(h, NSR_ERR_INVALID_ARG, "nsr_debug_relu_bits: bad argument");
+  NSR_TCUDA(h, cudaSetDevice(h->cfg.device));
+  k_relu_bits<<<h->sm_count * 4, 256, 0, (cudaStream_t)stream>>>(x, n_rows, (uint32_t*)bits_out);
+  h->launches += 1;
+  NSR_TCUDA(h, cudaGetLastError());
+  return NSR_OK;
+}
+
+extern "C" int nsr_debug_dx(NsrHandle* h, int which, int layer_idx, const void* a_img, void* out_img, const void* mask_bits,
                             const float* dsig, const float* wsig, int64_t n_rows, NsrStream stream) {
   if (!h) return NSR_ERR_INVALID_ARG;
   int rc = train_supported(h);
@@ -1203,7 +1288,7 @@ extern "C" int nsr_debug_dx(NsrHandle* h, int which, int layer_idx, const void* 
   DxArgs a{};
   a.a_img = (const uint8_t*)a_img; a.nkc = WT.l[layer_idx].n_out / 64;
   a.wt_img = h->net[which].wt_image + (size_t)WT.l[layer_idx].chunk0 * kWtChunkBytes;
-  a.out_img = (uint8_t*)out_img; a.mask_img = (const uint8_t*)mask_img; a.dsig = dsig; a.wsig = wsig;
+  a.out_img = (uint8_t*)out_img; a.mask_bits = (const uint32_t*)mask_bits; a.dsig = dsig; a.wsig = wsig;
   a.n_tiles = (n_rows + kT - 1) / kT;
   NSR_TCUDA(h, launch_dx(h, a, (cudaStream_t)stream));
   return NSR_OK;

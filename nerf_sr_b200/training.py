@@ -159,10 +159,32 @@ def unpack_image(self: Renderer, img: torch.Tensor, n_rows: int, n_cols: int, ld
     return out
 
 
-def debug_dx(self: Renderer, which: int, layer_idx: int, a_img: torch.Tensor, n_rows: int, mask_img=None, dsig=None, wsig=None):
+def relu_bits(self: Renderer, x: torch.Tensor) -> torch.Tensor:
+    """[rows,256] fp32 -> the 1-bit-per-activation ReLU mask layout the forward stashes (test seam)."""
+    x = self._f32(x)
+    rows = x.shape[0]
+    out = torch.empty(((rows + 127) // 128) * 128 * 8, dtype=torch.int32, device=self.device)
+    self._check(self.lib.nsr_debug_relu_bits(self._h, x.data_ptr(), rows, out.data_ptr(), self._stream()))
+    return out
+
+
+def stash_mask(self: Renderer, n_rays: int, which: int, layer: int) -> torch.Tensor:
+    """ReLU mask of h_layer (1..8) of pass `which` after render_train, as a [P,256] bool tensor (test seam)."""
+    L = train_layout(self, n_rays)
+    ws = self._train_ws
+    base = (-ws.data_ptr()) % 256
+    S = self.n_fine if which else self.n_coarse
+    tiles = L[f"tiles{which}"]
+    off = base + L[f"mask{which}"] + (layer - 1) * tiles * 128 * 32
+    words = ws[off: off + tiles * 128 * 32].view(torch.int32).view(tiles * 128, 8)
+    bits = (words.unsqueeze(-1) >> torch.arange(32, device=ws.device, dtype=torch.int32)) & 1
+    return bits.reshape(tiles * 128, 256)[: n_rays * S].bool()
+
+
+def debug_dx(self: Renderer, which: int, layer_idx: int, a_img: torch.Tensor, n_rows: int, mask_bits=None, dsig=None, wsig=None):
     out = torch.empty(image_bytes(n_rows, 256), dtype=torch.uint8, device=self.device)
     self._check(self.lib.nsr_debug_dx(self._h, which, layer_idx, a_img.data_ptr(), out.data_ptr(),
-                                      mask_img.data_ptr() if mask_img is not None else None,
+                                      mask_bits.data_ptr() if mask_bits is not None else None,
                                       dsig.data_ptr() if dsig is not None else None,
                                       wsig.data_ptr() if wsig is not None else None, n_rows, self._stream()))
     return out
@@ -179,10 +201,10 @@ def debug_dw(self: Renderer, a_img: torch.Tensor, a_cols: int, blk0: int, blk1: 
 
 def train_layout(self: Renderer, n_rays: int) -> Dict[str, int]:
     """Offsets of the stash regions inside the train workspace (test seam)."""
-    arr = (C.c_int64 * 16)()
+    arr = (C.c_int64 * 18)()
     self._check(self.lib.nsr_debug_train_layout(self._h, n_rays, arr))
     keys = ["enc0", "h0", "dir0", "raw0", "z0", "tiles0", "enc1", "h1", "dir1", "raw1", "z1", "tiles1",
-            "dhead", "dzdir", "g0", "g1"]
+            "dhead", "dzdir", "g0", "g1", "mask0", "mask1"]
     return dict(zip(keys, [int(x) for x in arr]))
 
 
@@ -205,7 +227,7 @@ def stash_activation(self: Renderer, n_rays: int, which: int, layer: int) -> tor
     return unpack_image(self, img, rows, cols)
 
 
-for _f in (train_layout, stash_activation, render_train, backward, lr_loss_grad, clip_coef, adam_step, pack_image, unpack_image, debug_dx, debug_dw):
+for _f in (train_layout, stash_activation, stash_mask, relu_bits, render_train, backward, lr_loss_grad, clip_coef, adam_step, pack_image, unpack_image, debug_dx, debug_dw):
     setattr(Renderer, _f.__name__, _f)
 
 

