@@ -166,6 +166,158 @@ def workload_config(n_gpus):
             "l2": "flushed between timed steps (256 MiB write)"}
 
 
+# ------------------------------------------------------------------------------------------------
+# --workload train: BASELINE configs[2] shape (LLFF-like rays, 512 LR pixels x 2x2 SS = 2048 rays per rank per
+# step, 64 + 128 samples, sigma noise 1.0): forward (train mode) + LR loss + backward + gradient all-reduce (N > 1)
+# + Adam + weight re-pack, the reference's optimize_parameters (models/nerf_downX_model.py:398-408).
+# ------------------------------------------------------------------------------------------------
+TRAIN_N_LR = 512
+
+
+def train_inputs(rank: int):
+    from nerf_sr_b200 import synthetic as S
+    cfg = S.RenderConfig(noise_std=1.0, N_coarse=N_COARSE, N_importance=N_IMPORTANCE, downscale=SS)
+    pc, pf = S.make_mlp_params(cfg, 21), S.make_mlp_params(cfg, 8)
+    rays = S.synthetic_rays(TRAIN_N_LR * SS * SS, 300 + rank, "llff")
+    target = torch.rand(TRAIN_N_LR, 3, generator=torch.Generator().manual_seed(500 + rank))
+    return cfg, pc, pf, rays, target
+
+
+def oracle_train_rate(cfg, pc, pf, rays, target, device, n_lr: int, repeats: int):
+    """The reference's training iteration (oracle port: torch autograd + Adam restatement) on `device`."""
+    from oracle import nerf_oracle as O
+    from oracle import train_oracle as T
+    dev = torch.device(device)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    st = T.TrainState({k: v.to(dev) for k, v in pc.items()}, {k: v.to(dev) for k, v in pf.items()})
+    r, t = rays[: n_lr * SS * SS].to(dev), target[:n_lr].to(dev)
+    g = torch.Generator(device=dev).manual_seed(0)
+    tc = T.TrainConfig()
+
+    def draw():
+        n = r.shape[0]
+        return O.RenderRng(torch.rand(n, cfg.N_coarse, device=dev, generator=g), torch.randn(n, cfg.N_coarse, device=dev, generator=g),
+                           torch.rand(n, cfg.N_importance, device=dev, generator=g),
+                           torch.randn(n, cfg.N_coarse + cfg.N_importance, device=dev, generator=g))
+    T.optimize_parameters(st, r, t, cfg, tc, draw(), SS)
+    times = []
+    for _ in range(repeats):
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        T.optimize_parameters(st, r, t, cfg, tc, draw(), SS)
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+    times.sort()
+    return r.shape[0] / times[len(times) // 2]
+
+
+def train_config(world):
+    return {"workload": "BASELINE configs[2] shape: LLFF-like rays, 512 LR pixels x 2x2 SS = 2048 rays per GPU per step, 64 coarse + "
+                        "128 fine samples, sigma noise 1.0, random-init 256-wide coarse+fine MLP; one step = forward (train mode) + "
+                        "LR MSE loss + backward + Adam + weight re-pack",
+            "rays_per_step_per_gpu": TRAIN_N_LR * SS * SS, "n_coarse": N_COARSE, "n_fine": N_COARSE + N_IMPORTANCE, "supersampling": SS,
+            "parallelism": f"ray-sharded x{world}" + (", NCCL all-reduce (mean) of the 4.77 MB gradient bucket per step" if world > 1 else ""),
+            "l2": "working set per step (5 GB activation stash) exceeds L2"}
+
+
+def run_train(args, rank, world, local):
+    import torch.distributed as dist
+    from nerf_sr_b200 import Renderer, Trainer
+    dev = torch.device(f"cuda:{local}")
+    cfg, pc, pf, rays_cpu, target_cpu = train_inputs(rank)
+    r = Renderer(cfg, dev, precision="bf16x3")
+    tr = Trainer(r, pc, pf, downscale=SS)
+    rays, target = rays_cpu.to(dev), target_cpu.to(dev)
+    rays_pin, target_pin = rays_cpu.pin_memory(), target_cpu.pin_memory()
+    gen = torch.Generator(device=dev).manual_seed(rank)
+    n = rays.shape[0]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        tr.optimize_parameters(rays, target, tr.draw_rng(n, gen))
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    launches0 = r.launch_count
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        tr.optimize_parameters(rays, target, tr.draw_rng(n, gen))
+    b.record()
+    barrier()
+    dev_ms = a.elapsed_time(b)
+    launches = r.launch_count - launches0
+    # end to end: the batch comes from pinned host memory every step, the step's losses go back to the host
+    dev_rays, dev_tgt = torch.empty_like(rays), torch.empty_like(target)
+    host_metrics = torch.empty(4, dtype=torch.float32).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        dev_rays.copy_(rays_pin, non_blocking=True)
+        dev_tgt.copy_(target_pin, non_blocking=True)
+        m = tr.optimize_parameters(dev_rays, dev_tgt, tr.draw_rng(n, gen))
+        host_metrics.copy_(m, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = (float(x) for x in t.tolist())
+    if rank == 0:
+        pk, pk_kind = peaks()
+        total = n * world * args.steps
+        value = total / (dev_ms / 1e3)
+        flop_step = n * (N_COARSE + N_COARSE + N_IMPORTANCE) * FLOP_PER_POINT * 3      # forward + 2x backward (SURVEY.md 8d)
+        achieved = flop_step * args.steps / (dev_ms / 1e3) / 1e12
+        peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+        line = {
+            "metric": "training rays/sec (64+128 samples, 2x SS; forward + backward + Adam)", "value": value, "unit": "rays/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3 split (fp32 accumulate, fp32 master weights)",
+            "data": "synthetic", "config": train_config(world),
+            "e2e": {"value": total / (e2e_ms / 1e3), "unit": "rays/s", "h2d_bytes_per_step": n * 8 * 4 + (n // (SS * SS)) * 3 * 4,
+                    "d2h_bytes_per_step": 16, "api": "Trainer.optimize_parameters (pinned host batch in, losses out)"},
+            "gpu_launches": int(launches),
+            "final_loss": [float(x) for x in host_metrics.tolist()],
+            "roofline": {"bound": "hbm", "kernel": "whole step (k_tc_pass stash variant, k_tg_dx, k_tg_dw; see DESIGN.md section 11)",
+                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "peak_kind": f"{pk_kind} cuBLAS bf16 sustained", "issued_frac": 3 * achieved / peak,
+                         "flop_per_step": flop_step, "traffic": None,
+                         "note": "algorithmic FLOP of the step against the tensor peak; the backward GEMM kernels stream their operands "
+                                 "from HBM (58 KB per point) and are HBM-bound, profiles/r01_train_*.md"},
+            "clocks": sampler.summary(),
+        }
+        if world == 1:
+            try:
+                line["torch_gpu_reference_port"] = {
+                    "value": oracle_train_rate(cfg, pc, pf, rays_cpu, target_cpu, f"cuda:{local}", TRAIN_N_LR, 3), "unit": "rays/s",
+                    "what": "oracle port of optimize_parameters (the reference's PyTorch autograd + Adam op sequence) on this GPU, "
+                            "fp32, allow_tf32 off, 2048 rays per step; not the product path"}
+            except Exception as e:
+                line["torch_gpu_reference_port"] = {"unavailable": str(e)[:200]}
+            if not args.no_cpu_baseline:
+                ncpu = os.cpu_count() or 1
+                torch.set_num_threads(min(ncpu, 32))
+                rate = oracle_train_rate(cfg, pc, pf, rays_cpu, target_cpu, "cpu", 64, 3)
+                line["cpu_baseline"] = {"value": rate, "unit": "rays/s", "cores": min(ncpu, 32), "host_cores": ncpu, "kind": "port",
+                                        "sample": "256 rays (64 LR pixels) per step, median of 3 full iterations of the oracle port "
+                                                  "(torch CPU autograd + Adam)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    r.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -174,6 +326,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16x3", choices=["fp32_simt", "bf16x3", "fp16x3", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="render", choices=["render", "train"],
+                    help="render = the headline metric (BASELINE configs[1]); train = the training iteration (configs[2] shape)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -207,6 +361,10 @@ def main():
             sys.stdout.flush()
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
+
+    if args.workload == "train":
+        run_train(args, rank, world, local)
+        return
 
     cfg, pc, pf, rays_cpu = make_inputs(seed_offset=rank)
     r = Renderer(cfg, dev, precision=args.precision)

@@ -511,10 +511,14 @@ __device__ __forceinline__ void frontend_role(const TcKernelArgs& a, uint8_t* sm
       const int sw = (j ^ (t & 7)) << 4;
       *reinterpret_cast<uint4*>(row_hi + sw) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
       *reinterpret_cast<uint4*>(row_lo + sw) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-      if (STASH) {
-        uint8_t* g = a.stash_enc + (size_t)tile * kStageBytes + t * 128 + sw;
-        *reinterpret_cast<uint4*>(g) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(g + kPlaneBytes) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+    if (STASH) {   // the same swizzled row image -> global stash, 32 bytes per store (re-read from smem: own writes)
+      uint8_t* g = a.stash_enc + (size_t)tile * kStageBytes + t * 128;
+#pragma unroll
+      for (int pr = 0; pr < 4; ++pr) {
+        const int pos = 32 * pr;
+        stg256(g + pos, *reinterpret_cast<const uint4*>(row_hi + pos), *reinterpret_cast<const uint4*>(row_hi + pos + 16));
+        stg256(g + kPlaneBytes + pos, *reinterpret_cast<const uint4*>(row_lo + pos), *reinterpret_cast<const uint4*>(row_lo + pos + 16));
       }
     }
     TR(5002);
@@ -610,10 +614,12 @@ __device__ __forceinline__ void epi_layer(int L, float relu_floor, uint32_t g, u
       uint8_t* gp = stash_row + (size_t)q4 * kStageBytes;        // k chunk = 64-column quarter
       const int r7 = lane & 7;                                   // tile row = 32*quarter + lane
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        const int sw = ((4 * hh + jj) ^ r7) << 4;
-        *reinterpret_cast<uint4*>(gp + sw) = make_uint4(whi[4 * jj], whi[4 * jj + 1], whi[4 * jj + 2], whi[4 * jj + 3]);
-        *reinterpret_cast<uint4*>(gp + kPlaneBytes + sw) = make_uint4(wlo[4 * jj], wlo[4 * jj + 1], wlo[4 * jj + 2], wlo[4 * jj + 3]);
+      for (int t2 = 0; t2 < 2; ++t2) {                           // 16-byte chunks (4hh + 2 t2, + 1): one 32-byte store each
+        const int e = 8 * t2;
+        store_chunk_pair(gp, 2 * hh + t2, r7, make_uint4(whi[e], whi[e + 1], whi[e + 2], whi[e + 3]),
+                         make_uint4(whi[e + 4], whi[e + 5], whi[e + 6], whi[e + 7]));
+        store_chunk_pair(gp + kPlaneBytes, 2 * hh + t2, r7, make_uint4(wlo[e], wlo[e + 1], wlo[e + 2], wlo[e + 3]),
+                         make_uint4(wlo[e + 4], wlo[e + 5], wlo[e + 6], wlo[e + 7]));
       }
       if (mask_row) mask_row[2 * q4 + hh] = relu_bits;          // columns [64 q4 + 32 hh, +32)
     }
@@ -716,6 +722,7 @@ __device__ __forceinline__ void epilogue_role(const TcKernelArgs& a, uint8_t* sm
       for (int c = 0; c < 2; ++c) {
         const int col0 = 64 * hh + 32 * c;
         uint32_t r[32];
+        uint32_t dhi[16], dlo[16];
         TMEM_LD32(tlane + (uint32_t)col0, r);
         tc_wait_ld();
 #pragma unroll
@@ -729,14 +736,20 @@ __device__ __forceinline__ void epilogue_role(const TcKernelArgs& a, uint8_t* sm
           rgb_p[0] = fmaf(v0, w0.x, rgb_p[0]); rgb_p[0] = fmaf(v1, w0.y, rgb_p[0]); rgb_p[0] = fmaf(v2, w0.z, rgb_p[0]); rgb_p[0] = fmaf(v3, w0.w, rgb_p[0]);
           rgb_p[1] = fmaf(v0, w1.x, rgb_p[1]); rgb_p[1] = fmaf(v1, w1.y, rgb_p[1]); rgb_p[1] = fmaf(v2, w1.z, rgb_p[1]); rgb_p[1] = fmaf(v3, w1.w, rgb_p[1]);
           rgb_p[2] = fmaf(v0, w2.x, rgb_p[2]); rgb_p[2] = fmaf(v1, w2.y, rgb_p[2]); rgb_p[2] = fmaf(v2, w2.z, rgb_p[2]); rgb_p[2] = fmaf(v3, w2.w, rgb_p[2]);
-          if (STASH) {   // dir layer activations (post-ReLU) -> tile image, chunk hh, 16-B chunk 4c + j/8
-            uint32_t dh0, dl0, dh1, dl1;
-            Split<FMT>::apply(v0, v1, dh0, dl0);
-            Split<FMT>::apply(v2, v3, dh1, dl1);
-            uint8_t* gp = a.stash_dir + ((size_t)(first_tile + it * (long long)tile_stride) * 2 + (size_t)hh) * (size_t)kStageBytes +
-                          (size_t)row * 128 + (size_t)((((4 * c + (j >> 3)) ^ (row & 7)) << 4) + ((j & 4) << 1));
-            *reinterpret_cast<uint2*>(gp) = make_uint2(dh0, dh1);
-            *reinterpret_cast<uint2*>(gp + kPlaneBytes) = make_uint2(dl0, dl1);
+          if (STASH) {
+            Split<FMT>::apply(v0, v1, dhi[j / 2], dlo[j / 2]);
+            Split<FMT>::apply(v2, v3, dhi[j / 2 + 1], dlo[j / 2 + 1]);
+          }
+        }
+        if (STASH) {   // dir layer activations (post-ReLU) -> tile image, chunk hh, 16-B chunks 4c .. 4c+3
+          uint8_t* gp = a.stash_dir + ((size_t)(first_tile + it * (long long)tile_stride) * 2 + (size_t)hh) * (size_t)kStageBytes + (size_t)row * 128;
+#pragma unroll
+          for (int t2 = 0; t2 < 2; ++t2) {
+            const int e = 8 * t2;
+            store_chunk_pair(gp, 2 * c + t2, row & 7, make_uint4(dhi[e], dhi[e + 1], dhi[e + 2], dhi[e + 3]),
+                             make_uint4(dhi[e + 4], dhi[e + 5], dhi[e + 6], dhi[e + 7]));
+            store_chunk_pair(gp + kPlaneBytes, 2 * c + t2, row & 7, make_uint4(dlo[e], dlo[e + 1], dlo[e + 2], dlo[e + 3]),
+                             make_uint4(dlo[e + 4], dlo[e + 5], dlo[e + 6], dlo[e + 7]));
           }
         }
       }

@@ -128,6 +128,20 @@ __host__ __device__ constexpr uint32_t umma_idesc(int fmt, int M, int N) {
                  "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]),        \
                  "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory")
 
+// 256-bit global store (sm_100: STG.256).  p must be 32-byte aligned.
+__device__ __forceinline__ void stg256(void* p, uint4 a, uint4 b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+// Store the 16-byte chunks (2*pair, 2*pair+1) of one 128-byte row of a SWIZZLE_128B tile image with ONE
+// 32-byte store: chunk j lives at position j ^ (row & 7), so an even/odd pair always shares an aligned
+// 32-byte sector (in swapped order when the row index is odd).  row_base: start of the row (128-B aligned).
+__device__ __forceinline__ void store_chunk_pair(uint8_t* row_base, int pair, int r7, uint4 c_even, uint4 c_odd) {
+  const int pos = (((2 * pair) ^ r7) & ~1) << 4;
+  const bool swp = (r7 & 1) != 0;
+  stg256(row_base + pos, swp ? c_odd : c_even, swp ? c_even : c_odd);
+}
+
 // ---- hi/lo split of two fp32 values into packed 16-bit pairs (even k in the low half) ----
 template <int FMT> struct Split;
 template <> struct Split<1> {   // bf16

@@ -287,50 +287,51 @@ k_render_bwd(const RenderBwdArgs a) {
         uint32_t h0, l0, h1, l1;
         Split<FMT>::apply(dsg, drgb[0], h0, l0);
         Split<FMT>::apply(drgb[1], drgb[2], h1, l1);
-        uint8_t* g = a.dhead + (size_t)tile * kChunk;
+        uint8_t* g = a.dhead + (size_t)tile * kChunk + (size_t)row * 128;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          uint8_t* q = g + img_off(row, j);
-          *reinterpret_cast<uint4*>(q) = (j == 0) ? make_uint4(h0, h1, 0u, 0u) : zero4;
-          *reinterpret_cast<uint4*>(q + kPlane) = (j == 0) ? make_uint4(l0, l1, 0u, 0u) : zero4;
+        for (int pr = 0; pr < 4; ++pr) {
+          store_chunk_pair(g, pr, row & 7, pr == 0 ? make_uint4(h0, h1, 0u, 0u) : zero4, zero4);
+          store_chunk_pair(g + kPlane, pr, row & 7, pr == 0 ? make_uint4(l0, l1, 0u, 0u) : zero4, zero4);
         }
       }
       {   // encdir: the ray's 27 encoded view-direction channels (+ zero pad to 64)
-        uint8_t* g = a.encdir + (size_t)tile * kChunk;
+        uint8_t* g = a.encdir + (size_t)tile * kChunk + (size_t)row * 128;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          uint32_t hi[4] = {0u, 0u, 0u, 0u}, lo[4] = {0u, 0u, 0u, 0u};
-          if (j < 4 && valid) {
+        for (int pr = 0; pr < 4; ++pr) {
+          uint32_t hi[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u}, lo[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+          if (pr < 2 && valid) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) Split<FMT>::apply(senc[8 * j + 2 * q], senc[8 * j + 2 * q + 1], hi[q], lo[q]);
+            for (int q = 0; q < 8; ++q) Split<FMT>::apply(senc[16 * pr + 2 * q], senc[16 * pr + 2 * q + 1], hi[q], lo[q]);
           }
-          uint8_t* q = g + img_off(row, j);
-          *reinterpret_cast<uint4*>(q) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(q + kPlane) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          store_chunk_pair(g, pr, row & 7, make_uint4(hi[0], hi[1], hi[2], hi[3]), make_uint4(hi[4], hi[5], hi[6], hi[7]));
+          store_chunk_pair(g + kPlane, pr, row & 7, make_uint4(lo[0], lo[1], lo[2], lo[3]), make_uint4(lo[4], lo[5], lo[6], lo[7]));
         }
       }
       // dZ_dir = (d rgb_pre . W_rgb) masked by the dir layer's ReLU (networks.py:221-222)
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
-        uint8_t* g = a.dzdir + (size_t)(tile * 2 + c) * kChunk;
+        uint8_t* g = a.dzdir + (size_t)(tile * 2 + c) * kChunk + (size_t)row * 128;
         const uint8_t* m = a.stash_dir + (size_t)(tile * 2 + c) * kChunk;
 #pragma unroll 2
-        for (int j = 0; j < 8; ++j) {
-          const size_t off = img_off(row, j);
-          const uint4 mk = *reinterpret_cast<const uint4*>(m + off);
-          const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
-          uint32_t hi[4], lo[4];
+        for (int pr = 0; pr < 4; ++pr) {
+          uint32_t hi[8], lo[8];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int n = 64 * c + 8 * j + 2 * q;
-            float d0 = drgb[0] * swr[n] + drgb[1] * swr[128 + n] + drgb[2] * swr[256 + n];
-            float d1 = drgb[0] * swr[n + 1] + drgb[1] * swr[128 + n + 1] + drgb[2] * swr[256 + n + 1];
-            if ((mw[q] & 0x7fffu) == 0u) d0 = 0.f;
-            if ((mw[q] & 0x7fff0000u) == 0u) d1 = 0.f;
-            Split<FMT>::apply(d0, d1, hi[q], lo[q]);
+          for (int jj = 0; jj < 2; ++jj) {
+            const int j = 2 * pr + jj;
+            const uint4 mk = *reinterpret_cast<const uint4*>(m + img_off(row, j));
+            const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int n = 64 * c + 8 * j + 2 * q;
+              float d0 = drgb[0] * swr[n] + drgb[1] * swr[128 + n] + drgb[2] * swr[256 + n];
+              float d1 = drgb[0] * swr[n + 1] + drgb[1] * swr[128 + n + 1] + drgb[2] * swr[256 + n + 1];
+              if ((mw[q] & 0x7fffu) == 0u) d0 = 0.f;
+              if ((mw[q] & 0x7fff0000u) == 0u) d1 = 0.f;
+              Split<FMT>::apply(d0, d1, hi[4 * jj + q], lo[4 * jj + q]);
+            }
           }
-          *reinterpret_cast<uint4*>(g + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(g + off + kPlane) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          store_chunk_pair(g, pr, row & 7, make_uint4(hi[0], hi[1], hi[2], hi[3]), make_uint4(hi[4], hi[5], hi[6], hi[7]));
+          store_chunk_pair(g + kPlane, pr, row & 7, make_uint4(lo[0], lo[1], lo[2], lo[3]), make_uint4(lo[4], lo[5], lo[6], lo[7]));
         }
       }
     }
