@@ -701,9 +701,14 @@ __global__ void __launch_bounds__(256) k_grad_reduce(const RedArgs a) {
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int r = idx / J.cols, c = idx % J.cols;
     const float* p = J.part + (size_t)(J.row0 + r) * J.N + c;
-    float s = 0.f;
-    for (int k = 0; k < J.n_split; ++k) s += p[(size_t)k * 128 * J.N];
-    a.grad[J.dst + (long long)r * J.ld + J.col0 + c] = s;
+    const size_t stride = (size_t)128 * J.N;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;       // four independent chains (fixed order: deterministic)
+    int k = 0;
+    for (; k + 4 <= J.n_split; k += 4) {
+      s0 += p[(size_t)k * stride]; s1 += p[(size_t)(k + 1) * stride]; s2 += p[(size_t)(k + 2) * stride]; s3 += p[(size_t)(k + 3) * stride];
+    }
+    for (; k < J.n_split; ++k) s0 += p[(size_t)k * stride];
+    a.grad[J.dst + (long long)r * J.ld + J.col0 + c] = (s0 + s1) + (s2 + s3);
   }
   if (J.bias_dst >= 0) {
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < J.rows; r += gridDim.x * blockDim.x) {
@@ -1045,7 +1050,7 @@ static int backward_net(NsrHandle_* h, int which, const float* rays, int64_t n, 
   }
   if (P.err != cudaSuccess) return tfail(h, NSR_ERR_CUDA, std::string("dW launch: ") + cudaGetErrorString(P.err));
   {
-    const dim3 grid(32, (unsigned)P.red.n_jobs);
+    const dim3 grid(128, (unsigned)P.red.n_jobs);     // one element per thread for the 128 x 256 jobs
     k_grad_reduce<<<grid, 256, 0, st>>>(P.red);
     h->launches += 1;
     NSR_TCUDA(h, cudaGetLastError());
