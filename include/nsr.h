@@ -238,6 +238,17 @@ NSR_API int nsr_generate_rays(NsrHandle* h, const float* c2w_host, int H, int W,
 NSR_API int nsr_lr_metrics(NsrHandle* h, const float* hr_rgb, const float* target_lr, int64_t n_lr, int s,
                            float* lr_rgb_out, float* metrics_out, NsrStream stream);
 
+/* Replaces (scope row f-3, frame assembly): unflatten_reshape + depth2im + the [pred | gt | depth] concat of
+ * calculate_vis + _save_image's float -> uint8 conversion (models/nerf_downX_model.py:410-450;
+ * utils/visualizer.py:40-60,164-176), i.e. everything between the render outputs and the bytes handed to the
+ * PNG / GIF encoder.  rgb [H*W,3], depth [H*W], gt [H*W,3] or null: rows in the renderer's LR-pixel-major /
+ * sub-pixel-minor order (s = 1: plain raster).  out_rgb8: [H][W*(gt?3:2)][3] uint8 in the reference's channel
+ * order before its final RGB->BGR swap (the depth panel is OpenCV COLORMAP_JET of
+ * uint8(255 (d - near) / max(far - near, 1e-8)), numpy cast semantics incl. wrap-around).  depth_mat (optional):
+ * [H][W] fp32 = np.nan_to_num of the raster depth, the matrix the reference saves as *-depth*.npz. */
+NSR_API int nsr_assemble_frame(NsrHandle* h, const float* rgb, const float* depth, const float* gt, int H, int W, int s,
+                               float near_plane, float far_plane, uint8_t* out_rgb8, float* depth_mat, NsrStream stream);
+
 /* ---- host-buffer convenience (the end-to-end call) ------------------------ */
 
 /* forward over a whole frame / batch with HOST buffers: stages rays through

@@ -67,6 +67,8 @@ SIGNATURES = {
     "nsr_generate_rays": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_float, C.c_int,
                                     C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     "nsr_lr_metrics": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nsr_assemble_frame": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float,
+                                     C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nsr_render_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "nsr_render_pose_host": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_float, C.c_int, C.c_int,
                                        C.c_float, C.c_float, C.c_void_p, C.c_void_p]),

@@ -8,6 +8,7 @@
 #include <new>
 
 #include "nsr_internal.h"
+#include "nsr_jet_lut.h"
 
 using namespace nsr;
 
@@ -378,6 +379,8 @@ extern "C" int nsr_create(const NsrConfig* cfg, NsrHandle** out_handle) {
   if (e == cudaSuccess) e = cudaMalloc(&h->d_tables, sizeof(SampleTables));
   if (e == cudaSuccess) e = cudaMalloc(&h->d_partials, 1024 * sizeof(double));
   if (e == cudaSuccess) e = cudaMemcpy(h->d_tables, &T, sizeof(T), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_jet, sizeof(kJetLut));
+  if (e == cudaSuccess) e = cudaMemcpy(h->d_jet, kJetLut, sizeof(kJetLut), cudaMemcpyHostToDevice);
   const size_t blob = simt_blob_floats(h);
   for (int w = 0; w < 2 && e == cudaSuccess; ++w) {
     e = cudaMalloc(&h->net[w].simt_blob, blob * sizeof(float));
@@ -407,6 +410,7 @@ extern "C" int nsr_destroy(NsrHandle* h) {
   }
   cudaFree(h->d_tables);
   cudaFree(h->d_partials);
+  cudaFree(h->d_jet);
   cudaFree(h->frame_rays);
   if (h->frame_ev) cudaEventDestroy(h->frame_ev);
   for (int i = 0; i < 2; ++i) {
@@ -658,6 +662,59 @@ extern "C" int nsr_lr_metrics(NsrHandle* h, const float* hr_rgb, const float* ta
   k_lr_metrics_partial<<<blocks, 256, 0, (cudaStream_t)stream>>>(hr_rgb, target_lr, n_lr, s * s, lr_rgb_out, h->d_partials);
   k_lr_metrics_final<<<1, 32, 0, (cudaStream_t)stream>>>(h->d_partials, blocks, n_lr * 3, metrics_out);
   h->launches += 2;
+  NSR_CUDA(h, cudaGetLastError());
+  return NSR_OK;
+}
+
+// ----------------------------------------------------------------------------
+// frame assembly (scope row f-3)
+// ----------------------------------------------------------------------------
+// numpy's float32 -> uint8 astype on x86-64: truncate through int32 (out of range / NaN -> INT32_MIN), low byte
+__device__ __forceinline__ uint32_t cast_u8(float v) {
+  if (!(fabsf(v) < 2147483648.f)) return 0u;
+  return (uint32_t)__float2int_rz(v) & 0xFFu;
+}
+
+__global__ void __launch_bounds__(256)
+k_assemble_frame(const float* __restrict__ rgb, const float* __restrict__ depth, const float* __restrict__ gt, int H, int W,
+                 int s, float near, float far, const uint32_t* __restrict__ jet, uint8_t* __restrict__ out,
+                 float* __restrict__ depth_mat) {
+  const int panels = gt ? 3 : 2;
+  const int w1 = W / s;
+  const float denom = fmaxf(__fsub_rn(far, near), 1e-8f);
+  const int64_t total = (int64_t)H * W;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int y = (int)(i / W), x = (int)(i % W);
+    // inverse of the dataset's '(h s1) (w s2) c -> (h w) (s1 s2) c' grouping (nerf_downX_model.py:410-416)
+    const int64_t src = ((int64_t)(y / s) * w1 + (x / s)) * (s * s) + (y % s) * s + (x % s);
+    uint8_t* o = out + ((int64_t)y * W * panels + x) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[c] = (uint8_t)cast_u8(__fmul_rn(rgb[src * 3 + c], 255.f));      // visualizer.py:54
+    if (gt) {
+      uint8_t* og = o + (int64_t)W * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) og[c] = (uint8_t)cast_u8(__fmul_rn(gt[src * 3 + c], 255.f));
+    }
+    float d = depth[src];
+    if (d != d) d = 0.f;                                     // np.nan_to_num
+    else if (isinf(d)) d = d > 0.f ? 3.4028234663852886e38f : -3.4028234663852886e38f;
+    if (depth_mat) depth_mat[i] = d;
+    const float xn = __fdiv_rn(__fsub_rn(d, near), denom);    // visualizer.py:170
+    const uint32_t e = jet[cast_u8(__fmul_rn(255.f, xn))];     // :171-172, then (lut / 255.) * 255. -> uint8 is the identity
+    uint8_t* od = o + (int64_t)W * 3 * (panels - 1);
+    od[0] = (uint8_t)(e & 0xFFu); od[1] = (uint8_t)((e >> 8) & 0xFFu); od[2] = (uint8_t)((e >> 16) & 0xFFu);
+  }
+}
+
+extern "C" int nsr_assemble_frame(NsrHandle* h, const float* rgb, const float* depth, const float* gt, int H, int W, int s,
+                                  float near_plane, float far_plane, uint8_t* out_rgb8, float* depth_mat, NsrStream stream) {
+  if (!h) return NSR_ERR_INVALID_ARG;
+  if (!rgb || !depth || !out_rgb8 || H <= 0 || W <= 0 || s < 1) return fail(h, NSR_ERR_INVALID_ARG, "nsr_assemble_frame: bad argument");
+  if (H % s || W % s) return fail(h, NSR_ERR_INVALID_ARG, "H and W must be multiples of the supersampling factor");
+  NSR_CUDA(h, cudaSetDevice(h->cfg.device));
+  k_assemble_frame<<<grid_for((int64_t)H * W, 256, h->sm_count * 16), 256, 0, (cudaStream_t)stream>>>(
+      rgb, depth, gt, H, W, s, near_plane, far_plane, h->d_jet, out_rgb8, depth_mat);
+  h->launches += 1;
   NSR_CUDA(h, cudaGetLastError());
   return NSR_OK;
 }

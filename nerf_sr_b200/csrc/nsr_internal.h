@@ -52,6 +52,7 @@ struct NsrHandle_ {
   nsr::SampleTables* d_tables = nullptr;
   nsr::SampleTables h_tables;
   double* d_partials = nullptr;     // [1024] block partial sums for nsr_lr_metrics
+  uint32_t* d_jet = nullptr;        // [256] packed COLORMAP_JET entries (nsr_assemble_frame)
   nsr::NetImages net[2];
   std::vector<int64_t> param_numel;
   int sm_count = 0;

@@ -254,6 +254,21 @@ class Renderer:
                                             m.data_ptr(), self._stream()))
         return lr, m
 
+    def assemble_frame(self, rgb: torch.Tensor, depth: torch.Tensor, H: int, W: int, s: int, near: float, far: float,
+                       gt: Optional[torch.Tensor] = None, want_depth_mat: bool = True):
+        """calculate_vis + _save_image conversion (models/nerf_downX_model.py:410-450, utils/visualizer.py:40-60,
+        164-176): (uint8 [H, W*(2|3), 3] = [pred | gt | JET depth], fp32 depth matrix [H, W]) on the device."""
+        rgb, depth = self._f32(rgb), self._f32(depth)
+        if rgb.shape[0] != H * W or depth.numel() != H * W:
+            raise NsrError(1, f"expected {H}*{W} rows")
+        g = self._f32(gt) if gt is not None else None
+        panels = 3 if gt is not None else 2
+        out = torch.empty(H, W * panels, 3, dtype=torch.uint8, device=self.device)
+        mat = torch.empty(H, W, dtype=torch.float32, device=self.device) if want_depth_mat else None
+        self._check(self.lib.nsr_assemble_frame(self._h, rgb.data_ptr(), depth.data_ptr(), _ptr(g), H, W, s, float(near), float(far),
+                                                out.data_ptr(), _ptr(mat), self._stream()))
+        return out, mat
+
     def generate_rays(self, c2w, H: int, W: int, focal: float, s: int = 1, ndc: bool = False,
                       near: float = 2.0, far: float = 6.0) -> torch.Tensor:
         c = torch.as_tensor(c2w, dtype=torch.float32).reshape(12).cpu()
