@@ -396,3 +396,79 @@ def test_train_api_errors():
         r.backward(O.synthetic_rays(8, 1, "blender").to(DEV), None, {"coarse_comp_rgbs": torch.zeros(8, 3, device=DEV),
                                                                         "coarse_weights": torch.zeros(8, 64, device=DEV)})
     r.close()
+
+
+def test_patch_model_train_mode_on_a_reference_lookalike():
+    """INTEGRATION.md step 3 with grad enabled: forward_rays returns autograd-connected tensors, so the reference's own
+    loss code -- here colour MSE plus its optional variance and depth-variance terms (models/nerf_downX_model.py:
+    332-353,374-378) -- and loss.backward() fill p.grad of netCoarse / netFine from the CUDA backward."""
+    import torch.nn as nn
+    from types import SimpleNamespace
+    from nerf_sr_b200 import patch_model
+    fx = TrainFixture("train_step_llff_clip")          # sigma noise 1.0, LLFF-like rays
+
+    class Net(nn.Module):      # parameter names = models/networks.py:149-180
+        def __init__(self, p):
+            super().__init__()
+            for i in range(8):
+                w = p[f"xyz_encoding_{i+1}.0.weight"]
+                setattr(self, f"xyz_encoding_{i+1}", nn.Sequential(nn.Linear(w.shape[1], w.shape[0]), nn.ReLU(True)))
+            self.xyz_encoding_final = nn.Linear(256, 256)
+            self.dir_encoding = nn.Sequential(nn.Linear(283, 128), nn.ReLU(True))
+            self.sigma = nn.Linear(256, 1)
+            self.rgb = nn.Sequential(nn.Linear(128, 3), nn.Sigmoid())
+            self.load_state_dict(p)
+
+    class NeRFDownXModel:
+        pass
+
+    m = NeRFDownXModel()
+    m.opt = SimpleNamespace(**{**fx.cfg.__dict__, "skips": list(fx.cfg.skips)})
+    m.device = torch.device(DEV)
+    m.netCoarse = nn.DataParallel(Net(fx.p_coarse).to(DEV))
+    m.netFine = nn.DataParallel(Net(fx.p_fine).to(DEV))
+    m.randomized = True
+    m.forward_rays = lambda rays: (_ for _ in ()).throw(AssertionError("reference path must not run"))
+    patch_model(m, "bf16x3")
+    rays, tgt = fx.rays.to(DEV), fx.target.to(DEV)
+    n, s = rays.shape[0], fx.s
+
+    def losses(out, target, far):
+        rc, rf = out["coarse_comp_rgbs"], out["fine_comp_rgbs"]
+        L = torch.nn.functional.mse_loss(rc.reshape(-1, s * s, 3).mean(1), target) + \
+            torch.nn.functional.mse_loss(rf.reshape(-1, s * s, 3).mean(1), target)
+        L = L + 0.01 * torch.sum(torch.var(rc.reshape(-1, s * s, 3), dim=1)) + 0.01 * torch.sum(torch.var(rf.reshape(-1, s * s, 3), dim=1))
+        L = L + 0.01 * torch.sum(torch.var(out["fine_depth"].reshape(-1, s * s, 1) / far, dim=1))
+        return L
+
+    torch.manual_seed(7)
+    out = m.forward_rays(rays)
+    assert out["fine_comp_rgbs"].requires_grad and not out["fine_weights"].requires_grad
+    losses(out, tgt, 1.0).backward()
+    # the same draws, in the reference's order (models/utils.py:41, :210, :73, :210)
+    torch.manual_seed(7)
+    rng = {"u_coarse": torch.rand(n, 64, device=DEV), "noise_coarse": torch.randn(n, 64, device=DEV),
+           "u_fine": torch.rand(n, 64, device=DEV), "noise_fine": torch.randn(n, 128, device=DEV)}
+    z_f = m._nsr_renderer.render_train(rays, rng, want_z_fine=True)["z_fine"].cpu().double()
+    pc = {k: v.double().requires_grad_(True) for k, v in fx.p_coarse.items()}
+    pf = {k: v.double().requires_grad_(True) for k, v in fx.p_fine.items()}
+    orng = O.RenderRng(*[rng[k].cpu().double() for k in ("u_coarse", "noise_coarse", "u_fine", "noise_fine")])
+    o = O.forward_rays(pc, pf, fx.rays.double(), fx.cfg, orng, z_fine_override=z_f)
+    losses(o, fx.target.double(), 1.0).backward()
+    for net, ref in ((m.netCoarse, pc), (m.netFine, pf)):
+        named = dict(net.module.named_parameters())
+        got = torch.cat([named[k].grad.reshape(-1) for k in ref]).cpu()
+        want = torch.cat([v.grad.reshape(-1) for v in ref.values()])
+        cos = float(torch.nn.functional.cosine_similarity(got.double()[None], want[None]))
+        err = _rel(got, want)
+        _report(test="patch_model_train", rel_l2=err, cos=cos)
+        assert cos > 0.9995 and err < 3e-2, (err, cos)
+    # eval mode afterwards picks up changed parameters (version counters) and runs without autograd
+    with torch.no_grad():
+        m.randomized = False
+        e1 = m.forward_rays(rays)
+        m.netFine.module.sigma.bias.add_(0.5)
+        e2 = m.forward_rays(rays)
+    assert not e1["fine_comp_rgbs"].requires_grad
+    assert not torch.equal(e1["fine_opacity"], e2["fine_opacity"])
+    m._nsr_renderer.close()
