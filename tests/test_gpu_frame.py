@@ -50,3 +50,48 @@ def test_assemble_frame_full_size_against_oracle():
     with pytest.raises(NsrError):
         r.assemble_frame(out["fine_comp_rgbs"], out["fine_depth"], H, W, 3, 2.0, 6.0)
     r.close()
+
+
+def test_render_test_pose_and_path_sweep():
+    """Scope rows f-4 + f-3 together: a pose path -> per-pose rays on the device -> render -> LR/HR frames, i.e. the
+    reference's test sweep (dataset test branch + forward + comp_low_res_output + calculate_vis) with 48 bytes going
+    up per frame.  Frames are byte-equal to the oracle's assembly of the same render outputs; the LLFF (NDC) branch
+    is checked the same way."""
+    from nerf_sr_b200 import Renderer, paths
+    cfg = O.RenderConfig(white_bkgd=True)
+    r = Renderer(cfg, torch.device(DEV), precision="bf16x3")
+    r.load_state_dict(0, O.make_mlp_params(cfg, 4)); r.load_state_dict(1, O.make_mlp_params(cfg, 17))
+    H, W, s, focal = 48, 64, 2, 70.0
+    poses = paths.spheric_poses(4.0, 5).astype(np.float32)
+    frames = []
+    for host in r.render_path(poses, H, W, focal, s, ndc=False, near=2.0, far=6.0,
+                              keys=("fine_pred", "fine_pred_ori", "fine_depth_mat_ori", "coarse_pred")):
+        frames.append({k: v.clone() for k, v in host.items()})
+    assert len(frames) == 5
+    for k, (c2w, fr) in enumerate(zip(poses, frames)):
+        rays = r.generate_rays(c2w, H, W, focal, s=s, near=2.0, far=6.0)
+        # (the rotation's multiply-adds round differently from the oracle's CPU matmul: same tolerance as the raygen golden test)
+        assert torch.allclose(rays.cpu(), O.build_frame_rays(torch.from_numpy(c2w), H, W, focal, s, 2.0, 6.0), rtol=1e-5, atol=1e-5)
+        out = r.forward_rays(rays, want_weights=False)
+        with np.errstate(all="ignore"):
+            ref_hr, ref_mat = F.assemble_frame(out["fine_comp_rgbs"].cpu().numpy(), out["fine_depth"].cpu().numpy(), H, W, s, 2.0, 6.0)
+            lr_rgb = O.box_average(out["fine_comp_rgbs"].cpu(), s).numpy()
+            lr_dep = O.box_average(out["fine_depth"].cpu(), s).numpy()
+            ref_lr, _ = F.assemble_frame(lr_rgb, lr_dep, H // s, W // s, 1, 2.0, 6.0)
+        assert np.array_equal(fr["fine_pred_ori"].numpy(), ref_hr), k
+        assert np.array_equal(fr["fine_depth_mat_ori"].numpy(), ref_mat), k
+        assert fr["fine_pred"].shape == (H // s, 2 * (W // s), 3)
+        # the LR box average sums in a different order than torch.mean: allow one grey level on a few pixels
+        diff = np.abs(fr["fine_pred"].numpy().astype(int) - ref_lr.astype(int))
+        assert diff.max() <= 1 or (diff > 1).mean() < 1e-3, k
+    assert not np.array_equal(frames[0]["fine_pred_ori"].numpy(), frames[2]["fine_pred_ori"].numpy())
+    # forward-facing branch: NDC rays at near plane 1.0, near/far = 0/1 (data/llff_downX_dataset.py:473-481)
+    sp = paths.spiral_poses(np.array([0.3, 0.2, 0.05]), 3.5, 4).astype(np.float32)
+    res = r.render_test_pose(sp[1], H, W, focal, s, ndc=True)
+    rays = r.generate_rays(sp[1], H, W, focal, s=s, ndc=True)
+    assert torch.allclose(rays.cpu(), O.build_frame_rays(torch.from_numpy(sp[1]), H, W, focal, s, 0.0, 1.0, ndc=True), rtol=1e-5, atol=1e-5)
+    out = r.forward_rays(rays, want_weights=False)
+    with np.errstate(all="ignore"):
+        ref_hr, _ = F.assemble_frame(out["coarse_comp_rgbs"].cpu().numpy(), out["coarse_depth"].cpu().numpy(), H, W, s, 0.0, 1.0)
+    assert np.array_equal(res["coarse_pred_ori"].cpu().numpy(), ref_hr)
+    r.close()

@@ -66,3 +66,22 @@ def test_config_from_reference_style_opt():
 def test_state_dict_order_matches_oracle_shapes():
     from nerf_sr_b200 import state_dict_order
     assert state_dict_order(8) == [n for n, _ in O.mlp_param_shapes(O.RenderConfig())]
+
+
+def test_pose_paths_match_reference_golden():
+    """Scope row f-4: nerf_sr_b200/paths.py against outputs of the reference's own generators
+    (oracle/make_golden_paths.py; data/llff_downX_dataset.py:20-160)."""
+    import numpy as np
+    from conftest import GOLDEN_DIR
+    from nerf_sr_b200 import paths as P
+    z = np.load(os.path.join(GOLDEN_DIR, "pose_paths.npz"))
+    rx, ry, rz, focus, n = z["spiral_in"]
+    assert np.allclose(P.spiral_poses(np.array([rx, ry, rz]), float(focus), int(n)), z["spiral"], rtol=0, atol=1e-14)
+    radius, n = z["spheric_in"]
+    sp = P.spheric_poses(float(radius), int(n))
+    assert np.allclose(sp, z["spheric"], rtol=0, atol=1e-14)
+    assert sp.shape == (int(n), 3, 4) and np.allclose(np.linalg.det(sp[:, :, :3]), 1.0)    # proper rotations
+    centered, avg = P.center_poses(z["poses"])
+    assert np.allclose(centered, z["centered"], rtol=0, atol=1e-13) and np.allclose(avg, z["avg"], rtol=0, atol=1e-14)
+    c2, a2 = P.center_poses(centered)              # centring is idempotent: the average of centred poses is the identity frame
+    assert np.allclose(a2[:, :3], np.eye(3), atol=1e-12) and np.allclose(a2[:, 3], 0, atol=1e-12)
