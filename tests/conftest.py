@@ -21,7 +21,8 @@ def pytest_configure(config):
 
 def golden_names():
     return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR)
-                  if f.endswith(".npz") and f not in ("raygen.npz", "frame_assembly.npz") and not f.startswith("train_step_"))
+                  if f.endswith(".npz") and f not in ("raygen.npz", "frame_assembly.npz", "pose_paths.npz")
+                  and not f.startswith("train_step_"))
 
 
 def train_golden_names():
