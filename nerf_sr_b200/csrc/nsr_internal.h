@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <atomic>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/nsr.h"
@@ -72,6 +73,7 @@ struct NsrHandle_ {
   float* frame_rays = nullptr;      // nsr_render_pose_host: device rays of one frame
   size_t frame_rays_cap = 0;
   cudaEvent_t frame_ev = nullptr;
+  std::vector<std::pair<void*, int64_t>> train_stash;   // workspaces filled by nsr_render_train -> n_rays
 };
 
 namespace nsr {

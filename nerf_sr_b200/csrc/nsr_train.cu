@@ -1123,6 +1123,14 @@ extern "C" int nsr_render_train(NsrHandle* h, const float* rays, int64_t n_rays,
     a.trace = nullptr; a.debug_flags = 0;
     NSR_TCUDA(h, tc_pass(h, w, a, st));
   }
+  // remember (host side, no sync) which workspaces hold a stash and for how many rays, so nsr_backward can refuse
+  // a buffer that was filled for another batch -- the layout depends on n_rays
+  {
+    auto& v = h->train_stash;
+    for (size_t i = 0; i < v.size(); ++i) if (v[i].first == train_ws) { v.erase(v.begin() + i); break; }
+    if (v.size() >= 16) v.erase(v.begin());
+    v.emplace_back(train_ws, n_rays);
+  }
   if (out->z_fine)
     NSR_TCUDA(h, cudaMemcpyAsync(out->z_fine, ws + L.z[1], (size_t)n_rays * L.S[1] * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return NSR_OK;
@@ -1137,6 +1145,13 @@ extern "C" int nsr_backward(NsrHandle* h, const float* rays, int64_t n_rays, int
   if (!rays || !g || !grad_coarse || !grad_fine || n_rays <= 0) return tfail(h, NSR_ERR_INVALID_ARG, "nsr_backward: bad argument");
   const TrainWs L = train_layout(h, n_rays);
   if (!train_ws || train_ws_bytes < L.total) return tfail(h, NSR_ERR_WORKSPACE, "train workspace too small: need " + std::to_string(L.total));
+  {
+    int64_t stashed = -1;
+    for (const auto& e : h->train_stash) if (e.first == train_ws) stashed = e.second;
+    if (stashed != n_rays)
+      return tfail(h, NSR_ERR_INVALID_ARG, stashed < 0 ? "nsr_backward: train_ws was not filled by nsr_render_train"
+                                                       : "nsr_backward: train_ws holds a stash for " + std::to_string(stashed) + " rays");
+  }
   NSR_TCUDA(h, cudaSetDevice(h->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)(((uintptr_t)train_ws + 255) & ~(uintptr_t)255);

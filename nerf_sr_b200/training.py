@@ -52,9 +52,16 @@ def _train_workspace(self: Renderer, n_rays: int) -> torch.Tensor:
     return ws
 
 
-def render_train(self: Renderer, rays: torch.Tensor, rng=None, want_weights: bool = True, want_z_fine: bool = False):
+def new_train_workspace(self: Renderer, n_rays: int) -> torch.Tensor:
+    """A private stash buffer for one forward/backward pair (several may be in flight at once)."""
+    return torch.empty(self.lib.nsr_train_workspace_bytes(self._h, n_rays), dtype=torch.uint8, device=self.device)
+
+
+def render_train(self: Renderer, rays: torch.Tensor, rng=None, want_weights: bool = True, want_z_fine: bool = False,
+                 ws: Optional[torch.Tensor] = None):
     """forward_rays in train mode, keeping the activation stash for ``backward`` (same outputs as
-    forward_rays).  The stash lives in a renderer-owned buffer: one forward/backward pair at a time."""
+    forward_rays).  The stash goes to ``ws`` (new_train_workspace) or, by default, to a renderer-owned buffer that the
+    next render_train overwrites: pass the same ``ws`` to ``backward``."""
     rays = self._f32(rays)
     n, stride = rays.shape
     dev, f32 = self.device, torch.float32
@@ -72,14 +79,17 @@ def render_train(self: Renderer, rays: torch.Tensor, rng=None, want_weights: boo
         setattr(o, k, v.data_ptr())
     keep: list = []
     r = _rng_struct(self, rng, keep)
-    ws = _train_workspace(self, n)
+    if ws is None:
+        ws = _train_workspace(self, n)
     self._check(self.lib.nsr_render_train(self._h, rays.data_ptr(), n, stride, C.byref(r) if r is not None else None,
                                           C.byref(o), ws.data_ptr(), ws.numel(), self._stream()))
     return out
 
 
-def backward(self: Renderer, rays: torch.Tensor, rng, grads: Mapping[str, Optional[torch.Tensor]]):
-    """dL/d(outputs) -> (grad_coarse_flat, grad_fine_flat): flat fp32 gradients in state_dict order."""
+def backward(self: Renderer, rays: torch.Tensor, rng, grads: Mapping[str, Optional[torch.Tensor]],
+             ws: Optional[torch.Tensor] = None):
+    """dL/d(outputs) -> (grad_coarse_flat, grad_fine_flat): flat fp32 gradients in state_dict order.
+    ``ws``: the stash buffer the matching render_train filled (default: the renderer-owned one)."""
     rays = self._f32(rays)
     n, stride = rays.shape
     g = NsrOutGrads()
@@ -97,7 +107,8 @@ def backward(self: Renderer, rays: torch.Tensor, rng, grads: Mapping[str, Option
     numel = int(self.lib.nsr_grad_numel(self._h))
     gc = torch.empty(numel, device=self.device, dtype=torch.float32)
     gf = torch.empty(numel, device=self.device, dtype=torch.float32)
-    ws = _train_workspace(self, n)
+    if ws is None:
+        ws = _train_workspace(self, n)
     self._check(self.lib.nsr_backward(self._h, rays.data_ptr(), n, stride, C.byref(r) if r is not None else None, C.byref(g),
                                       gc.data_ptr(), gf.data_ptr(), ws.data_ptr(), ws.numel(), self._stream()))
     return gc, gf
@@ -227,7 +238,7 @@ def stash_activation(self: Renderer, n_rays: int, which: int, layer: int) -> tor
     return unpack_image(self, img, rows, cols)
 
 
-for _f in (train_layout, stash_activation, stash_mask, relu_bits, render_train, backward, lr_loss_grad, clip_coef, adam_step, pack_image, unpack_image, debug_dx, debug_dw):
+for _f in (train_layout, stash_activation, stash_mask, relu_bits, new_train_workspace, render_train, backward, lr_loss_grad, clip_coef, adam_step, pack_image, unpack_image, debug_dx, debug_dw):
     setattr(Renderer, _f.__name__, _f)
 
 
@@ -253,8 +264,9 @@ class RenderFunction(torch.autograd.Function):
         with torch.no_grad():
             renderer.load_params(0, params[:n_coarse])
             renderer.load_params(1, params[n_coarse:])
-            out = renderer.render_train(rays, rng)
-        ctx.renderer, ctx.rays, ctx.rng = renderer, rays, rng
+            ws = new_train_workspace(renderer, rays.shape[0])     # private: several forwards may precede their backwards
+            out = renderer.render_train(rays, rng, ws=ws)
+        ctx.renderer, ctx.rays, ctx.rng, ctx.ws = renderer, rays, rng, ws
         ctx.shapes = [tuple(p.shape) for p in params]
         ctx.n_coarse = n_coarse
         ctx.set_materialize_grads(False)
@@ -265,7 +277,8 @@ class RenderFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *gouts):
         grads = dict(zip(OUT_KEYS, gouts))
-        gc, gf = ctx.renderer.backward(ctx.rays, ctx.rng, grads)
+        gc, gf = ctx.renderer.backward(ctx.rays, ctx.rng, grads, ws=ctx.ws)
+        ctx.ws = None                                             # release the stash
         nc = ctx.n_coarse
         pg = unflatten_grads(gc, ctx.shapes[:nc]) + unflatten_grads(gf, ctx.shapes[nc:])
         return (None, None, None, None, *pg)

@@ -174,7 +174,7 @@ def test_lr_loss_grad_against_autograd(s, lam):
     psnr = -10 * torch.log10(torch.mean((lr_ref.detach() - tgt) ** 2))
     lr, m, ghr = r.lr_loss_grad(hr.detach().to(DEV), tgt.to(DEV), s, lam)
     assert torch.allclose(lr.cpu(), lr_ref.detach(), rtol=0, atol=5e-7)      # torch.mean sums in a different order
-    assert float(m[0]) == pytest.approx(float(loss), rel=1e-5) and float(m[1]) == pytest.approx(float(psnr), rel=1e-5)
+    assert float(m[0]) == pytest.approx(float(loss.detach()), rel=1e-5) and float(m[1]) == pytest.approx(float(psnr), rel=1e-5)
     scale = 2.0 * lam / (3 * n_lr) / (s * s)      # lr differs from torch.mean by ~1e-7 where the sum order differs
     assert torch.allclose(ghr.cpu(), hr.grad, rtol=1e-5, atol=1e-6 * scale)
     r.close()
@@ -472,3 +472,73 @@ def test_patch_model_train_mode_on_a_reference_lookalike():
     assert not e1["fine_comp_rgbs"].requires_grad
     assert not torch.equal(e1["fine_opacity"], e2["fine_opacity"])
     m._nsr_renderer.close()
+
+
+def test_two_forwards_in_flight_and_stash_guard():
+    """The autograd bridge keeps a private stash per forward, so two forward_rays calls (e.g. main rays and reference-view
+    rays, models/nerf_downX_model.py:318-324) can precede their backwards; and nsr_backward refuses a workspace that was
+    filled for another batch size or never filled."""
+    from nerf_sr_b200 import NsrError, RenderFunction
+    from nerf_sr_b200.training import OUT_KEYS
+    fx = TrainFixture("train_step_blender")
+    r = _renderer(fx.cfg, fx.p_coarse, fx.p_fine)
+    names = list(fx.p_coarse)
+    pcs = [torch.nn.Parameter(fx.p_coarse[n].clone().to(DEV)) for n in names]
+    pfs = [torch.nn.Parameter(fx.p_fine[n].clone().to(DEV)) for n in names]
+    ra, rb = fx.rays[:128].to(DEV), fx.rays[128:192].to(DEV)
+
+    def grads(order):
+        for p in pcs + pfs:
+            p.grad = None
+        oa = dict(zip(OUT_KEYS, RenderFunction.apply(r, ra, None, len(pcs), *pcs, *pfs)))
+        ob = dict(zip(OUT_KEYS, RenderFunction.apply(r, rb, None, len(pcs), *pcs, *pfs)))
+        la, lb = oa["fine_comp_rgbs"].square().mean() + oa["coarse_comp_rgbs"].mean(), ob["fine_comp_rgbs"].mean()
+        if order == "joint":
+            (la + lb).backward()
+        else:
+            lb.backward(); la.backward()
+        return torch.cat([p.grad.reshape(-1) for p in pcs + pfs]).clone()
+    g1, g2 = grads("joint"), grads("separate")
+    assert torch.isfinite(g1).all() and _rel(g1, g2) < 1e-6
+    out = r.render_train(ra, None)
+    with pytest.raises(NsrError):
+        r.backward(rb, None, {"coarse_comp_rgbs": torch.zeros(64, 3, device=DEV)})       # stash holds 128 rays
+    with pytest.raises(NsrError):
+        r.backward(ra, None, {"coarse_comp_rgbs": torch.zeros(128, 3, device=DEV)}, ws=r.new_train_workspace(128))
+    r.close()
+
+
+@pytest.mark.parametrize("variant", ["softplus_gamma_lindisp", "color_none", "vanilla_viewdir_column"])
+def test_gradients_option_variants(variant):
+    """The backward's activation branches (rendering.py:70-73 softplus, nerf_downX_model.py:271 gamma, networks.py:173-176
+    colour activation none) and the vanilla model's view-direction column, against the oracle's autograd in fp64."""
+    kw = {"softplus_gamma_lindisp": dict(sigma_activation="softplus", gamma_correct=True, lindisp=True),
+          "color_none": dict(color_activation="none", white_bkgd=True),
+          "vanilla_viewdir_column": dict(white_bkgd=True, viewdir_offset=8)}[variant]
+    cfg = O.RenderConfig(**kw)
+    pc, pf = O.make_mlp_params(cfg, 4), O.make_mlp_params(cfg, 17)
+    from nerf_sr_b200 import Renderer
+    r = Renderer(cfg, torch.device(DEV), precision="bf16x3", viewdir_offset=cfg.viewdir_offset)
+    r.load_state_dict(0, pc); r.load_state_dict(1, pf)
+    n = 96
+    rays = O.synthetic_rays(n, 21, "blender")
+    if cfg.viewdir_offset == 8:
+        vd = torch.nn.functional.normalize(torch.randn(n, 3, generator=torch.Generator().manual_seed(5)), dim=-1)
+        rays = torch.cat([rays, vd], 1).contiguous()
+    g = torch.Generator().manual_seed(9)
+    g_c, g_f = torch.randn(n, 3, generator=g) / n, torch.randn(n, 3, generator=g) / n
+    dev_rays = rays.to(DEV)
+    z_f = r.render_train(dev_rays, None, want_z_fine=True)["z_fine"].cpu()
+    gc, gf = r.backward(dev_rays, None, {"coarse_comp_rgbs": g_c.to(DEV), "fine_comp_rgbs": g_f.to(DEV)})
+    p64c = {k: v.double().requires_grad_(True) for k, v in pc.items()}
+    p64f = {k: v.double().requires_grad_(True) for k, v in pf.items()}
+    o = O.forward_rays(p64c, p64f, rays.double(), cfg, None, z_fine_override=z_f.double())
+    ((o["coarse_comp_rgbs"] * g_c.double()).sum() + (o["fine_comp_rgbs"] * g_f.double()).sum()).backward()
+    for flat, ref in ((gc, p64c), (gf, p64f)):
+        want = torch.cat([v.grad.reshape(-1) for v in ref.values()])
+        assert torch.isfinite(flat).all()
+        err = _rel(flat, want)
+        cos = float(torch.nn.functional.cosine_similarity(flat.double().cpu()[None], want[None]))
+        _report(test="grad_variants", variant=variant, rel_l2=err, cos=cos)
+        assert cos > 0.9995 and err < 3e-2, (variant, err, cos)
+    r.close()
