@@ -566,6 +566,182 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_tg_dx(const DxArgs a) {
 }
 
 // ---------------------------------------------------------------------------
+// k_tg_dxchain: the whole dX chain of one net, fused per 128-point tile (dir -> final -> L8 .. L2).
+//
+// Same on-chip dataflow as the forward pass (nsr_tc.cu): the gradient of a layer's input never leaves the SM
+// between layers -- the epilogue writes it back into TMEM as the next layer's A operand (hi/lo planes, TS-form
+// MMAs) -- and the transposed weights stream through a shared-memory ring from L2.  HBM sees only what the dW
+// GEMMs need afterwards: each layer's dZ image written once (256-bit stores), the 1-bit ReLU masks read once.
+// This removes, per point and layer, the 1 KB re-read of dZ and half of the per-SM operand ingest that bound the
+// layer-by-layer k_tg_dx (profiles/r01_train_ncu_full.md).
+//   warp 0: producer   (dZ_dir tile -> smem once per tile; 34 transposed-weight chunks of 64 KB per tile, 2-slot ring)
+//   warp 1: MMA issue  (M=128 N=256 K=16 kind::f16, 3 MMAs per product; layer 0 SS, layers 1..8 TS)
+//   warps 2-9: epilogue (2 per TMEM lane quarter, 128 accumulator columns each)
+// TMEM: [0,256) fp32 accumulator, [256,384) A hi plane, [384,512) A lo plane.
+// ---------------------------------------------------------------------------
+struct ChainArgs {
+  const uint8_t* dzdir;     // [n_tiles][2][32 KB]
+  const uint8_t* wt;        // 34 chunks x 64 KB in consumption order (build_wt_table)
+  uint8_t* dz;              // [9][n_tiles][4][32 KB]: 0 = d feat, 1 = dZ_8, ..., 8 = dZ_1
+  const uint32_t* mask;     // [8][n_tiles][128][8]: ReLU bits of h_1..h_8
+  const float* dsig; const float* wsig;
+  long long n_tiles;
+};
+constexpr int kChainThreads = 320;
+constexpr int kChRing = 0;                          // 2 x 64 KB
+constexpr int kChIn = 2 * kWtChunkBytes;            // 131072: dZ_dir tile, 64 KB
+constexpr int kChAux = kChIn + 2 * kChunk;          // 196608: w_sigma
+constexpr int kChBar = kChAux + 1024;
+constexpr int kChTmem = kChBar + 16 * 8;
+constexpr int kSmemChainBytes = kChTmem + 16;
+enum { C_FULL = 0, C_EMPTY = 2, C_INFULL = 4, C_INEMPTY = 5, C_ACCFULL = 6, C_AREADY = 7 };
+
+template <int FMT>
+__global__ void __launch_bounds__(kChainThreads, 1) k_tg_dxchain(const ChainArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* sm = smem_raw;
+  const uint32_t sm_base = smem_u32(sm);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long my_tiles = (a.n_tiles > blockIdx.x) ? (a.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  for (int i = threadIdx.x; i < 256; i += kChainThreads) reinterpret_cast<float*>(sm + kChAux)[i] = a.wsig[i];
+  if (sm_base & 1023u) { if (threadIdx.x == 0) printf("[nsr_train] dynamic smem base %u not 1024-aligned\n", sm_base); __trap(); }
+  const uint32_t bar = sm_base + kChBar;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(bar + 8 * (C_FULL + i), 1); mbar_init(bar + 8 * (C_EMPTY + i), 1); }
+    mbar_init(bar + 8 * C_INFULL, 1); mbar_init(bar + 8 * C_INEMPTY, 1);
+    mbar_init(bar + 8 * C_ACCFULL, 1); mbar_init(bar + 8 * C_AREADY, 8);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sm_base + kChTmem), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + kChTmem);
+
+  if (warp == 0) {
+    if (elect_one()) {
+      uint32_t n = 0;
+      for (long long it = 0; it < my_tiles; ++it) {
+        const long long tile = blockIdx.x + it * (long long)gridDim.x;
+        mbar_wait(bar + 8 * C_INEMPTY, (uint32_t)((it & 1) ^ 1));
+        mbar_expect_tx(bar + 8 * C_INFULL, 2 * kChunk);
+        bulk_copy_g2s(sm_base + kChIn, a.dzdir + (size_t)tile * 2 * kChunk, kChunk, bar + 8 * C_INFULL);
+        bulk_copy_g2s(sm_base + kChIn + kChunk, a.dzdir + (size_t)tile * 2 * kChunk + kChunk, kChunk, bar + 8 * C_INFULL);
+        for (int cg = 0; cg < kWtChunks; ++cg, ++n) {
+          const uint32_t slot = n & 1u, par = (n >> 1) & 1u;
+          mbar_wait(bar + 8 * (C_EMPTY + slot), par ^ 1u);
+          const uint32_t full = bar + 8 * (C_FULL + slot);
+          const uint32_t dst = sm_base + kChRing + slot * kWtChunkBytes;
+          mbar_expect_tx(full, kWtChunkBytes);
+          bulk_copy_g2s(dst, a.wt + (size_t)cg * kWtChunkBytes, 32768, full);
+          bulk_copy_g2s(dst + 32768, a.wt + (size_t)cg * kWtChunkBytes + 32768, 32768, full);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc = gemm_idesc(FMT, 128, 256, 0, 0);
+      uint32_t n = 0, g = 0;
+      for (long long it = 0; it < my_tiles; ++it) {
+        for (int l = 0; l < 9; ++l, ++g) {
+          if (g > 0) { mbar_wait(bar + 8 * C_AREADY, (g - 1) & 1u); tc_fence_after(); }    // accumulator drained, A planes written
+          if (l == 0) { mbar_wait(bar + 8 * C_INFULL, (uint32_t)(it & 1)); tc_fence_after(); }
+          const int nkc = (l == 0) ? 2 : 4;
+          for (int c = 0; c < nkc; ++c, ++n) {
+            const uint32_t slot = n & 1u, par = (n >> 1) & 1u;
+            mbar_wait(bar + 8 * (C_FULL + slot), par);
+            tc_fence_after();
+            const uint32_t sb = sm_base + kChRing + slot * kWtChunkBytes;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t bh = kmajor_desc(sb + 32 * k), bl = kmajor_desc(sb + 32768 + 32 * k);
+              const uint32_t acc = (c | k) ? 1u : 0u;
+              if (l == 0) {
+                const uint32_t sa = sm_base + kChIn + (uint32_t)c * kChunk;
+                const uint64_t ah = kmajor_desc(sa + 32 * k), al = kmajor_desc(sa + kPlane + 32 * k);
+                mma_ss(tmem, ah, bh, idesc, acc);
+                mma_ss(tmem, al, bh, idesc, 1u);
+                mma_ss(tmem, ah, bl, idesc, 1u);
+              } else {
+                const uint32_t ah = tmem + 256u + 32u * (uint32_t)c + 8u * (uint32_t)k;
+                mma_ts(tmem, ah, bh, idesc, acc);
+                mma_ts(tmem, ah + 128u, bh, idesc, 1u);
+                mma_ts(tmem, ah, bl, idesc, 1u);
+              }
+            }
+            tc_commit(bar + 8 * (C_EMPTY + slot));
+          }
+          if (l == 0) tc_commit(bar + 8 * C_INEMPTY);
+          tc_commit(bar + 8 * C_ACCFULL);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3, hh = (warp - 2) >> 2;
+    const int row = 32 * q + lane, r7 = lane & 7;
+    const uint32_t tlane = tmem + ((uint32_t)(32 * q) << 16);
+    const float* wsig = reinterpret_cast<const float*>(sm + kChAux);
+    uint32_t g = 0;
+    for (long long it = 0; it < my_tiles; ++it) {
+      const long long tile = blockIdx.x + it * (long long)gridDim.x;
+      const float ds = a.dsig[tile * kT + row];
+#pragma unroll 1
+      for (int l = 0; l < 9; ++l, ++g) {
+        uint32_t mb[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+        if (l >= 1) {      // output of step l is the gradient w.r.t. h_{9-l}: gate with that layer's ReLU bits
+          const uint4 m = *reinterpret_cast<const uint4*>(a.mask + (((size_t)(8 - l) * (size_t)a.n_tiles + (size_t)tile) * kT + row) * 8 + 4 * hh);
+          mb[0] = m.x; mb[1] = m.y; mb[2] = m.z; mb[3] = m.w;
+        }
+        uint8_t* orow = a.dz + (((size_t)l * (size_t)a.n_tiles + (size_t)tile) * 4) * kChunk + (size_t)row * 128;
+        mbar_wait(bar + 8 * C_ACCFULL, g & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int col0 = 128 * hh + 32 * b;
+          uint32_t r[32];
+          TMEM_LD32(tlane + (uint32_t)col0, r);
+          tc_wait_ld();
+          uint32_t whi[16], wlo[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            float v0 = __uint_as_float(r[2 * e]), v1 = __uint_as_float(r[2 * e + 1]);
+            if (l == 1) { v0 = fmaf(ds, wsig[col0 + 2 * e], v0); v1 = fmaf(ds, wsig[col0 + 2 * e + 1], v1); }
+            if (!((mb[b] >> (2 * e)) & 1u)) v0 = 0.f;
+            if (!((mb[b] >> (2 * e + 1)) & 1u)) v1 = 0.f;
+            Split<FMT>::apply(v0, v1, whi[e], wlo[e]);
+          }
+          if (l < 8) {       // next layer's A operand (hi and lo planes), two k-values per TMEM column
+            TMEM_ST16(tlane + 256u + (uint32_t)(col0 / 2), whi);
+            TMEM_ST16(tlane + 384u + (uint32_t)(col0 / 2), wlo);
+          }
+          uint8_t* gp = orow + (size_t)(col0 >> 6) * kChunk;
+#pragma unroll
+          for (int t2 = 0; t2 < 2; ++t2) {
+            const int e = 8 * t2;
+            store_chunk_pair(gp, 2 * (b & 1) + t2, r7, make_uint4(whi[e], whi[e + 1], whi[e + 2], whi[e + 3]),
+                             make_uint4(whi[e + 4], whi[e + 5], whi[e + 6], whi[e + 7]));
+            store_chunk_pair(gp + kPlane, 2 * (b & 1) + t2, r7, make_uint4(wlo[e], wlo[e + 1], wlo[e + 2], wlo[e + 3]),
+                             make_uint4(wlo[e + 4], wlo[e + 5], wlo[e + 6], wlo[e + 7]));
+          }
+        }
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar + 8 * C_AREADY);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+// ---------------------------------------------------------------------------
 // k_tg_dw: partial[split][m][n] = sum over this CTA's tiles of A[p][m] * B[p][n]; bias partial = sum A[p][m]
 // ---------------------------------------------------------------------------
 struct DwJob {
@@ -839,7 +1015,7 @@ struct TrainWs {
   // per pass (0 coarse, 1 fine)
   size_t enc[2], hh[2], dir[2], mask[2], raw[2], z[2];
   // shared by the two backward passes
-  size_t dhead, encdir, dzdir, g0, g1, dsig, part;
+  size_t dhead, encdir, dzdir, dz, dsig, part;     // dz: [9][T][4 chunks]: d feat, dZ_8 .. dZ_1
   size_t part_region;       // bytes of one dW launch's partial region
   size_t total;
   long long tiles[2];
@@ -865,8 +1041,7 @@ static TrainWs train_layout(const NsrHandle_* h, int64_t n) {
   L.dhead = off; off += T * kChunk;
   L.encdir = off; off += T * kChunk;
   L.dzdir = off; off += T * 2 * kChunk;
-  L.g0 = off; off += T * 4 * kChunk;
-  L.g1 = off; off += T * 4 * kChunk;
+  L.dz = off; off += 9 * T * 4 * kChunk;
   L.dsig = off; off += al256(T * kT * sizeof(float));
   L.part_region = al256((size_t)kMaxSplit * 128 * 257 * sizeof(float));
   L.part = off; off += (size_t)kDwLaunchesPerNet * L.part_region;
@@ -962,7 +1137,6 @@ static int backward_net(NsrHandle_* h, int which, const float* rays, int64_t n, 
   uint8_t* dhead = (uint8_t*)(ws + L.dhead);
   uint8_t* encdir = (uint8_t*)(ws + L.encdir);
   uint8_t* dzdir = (uint8_t*)(ws + L.dzdir);
-  uint8_t* G[2] = {(uint8_t*)(ws + L.g0), (uint8_t*)(ws + L.g1)};
   float* dsig = (float*)(ws + L.dsig);
   auto h_layer = [&](int l) { return hh + (size_t)(l - 1) * (size_t)tiles * 4 * kChunk; };   // l = 1..8 activations, 9 = feat
   auto m_layer = [&](int l) { return (const uint32_t*)(ws + L.mask[which]) + (size_t)(l - 1) * (size_t)tiles * kT * 8; };   // l = 1..8
@@ -986,14 +1160,42 @@ static int backward_net(NsrHandle_* h, int which, const float* rays, int64_t n, 
     NSR_TCUDA(h, cudaGetLastError());
   }
 
-  DwPlanner P{h, st, tiles, ws + L.part, L.part_region};
-  P.red.grad = grad_flat;
   const WtTable WT = build_wt_table(h->rp.ch_dir, h->cfg.no_dir != 0);
   auto wt = [&](int idx) { return net.wt_image + (size_t)WT.l[idx].chunk0 * kWtChunkBytes; };
+  // dz(i): i = 0 d feat, 1 dZ_8, ..., 8 dZ_1 (each [tiles][4 chunks])
+  auto dzi = [&](int i) { return (uint8_t*)(ws + L.dz) + (size_t)i * (size_t)tiles * 4 * kChunk; };
+
+  // ---- the dX chain: dir -> final -> L8 .. L2 ----
+  if (!(h->debug_flags & 2)) {
+    ChainArgs a{};
+    a.dzdir = dzdir; a.wt = net.wt_image; a.dz = dzi(0); a.mask = (const uint32_t*)(ws + L.mask[which]);
+    a.dsig = dsig; a.wsig = net.tc_consts + kcWsig; a.n_tiles = tiles;
+    const int grid = (int)(tiles < h->sm_count ? tiles : h->sm_count);
+    if (fmt_of(h) == 1) {
+      NSR_TCUDA(h, cudaFuncSetAttribute(k_tg_dxchain<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemChainBytes));
+      k_tg_dxchain<1><<<grid, kChainThreads, kSmemChainBytes, st>>>(a);
+    } else {
+      NSR_TCUDA(h, cudaFuncSetAttribute(k_tg_dxchain<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemChainBytes));
+      k_tg_dxchain<0><<<grid, kChainThreads, kSmemChainBytes, st>>>(a);
+    }
+    h->launches += 1;
+    NSR_TCUDA(h, cudaGetLastError());
+  } else {       // debug flag 2: the layer-by-layer kernels (k_tg_dx), kept as the cross-check of the fused chain
+    for (int i = 0; i < 9; ++i) {
+      DxArgs a{};
+      a.a_img = (i == 0) ? dzdir : dzi(i - 1); a.nkc = (i == 0) ? 2 : 4; a.wt_img = wt(i); a.out_img = dzi(i);
+      a.mask_bits = (i == 0) ? nullptr : m_layer(9 - i);
+      if (i == 1) { a.dsig = dsig; a.wsig = net.tc_consts + kcWsig; }
+      a.n_tiles = tiles;
+      NSR_TCUDA(h, launch_dx(h, a, st));
+    }
+  }
+
+  // ---- dW GEMMs ----
+  DwPlanner P{h, st, tiles, ws + L.part, L.part_region};
+  P.red.grad = grad_flat;
   using JS = DwPlanner::JobSpec;
   const int ld_dir = h->cfg.no_dir ? 256 : 256 + h->rp.ch_dir;
-
-  // ---- heads and dir layer ----
   {   // rgb.0: dW = dHead[:,1:4]^T . dir_act, db
     const JS js[1] = {{dhead, 1, 0, 0, 1, 3, off[22], 128, 0, off[23]}};
     P.launch(dir, 2, 0, 2, 128, js, 1);
@@ -1006,28 +1208,16 @@ static int backward_net(NsrHandle_* h, int which, const float* rays, int64_t n, 
       P.launch(encdir, 1, 0, 1, h->rp.ch_dir, jd, 1);
     }
   }
-  {   // d feat = dZ_dir . W_dir[:, :256]   (xyz_encoding_final has no activation: no mask)
-    DxArgs a{};
-    a.a_img = dzdir; a.nkc = 2; a.wt_img = wt(0); a.out_img = G[0]; a.mask_bits = nullptr; a.n_tiles = tiles;
-    NSR_TCUDA(h, launch_dx(h, a, st));
-  }
   {   // xyz_encoding_final: dW = d feat^T . h8 ; sigma head: dW = d sigma^T . h8, db
-    const JS js[3] = {{G[0], 4, 0, 1, 0, 128, off[16], 256, 0, off[17]},
-                      {G[0], 4, 2, 3, 0, 128, off[16] + 128 * 256, 256, 0, off[17] + 128},
+    const uint8_t* df = dzi(0);
+    const JS js[3] = {{df, 4, 0, 1, 0, 128, off[16], 256, 0, off[17]},
+                      {df, 4, 2, 3, 0, 128, off[16] + 128 * 256, 256, 0, off[17] + 128},
                       {dhead, 1, 0, 0, 0, 1, off[20], 256, 0, off[21]}};
     P.launch(h_layer(8), 4, 0, 4, 256, js, 3);
   }
-  {   // dZ_8 = (d feat . W_final + d sigma x w_sigma) . [h8 > 0]
-    DxArgs a{};
-    a.a_img = G[0]; a.nkc = 4; a.wt_img = wt(1); a.out_img = G[1]; a.mask_bits = m_layer(8);
-    a.dsig = dsig; a.wsig = net.tc_consts + kcWsig; a.n_tiles = tiles;
-    NSR_TCUDA(h, launch_dx(h, a, st));
-  }
-  // ---- trunk: L = 8 .. 1 ; dZ_L lives in G[cur] ----
-  int cur = 1;
-  for (int Lyr = 8; Lyr >= 1; --Lyr) {
+  for (int Lyr = 8; Lyr >= 1; --Lyr) {     // trunk
     const int pw = 2 * (Lyr - 1), pb = pw + 1;
-    const uint8_t* dz = G[cur];
+    const uint8_t* dz = dzi(9 - Lyr);
     if (Lyr == 1) {          // input = enc (63 columns)
       const JS js[2] = {{dz, 4, 0, 1, 0, 128, off[pw], 63, 0, off[pb]}, {dz, 4, 2, 3, 0, 128, off[pw] + 128 * 63, 63, 0, off[pb] + 128}};
       P.launch(enc, 1, 0, 1, 63, js, 2);
@@ -1039,13 +1229,6 @@ static int backward_net(NsrHandle_* h, int which, const float* rays, int64_t n, 
     } else {
       const JS js[2] = {{dz, 4, 0, 1, 0, 128, off[pw], 256, 0, off[pb]}, {dz, 4, 2, 3, 0, 128, off[pw] + 128 * 256, 256, 0, off[pb] + 128}};
       P.launch(h_layer(Lyr - 1), 4, 0, 4, 256, js, 2);
-    }
-    if (P.err != cudaSuccess) return tfail(h, NSR_ERR_CUDA, std::string("dW launch: ") + cudaGetErrorString(P.err));
-    if (Lyr >= 2) {          // dZ_{L-1} = (dZ_L . W_L[:, h part]) . [h_{L-1} > 0]
-      DxArgs a{};
-      a.a_img = dz; a.nkc = 4; a.wt_img = wt(2 + (8 - Lyr)); a.out_img = G[cur ^ 1]; a.mask_bits = m_layer(Lyr - 1); a.n_tiles = tiles;
-      NSR_TCUDA(h, launch_dx(h, a, st));
-      cur ^= 1;
     }
   }
   if (P.err != cudaSuccess) return tfail(h, NSR_ERR_CUDA, std::string("dW launch: ") + cudaGetErrorString(P.err));
@@ -1243,7 +1426,7 @@ extern "C" int nsr_debug_train_layout(const NsrHandle* h, int64_t n_rays, int64_
   const TrainWs L = train_layout(h, n_rays);
   const int64_t v[18] = {(int64_t)L.enc[0], (int64_t)L.hh[0], (int64_t)L.dir[0], (int64_t)L.raw[0], (int64_t)L.z[0], L.tiles[0],
                          (int64_t)L.enc[1], (int64_t)L.hh[1], (int64_t)L.dir[1], (int64_t)L.raw[1], (int64_t)L.z[1], L.tiles[1],
-                         (int64_t)L.dhead, (int64_t)L.dzdir, (int64_t)L.g0, (int64_t)L.g1, (int64_t)L.mask[0], (int64_t)L.mask[1]};
+                         (int64_t)L.dhead, (int64_t)L.dzdir, (int64_t)L.dz, (int64_t)(L.dz + 4 * (size_t)kChunk * (size_t)(L.tiles[0] > L.tiles[1] ? L.tiles[0] : L.tiles[1])), (int64_t)L.mask[0], (int64_t)L.mask[1]};
   for (int i = 0; i < 18; ++i) out16[i] = v[i];
   return NSR_OK;
 }

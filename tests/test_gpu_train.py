@@ -542,3 +542,27 @@ def test_gradients_option_variants(variant):
         _report(test="grad_variants", variant=variant, rel_l2=err, cos=cos)
         assert cos > 0.9995 and err < 3e-2, (variant, err, cos)
     r.close()
+
+
+def test_fused_dx_chain_equals_layerwise_kernels():
+    """k_tg_dxchain (dZ stays in TMEM between layers) against the layer-by-layer k_tg_dx launches (debug flag 2):
+    same MMAs in the same order, so the gradients must agree to rounding; ragged tile counts in both passes."""
+    from nerf_sr_b200 import Trainer
+    cfg = O.RenderConfig(white_bkgd=True, noise_std=0.5)
+    pc, pf = O.make_mlp_params(cfg, 4), O.make_mlp_params(cfg, 17)
+    r = _renderer(cfg, pc, pf)
+    tr = Trainer(r, pc, pf, downscale=2)
+    n_lr = 151 * 3 + 1                                   # > 148 coarse tiles per CTA round, odd ray count per tile pair
+    rays = O.synthetic_rays(n_lr * 4, 33, "blender").to(DEV)
+    tgt = torch.rand(n_lr, 3, generator=torch.Generator().manual_seed(4)).to(DEV)
+    rng = tr.draw_rng(rays.shape[0], torch.Generator(device=DEV).manual_seed(1))
+    gc1, gf1 = tr.forward_backward(rays, tgt, rng)
+    r.lib.nsr_debug_set_flags(r._h, 2)
+    gc2, gf2 = tr.forward_backward(rays, tgt, rng)
+    r.lib.nsr_debug_set_flags(r._h, 0)
+    torch.cuda.synchronize()
+    e1, e2 = _rel(gc1, gc2), _rel(gf1, gf2)
+    _report(test="chain_vs_layerwise", coarse=e1, fine=e2)
+    assert torch.isfinite(gc1).all() and torch.isfinite(gf1).all()
+    assert e1 < 1e-6 and e2 < 1e-6, (e1, e2)
+    r.close()
