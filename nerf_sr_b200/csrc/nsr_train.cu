@@ -574,9 +574,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_tg_dx(const DxArgs a) {
 // GEMMs need afterwards: each layer's dZ image written once (256-bit stores), the 1-bit ReLU masks read once.
 // This removes, per point and layer, the 1 KB re-read of dZ and half of the per-SM operand ingest that bound the
 // layer-by-layer k_tg_dx (profiles/r01_train_ncu_full.md).
-//   warp 0: producer   (dZ_dir tile -> smem once per tile; 34 transposed-weight chunks of 64 KB per tile, 2-slot ring)
+//   warp 0: producer   (a 6-slot ring of 32 KB entries: per tile the two dZ_dir chunks and, for each of the 34
+//                       transposed-weight chunks, its hi plane and its lo plane -- 70 entries; a freed entry has two
+//                       chunks' worth of MMA time to refill, which a 2 x 64 KB ring did not give)
 //   warp 1: MMA issue  (M=128 N=256 K=16 kind::f16, 3 MMAs per product; layer 0 SS, layers 1..8 TS)
-//   warps 2-9: epilogue (2 per TMEM lane quarter, 128 accumulator columns each)
+//   warps 2-17: epilogue (4 per TMEM lane quarter, 64 accumulator columns each)
 // TMEM: [0,256) fp32 accumulator, [256,384) A hi plane, [384,512) A lo plane.
 // ---------------------------------------------------------------------------
 struct ChainArgs {
@@ -587,14 +589,15 @@ struct ChainArgs {
   const float* dsig; const float* wsig;
   long long n_tiles;
 };
-constexpr int kChainThreads = 320;
-constexpr int kChRing = 0;                          // 2 x 64 KB
-constexpr int kChIn = 2 * kWtChunkBytes;            // 131072: dZ_dir tile, 64 KB
-constexpr int kChAux = kChIn + 2 * kChunk;          // 196608: w_sigma
+constexpr int kChainThreads = 576;
+constexpr int kChainEpiWarps = 16;
+constexpr int kChSlots = 6;
+constexpr int kChRing = 0;                          // 6 x 32 KB
+constexpr int kChAux = kChSlots * kChunk;           // 196608: w_sigma
 constexpr int kChBar = kChAux + 1024;
 constexpr int kChTmem = kChBar + 16 * 8;
 constexpr int kSmemChainBytes = kChTmem + 16;
-enum { C_FULL = 0, C_EMPTY = 2, C_INFULL = 4, C_INEMPTY = 5, C_ACCFULL = 6, C_AREADY = 7 };
+enum { C_FULL = 0, C_EMPTY = 6, C_ACCFULL = 12, C_AREADY = 13 };
 
 template <int FMT>
 __global__ void __launch_bounds__(kChainThreads, 1) k_tg_dxchain(const ChainArgs a) {
@@ -607,9 +610,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_tg_dxchain(const ChainArgs
   if (sm_base & 1023u) { if (threadIdx.x == 0) printf("[nsr_train] dynamic smem base %u not 1024-aligned\n", sm_base); __trap(); }
   const uint32_t bar = sm_base + kChBar;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(bar + 8 * (C_FULL + i), 1); mbar_init(bar + 8 * (C_EMPTY + i), 1); }
-    mbar_init(bar + 8 * C_INFULL, 1); mbar_init(bar + 8 * C_INEMPTY, 1);
-    mbar_init(bar + 8 * C_ACCFULL, 1); mbar_init(bar + 8 * C_AREADY, 8);
+    for (int i = 0; i < kChSlots; ++i) { mbar_init(bar + 8 * (C_FULL + i), 1); mbar_init(bar + 8 * (C_EMPTY + i), 1); }
+    mbar_init(bar + 8 * C_ACCFULL, 1); mbar_init(bar + 8 * C_AREADY, kChainEpiWarps);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -623,21 +625,20 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_tg_dxchain(const ChainArgs
 
   if (warp == 0) {
     if (elect_one()) {
-      uint32_t n = 0;
+      uint32_t slot = 0, par = 0;
+      auto push = [&](const uint8_t* src) {
+        mbar_wait(bar + 8 * (C_EMPTY + slot), par ^ 1u);
+        const uint32_t full = bar + 8 * (C_FULL + slot);
+        mbar_expect_tx(full, kChunk);
+        bulk_copy_g2s(sm_base + kChRing + slot * kChunk, src, kChunk, full);
+        if (++slot == kChSlots) { slot = 0; par ^= 1u; }
+      };
       for (long long it = 0; it < my_tiles; ++it) {
         const long long tile = blockIdx.x + it * (long long)gridDim.x;
-        mbar_wait(bar + 8 * C_INEMPTY, (uint32_t)((it & 1) ^ 1));
-        mbar_expect_tx(bar + 8 * C_INFULL, 2 * kChunk);
-        bulk_copy_g2s(sm_base + kChIn, a.dzdir + (size_t)tile * 2 * kChunk, kChunk, bar + 8 * C_INFULL);
-        bulk_copy_g2s(sm_base + kChIn + kChunk, a.dzdir + (size_t)tile * 2 * kChunk + kChunk, kChunk, bar + 8 * C_INFULL);
-        for (int cg = 0; cg < kWtChunks; ++cg, ++n) {
-          const uint32_t slot = n & 1u, par = (n >> 1) & 1u;
-          mbar_wait(bar + 8 * (C_EMPTY + slot), par ^ 1u);
-          const uint32_t full = bar + 8 * (C_FULL + slot);
-          const uint32_t dst = sm_base + kChRing + slot * kWtChunkBytes;
-          mbar_expect_tx(full, kWtChunkBytes);
-          bulk_copy_g2s(dst, a.wt + (size_t)cg * kWtChunkBytes, 32768, full);
-          bulk_copy_g2s(dst + 32768, a.wt + (size_t)cg * kWtChunkBytes + 32768, 32768, full);
+        for (int cg = 0; cg < kWtChunks; ++cg) {
+          if (cg < 2) push(a.dzdir + ((size_t)tile * 2 + cg) * kChunk);        // layer 0: its A chunk first
+          push(a.wt + (size_t)cg * kWtChunkBytes);                             // hi plane (256 rows x 128 B)
+          push(a.wt + (size_t)cg * kWtChunkBytes + 32768);                     // lo plane
         }
       }
     }
@@ -645,23 +646,27 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_tg_dxchain(const ChainArgs
   } else if (warp == 1) {
     if (elect_one()) {
       const uint32_t idesc = gemm_idesc(FMT, 128, 256, 0, 0);
-      uint32_t n = 0, g = 0;
+      uint32_t slot = 0, par = 0, g = 0;
+      auto take = [&]() -> uint32_t {          // wait for the next ring entry, return its smem address
+        mbar_wait(bar + 8 * (C_FULL + slot), par);
+        const uint32_t addr = sm_base + kChRing + slot * kChunk;
+        if (++slot == kChSlots) { slot = 0; par ^= 1u; }
+        return addr;
+      };
       for (long long it = 0; it < my_tiles; ++it) {
         for (int l = 0; l < 9; ++l, ++g) {
           if (g > 0) { mbar_wait(bar + 8 * C_AREADY, (g - 1) & 1u); tc_fence_after(); }    // accumulator drained, A planes written
-          if (l == 0) { mbar_wait(bar + 8 * C_INFULL, (uint32_t)(it & 1)); tc_fence_after(); }
           const int nkc = (l == 0) ? 2 : 4;
-          for (int c = 0; c < nkc; ++c, ++n) {
-            const uint32_t slot = n & 1u, par = (n >> 1) & 1u;
-            mbar_wait(bar + 8 * (C_FULL + slot), par);
+          for (int c = 0; c < nkc; ++c) {
+            const uint32_t s0 = slot;
+            const uint32_t sa = (l == 0) ? take() : 0u;
+            const uint32_t sh = take(), sl = take();
             tc_fence_after();
-            const uint32_t sb = sm_base + kChRing + slot * kWtChunkBytes;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const uint64_t bh = kmajor_desc(sb + 32 * k), bl = kmajor_desc(sb + 32768 + 32 * k);
+              const uint64_t bh = kmajor_desc(sh + 32 * k), bl = kmajor_desc(sl + 32 * k);
               const uint32_t acc = (c | k) ? 1u : 0u;
               if (l == 0) {
-                const uint32_t sa = sm_base + kChIn + (uint32_t)c * kChunk;
                 const uint64_t ah = kmajor_desc(sa + 32 * k), al = kmajor_desc(sa + kPlane + 32 * k);
                 mma_ss(tmem, ah, bh, idesc, acc);
                 mma_ss(tmem, al, bh, idesc, 1u);
@@ -673,16 +678,16 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_tg_dxchain(const ChainArgs
                 mma_ts(tmem, ah, bl, idesc, 1u);
               }
             }
-            tc_commit(bar + 8 * (C_EMPTY + slot));
+            uint32_t f = s0;                    // release the entries this chunk used
+            for (int i = 0; i < (l == 0 ? 3 : 2); ++i) { tc_commit(bar + 8 * (C_EMPTY + f)); if (++f == kChSlots) f = 0; }
           }
-          if (l == 0) tc_commit(bar + 8 * C_INEMPTY);
           tc_commit(bar + 8 * C_ACCFULL);
         }
       }
     }
     __syncwarp();
   } else {
-    const int q = warp & 3, hh = (warp - 2) >> 2;
+    const int q = warp & 3, part = (warp - 2) >> 2;          // part: 64-column slice of the 256 accumulator columns
     const int row = 32 * q + lane, r7 = lane & 7;
     const uint32_t tlane = tmem + ((uint32_t)(32 * q) << 16);
     const float* wsig = reinterpret_cast<const float*>(sm + kChAux);
@@ -692,17 +697,17 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_tg_dxchain(const ChainArgs
       const float ds = a.dsig[tile * kT + row];
 #pragma unroll 1
       for (int l = 0; l < 9; ++l, ++g) {
-        uint32_t mb[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+        uint32_t mb[2] = {0xffffffffu, 0xffffffffu};
         if (l >= 1) {      // output of step l is the gradient w.r.t. h_{9-l}: gate with that layer's ReLU bits
-          const uint4 m = *reinterpret_cast<const uint4*>(a.mask + (((size_t)(8 - l) * (size_t)a.n_tiles + (size_t)tile) * kT + row) * 8 + 4 * hh);
-          mb[0] = m.x; mb[1] = m.y; mb[2] = m.z; mb[3] = m.w;
+          const uint2 m = *reinterpret_cast<const uint2*>(a.mask + (((size_t)(8 - l) * (size_t)a.n_tiles + (size_t)tile) * kT + row) * 8 + 2 * part);
+          mb[0] = m.x; mb[1] = m.y;
         }
         uint8_t* orow = a.dz + (((size_t)l * (size_t)a.n_tiles + (size_t)tile) * 4) * kChunk + (size_t)row * 128;
         mbar_wait(bar + 8 * C_ACCFULL, g & 1u);
         tc_fence_after();
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const int col0 = 128 * hh + 32 * b;
+        for (int b = 0; b < 2; ++b) {
+          const int col0 = 64 * part + 32 * b;
           uint32_t r[32];
           TMEM_LD32(tlane + (uint32_t)col0, r);
           tc_wait_ld();
@@ -723,9 +728,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_tg_dxchain(const ChainArgs
 #pragma unroll
           for (int t2 = 0; t2 < 2; ++t2) {
             const int e = 8 * t2;
-            store_chunk_pair(gp, 2 * (b & 1) + t2, r7, make_uint4(whi[e], whi[e + 1], whi[e + 2], whi[e + 3]),
+            store_chunk_pair(gp, 2 * b + t2, r7, make_uint4(whi[e], whi[e + 1], whi[e + 2], whi[e + 3]),
                              make_uint4(whi[e + 4], whi[e + 5], whi[e + 6], whi[e + 7]));
-            store_chunk_pair(gp + kPlane, 2 * (b & 1) + t2, r7, make_uint4(wlo[e], wlo[e + 1], wlo[e + 2], wlo[e + 3]),
+            store_chunk_pair(gp + kPlane, 2 * b + t2, r7, make_uint4(wlo[e], wlo[e + 1], wlo[e + 2], wlo[e + 3]),
                              make_uint4(wlo[e + 4], wlo[e + 5], wlo[e + 6], wlo[e + 7]));
           }
         }
