@@ -223,6 +223,25 @@ def train_config(world):
             "l2": "working set per step (5 GB activation stash) exceeds L2"}
 
 
+def run_reference_train(args, rank):
+    """--impl reference --workload train: the reference's training iteration (oracle port) on the host cores."""
+    if rank != 0:
+        return
+    cfg, pc, pf, rays, target = train_inputs(0)
+    ncpu = os.cpu_count() or 1
+    torch.set_num_threads(min(ncpu, 32))
+    n_lr = 64
+    rate = oracle_train_rate(cfg, pc, pf, rays, target, "cpu", n_lr, max(1, args.steps))
+    line = {"impl": "reference", "metric": "training rays/sec (64+128 samples, 2x SS; forward + backward + Adam)", "value": rate,
+            "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n_lr * SS * SS / rate,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": train_config(1),
+            "cpu_baseline": {"value": rate, "unit": "rays/s", "cores": min(ncpu, 32), "host_cores": ncpu, "kind": "port",
+                             "sample": f"{n_lr * SS * SS} rays ({n_lr} LR pixels) per step, median of {max(1, args.steps)} iterations of the oracle "
+                                       "port (torch CPU autograd + Adam)"},
+            "e2e": {"value": rate, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
 def run_train(args, rank, world, local):
     import torch.distributed as dist
     from nerf_sr_b200 import Renderer, Trainer
@@ -335,7 +354,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        if args.workload == "train":
+            run_reference_train(args, rank)
+        else:
+            run_reference(args, rank, world)
         return
 
     import torch.distributed as dist
