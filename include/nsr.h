@@ -308,6 +308,32 @@ NSR_API int nsr_backward(NsrHandle* h, const float* rays, int64_t n_rays, int ra
 NSR_API int nsr_lr_loss_grad(NsrHandle* h, const float* hr_rgb, const float* target_lr, int64_t n_lr, int s, float lambda,
                              float* lr_rgb_out, float* metrics_out, float* g_hr_out, NsrStream stream);
 
+/* Replaces (scope row f-2, completed): every term of calculate_losses for ONE net's outputs and its backward down to
+ * the HR composite colour / depth (models/nerf_downX_model.py:326-378):
+ *   comp_low_res_output's box averages (:337-348), lambda_*_mse * ColorMSELoss + PSNR (:357-359,380-382),
+ *   --use_var_loss: sum over LR pixels and channels of torch.var over the s*s sub-pixel colours (:331-335,374-375),
+ *   --use_depth_var_loss: the same for depth / self.far (:349-353,376-378),
+ *   --sisr_path: ColorMSELoss of the HR colours against data_rgbs_sr (:364-367).
+ * A zero lambda_var / lambda_depth_var switches that term off; target_hr null switches the SR term off. */
+typedef struct NsrLossTerms {
+  uint32_t struct_size;        /* = sizeof(NsrLossTerms)                        */
+  int32_t  s;                  /* --downscale                                   */
+  float    lambda_mse;         /* --lambda_coarse_mse | --lambda_fine_mse       */
+  float    lambda_var;         /* --lambda_*_var when --use_var_loss, else 0    */
+  float    lambda_depth_var;   /* --lambda_*_depth_var when --use_depth_var_loss */
+  float    far_plane;          /* self.far = rays[0,7] (:284)                   */
+  int32_t  reserved[6];
+} NsrLossTerms;
+
+/* hr_rgb [n_lr*s*s,3], hr_depth [n_lr*s*s] (null unless a depth output / term is wanted), target_lr [n_lr,3],
+ * target_hr [n_lr*s*s,3] or null.  Outputs (each may be null except metrics_out): lr_rgb_out [n_lr,3],
+ * lr_depth_out [n_lr], g_rgb_out [n_lr*s*s,3] = d total / d hr_rgb, g_depth_out [n_lr*s*s] = d total / d hr_depth,
+ * metrics_out: device float[8] = {lambda_mse * mse, psnr, var_sum, depth_var_sum, mse_sr, total, 0, 0} with
+ * total = lambda_mse * mse + mse_sr + lambda_var * var_sum + lambda_depth_var * depth_var_sum.  No host sync. */
+NSR_API int nsr_loss_epilogue(NsrHandle* h, const float* hr_rgb, const float* hr_depth, const float* target_lr,
+                              const float* target_hr, int64_t n_lr, const NsrLossTerms* terms, float* lr_rgb_out,
+                              float* lr_depth_out, float* metrics_out, float* g_rgb_out, float* g_depth_out, NsrStream stream);
+
 /* Replaces: nn.utils.clip_grad_norm_ over chain(netCoarse, netFine) (models/nerf_downX_model.py:404-405).
  * coef_out: device float[2] = {min(1, max_norm / (total_norm + 1e-6)), total_norm}; grad_b may be null. */
 NSR_API int nsr_clip_coef(NsrHandle* h, const float* grad_a, const float* grad_b, int64_t numel, float max_norm,

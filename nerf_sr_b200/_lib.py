@@ -42,6 +42,11 @@ class NsrOutGrads(C.Structure):
                 ("coarse_comp_rgbs", "coarse_depth", "coarse_opacity", "fine_comp_rgbs", "fine_depth", "fine_opacity")]
 
 
+class NsrLossTerms(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("s", C.c_int32), ("lambda_mse", C.c_float), ("lambda_var", C.c_float),
+                ("lambda_depth_var", C.c_float), ("far_plane", C.c_float), ("reserved", C.c_int32 * 6)]
+
+
 class NsrPassOutputs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("comp_rgbs", "depth", "opacity", "weights", "raw")]
 
@@ -81,6 +86,8 @@ SIGNATURES = {
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "nsr_lr_loss_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nsr_loss_epilogue": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(NsrLossTerms),
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nsr_clip_coef": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_void_p]),
     "nsr_adam_step": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                 C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_float, C.c_void_p]),

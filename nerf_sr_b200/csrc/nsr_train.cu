@@ -933,6 +933,112 @@ k_lr_loss_grad(const float* __restrict__ hr, const float* __restrict__ target, i
   if (threadIdx.x == 0) partials[blockIdx.x] = sh[0];
 }
 
+// All of calculate_losses' terms for one net's outputs (models/nerf_downX_model.py:326-378) and their gradients
+// down to the HR composite colour / depth: box average + lambda * MSE + PSNR, the s x s sub-pixel variance sums
+// of colour and of depth / far (torch.var: unbiased, two-pass), and the MSE of the HR colours against the SISR
+// image.  One thread per LR pixel (its s*s rows are contiguous: 16 s^2 bytes in, 16 s^2 out); four fp64 partial
+// sums per block, fixed-order final reduction (deterministic, no atomics).
+struct LossTerms {
+  int ss;
+  float g_mse;        // 2 lambda_mse / (3 n_lr) / s^2
+  float g_var;        // 2 lambda_var / (s^2 - 1)
+  float g_dvar;       // 2 lambda_depth_var / (s^2 - 1) / far
+  float g_sr;         // 2 / (3 n_lr s^2)
+  float far_plane;
+  int want_var, want_dvar;
+};
+
+__global__ void __launch_bounds__(256)
+k_loss_epilogue(const float* __restrict__ rgb, const float* __restrict__ depth, const float* __restrict__ target,
+                const float* __restrict__ target_hr, int64_t n_lr, LossTerms t, float* __restrict__ lr_rgb,
+                float* __restrict__ lr_depth, float* __restrict__ g_rgb, float* __restrict__ g_depth,
+                double* __restrict__ partials) {
+  double a_mse = 0.0, a_var = 0.0, a_dvar = 0.0, a_sr = 0.0;
+  const int ss = t.ss;
+  const float inv_nm1 = ss > 1 ? 1.f / (float)(ss - 1) : 0.f;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n_lr; p += (int64_t)gridDim.x * blockDim.x) {
+    const float* x = rgb + p * ss * 3;
+    float mean[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float sum = 0.f;
+      for (int k = 0; k < ss; ++k) sum = __fadd_rn(sum, x[k * 3 + c]);
+      mean[c] = __fdiv_rn(sum, (float)ss);
+      if (lr_rgb) lr_rgb[p * 3 + c] = mean[c];
+      const float d = __fsub_rn(mean[c], target[p * 3 + c]);
+      a_mse += (double)__fmul_rn(d, d);
+      float m2 = 0.f;
+      const float gm = t.g_mse * d;
+      for (int k = 0; k < ss; ++k) {
+        const float v = x[k * 3 + c];
+        const float dev = v - mean[c];
+        m2 = fmaf(dev, dev, m2);
+        float g = gm + t.g_var * dev;
+        if (target_hr) {
+          const float e = v - target_hr[(p * ss + k) * 3 + c];
+          a_sr += (double)(e * e);
+          g = fmaf(t.g_sr, e, g);
+        }
+        if (g_rgb) g_rgb[(p * ss + k) * 3 + c] = g;
+      }
+      if (t.want_var) a_var += (double)(m2 * inv_nm1);
+    }
+    if (depth) {
+      const float* dp = depth + p * ss;
+      float sum = 0.f;
+      for (int k = 0; k < ss; ++k) sum = __fadd_rn(sum, dp[k]);
+      if (lr_depth) lr_depth[p] = __fdiv_rn(sum, (float)ss);
+      if (t.want_dvar) {
+        // torch.var(depth / far): the division comes first (:351)
+        float sf = 0.f;
+        for (int k = 0; k < ss; ++k) sf += __fdiv_rn(dp[k], t.far_plane);
+        const float mf = __fdiv_rn(sf, (float)ss);
+        float m2 = 0.f;
+        for (int k = 0; k < ss; ++k) {
+          const float dev = __fdiv_rn(dp[k], t.far_plane) - mf;
+          m2 = fmaf(dev, dev, m2);
+          if (g_depth) g_depth[p * ss + k] = t.g_dvar * dev;
+        }
+        a_dvar += (double)(m2 * inv_nm1);
+      } else if (g_depth) {
+        for (int k = 0; k < ss; ++k) g_depth[p * ss + k] = 0.f;
+      }
+    }
+  }
+  __shared__ double sh[4][256];
+  sh[0][threadIdx.x] = a_mse; sh[1][threadIdx.x] = a_var; sh[2][threadIdx.x] = a_dvar; sh[3][threadIdx.x] = a_sr;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sh[j][threadIdx.x] += sh[j][threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < 4) partials[blockIdx.x * 4 + threadIdx.x] = sh[threadIdx.x][0];
+}
+
+// metrics[8] = {lambda_mse * mse, psnr, var_sum, depth_var_sum, mse_sr, total, 0, 0}
+__global__ void k_loss_epilogue_final(const double* __restrict__ partials, int n_blocks, int64_t n_lr, int ss, float lambda_mse,
+                                      float lambda_var, float lambda_dvar, int has_sr, float* __restrict__ metrics) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int i = 0; i < n_blocks; ++i)
+      for (int j = 0; j < 4; ++j) s[j] += partials[i * 4 + j];
+    const float mse = (float)(s[0] / (double)(n_lr * 3));
+    const float var = (float)s[1], dvar = (float)s[2];
+    const float sr = has_sr ? (float)(s[3] / (double)(n_lr * ss * 3)) : 0.f;
+    metrics[0] = mse * lambda_mse;
+    metrics[1] = -10.f * log10f(mse);
+    metrics[2] = var;
+    metrics[3] = dvar;
+    metrics[4] = sr;
+    metrics[5] = mse * lambda_mse + sr + lambda_var * var + lambda_dvar * dvar;
+    metrics[6] = 0.f;
+    metrics[7] = 0.f;
+  }
+}
+
 __global__ void k_loss_final(const double* __restrict__ partials, int n_blocks, int64_t n_elems, float lambda,
                              float* __restrict__ metrics) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -1374,6 +1480,42 @@ extern "C" int nsr_lr_loss_grad(NsrHandle* h, const float* hr_rgb, const float* 
   const float scale = (float)(2.0 * (double)lambda / ((double)n_lr * 3.0) / (double)(s * s));
   k_lr_loss_grad<<<blocks, 256, 0, (cudaStream_t)stream>>>(hr_rgb, target_lr, n_lr, s * s, scale, lr_rgb_out, g_hr_out, h->d_partials);
   k_loss_final<<<1, 32, 0, (cudaStream_t)stream>>>(h->d_partials, blocks, n_lr * 3, lambda, metrics_out);
+  h->launches += 2;
+  NSR_TCUDA(h, cudaGetLastError());
+  return NSR_OK;
+}
+
+extern "C" int nsr_loss_epilogue(NsrHandle* h, const float* hr_rgb, const float* hr_depth, const float* target_lr,
+                                 const float* target_hr, int64_t n_lr, const NsrLossTerms* terms, float* lr_rgb_out,
+                                 float* lr_depth_out, float* metrics_out, float* g_rgb_out, float* g_depth_out, NsrStream stream) {
+  if (!h) return NSR_ERR_INVALID_ARG;
+  if (!hr_rgb || !target_lr || !metrics_out || !terms || n_lr <= 0) return tfail(h, NSR_ERR_INVALID_ARG, "nsr_loss_epilogue: bad argument");
+  if (terms->struct_size != sizeof(NsrLossTerms)) return tfail(h, NSR_ERR_INVALID_ARG, "nsr_loss_epilogue: NsrLossTerms.struct_size mismatch");
+  const int s = terms->s;
+  if (s < 1 || s > 16) return tfail(h, NSR_ERR_INVALID_ARG, "nsr_loss_epilogue: downscale must be in [1,16]");
+  const bool want_var = terms->lambda_var != 0.f, want_dvar = terms->lambda_depth_var != 0.f;
+  if ((want_var || want_dvar) && s < 2)
+    return tfail(h, NSR_ERR_UNSUPPORTED, "nsr_loss_epilogue: the sub-pixel variance terms need downscale >= 2 (unbiased variance of one sample is NaN)");
+  if (want_dvar && (!hr_depth || !(terms->far_plane != 0.f)))
+    return tfail(h, NSR_ERR_INVALID_ARG, "nsr_loss_epilogue: the depth-variance term needs hr_depth and a non-zero far plane");
+  if ((lr_depth_out || g_depth_out) && !hr_depth) return tfail(h, NSR_ERR_INVALID_ARG, "nsr_loss_epilogue: depth outputs need hr_depth");
+  NSR_TCUDA(h, cudaSetDevice(h->cfg.device));
+  const int ss = s * s;
+  LossTerms t;
+  t.ss = ss;
+  t.g_mse = (float)(2.0 * (double)terms->lambda_mse / ((double)n_lr * 3.0) / (double)ss);
+  t.g_var = want_var ? (float)(2.0 * (double)terms->lambda_var / (double)(ss - 1)) : 0.f;
+  t.g_dvar = want_dvar ? (float)(2.0 * (double)terms->lambda_depth_var / (double)(ss - 1) / (double)terms->far_plane) : 0.f;
+  t.g_sr = target_hr ? (float)(2.0 / ((double)n_lr * (double)ss * 3.0)) : 0.f;
+  t.far_plane = terms->far_plane;
+  t.want_var = want_var;
+  t.want_dvar = want_dvar;
+  int64_t blocks64 = (n_lr + 255) / 256;
+  const int blocks = (int)(blocks64 > 256 ? 256 : blocks64);      // 4 partials per block in the 1024-entry buffer
+  k_loss_epilogue<<<blocks, 256, 0, (cudaStream_t)stream>>>(hr_rgb, hr_depth, target_lr, target_hr, n_lr, t, lr_rgb_out, lr_depth_out,
+                                                            g_rgb_out, g_depth_out, h->d_partials);
+  k_loss_epilogue_final<<<1, 32, 0, (cudaStream_t)stream>>>(h->d_partials, blocks, n_lr, ss, terms->lambda_mse, terms->lambda_var,
+                                                            terms->lambda_depth_var, target_hr != nullptr, metrics_out);
   h->launches += 2;
   NSR_TCUDA(h, cudaGetLastError());
   return NSR_OK;

@@ -6,7 +6,7 @@
                               reference's ``loss_tot.backward(); optimizer.step()`` run unchanged
                               (models/nerf_downX_model.py:390-408)
     Trainer.optimize_parameters   the whole reference iteration on the device: forward (train mode) ->
-                              box average + ColorMSELoss (+PSNR) -> backward -> [gradient all-reduce] ->
+                              box average + ColorMSELoss (+PSNR, + the sub-pixel variance / SISR terms) -> backward -> [gradient all-reduce] ->
                               clip -> Adam -> re-pack; no host sync, losses stay on the device.
 
 PyTorch provides device memory, streams, RNG draws (in the reference's order) and NCCL only; every
@@ -20,7 +20,7 @@ from typing import Dict, List, Mapping, Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import NsrError, NsrOutGrads, NsrOutputs, NsrRng
+from ._lib import NsrError, NsrLossTerms, NsrOutGrads, NsrOutputs, NsrRng
 from .renderer import Renderer, state_dict_order
 
 OUT_KEYS = ("coarse_comp_rgbs", "coarse_depth", "coarse_opacity", "coarse_weights",
@@ -127,6 +127,47 @@ def lr_loss_grad(self: Renderer, hr_rgb: torch.Tensor, target_lr: torch.Tensor, 
     self._check(self.lib.nsr_lr_loss_grad(self._h, hr_rgb.data_ptr(), target_lr.data_ptr(), n_lr, s, float(lam), lr.data_ptr(),
                                           m.data_ptr(), g.data_ptr() if g is not None else None, self._stream()))
     return lr, m, g
+
+
+def loss_epilogue(self: Renderer, hr_rgb: torch.Tensor, target_lr: torch.Tensor, s: int, lambda_mse: float = 1.0,
+                  hr_depth: Optional[torch.Tensor] = None, lambda_var: float = 0.0, lambda_depth_var: float = 0.0,
+                  far: float = 0.0, target_hr: Optional[torch.Tensor] = None, want_grad: bool = True) -> Dict[str, torch.Tensor]:
+    """Every term of the reference's ``calculate_losses`` for one net's outputs (models/nerf_downX_model.py:326-378)
+    and its gradient down to the HR outputs, in one launch (nsr_loss_epilogue).  ``lambda_var`` /
+    ``lambda_depth_var`` = 0 switch the sub-pixel variance terms off (``--use_var_loss`` / ``--use_depth_var_loss``
+    not given); ``target_hr`` is ``data_rgbs_sr`` (``--sisr_path``); ``far`` is the reference's ``self.far``.
+    Returns lr_rgb [n_lr,3], lr_depth [n_lr] (if hr_depth), metrics [8] = (lambda*mse, psnr, var_sum,
+    depth_var_sum, mse_sr, total, 0, 0), g_rgb, g_depth (if want_grad)."""
+    hr_rgb, target_lr = self._f32(hr_rgb), self._f32(target_lr)
+    n_lr = target_lr.shape[0]
+    n = n_lr * s * s
+    if hr_rgb.shape[0] != n:
+        raise NsrError(1, f"hr_rgb has {hr_rgb.shape[0]} rows, expected {n_lr}*{s}*{s}")
+    dev, f32 = self.device, torch.float32
+    out = {"lr_rgb": torch.empty(n_lr, 3, device=dev, dtype=f32), "metrics": torch.empty(8, device=dev, dtype=f32)}
+    if hr_depth is not None:
+        hr_depth = self._f32(hr_depth).reshape(-1)
+        if hr_depth.shape[0] != n:
+            raise NsrError(1, f"hr_depth has {hr_depth.shape[0]} rows, expected {n}")
+        out["lr_depth"] = torch.empty(n_lr, device=dev, dtype=f32)
+    if target_hr is not None:
+        target_hr = self._f32(target_hr)
+        if tuple(target_hr.shape) != (n, 3):
+            raise NsrError(1, f"target_hr is {tuple(target_hr.shape)}, expected ({n}, 3)")
+    if want_grad:
+        out["g_rgb"] = torch.empty(n, 3, device=dev, dtype=f32)
+        if hr_depth is not None:
+            out["g_depth"] = torch.empty(n, device=dev, dtype=f32)
+    t = NsrLossTerms()
+    t.struct_size = C.sizeof(NsrLossTerms)
+    t.s, t.lambda_mse, t.lambda_var, t.lambda_depth_var, t.far_plane = int(s), float(lambda_mse), float(lambda_var), \
+        float(lambda_depth_var), float(far)
+    ptr = lambda k: out[k].data_ptr() if k in out else None
+    self._check(self.lib.nsr_loss_epilogue(self._h, hr_rgb.data_ptr(), hr_depth.data_ptr() if hr_depth is not None else None,
+                                           target_lr.data_ptr(), target_hr.data_ptr() if target_hr is not None else None,
+                                           n_lr, C.byref(t), ptr("lr_rgb"), ptr("lr_depth"), ptr("metrics"), ptr("g_rgb"),
+                                           ptr("g_depth"), self._stream()))
+    return out
 
 
 def clip_coef(self: Renderer, grad_a: torch.Tensor, grad_b: Optional[torch.Tensor], max_norm: float) -> torch.Tensor:
@@ -238,7 +279,7 @@ def stash_activation(self: Renderer, n_rays: int, which: int, layer: int) -> tor
     return unpack_image(self, img, rows, cols)
 
 
-for _f in (train_layout, stash_activation, stash_mask, relu_bits, new_train_workspace, render_train, backward, lr_loss_grad, clip_coef, adam_step, pack_image, unpack_image, debug_dx, debug_dw):
+for _f in (train_layout, stash_activation, stash_mask, relu_bits, new_train_workspace, render_train, backward, lr_loss_grad, loss_epilogue, clip_coef, adam_step, pack_image, unpack_image, debug_dx, debug_dw):
     setattr(Renderer, _f.__name__, _f)
 
 
@@ -321,7 +362,10 @@ class Trainer:
     def __init__(self, renderer: Renderer, params_coarse: Mapping[str, torch.Tensor], params_fine: Mapping[str, torch.Tensor],
                  lr: float = 5e-4, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8, lambda_coarse_mse: float = 1.0,
                  lambda_fine_mse: float = 1.0, grad_clip_val: float = 0.0, grad_clip_type: str = "norm", downscale: int = 2,
-                 group=None):
+                 group=None, lambda_coarse_var: float = 0.0, lambda_fine_var: float = 0.0, lambda_coarse_depth_var: float = 0.0,
+                 lambda_fine_depth_var: float = 0.0):
+        """lambda_*_var / lambda_*_depth_var: the reference's ``--lambda_*`` values when ``--use_var_loss`` /
+        ``--use_depth_var_loss`` are given (models/nerf_downX_model.py:107-112), 0 (default) otherwise."""
         self.r = renderer
         dev = renderer.device
         names = state_dict_order(renderer.cfg.D)
@@ -333,6 +377,9 @@ class Trainer:
         self.v = [torch.zeros(numel, device=dev), torch.zeros(numel, device=dev)]
         self.lr, self.beta1, self.beta2, self.eps = lr, beta1, beta2, eps
         self.lam = (lambda_coarse_mse, lambda_fine_mse)
+        self.lam_var = (lambda_coarse_var, lambda_fine_var)
+        self.lam_dvar = (lambda_coarse_depth_var, lambda_fine_depth_var)
+        self.last_terms: Optional[torch.Tensor] = None
         self.clip_val, self.clip_type = grad_clip_val, grad_clip_type
         self.s = downscale
         self.step = 0
@@ -357,18 +404,39 @@ class Trainer:
             rng["noise_fine"] = torch.randn(n_rays, c.n_coarse + c.n_importance, device=dev, generator=generator)
         return rng
 
-    def forward_backward(self, rays: torch.Tensor, target_lr: torch.Tensor, rng=None):
-        """forward + loss + backward; returns (grad_coarse_flat, grad_fine_flat), sets last_metrics."""
+    def forward_backward(self, rays: torch.Tensor, target_lr: torch.Tensor, rng=None, target_sr: Optional[torch.Tensor] = None,
+                         far: Optional[float] = None):
+        """forward + loss + backward; returns (grad_coarse_flat, grad_fine_flat), sets last_metrics.
+        ``target_sr`` [N,3]: the SISR supervision ``data_rgbs_sr`` (``--sisr_path``).  ``far``: the reference's
+        ``self.far`` for the depth-variance term (default: read from ``rays[0, 7]`` like the reference -- one host sync;
+        datasets have a constant far plane, pass it to stay asynchronous).  With any of the extra terms on,
+        ``last_terms`` [2,8] holds (lambda*mse, psnr, var_sum, depth_var_sum, mse_sr, total, 0, 0) per net."""
         r = self.r
         out = r.render_train(rays, rng, want_weights=False)
+        if target_sr is not None or any(self.lam_var) or any(self.lam_dvar):
+            if any(self.lam_dvar) and far is None:
+                far = float(rays[0, 7])                           # models/nerf_downX_model.py:284
+            terms, grads = [], {}
+            for w, net in enumerate(("coarse", "fine")):
+                e = r.loss_epilogue(out[f"{net}_comp_rgbs"], target_lr, self.s, self.lam[w],
+                                    hr_depth=out[f"{net}_depth"] if self.lam_dvar[w] else None, lambda_var=self.lam_var[w],
+                                    lambda_depth_var=self.lam_dvar[w], far=far or 0.0, target_hr=target_sr)
+                terms.append(e["metrics"])
+                grads[f"{net}_comp_rgbs"] = e["g_rgb"]
+                if "g_depth" in e:
+                    grads[f"{net}_depth"] = e["g_depth"]
+            self.last_terms = torch.stack(terms)
+            self.last_metrics = torch.cat([terms[0][:2], terms[1][:2]])
+            return r.backward(rays, rng, grads)
         _, mc, g_c = r.lr_loss_grad(out["coarse_comp_rgbs"], target_lr, self.s, self.lam[0])
         _, mf, g_f = r.lr_loss_grad(out["fine_comp_rgbs"], target_lr, self.s, self.lam[1])
         self.last_metrics = torch.cat([mc, mf])
         return r.backward(rays, rng, {"coarse_comp_rgbs": g_c, "fine_comp_rgbs": g_f})
 
-    def optimize_parameters(self, rays: torch.Tensor, target_lr: torch.Tensor, rng=None, lr: Optional[float] = None):
+    def optimize_parameters(self, rays: torch.Tensor, target_lr: torch.Tensor, rng=None, lr: Optional[float] = None,
+                            target_sr: Optional[torch.Tensor] = None, far: Optional[float] = None):
         r = self.r
-        gc, gf = self.forward_backward(rays, target_lr, rng)
+        gc, gf = self.forward_backward(rays, target_lr, rng, target_sr=target_sr, far=far)
         if self.group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
                                       and torch.distributed.get_world_size() > 1):
             from .parallel import allreduce_mean_

@@ -40,6 +40,19 @@ FIXTURES = {
                                            "--grad_clip_type", "value"],
                                      cfg=dict(white_bkgd=True, downscale=4),
                                      tcfg=dict(grad_clip_val=1e-4, grad_clip_type="value")),
+    # sub-pixel variance terms (--use_var_loss, --use_depth_var_loss; models/nerf_downX_model.py:331-335,349-353,374-378)
+    "train_step_var_losses": dict(n_lr=48, s=2, rays="blender", seeds=(4, 17), rng_seed=77,
+                                  args=["--white_bkgd", "--use_var_loss", "--lambda_coarse_var", "0.02",
+                                        "--use_depth_var_loss", "--lambda_fine_depth_var", "0.05"],
+                                  cfg=dict(white_bkgd=True),
+                                  tcfg=dict(use_var_loss=True, lambda_coarse_var=0.02, use_depth_var_loss=True,
+                                            lambda_fine_depth_var=0.05)),
+    # all loss terms of the fused epilogue at once, 4x4 SS, LLFF-like rays with sigma noise, SISR target (--sisr_path, :364-367)
+    "train_step_sr_var_s4": dict(n_lr=10, s=4, rays="llff", seeds=(21, 8), rng_seed=11, sisr=True,
+                                 args=["--noise_std", "1.0", "--downscale", "4", "--use_var_loss", "--use_depth_var_loss",
+                                       "--sisr_path", "/nonexistent/sisr", "--grad_clip_val", "0.1"],
+                                 cfg=dict(noise_std=1.0, downscale=4),
+                                 tcfg=dict(use_var_loss=True, use_depth_var_loss=True, grad_clip_val=0.1)),
 }
 
 
@@ -60,38 +73,62 @@ def build(name: str, spec: dict) -> dict:
     pc = O.make_mlp_params(cfg, spec["seeds"][0])
     pf = O.make_mlp_params(cfg, spec["seeds"][1])
     ref_shim.set_weights(model, pc, pf)
+    if tcfg.use_depth_var_loss:
+        # models/nerf_downX_model.py:351 divides a grad-requiring tensor by ``self.far``, a shape-(1,) numpy array (:284);
+        # torch refuses that (Tensor.__array__ on a tensor that requires grad), so the flag cannot run in train mode as
+        # written.  The harness -- not the reference tree -- hands the model the same value as a Python float, the
+        # scalar the expression means; everything else is the unmodified reference.
+        ref_forward_rays = model.forward_rays
+
+        def forward_rays_scalar_far(r):
+            out = ref_forward_rays(r)
+            model.far = float(model.far[0])
+            return out
+        model.forward_rays = forward_rays_scalar_far
     rays = O.synthetic_rays(n, seed=3000 + spec["seeds"][0], kind=spec["rays"])
     tg = torch.Generator().manual_seed(spec["rng_seed"] + 1)
     target = torch.rand(spec["n_lr"], 3, generator=tg)
+    target_sr = torch.rand(n, 3, generator=tg) if spec.get("sisr") else None
 
     state = T.TrainState(pc, pf)
     g = torch.Generator().manual_seed(spec["rng_seed"])
     torch.manual_seed(spec["rng_seed"])
     arrays = {"rays": rays.numpy(), "target": target.numpy()}
+    if target_sr is not None:
+        arrays["target_sr"] = target_sr.numpy()
     meta = dict(name=name, cfg=spec["cfg"], tcfg=spec["tcfg"], seeds=list(spec["seeds"]), s=s,
                 reference_args=spec["args"], torch=torch.__version__, steps=[])
     ref_params = lambda: [p for p in model.netCoarse.parameters()] + [p for p in model.netFine.parameters()]
     for step in range(2):
         # ---- reference iteration ----
-        model.set_input({"rays": rays.clone(), "rgbs": target.clone()})
+        model.set_input({"rays": rays.clone(), "rgbs": target.clone(),
+                         **({"rgbs_sr": target_sr.clone()} if target_sr is not None else {})})
         model.optimize_parameters()
         ref_grads = [p.grad.detach().clone() for p in ref_params()]
         ref_losses = dict(coarse_mse=model.loss_coarse_mse.detach(), fine_mse=model.loss_fine_mse.detach(),
                           tot=model.loss_tot.detach(), coarse_psnr=model.loss_coarse_psnr.detach(),
                           fine_psnr=model.loss_fine_psnr.detach())
+        if tcfg.use_var_loss:
+            ref_losses.update(coarse_var=model.loss_out_coarse_var.detach(), fine_var=model.loss_out_fine_var.detach())
+        if tcfg.use_depth_var_loss:
+            ref_losses.update(coarse_depth_var=model.loss_coarse_depth_var.detach(),
+                              fine_depth_var=model.loss_fine_depth_var.detach())
+        if target_sr is not None:
+            ref_losses.update(coarse_mse_sr=model.loss_coarse_mse_sr.detach(), fine_mse_sr=model.loss_fine_mse_sr.detach())
         # ---- oracle iteration on the same draws ----
         rng = O.RenderRng.draw(n, cfg, g)
         if step == 0:   # fp64 floor of the gradients at the initial weights
-            _, gc32, gf32, _ = T.loss_and_grads(state.pc, state.pf, rays, target, cfg, tcfg, rng, s)
+            _, gc32, gf32, _ = T.loss_and_grads(state.pc, state.pf, rays, target, cfg, tcfg, rng, s, target_sr=target_sr)
             d = lambda t: None if t is None else t.double()
             rng64 = O.RenderRng(d(rng.u_coarse), d(rng.noise_coarse), d(rng.u_fine), d(rng.noise_fine))
             _, gc64, gf64, _ = T.loss_and_grads({k: v.double() for k, v in state.pc.items()},
                                                 {k: v.double() for k, v in state.pf.items()},
-                                                rays.double(), target.double(), cfg, tcfg, rng64, s)
+                                                rays.double(), target.double(), cfg, tcfg, rng64, s,
+                                                target_sr=None if target_sr is None else target_sr.double())
             rel = lambda a, b: float(torch.linalg.vector_norm(a.double() - b) / (torch.linalg.vector_norm(b) + 1e-30))
             meta["fp64_floor_rel_l2"] = dict(
                 coarse={k: rel(gc32[k], gc64[k]) for k in gc32}, fine={k: rel(gf32[k], gf64[k]) for k in gf32})
-        losses, grads = T.optimize_parameters(state, rays, target, cfg, tcfg, rng, s)
+        losses, grads = T.optimize_parameters(state, rays, target, cfg, tcfg, rng, s, target_sr=target_sr)
         # ---- the pin ----
         for k in ref_losses:
             assert torch.equal(ref_losses[k], losses[k]), (name, step, k, float(ref_losses[k]), float(losses[k]))
@@ -126,7 +163,10 @@ def build(name: str, spec: dict) -> dict:
 def main() -> None:
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
+    only = sys.argv[1:]
     for name, spec in FIXTURES.items():
+        if only and name not in only:
+            continue
         arrays = build(name, spec)
         path = os.path.join(GOLDEN, name + ".npz")
         np.savez_compressed(path, **arrays)

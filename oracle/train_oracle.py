@@ -9,7 +9,9 @@ Restates, with plain torch CPU ops, what the reference does in one ``optimize_pa
   forward()                       :316-319  (train mode: stratified jitter, sigma noise)
   comp_low_res_output()           :326-353  (s x s box average of the composite colours)
   calculate_losses()              :355-388  (lambda_c * MSE(coarse_lr, target) + lambda_f * MSE(fine_lr, target),
-                                             PSNR of both; the var / sr / ref terms are out of scope)
+                                             PSNR of both; + the sub-pixel variance terms :331-335,349-353,
+                                             374-378 and the SR-target term :364-367; the ref-ray term is the
+                                             same MSE on a second ray batch and stays with the caller)
   loss_tot.backward()             :390-396  (torch autograd through exactly the ops nerf_oracle restates;
                                              the fine z-values use coarse_weights.detach(), :302)
   clip_grad_norm_/clip_grad_value_:403-407
@@ -48,26 +50,63 @@ class TrainConfig:
     lr_final: float = 5e-6
     n_epochs: int = 20
     n_epochs_decay: int = 10
+    # NeRFDownXModel.modify_commandline_options (models/nerf_downX_model.py:107-112)
+    use_var_loss: bool = False
+    lambda_coarse_var: float = 0.01
+    lambda_fine_var: float = 0.01
+    use_depth_var_loss: bool = False
+    lambda_coarse_depth_var: float = 0.01
+    lambda_fine_depth_var: float = 0.01
 
 
 def loss_and_grads(pc: Dict[str, Tensor], pf: Dict[str, Tensor], rays: Tensor, target_lr: Tensor,
                    cfg: O.RenderConfig, tcfg: TrainConfig, rng: Optional[O.RenderRng] = None,
-                   s: int = 2, z_fine_override: Optional[Tensor] = None, extras: Optional[dict] = None):
+                   s: int = 2, z_fine_override: Optional[Tensor] = None, extras: Optional[dict] = None,
+                   target_sr: Optional[Tensor] = None):
     """One forward + backward.  Returns (losses dict, grads_coarse dict, grads_fine dict, outputs dict).
-    target_lr: [N/s^2, 3].  Gradients are None-free: parameters the loss does not reach get zeros
+    target_lr: [N/s^2, 3].  target_sr: [N, 3] or None = ``data_rgbs_sr`` (``--sisr_path``, :364-367).
+    Gradients are None-free: parameters the loss does not reach get zeros
     (the reference leaves .grad = None for them; Adam then skips the parameter)."""
     pc_r = {k: v.detach().clone().requires_grad_(True) for k, v in pc.items()}
     pf_r = {k: v.detach().clone().requires_grad_(True) for k, v in pf.items()}
     out = O.forward_rays(pc_r, pf_r, rays, cfg, rng, z_fine_override=z_fine_override, extras=extras)
-    lr_c = O.box_average(out["coarse_comp_rgbs"], s)                          # :337-338
+    # comp_low_res_output (:326-353).  The ops are created in the reference's order: autograd sums the branches
+    # that meet at one output in reverse creation order, and fp32 addition of three terms is not associative.
+    n_lr = target_lr.shape[0]
+    fine = cfg.N_importance > 0
+    grp = lambda x: torch.reshape(x, (n_lr, s * s, -1))
+    losses = {}
+    c_rgb_ori = out["coarse_comp_rgbs"].clone()                               # :327
+    if tcfg.use_var_loss:                                                     # :331-335
+        losses["coarse_var"] = subpixel_variance_sum(out["coarse_comp_rgbs"], n_lr, s)
+        losses["fine_var"] = subpixel_variance_sum(out["fine_comp_rgbs"], n_lr, s)
+    lr_c = torch.mean(grp(out["coarse_comp_rgbs"]), dim=1)                    # :337-338
+    c_depth_ori = out["coarse_depth"].clone()                                 # :339
+    if fine:
+        f_rgb_ori = out["fine_comp_rgbs"].clone()                             # :343
+        lr_f = torch.mean(grp(out["fine_comp_rgbs"]), dim=1)                  # :344-345
+        f_depth_ori = out["fine_depth"].clone()                               # :346
+    if tcfg.use_depth_var_loss:                                               # :349-353
+        far = float(rays[0, 7])                                               # self.far, :284 (see subpixel_variance_sum)
+        losses["coarse_depth_var"] = subpixel_variance_sum(c_depth_ori, n_lr, s, far)
+        losses["fine_depth_var"] = subpixel_variance_sum(f_depth_ori, n_lr, s, far)
+    # calculate_losses (:355-378)
     loss_c = torch.nn.functional.mse_loss(lr_c, target_lr) * tcfg.lambda_coarse_mse   # :357
-    losses = {"coarse_mse": loss_c}
+    losses["coarse_mse"] = loss_c
     tot = loss_c
-    if cfg.N_importance > 0:
-        lr_f = O.box_average(out["fine_comp_rgbs"], s)                        # :343-344
+    if fine:
         loss_f = torch.nn.functional.mse_loss(lr_f, target_lr) * tcfg.lambda_fine_mse  # :359
         losses["fine_mse"] = loss_f
         tot = tot + loss_f                                                    # :362
+    if target_sr is not None:                                                 # :364-367 (HR outputs vs the SISR image)
+        losses["coarse_mse_sr"] = torch.nn.functional.mse_loss(c_rgb_ori, target_sr)
+        losses["fine_mse_sr"] = torch.nn.functional.mse_loss(f_rgb_ori, target_sr)
+        tot = tot + (losses["coarse_mse_sr"] + losses["fine_mse_sr"])
+    if tcfg.use_var_loss:                                                     # :374-375
+        tot = tot + (tcfg.lambda_coarse_var * losses["coarse_var"] + tcfg.lambda_fine_var * losses["fine_var"])
+    if tcfg.use_depth_var_loss:                                               # :376-378
+        tot = tot + (tcfg.lambda_coarse_depth_var * losses["coarse_depth_var"]
+                     + tcfg.lambda_fine_depth_var * losses["fine_depth_var"])
     losses["tot"] = tot
     tot.backward()                                                            # :396
     with torch.no_grad():                                                     # :379-384
@@ -77,6 +116,18 @@ def loss_and_grads(pc: Dict[str, Tensor], pf: Dict[str, Tensor], rays: Tensor, t
     gc = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in pc_r.items()}
     gf = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in pf_r.items()}
     return ({k: v.detach() for k, v in losses.items()}, gc, gf, {k: v.detach() for k, v in out.items()})
+
+
+def subpixel_variance_sum(x: Tensor, n_lr: int, s: int, divisor=None) -> Tensor:
+    """``torch.sum(torch.var(torch.reshape(x, (n_lr, s*s, -1)) [/ far], dim=1))`` -- unbiased variance over the
+    s*s sub-pixel rays of each LR pixel, summed over pixels and channels (models/nerf_downX_model.py:331-335,
+    349-353).  ``divisor`` is the reference's ``self.far``: there a shape-(1,) float32 numpy array (:284), which torch
+    refuses to divide a grad-requiring tensor by; the value as a Python float is what the expression means (and what
+    oracle/make_golden_train.py hands the reference model when it pins this term)."""
+    y = torch.reshape(x, (n_lr, s * s, -1))
+    if divisor is not None:
+        y = y / divisor
+    return torch.sum(torch.var(y, dim=1))
 
 
 def clip_grads(grads: List[Tensor], tcfg: TrainConfig) -> Optional[Tensor]:
@@ -146,9 +197,10 @@ class TrainState:
 
 def optimize_parameters(state: TrainState, rays: Tensor, target_lr: Tensor, cfg: O.RenderConfig,
                         tcfg: TrainConfig, rng: Optional[O.RenderRng], s: int = 2, lr: Optional[float] = None,
-                        z_fine_override: Optional[Tensor] = None):
+                        z_fine_override: Optional[Tensor] = None, target_sr: Optional[Tensor] = None):
     """One full reference training iteration on ``state`` (in place).  Returns (losses, grads list)."""
-    losses, gc, gf, _ = loss_and_grads(state.pc, state.pf, rays, target_lr, cfg, tcfg, rng, s, z_fine_override)
+    losses, gc, gf, _ = loss_and_grads(state.pc, state.pf, rays, target_lr, cfg, tcfg, rng, s, z_fine_override,
+                                       target_sr=target_sr)
     grads = [gc[k] for k in state.pc] + [gf[k] for k in state.pf]
     clip_grads(grads, tcfg)
     state.step += 1

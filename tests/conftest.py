@@ -22,7 +22,20 @@ def pytest_configure(config):
 def golden_names():
     return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR)
                   if f.endswith(".npz") and f not in ("raygen.npz", "frame_assembly.npz", "pose_paths.npz")
-                  and not f.startswith("train_step_"))
+                  and not f.startswith("train_step_") and not f.startswith("scene_"))
+
+
+def materialize_scene(name, dest):
+    """Write the raw capture files stored in tests/golden/<name>.npz (COLMAP binaries / transforms JSON / PNGs, the
+    inputs oracle/make_golden_scenes.py fed to the reference's dataset classes) under ``dest``; returns (npz, meta)."""
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    for key in z.files:
+        if key.startswith("file_"):
+            path = os.path.join(dest, key[len("file_"):])
+            os.makedirs(os.path.dirname(path), exist_ok=True)
+            with open(path, "wb") as fh:
+                fh.write(z[key].tobytes())
+    return z, json.loads(bytes(z["meta_json"]).decode())
 
 
 def train_golden_names():
@@ -44,6 +57,7 @@ class TrainFixture:
         self.s = int(self.meta["s"])
         self.rays = torch.from_numpy(z["rays"])
         self.target = torch.from_numpy(z["target"])
+        self.target_sr = torch.from_numpy(z["target_sr"]) if "target_sr" in z.files else None   # data_rgbs_sr (--sisr_path)
         self.rng = []
         for step in range(2):
             get = lambda f: torch.from_numpy(z[f"rng{step}_{f}"]) if f"rng{step}_{f}" in z.files else None

@@ -220,13 +220,79 @@ def test_clip_and_adam_against_torch():
     r.close()
 
 
+@pytest.mark.parametrize("s,n_lr,terms", [(2, 777, "all"), (4, 1001, "all"), (3, 50, "all"), (2, 70001, "var"), (2, 300, "sr"),
+                                          (2, 300, "mse"), (1, 64, "sr")])
+def test_loss_epilogue_against_autograd(s, n_lr, terms):
+    """nsr_loss_epilogue: every term of calculate_losses (box average + lambda*MSE + PSNR, sub-pixel variance of colour
+    and of depth/far, SISR MSE) and the gradient to the HR outputs, against torch autograd over the reference's
+    expressions (models/nerf_downX_model.py:326-378; restated in oracle.train_oracle.subpixel_variance_sum)."""
+    cfg = O.RenderConfig()
+    r = _renderer(cfg, O.make_mlp_params(cfg, 4), O.make_mlp_params(cfg, 17))
+    g = torch.Generator().manual_seed(5 + s)
+    n = n_lr * s * s
+    hr = torch.rand(n, 3, generator=g, dtype=torch.float64, requires_grad=True)
+    depth = (2 + 4 * torch.rand(n, generator=g, dtype=torch.float64)).requires_grad_(True)
+    tgt = torch.rand(n_lr, 3, generator=g, dtype=torch.float64)
+    tgt_hr = torch.rand(n, 3, generator=g, dtype=torch.float64) if terms in ("all", "sr") else None
+    lam, lam_v, lam_d, far = 0.7, (0.02 if terms in ("all", "var") else 0.0), (0.05 if terms in ("all", "var") else 0.0), 6.0
+    lr_ref = O.box_average(hr, s)
+    mse = torch.nn.functional.mse_loss(lr_ref, tgt)
+    tot = mse * lam
+    ref = {"mse": float(mse * lam), "psnr": float(-10 * torch.log10(mse)), "var": 0.0, "dvar": 0.0, "sr": 0.0}
+    if tgt_hr is not None:
+        sr = torch.nn.functional.mse_loss(hr, tgt_hr)
+        tot = tot + sr
+        ref["sr"] = float(sr)
+    if lam_v:
+        v = T.subpixel_variance_sum(hr, n_lr, s)
+        tot = tot + lam_v * v
+        ref["var"] = float(v)
+    if lam_d:
+        dv = T.subpixel_variance_sum(depth, n_lr, s, far)
+        tot = tot + lam_d * dv
+        ref["dvar"] = float(dv)
+    tot.backward()
+    f = lambda t: None if t is None else t.detach().float().to(DEV)
+    e = r.loss_epilogue(f(hr), f(tgt), s, lam, hr_depth=f(depth), lambda_var=lam_v, lambda_depth_var=lam_d, far=far, target_hr=f(tgt_hr))
+    torch.cuda.synchronize()
+    m = e["metrics"].cpu()
+    assert torch.allclose(e["lr_rgb"].cpu().double(), lr_ref.detach(), rtol=0, atol=5e-7)
+    assert torch.allclose(e["lr_depth"].cpu().double(), O.box_average(depth.detach(), s).reshape(-1), rtol=0, atol=2e-6)
+    for i, k in enumerate(("mse", "psnr", "var", "dvar", "sr")):
+        assert float(m[i]) == pytest.approx(ref[k], rel=2e-5, abs=1e-9), (k, float(m[i]), ref[k])
+    assert float(m[5]) == pytest.approx(float(tot.detach()), rel=2e-5)
+    g_rgb, g_depth = e["g_rgb"].cpu().double(), e["g_depth"].cpu().double()
+    assert torch.allclose(g_rgb, hr.grad, rtol=1e-4, atol=2e-7 * float(hr.grad.abs().max())), float((g_rgb - hr.grad).abs().max())
+    gd_ref = depth.grad if depth.grad is not None else torch.zeros(n, dtype=torch.float64)
+    assert torch.allclose(g_depth, gd_ref, rtol=1e-4, atol=2e-6 * float(gd_ref.abs().max()) + 1e-30), float((g_depth - gd_ref).abs().max())
+    # errors: variance terms at s = 1, depth term without depth
+    from nerf_sr_b200 import NsrError
+    if s == 1:
+        with pytest.raises(NsrError):
+            r.loss_epilogue(f(hr), f(tgt), 1, 1.0, lambda_var=0.01)
+    with pytest.raises(NsrError):
+        r.loss_epilogue(f(hr), f(tgt), s, 1.0, lambda_depth_var=0.01, far=6.0)
+    r.close()
+
+
 # ----------------------------------------------------------------------------- full gradients
+def _trainer_kwargs(fx):
+    """Trainer arguments for a fixture's reference flags (lambda_*_var count only when --use_*_loss is given)."""
+    t = fx.tcfg
+    return dict(lambda_coarse_mse=t.lambda_coarse_mse, lambda_fine_mse=t.lambda_fine_mse, downscale=fx.s,
+                lambda_coarse_var=t.lambda_coarse_var if t.use_var_loss else 0.0,
+                lambda_fine_var=t.lambda_fine_var if t.use_var_loss else 0.0,
+                lambda_coarse_depth_var=t.lambda_coarse_depth_var if t.use_depth_var_loss else 0.0,
+                lambda_fine_depth_var=t.lambda_fine_depth_var if t.use_depth_var_loss else 0.0)
+
+
 def _oracle_grads(fx, z_f, rng, dtype=torch.float32):
     cast = lambda t: None if t is None else t.to(dtype)
     rr = None if rng is None else O.RenderRng(cast(rng.u_coarse), cast(rng.noise_coarse), cast(rng.u_fine), cast(rng.noise_fine))
     pc = {k: v.to(dtype) for k, v in fx.p_coarse.items()}
     pf = {k: v.to(dtype) for k, v in fx.p_fine.items()}
-    return T.loss_and_grads(pc, pf, fx.rays.to(dtype), fx.target.to(dtype), fx.cfg, fx.tcfg, rr, fx.s, z_fine_override=z_f.to(dtype))
+    return T.loss_and_grads(pc, pf, fx.rays.to(dtype), fx.target.to(dtype), fx.cfg, fx.tcfg, rr, fx.s, z_fine_override=z_f.to(dtype),
+                            target_sr=None if fx.target_sr is None else fx.target_sr.to(dtype))
 
 
 @pytest.mark.parametrize("prec", ["bf16x3"])
@@ -235,13 +301,13 @@ def test_gradients_against_oracle_autograd(name, prec):
     from nerf_sr_b200 import Trainer
     fx = TrainFixture(name)
     r = _renderer(fx.cfg, fx.p_coarse, fx.p_fine, prec)
-    tr = Trainer(r, fx.p_coarse, fx.p_fine, lambda_coarse_mse=fx.tcfg.lambda_coarse_mse, lambda_fine_mse=fx.tcfg.lambda_fine_mse,
-                 downscale=fx.s)
+    tr = Trainer(r, fx.p_coarse, fx.p_fine, **_trainer_kwargs(fx))
     rng = rng_dict(fx.rng[0])
     rays = fx.rays.to(DEV)
     out = r.render_train(rays, rng, want_z_fine=True)
     z_f = out["z_fine"].cpu()
-    gc, gf = tr.forward_backward(rays, fx.target.to(DEV), rng)
+    gc, gf = tr.forward_backward(rays, fx.target.to(DEV), rng, target_sr=None if fx.target_sr is None else fx.target_sr.to(DEV),
+                                 far=float(fx.rays[0, 7]))
     torch.cuda.synchronize()
     assert torch.isfinite(gc).all() and torch.isfinite(gf).all()
     losses, oc, of, _ = _oracle_grads(fx, z_f, fx.rng[0])
@@ -250,6 +316,14 @@ def test_gradients_against_oracle_autograd(name, prec):
     assert float(m[0]) == pytest.approx(float(losses["coarse_mse"]), rel=2e-3)
     assert float(m[2]) == pytest.approx(float(losses["fine_mse"]), rel=2e-3)
     assert float(m[1]) == pytest.approx(float(losses["coarse_psnr"]), rel=2e-3)
+    if tr.last_terms is not None:           # the sub-pixel variance / SISR terms of the fused epilogue
+        lt = tr.last_terms.cpu()
+        for w, net in enumerate(("coarse", "fine")):
+            for col, key in ((2, f"{net}_var"), (3, f"{net}_depth_var"), (4, f"{net}_mse_sr")):
+                if key in losses:
+                    _report(test="loss_terms", fixture=name, term=key, got=float(lt[w, col]), oracle=float(losses[key]))
+                    assert float(lt[w, col]) == pytest.approx(float(losses[key]), rel=5e-3), (key, float(lt[w, col]), float(losses[key]))
+        assert float(lt[0, 5] + lt[1, 5]) == pytest.approx(float(losses["tot"]), rel=3e-3)
     worst = 0.0
     for net, flat, ref32, ref64 in (("coarse", gc, oc, oc64), ("fine", gf, of, of64)):
         off = 0
@@ -351,6 +425,29 @@ def test_trainer_trajectory_against_oracle():
     assert mine[0] == pytest.approx(fx.meta["steps"][0]["tot"], rel=2e-3)
     for a, b in zip(mine, ref):
         assert a == pytest.approx(b, rel=0.08), (mine, ref)
+    r.close()
+
+
+def test_trainer_with_all_loss_terms_tracks_the_reference():
+    """Two full iterations with every loss term on (variance, depth variance, SISR target, norm clipping, sigma noise,
+    4x4 SS) on the draws of tests/golden/train_step_sr_var_s4.npz: the totals must follow the numbers the unmodified
+    reference produced (oracle/make_golden_train.py)."""
+    from nerf_sr_b200 import Trainer
+    fx = TrainFixture("train_step_sr_var_s4")
+    r = _renderer(fx.cfg, fx.p_coarse, fx.p_fine)
+    tr = Trainer(r, fx.p_coarse, fx.p_fine, lr=fx.tcfg.lr, grad_clip_val=fx.tcfg.grad_clip_val, grad_clip_type=fx.tcfg.grad_clip_type,
+                 **_trainer_kwargs(fx))
+    rays, tgt, tsr = fx.rays.to(DEV), fx.target.to(DEV), fx.target_sr.to(DEV)
+    tots = []
+    for it in range(2):
+        tr.optimize_parameters(rays, tgt, rng_dict(fx.rng[it]), target_sr=tsr, far=float(fx.rays[0, 7]))
+        tots.append(float(tr.last_terms[0, 5] + tr.last_terms[1, 5]))
+    want = [st["tot"] for st in fx.meta["steps"]]
+    _report(test="trajectory_all_terms", mine=tots, reference=want)
+    # step 0: same weights; only the fine sample positions differ at fp32 round-off (SURVEY.md 0.6).  step 1 is after one
+    # Adam update, whose first step has magnitude lr regardless of gradient scale (sign-like), hence the wider band
+    assert tots[0] == pytest.approx(want[0], rel=1e-2), (tots, want)
+    assert tots[1] == pytest.approx(want[1], rel=0.1), (tots, want)
     r.close()
 
 

@@ -1,0 +1,136 @@
+"""CPU: the scene loaders (nerf_sr_b200/scenes.py, scope row f-4) against the buffers the reference's own dataset
+classes produced from the same files (tests/golden/scene_*.npz, oracle/make_golden_scenes.py): COLMAP binary parsing,
+pose normalisation, depth bounds, val-image choice, LR / HR / SISR targets, test-sweep poses, Blender JSON; plus the
+parsers' behaviour on damaged files."""
+import os
+import struct
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import materialize_scene
+from nerf_sr_b200 import scenes as S
+from oracle import nerf_oracle as O
+from oracle import ref_shim
+
+
+def _llff_case(root, meta, case):
+    return S.load_llff_scene(root, meta["img_wh"], spheric_poses=case["spheric_poses"],
+                             sisr_path=os.path.join(root, "sisr") if case["sisr"] else None)
+
+
+def test_llff_scene_matches_reference_dataset(tmp_path):
+    z, meta = materialize_scene("scene_llff", str(tmp_path))
+    assert len(meta["cases"]) == 3
+    for case in meta["cases"]:
+        tag, s = case["tag"], case["downscale"]
+        sc = _llff_case(str(tmp_path), meta, case)
+        assert sc.focal == case["focal"] and sc.val_idx == case["val_idx"]
+        assert (sc.near, sc.far) == (case["near"], case["far"]) and sc.ndc == (not case["spheric_poses"])
+        # same numpy expressions on the same bytes: equal to the last bit in the build container; LAPACK's inverse may
+        # round differently on another host, hence 1e-12
+        assert np.allclose(sc.poses, z[f"{tag}/poses"], rtol=0, atol=1e-12)
+        assert np.allclose(sc.bounds, z[f"{tag}/bounds"], rtol=1e-12, atol=0)
+        assert [os.path.basename(p) for p in sc.image_paths] == sorted(os.path.basename(p) for p in sc.image_paths)
+        lr, hr, sr = [], [], []
+        for i in sc.train_indices():
+            a, b = S.load_image_targets(sc.image_paths[i], sc.img_wh, s, case["ds_method"])
+            lr.append(a), hr.append(b)
+            if case["sisr"]:
+                sr.append(S.load_sr_target(sc.sr_image_paths[i], sc.img_wh, s))
+        assert sc.val_idx not in sc.train_indices() and len(sc.train_indices()) == len(sc.image_paths) - 1
+        assert np.array_equal(np.concatenate(lr), z[f"{tag}/all_rgbs"])            # PIL decode + LANCZOS / s x s mean
+        assert np.array_equal(np.concatenate(hr), z[f"{tag}/all_rgbs_ori"])
+        if case["sisr"]:
+            assert np.array_equal(np.concatenate(sr), z[f"{tag}/all_rgbs_sr"])
+        assert np.allclose(sc.test_poses("test"), z[f"{tag}/poses_test"], rtol=0, atol=1e-12)
+        assert sc.test_poses("test_train") is sc.poses
+        vlr, vhr = S.load_image_targets(sc.image_paths[sc.val_idx], sc.img_wh, s, "avg")   # val samples always use the mean
+        assert np.array_equal(vlr, z[f"{tag}/val_rgbs"]) and np.array_equal(vhr, z[f"{tag}/val_rgbs_ori"])
+        # the ray buffers: the oracle's dataset-path restatement on the loader's poses == the reference's all_rays
+        w, h = sc.img_wh
+        rays = torch.cat([O.build_frame_rays(torch.from_numpy(sc.poses[i]).float(), h, w, sc.focal, s, sc.near, sc.far,
+                                             sc.ndc).view(-1, s * s, 8) for i in sc.train_indices()], 0)
+        assert torch.allclose(rays, torch.from_numpy(z[f"{tag}/all_rays"]), rtol=1e-6, atol=1e-6)
+
+
+def test_blender_scene_matches_reference_dataset(tmp_path):
+    z, meta = materialize_scene("scene_blender", str(tmp_path))
+    for case in meta["cases"]:
+        tag, s = case["tag"], case["downscale"]
+        sc = S.load_blender_scene(str(tmp_path), "train", meta["img_wh"])
+        assert sc.focal == case["focal"] and (sc.near, sc.far, sc.ndc, sc.white_back) == (2.0, 6.0, False, True)
+        assert np.array_equal(sc.poses, z[f"{tag}/poses"])
+        lr, hr = zip(*[S.load_image_targets(p, sc.img_wh, s, case["ds_method"], rgba=True) for p in sc.image_paths])
+        assert np.array_equal(np.concatenate(lr), z[f"{tag}/all_rgbs"])            # incl. the alpha blend onto white
+        assert np.array_equal(np.concatenate(hr), z[f"{tag}/all_rgbs_ori"])
+        te = S.load_blender_scene(str(tmp_path), "test", meta["img_wh"])
+        tlr, thr = S.load_image_targets(te.image_paths[1], te.img_wh, s, case["ds_method"], rgba=True)
+        assert np.array_equal(tlr, z[f"{tag}/test1_rgbs"]) and np.array_equal(thr, z[f"{tag}/test1_rgbs_ori"])
+        assert te.test_poses("test") is te.poses and len(te.poses) == 2
+    with pytest.raises(ValueError):
+        S.load_blender_scene(str(tmp_path), "train", (12, 8))
+
+
+def test_colmap_parsers_reject_damaged_files(tmp_path):
+    materialize_scene("scene_llff", str(tmp_path))
+    sparse = os.path.join(str(tmp_path), "sparse", "0")
+    cams = S.read_cameras_binary(os.path.join(sparse, "cameras.bin"))
+    assert cams[1].model == "SIMPLE_RADIAL" and (cams[1].width, cams[1].height) == (40, 30) and cams[1].params.shape == (4,)
+    imgs = S.read_images_binary(os.path.join(sparse, "images.bin"))
+    assert [im.id for im in imgs] == list(range(1, 7)) and all(im.name.endswith(".png") for im in imgs)
+    R = imgs[0].rotmat()
+    assert np.allclose(R @ R.T, np.eye(3), atol=1e-12) and np.linalg.det(R) == pytest.approx(1.0)
+    xyz, tracks = S.read_points3d_binary(os.path.join(sparse, "points3D.bin"))
+    assert xyz.shape == (60, 3) and len(tracks) == 60 and all(2 <= len(t) <= 6 for t in tracks)
+    for fn, reader in (("cameras.bin", S.read_cameras_binary), ("images.bin", S.read_images_binary),
+                       ("points3D.bin", S.read_points3d_binary)):
+        data = open(os.path.join(sparse, fn), "rb").read()
+        cut = os.path.join(str(tmp_path), "cut_" + fn)
+        open(cut, "wb").write(data[: len(data) - 5])
+        with pytest.raises(ValueError, match="truncated"):
+            reader(cut)
+    bad = os.path.join(str(tmp_path), "bad_model.bin")
+    open(bad, "wb").write(struct.pack("<QiiQQ", 1, 1, 99, 4, 4))
+    with pytest.raises(ValueError, match="unknown camera model"):
+        S.read_cameras_binary(bad)
+    empty = os.path.join(str(tmp_path), "empty.bin")
+    open(empty, "wb").write(struct.pack("<Q", 0))
+    assert S.read_cameras_binary(empty) == {} and S.read_images_binary(empty) == []
+    assert S.read_points3d_binary(empty)[0].shape == (0, 3)
+    with pytest.raises(ValueError, match="Downscale option"):
+        S.load_image_targets(os.path.join(str(tmp_path), "images", imgs[0].name), (24, 18), 2, "bicubic")
+    with pytest.raises(ValueError, match="mismatch"):
+        S.load_sr_target(os.path.join(str(tmp_path), "images", imgs[0].name), (24, 18), 2)
+
+
+def test_group_subpixels_is_the_dataset_rearrange():
+    import einops
+    x = np.arange(6 * 8 * 3, dtype=np.float32).reshape(6, 8, 3)
+    for s in (1, 2):
+        want = einops.rearrange(x, "(h s1) (w s2) c -> (h w) (s1 s2) c", s1=s, s2=s)
+        assert np.array_equal(S.group_subpixels(x, s), want)
+
+
+def test_take_batch_flattens_like_set_input():
+    buf = {"rays": torch.arange(5 * 4 * 8, dtype=torch.float32).view(5, 4, 8), "rgbs": torch.rand(5, 3),
+           "rgbs_ori": torch.rand(5, 4, 3)}
+    b = S.take_batch(buf, torch.tensor([3, 1]))
+    assert b["rays"].shape == (8, 8) and b["rgbs"].shape == (2, 3) and b["rgbs_ori"].shape == (8, 3)
+    assert torch.equal(b["rays"][:4], buf["rays"][3]) and torch.equal(b["rgbs"][1], buf["rgbs"][1])
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="reference tree only exists in the build container")
+def test_llff_loader_equals_live_reference_dataset(tmp_path):
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import make_golden_scenes as M
+    LLFF, _ = M.import_reference_datasets()
+    _, meta = materialize_scene("scene_llff", str(tmp_path))
+    opt = M.dataset_opt(dataset_root=str(tmp_path), img_wh=tuple(meta["img_wh"]), downscale=2, ds_method="avg")
+    ref = LLFF(opt, "train")
+    sc = S.load_llff_scene(str(tmp_path), meta["img_wh"])
+    assert np.array_equal(sc.poses, ref.poses) and np.array_equal(sc.bounds, ref.bounds) and sc.focal == ref.focal
+    lr = np.concatenate([S.load_image_targets(sc.image_paths[i], sc.img_wh, 2, "avg")[0] for i in sc.train_indices()])
+    assert np.array_equal(lr, ref.all_rgbs.numpy())
