@@ -230,6 +230,23 @@ NSR_API int nsr_generate_rays(NsrHandle* h, const float* c2w_host, int H, int W,
                       int s, int ndc, float near_plane, float far_plane,
                       float* rays_out, NsrStream stream);
 
+/* The same with the remaining dataset options (scope row f-4): --use_pixel_centers (options/base_options.py:59;
+ * models/utils.py:114) and --unified_dir (data/llff_downX_dataset.py:273-277: one direction per LR pixel from the
+ * (H/s, W/s) raster with focal // s, repeated over its sub-pixels). */
+typedef struct NsrRayGen {
+  uint32_t struct_size;        /* = sizeof(NsrRayGen)                           */
+  int32_t  H, W;               /* HR raster (opt.img_wh reversed)               */
+  int32_t  s;                  /* --downscale                                   */
+  float    focal;
+  int32_t  ndc;                /* forward-facing scene: NDC, near 0, far 1      */
+  float    near_plane, far_plane;
+  int32_t  use_pixel_centers;  /* --use_pixel_centers (reference default: 1)    */
+  int32_t  unified_dir;        /* --unified_dir                                 */
+  int32_t  reserved[6];
+} NsrRayGen;
+NSR_API int nsr_generate_rays_ex(NsrHandle* h, const float* c2w_host, const NsrRayGen* spec, float* rays_out,
+                                 NsrStream stream);
+
 /* Replaces (scope row f-2, the LR-image + loss epilogue): comp_low_res_output's box average followed by
  * ColorMSELoss and PSNR against the LR targets (models/nerf_downX_model.py:337-340,357,380;
  * models/criterions.py:7-15,27-36).  hr_rgb: [n_lr*s*s, 3] composite colours (sub-pixels contiguous);
@@ -313,8 +330,11 @@ NSR_API int nsr_lr_loss_grad(NsrHandle* h, const float* hr_rgb, const float* tar
  *   comp_low_res_output's box averages (:337-348), lambda_*_mse * ColorMSELoss + PSNR (:357-359,380-382),
  *   --use_var_loss: sum over LR pixels and channels of torch.var over the s*s sub-pixel colours (:331-335,374-375),
  *   --use_depth_var_loss: the same for depth / self.far (:349-353,376-378),
- *   --sisr_path: ColorMSELoss of the HR colours against data_rgbs_sr (:364-367).
- * A zero lambda_var / lambda_depth_var switches that term off; target_hr null switches the SR term off. */
+ *   --sisr_path: ColorMSELoss of the HR colours against data_rgbs_sr (:364-367), lambda_hr = 1;
+ *   --with_ref: the same HR ColorMSELoss for the reference-view batch (out_ref_* vs data_ref_rgbs, :369-372):
+ *               target_lr null, lambda_hr = 1 / s^2.
+ * A zero lambda_var / lambda_depth_var switches that term off; target_hr null switches the HR term off;
+ * target_lr null switches the LR term (box-average MSE, PSNR) off. */
 typedef struct NsrLossTerms {
   uint32_t struct_size;        /* = sizeof(NsrLossTerms)                        */
   int32_t  s;                  /* --downscale                                   */
@@ -322,14 +342,16 @@ typedef struct NsrLossTerms {
   float    lambda_var;         /* --lambda_*_var when --use_var_loss, else 0    */
   float    lambda_depth_var;   /* --lambda_*_depth_var when --use_depth_var_loss */
   float    far_plane;          /* self.far = rays[0,7] (:284)                   */
-  int32_t  reserved[6];
+  float    lambda_hr;          /* weight of the HR-target MSE (1 | 1/s^2)       */
+  int32_t  reserved[5];
 } NsrLossTerms;
 
-/* hr_rgb [n_lr*s*s,3], hr_depth [n_lr*s*s] (null unless a depth output / term is wanted), target_lr [n_lr,3],
- * target_hr [n_lr*s*s,3] or null.  Outputs (each may be null except metrics_out): lr_rgb_out [n_lr,3],
+/* hr_rgb [n_lr*s*s,3], hr_depth [n_lr*s*s] (null unless a depth output / term is wanted), target_lr [n_lr,3] or null,
+ * target_hr [n_lr*s*s,3] or null (at least one target).  Outputs (each may be null except metrics_out): lr_rgb_out [n_lr,3],
  * lr_depth_out [n_lr], g_rgb_out [n_lr*s*s,3] = d total / d hr_rgb, g_depth_out [n_lr*s*s] = d total / d hr_depth,
- * metrics_out: device float[8] = {lambda_mse * mse, psnr, var_sum, depth_var_sum, mse_sr, total, 0, 0} with
- * total = lambda_mse * mse + mse_sr + lambda_var * var_sum + lambda_depth_var * depth_var_sum.  No host sync. */
+ * metrics_out: device float[8] = {lambda_mse * mse, psnr, var_sum, depth_var_sum, lambda_hr * mse_hr, total, 0, 0}
+ * with total = lambda_mse * mse + lambda_hr * mse_hr + lambda_var * var_sum + lambda_depth_var * depth_var_sum.
+ * No host sync. */
 NSR_API int nsr_loss_epilogue(NsrHandle* h, const float* hr_rgb, const float* hr_depth, const float* target_lr,
                               const float* target_hr, int64_t n_lr, const NsrLossTerms* terms, float* lr_rgb_out,
                               float* lr_depth_out, float* metrics_out, float* g_rgb_out, float* g_depth_out, NsrStream stream);

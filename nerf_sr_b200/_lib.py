@@ -44,7 +44,13 @@ class NsrOutGrads(C.Structure):
 
 class NsrLossTerms(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("s", C.c_int32), ("lambda_mse", C.c_float), ("lambda_var", C.c_float),
-                ("lambda_depth_var", C.c_float), ("far_plane", C.c_float), ("reserved", C.c_int32 * 6)]
+                ("lambda_depth_var", C.c_float), ("far_plane", C.c_float), ("lambda_hr", C.c_float), ("reserved", C.c_int32 * 5)]
+
+
+class NsrRayGen(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("H", C.c_int32), ("W", C.c_int32), ("s", C.c_int32), ("focal", C.c_float),
+                ("ndc", C.c_int32), ("near_plane", C.c_float), ("far_plane", C.c_float), ("use_pixel_centers", C.c_int32),
+                ("unified_dir", C.c_int32), ("reserved", C.c_int32 * 6)]
 
 
 class NsrPassOutputs(C.Structure):
@@ -86,6 +92,7 @@ SIGNATURES = {
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "nsr_lr_loss_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nsr_generate_rays_ex": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(NsrRayGen), C.c_void_p, C.c_void_p]),
     "nsr_loss_epilogue": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(NsrLossTerms),
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nsr_clip_coef": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_void_p]),

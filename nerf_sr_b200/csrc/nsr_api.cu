@@ -201,7 +201,7 @@ __global__ void k_lr_metrics_final(const double* __restrict__ partials, int n_bl
 struct Pose { float m[12]; };
 
 __global__ void k_generate_rays(Pose c2w, int H, int W, float focal, int s, int ndc, float near_plane,
-                                float far_plane, float* __restrict__ rays) {
+                                float far_plane, float pixel_center, int unified_dir, float* __restrict__ rays) {
   // get_ray_directions + get_rays (+ get_ndc_rays) + '(h s1) (w s2) c -> (h w) (s1 s2) c'
   // (models/utils.py:98-196; data/blender_downX_dataset.py:207-215)
   const int64_t total = (int64_t)H * W;
@@ -214,9 +214,14 @@ __global__ void k_generate_rays(Pose c2w, int H, int W, float focal, int s, int 
     const int hh = (int)(lr / w_lr), ww = (int)(lr % w_lr);
     const int s1 = sub / s, s2 = sub % s;
     const int row = hh * s + s1, col = ww * s + s2;
-    const float i = (float)col + 0.5f, j = (float)row + 0.5f;
-    const float cx = __fdiv_rn(__fsub_rn(i, (float)W / 2.f), focal);
-    const float cy = -__fdiv_rn(__fsub_rn(j, (float)H / 2.f), focal);
+    // --unified_dir (data/llff_downX_dataset.py:273-277): one camera-space direction per LR pixel, computed on the
+    // (H/s, W/s) raster with focal // s and repeated over its s x s sub-pixels; NDC below still uses H, W, focal
+    const int dcol = unified_dir ? ww : col, drow = unified_dir ? hh : row;
+    const float dW = unified_dir ? (float)(W / s) : (float)W, dH = unified_dir ? (float)(H / s) : (float)H;
+    const float dfocal = unified_dir ? floorf(__fdiv_rn(focal, (float)s)) : focal;
+    const float i = (float)dcol + pixel_center, j = (float)drow + pixel_center;
+    const float cx = __fdiv_rn(__fsub_rn(i, dW / 2.f), dfocal);
+    const float cy = -__fdiv_rn(__fsub_rn(j, dH / 2.f), dfocal);
     const float cz = -1.f;
     // rays_d = directions @ c2w[:, :3].T
     float d[3];
@@ -636,20 +641,37 @@ extern "C" int nsr_box_average(NsrHandle* h, const float* in, int64_t n_lr, int 
   return NSR_OK;
 }
 
-extern "C" int nsr_generate_rays(NsrHandle* h, const float* c2w_host, int H, int W, float focal, int s, int ndc,
-                                 float near_plane, float far_plane, float* rays_out, NsrStream stream) {
-  if (!h) return NSR_ERR_INVALID_ARG;
+static int generate_rays_impl(NsrHandle* h, const float* c2w_host, int H, int W, float focal, int s, int ndc,
+                              float near_plane, float far_plane, int use_pixel_centers, int unified_dir, float* rays_out,
+                              NsrStream stream) {
   if (!c2w_host || !rays_out || H <= 0 || W <= 0 || s < 1 || !(focal > 0.f))
     return fail(h, NSR_ERR_INVALID_ARG, "nsr_generate_rays: bad argument");
   if (H % s || W % s) return fail(h, NSR_ERR_INVALID_ARG, "H and W must be multiples of the supersampling factor");
+  if (unified_dir && !(floorf(focal / (float)s) > 0.f))
+    return fail(h, NSR_ERR_INVALID_ARG, "nsr_generate_rays: unified_dir needs focal // s > 0");
   NSR_CUDA(h, cudaSetDevice(h->cfg.device));
   Pose p;
   memcpy(p.m, c2w_host, sizeof(p.m));
   k_generate_rays<<<grid_for((int64_t)H * W, 256, h->sm_count * 16), 256, 0, (cudaStream_t)stream>>>(
-      p, H, W, focal, s, ndc, near_plane, far_plane, rays_out);
+      p, H, W, focal, s, ndc, near_plane, far_plane, use_pixel_centers ? 0.5f : 0.f, unified_dir, rays_out);
   h->launches += 1;
   NSR_CUDA(h, cudaGetLastError());
   return NSR_OK;
+}
+
+extern "C" int nsr_generate_rays(NsrHandle* h, const float* c2w_host, int H, int W, float focal, int s, int ndc,
+                                 float near_plane, float far_plane, float* rays_out, NsrStream stream) {
+  if (!h) return NSR_ERR_INVALID_ARG;
+  return generate_rays_impl(h, c2w_host, H, W, focal, s, ndc, near_plane, far_plane, 1, 0, rays_out, stream);
+}
+
+extern "C" int nsr_generate_rays_ex(NsrHandle* h, const float* c2w_host, const NsrRayGen* spec, float* rays_out,
+                                    NsrStream stream) {
+  if (!h) return NSR_ERR_INVALID_ARG;
+  if (!spec || spec->struct_size != sizeof(NsrRayGen))
+    return fail(h, NSR_ERR_INVALID_ARG, "nsr_generate_rays_ex: NsrRayGen.struct_size mismatch");
+  return generate_rays_impl(h, c2w_host, spec->H, spec->W, spec->focal, spec->s, spec->ndc, spec->near_plane, spec->far_plane,
+                            spec->use_pixel_centers, spec->unified_dir, rays_out, stream);
 }
 
 extern "C" int nsr_lr_metrics(NsrHandle* h, const float* hr_rgb, const float* target_lr, int64_t n_lr, int s,

@@ -943,7 +943,7 @@ struct LossTerms {
   float g_mse;        // 2 lambda_mse / (3 n_lr) / s^2
   float g_var;        // 2 lambda_var / (s^2 - 1)
   float g_dvar;       // 2 lambda_depth_var / (s^2 - 1) / far
-  float g_sr;         // 2 / (3 n_lr s^2)
+  float g_sr;         // 2 lambda_hr / (3 n_lr s^2)
   float far_plane;
   int want_var, want_dvar;
 };
@@ -965,7 +965,7 @@ k_loss_epilogue(const float* __restrict__ rgb, const float* __restrict__ depth, 
       for (int k = 0; k < ss; ++k) sum = __fadd_rn(sum, x[k * 3 + c]);
       mean[c] = __fdiv_rn(sum, (float)ss);
       if (lr_rgb) lr_rgb[p * 3 + c] = mean[c];
-      const float d = __fsub_rn(mean[c], target[p * 3 + c]);
+      const float d = target ? __fsub_rn(mean[c], target[p * 3 + c]) : 0.f;
       a_mse += (double)__fmul_rn(d, d);
       float m2 = 0.f;
       const float gm = t.g_mse * d;
@@ -1018,18 +1018,19 @@ k_loss_epilogue(const float* __restrict__ rgb, const float* __restrict__ depth, 
   if (threadIdx.x < 4) partials[blockIdx.x * 4 + threadIdx.x] = sh[threadIdx.x][0];
 }
 
-// metrics[8] = {lambda_mse * mse, psnr, var_sum, depth_var_sum, mse_sr, total, 0, 0}
+// metrics[8] = {lambda_mse * mse, psnr, var_sum, depth_var_sum, lambda_hr * mse_hr, total, 0, 0}
 __global__ void k_loss_epilogue_final(const double* __restrict__ partials, int n_blocks, int64_t n_lr, int ss, float lambda_mse,
-                                      float lambda_var, float lambda_dvar, int has_sr, float* __restrict__ metrics) {
+                                      float lambda_var, float lambda_dvar, int has_lr, int has_sr, float lambda_hr,
+                                      float* __restrict__ metrics) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     double s[4] = {0.0, 0.0, 0.0, 0.0};
     for (int i = 0; i < n_blocks; ++i)
       for (int j = 0; j < 4; ++j) s[j] += partials[i * 4 + j];
-    const float mse = (float)(s[0] / (double)(n_lr * 3));
+    const float mse = has_lr ? (float)(s[0] / (double)(n_lr * 3)) : 0.f;
     const float var = (float)s[1], dvar = (float)s[2];
-    const float sr = has_sr ? (float)(s[3] / (double)(n_lr * ss * 3)) : 0.f;
+    const float sr = has_sr ? lambda_hr * (float)(s[3] / (double)(n_lr * ss * 3)) : 0.f;
     metrics[0] = mse * lambda_mse;
-    metrics[1] = -10.f * log10f(mse);
+    metrics[1] = has_lr ? -10.f * log10f(mse) : 0.f;
     metrics[2] = var;
     metrics[3] = dvar;
     metrics[4] = sr;
@@ -1489,7 +1490,8 @@ extern "C" int nsr_loss_epilogue(NsrHandle* h, const float* hr_rgb, const float*
                                  const float* target_hr, int64_t n_lr, const NsrLossTerms* terms, float* lr_rgb_out,
                                  float* lr_depth_out, float* metrics_out, float* g_rgb_out, float* g_depth_out, NsrStream stream) {
   if (!h) return NSR_ERR_INVALID_ARG;
-  if (!hr_rgb || !target_lr || !metrics_out || !terms || n_lr <= 0) return tfail(h, NSR_ERR_INVALID_ARG, "nsr_loss_epilogue: bad argument");
+  if (!hr_rgb || !metrics_out || !terms || n_lr <= 0) return tfail(h, NSR_ERR_INVALID_ARG, "nsr_loss_epilogue: bad argument");
+  if (!target_lr && !target_hr) return tfail(h, NSR_ERR_INVALID_ARG, "nsr_loss_epilogue: needs target_lr and / or target_hr");
   if (terms->struct_size != sizeof(NsrLossTerms)) return tfail(h, NSR_ERR_INVALID_ARG, "nsr_loss_epilogue: NsrLossTerms.struct_size mismatch");
   const int s = terms->s;
   if (s < 1 || s > 16) return tfail(h, NSR_ERR_INVALID_ARG, "nsr_loss_epilogue: downscale must be in [1,16]");
@@ -1503,10 +1505,10 @@ extern "C" int nsr_loss_epilogue(NsrHandle* h, const float* hr_rgb, const float*
   const int ss = s * s;
   LossTerms t;
   t.ss = ss;
-  t.g_mse = (float)(2.0 * (double)terms->lambda_mse / ((double)n_lr * 3.0) / (double)ss);
+  t.g_mse = target_lr ? (float)(2.0 * (double)terms->lambda_mse / ((double)n_lr * 3.0) / (double)ss) : 0.f;
   t.g_var = want_var ? (float)(2.0 * (double)terms->lambda_var / (double)(ss - 1)) : 0.f;
   t.g_dvar = want_dvar ? (float)(2.0 * (double)terms->lambda_depth_var / (double)(ss - 1) / (double)terms->far_plane) : 0.f;
-  t.g_sr = target_hr ? (float)(2.0 / ((double)n_lr * (double)ss * 3.0)) : 0.f;
+  t.g_sr = target_hr ? (float)(2.0 * (double)terms->lambda_hr / ((double)n_lr * (double)ss * 3.0)) : 0.f;
   t.far_plane = terms->far_plane;
   t.want_var = want_var;
   t.want_dvar = want_dvar;
@@ -1515,7 +1517,8 @@ extern "C" int nsr_loss_epilogue(NsrHandle* h, const float* hr_rgb, const float*
   k_loss_epilogue<<<blocks, 256, 0, (cudaStream_t)stream>>>(hr_rgb, hr_depth, target_lr, target_hr, n_lr, t, lr_rgb_out, lr_depth_out,
                                                             g_rgb_out, g_depth_out, h->d_partials);
   k_loss_epilogue_final<<<1, 32, 0, (cudaStream_t)stream>>>(h->d_partials, blocks, n_lr, ss, terms->lambda_mse, terms->lambda_var,
-                                                            terms->lambda_depth_var, target_hr != nullptr, metrics_out);
+                                                            terms->lambda_depth_var, target_lr != nullptr, target_hr != nullptr,
+                                                            terms->lambda_hr, metrics_out);
   h->launches += 2;
   NSR_TCUDA(h, cudaGetLastError());
   return NSR_OK;

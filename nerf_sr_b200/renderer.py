@@ -22,7 +22,7 @@ from typing import Dict, Mapping, Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import NsrConfig, NsrError, NsrOutputs, NsrPassOutputs, NsrRng, PRECISIONS
+from ._lib import NsrConfig, NsrError, NsrOutputs, NsrPassOutputs, NsrRayGen, NsrRng, PRECISIONS
 
 
 def state_dict_order(D: int = 8):
@@ -270,12 +270,23 @@ class Renderer:
         return out, mat
 
     def generate_rays(self, c2w, H: int, W: int, focal: float, s: int = 1, ndc: bool = False,
-                      near: float = 2.0, far: float = 6.0) -> torch.Tensor:
+                      near: float = 2.0, far: float = 6.0, use_pixel_centers: bool = True,
+                      unified_dir: bool = False) -> torch.Tensor:
+        """[H*W, 8] device rays of one pose, LR-pixel-major / sub-pixel-minor rows (nsr_generate_rays; the
+        --use_pixel_centers False / --unified_dir variants go through nsr_generate_rays_ex)."""
         c = torch.as_tensor(c2w, dtype=torch.float32).reshape(12).cpu()
         arr = (C.c_float * 12)(*c.tolist())
         rays = torch.empty(H * W, 8, device=self.device, dtype=torch.float32)
-        self._check(self.lib.nsr_generate_rays(self._h, arr, H, W, float(focal), s, int(ndc), float(near), float(far),
-                                               rays.data_ptr(), self._stream()))
+        if use_pixel_centers and not unified_dir:
+            self._check(self.lib.nsr_generate_rays(self._h, arr, H, W, float(focal), s, int(ndc), float(near), float(far),
+                                                   rays.data_ptr(), self._stream()))
+        else:
+            spec = NsrRayGen()
+            spec.struct_size = C.sizeof(NsrRayGen)
+            spec.H, spec.W, spec.s, spec.focal, spec.ndc = H, W, s, float(focal), int(ndc)
+            spec.near_plane, spec.far_plane = float(near), float(far)
+            spec.use_pixel_centers, spec.unified_dir = int(use_pixel_centers), int(unified_dir)
+            self._check(self.lib.nsr_generate_rays_ex(self._h, arr, C.byref(spec), rays.data_ptr(), self._stream()))
         return rays
 
     def render_frame_host(self, rays_host: torch.Tensor, s: int = 1):

@@ -22,8 +22,8 @@ Image decoding and resampling are PIL's (the reference's own third-party depende
 ``Image.open(..).convert('RGB').resize(.., Image.LANCZOS)``); nothing here touches the oracle.  Results are pinned
 to the reference's dataset classes in tests/golden/scene_*.npz (oracle/make_golden_scenes.py).
 
-Not mirrored (the reference path stays): ``--unified_dir``, ``--rand_dir``, ``--use_pixel_centers False`` (the ray kernel
-uses pixel centres, the reference default), the 'gan' / 'reg_patch' / 'train_crop' sampling modes."""
+Not mirrored (the reference path stays): ``--rand_dir`` (per-dataset random sub-pixel jitter from numpy's global RNG) and
+the 'gan' / 'reg_patch' / 'train_crop' sampling modes."""
 from __future__ import annotations
 
 import json
@@ -172,6 +172,8 @@ class Scene:
     val_idx: Optional[int] = None      # llff: the image closest to the centre (held out from training)
     spheric: bool = False
     rgba: bool = False                 # blender PNGs carry alpha, blended onto white
+    use_pixel_centers: bool = True     # --use_pixel_centers (options/base_options.py:59)
+    unified_dir: bool = False          # --unified_dir (llff): one view direction per LR pixel
     sr_image_paths: List[str] = field(default_factory=list)
 
     # ---- poses ------------------------------------------------------------------------------------
@@ -197,7 +199,8 @@ class Scene:
         w, h = self.img_wh
         if w % s or h % s:
             raise ValueError(f"img_wh {self.img_wh} is not divisible by downscale {s}")
-        return renderer.generate_rays(np.asarray(pose, dtype=np.float32), h, w, self.focal, s, self.ndc, self.near, self.far)
+        return renderer.generate_rays(np.asarray(pose, dtype=np.float32), h, w, self.focal, s, self.ndc, self.near, self.far,
+                                      use_pixel_centers=self.use_pixel_centers, unified_dir=self.unified_dir)
 
     def train_buffers(self, renderer, s: int, ds_method: str = "lanc", include_val: bool = False, with_sr: bool = False):
         """The reference's training buffers on the renderer's device: ``rays`` [n, s*s, 8] (all_rays), ``rgbs`` [n, 3]
@@ -254,7 +257,8 @@ def take_batch(buffers, index):
 
 # ---- scenes ---------------------------------------------------------------------------------------------
 def load_llff_scene(root: str, img_wh: Sequence[int], spheric_poses: bool = False, use_subset: bool = False,
-                    subset_num: int = 20, sisr_path: Optional[str] = None) -> Scene:
+                    subset_num: int = 20, sisr_path: Optional[str] = None, use_pixel_centers: bool = True,
+                    unified_dir: bool = False) -> Scene:
     """A COLMAP-reconstructed real scene (``<root>/sparse/0/*.bin`` + ``<root>/images``), normalised exactly like
     LLFFDownXDataset.read_meta (data/llff_downX_dataset.py:197-262)."""
     cams = read_cameras_binary(os.path.join(root, "sparse/0/cameras.bin"))
@@ -309,10 +313,10 @@ def load_llff_scene(root: str, img_wh: Sequence[int], spheric_poses: bool = Fals
         near, far = 0.0, 1.0
     return Scene("llff", root, (int(img_wh[0]), int(img_wh[1])), float(focal), poses, image_paths, bounds,
                  ndc=not spheric_poses, near=near, far=far, white_back=False, val_idx=val_idx, spheric=spheric_poses,
-                 sr_image_paths=sr_paths)
+                 sr_image_paths=sr_paths, use_pixel_centers=use_pixel_centers, unified_dir=unified_dir)
 
 
-def load_blender_scene(root: str, split: str, img_wh: Sequence[int]) -> Scene:
+def load_blender_scene(root: str, split: str, img_wh: Sequence[int], use_pixel_centers: bool = True) -> Scene:
     """A synthetic NeRF scene (``transforms_<split>.json`` + RGBA PNGs), BlenderDownXDataset.read_meta
     (data/blender_downX_dataset.py:70-90, :101-107)."""
     if img_wh[0] != img_wh[1]:
@@ -325,7 +329,7 @@ def load_blender_scene(root: str, split: str, img_wh: Sequence[int]) -> Scene:
     poses = np.stack([np.array(f["transform_matrix"])[:3, :4] for f in meta["frames"]], 0)
     image_paths = [os.path.join(root, f"{f['file_path']}.png") for f in meta["frames"]]
     return Scene("blender", root, (int(img_wh[0]), int(img_wh[1])), float(focal), poses, image_paths, np.array([2.0, 6.0]),
-                 ndc=False, near=2.0, far=6.0, white_back=True, rgba=True)
+                 ndc=False, near=2.0, far=6.0, white_back=True, rgba=True, use_pixel_centers=use_pixel_centers)
 
 
 # ---- images -> targets -----------------------------------------------------------------------------------

@@ -129,20 +129,26 @@ def lr_loss_grad(self: Renderer, hr_rgb: torch.Tensor, target_lr: torch.Tensor, 
     return lr, m, g
 
 
-def loss_epilogue(self: Renderer, hr_rgb: torch.Tensor, target_lr: torch.Tensor, s: int, lambda_mse: float = 1.0,
+def loss_epilogue(self: Renderer, hr_rgb: torch.Tensor, target_lr: Optional[torch.Tensor], s: int, lambda_mse: float = 1.0,
                   hr_depth: Optional[torch.Tensor] = None, lambda_var: float = 0.0, lambda_depth_var: float = 0.0,
-                  far: float = 0.0, target_hr: Optional[torch.Tensor] = None, want_grad: bool = True) -> Dict[str, torch.Tensor]:
+                  far: float = 0.0, target_hr: Optional[torch.Tensor] = None, want_grad: bool = True,
+                  lambda_hr: float = 1.0) -> Dict[str, torch.Tensor]:
     """Every term of the reference's ``calculate_losses`` for one net's outputs (models/nerf_downX_model.py:326-378)
     and its gradient down to the HR outputs, in one launch (nsr_loss_epilogue).  ``lambda_var`` /
     ``lambda_depth_var`` = 0 switch the sub-pixel variance terms off (``--use_var_loss`` / ``--use_depth_var_loss``
-    not given); ``target_hr`` is ``data_rgbs_sr`` (``--sisr_path``); ``far`` is the reference's ``self.far``.
+    not given); ``target_hr`` is ``data_rgbs_sr`` (``--sisr_path``, ``lambda_hr`` 1) or, with ``target_lr`` None, the
+    reference-view colours ``data_ref_rgbs`` (``--with_ref``, ``lambda_hr`` 1/s^2); ``far`` is the reference's ``self.far``.
     Returns lr_rgb [n_lr,3], lr_depth [n_lr] (if hr_depth), metrics [8] = (lambda*mse, psnr, var_sum,
-    depth_var_sum, mse_sr, total, 0, 0), g_rgb, g_depth (if want_grad)."""
-    hr_rgb, target_lr = self._f32(hr_rgb), self._f32(target_lr)
-    n_lr = target_lr.shape[0]
+    depth_var_sum, lambda_hr*mse_hr, total, 0, 0), g_rgb, g_depth (if want_grad)."""
+    hr_rgb = self._f32(hr_rgb)
+    if hr_rgb.shape[0] % (s * s):
+        raise NsrError(1, f"hr_rgb has {hr_rgb.shape[0]} rows, not a multiple of {s}*{s}")
+    n_lr = hr_rgb.shape[0] // (s * s)
     n = n_lr * s * s
-    if hr_rgb.shape[0] != n:
-        raise NsrError(1, f"hr_rgb has {hr_rgb.shape[0]} rows, expected {n_lr}*{s}*{s}")
+    if target_lr is not None:
+        target_lr = self._f32(target_lr)
+        if tuple(target_lr.shape) != (n_lr, 3):
+            raise NsrError(1, f"target_lr is {tuple(target_lr.shape)}, expected ({n_lr}, 3) for {hr_rgb.shape[0]} HR rows at s={s}")
     dev, f32 = self.device, torch.float32
     out = {"lr_rgb": torch.empty(n_lr, 3, device=dev, dtype=f32), "metrics": torch.empty(8, device=dev, dtype=f32)}
     if hr_depth is not None:
@@ -162,9 +168,11 @@ def loss_epilogue(self: Renderer, hr_rgb: torch.Tensor, target_lr: torch.Tensor,
     t.struct_size = C.sizeof(NsrLossTerms)
     t.s, t.lambda_mse, t.lambda_var, t.lambda_depth_var, t.far_plane = int(s), float(lambda_mse), float(lambda_var), \
         float(lambda_depth_var), float(far)
+    t.lambda_hr = float(lambda_hr)
     ptr = lambda k: out[k].data_ptr() if k in out else None
     self._check(self.lib.nsr_loss_epilogue(self._h, hr_rgb.data_ptr(), hr_depth.data_ptr() if hr_depth is not None else None,
-                                           target_lr.data_ptr(), target_hr.data_ptr() if target_hr is not None else None,
+                                           target_lr.data_ptr() if target_lr is not None else None,
+                                           target_hr.data_ptr() if target_hr is not None else None,
                                            n_lr, C.byref(t), ptr("lr_rgb"), ptr("lr_depth"), ptr("metrics"), ptr("g_rgb"),
                                            ptr("g_depth"), self._stream()))
     return out
@@ -380,6 +388,7 @@ class Trainer:
         self.lam_var = (lambda_coarse_var, lambda_fine_var)
         self.lam_dvar = (lambda_coarse_depth_var, lambda_fine_depth_var)
         self.last_terms: Optional[torch.Tensor] = None
+        self.last_ref_terms: Optional[torch.Tensor] = None
         self.clip_val, self.clip_type = grad_clip_val, grad_clip_type
         self.s = downscale
         self.step = 0
@@ -405,38 +414,70 @@ class Trainer:
         return rng
 
     def forward_backward(self, rays: torch.Tensor, target_lr: torch.Tensor, rng=None, target_sr: Optional[torch.Tensor] = None,
-                         far: Optional[float] = None):
+                         far: Optional[float] = None, ref_rays: Optional[torch.Tensor] = None,
+                         ref_rgbs: Optional[torch.Tensor] = None, ref_rng=None):
         """forward + loss + backward; returns (grad_coarse_flat, grad_fine_flat), sets last_metrics.
         ``target_sr`` [N,3]: the SISR supervision ``data_rgbs_sr`` (``--sisr_path``).  ``far``: the reference's
         ``self.far`` for the depth-variance term (default: read from ``rays[0, 7]`` like the reference -- one host sync;
         datasets have a constant far plane, pass it to stay asynchronous).  With any of the extra terms on,
-        ``last_terms`` [2,8] holds (lambda*mse, psnr, var_sum, depth_var_sum, mse_sr, total, 0, 0) per net."""
+        ``last_terms`` [2,8] holds (lambda*mse, psnr, var_sum, depth_var_sum, mse_sr, total, 0, 0) per net.
+        ``ref_rays`` [M,8] / ``ref_rgbs`` [M,3] / ``ref_rng``: the reference-view batch of ``--with_ref``
+        (models/nerf_downX_model.py:321-324, 369-372): a second forward (its train-mode draws come after the main
+        batch's) whose HR colours enter the loss as MSE / s^2; ``last_ref_terms`` [2] holds the two terms."""
         r = self.r
+        if ref_rays is not None:
+            return self._forward_backward_with_ref(rays, target_lr, rng, target_sr, far, ref_rays, ref_rgbs, ref_rng)
         out = r.render_train(rays, rng, want_weights=False)
         if target_sr is not None or any(self.lam_var) or any(self.lam_dvar):
-            if any(self.lam_dvar) and far is None:
-                far = float(rays[0, 7])                           # models/nerf_downX_model.py:284
-            terms, grads = [], {}
-            for w, net in enumerate(("coarse", "fine")):
-                e = r.loss_epilogue(out[f"{net}_comp_rgbs"], target_lr, self.s, self.lam[w],
-                                    hr_depth=out[f"{net}_depth"] if self.lam_dvar[w] else None, lambda_var=self.lam_var[w],
-                                    lambda_depth_var=self.lam_dvar[w], far=far or 0.0, target_hr=target_sr)
-                terms.append(e["metrics"])
-                grads[f"{net}_comp_rgbs"] = e["g_rgb"]
-                if "g_depth" in e:
-                    grads[f"{net}_depth"] = e["g_depth"]
-            self.last_terms = torch.stack(terms)
-            self.last_metrics = torch.cat([terms[0][:2], terms[1][:2]])
-            return r.backward(rays, rng, grads)
+            return r.backward(rays, rng, self._main_loss_grads(out, rays, target_lr, target_sr, far))
         _, mc, g_c = r.lr_loss_grad(out["coarse_comp_rgbs"], target_lr, self.s, self.lam[0])
         _, mf, g_f = r.lr_loss_grad(out["fine_comp_rgbs"], target_lr, self.s, self.lam[1])
         self.last_metrics = torch.cat([mc, mf])
         return r.backward(rays, rng, {"coarse_comp_rgbs": g_c, "fine_comp_rgbs": g_f})
 
-    def optimize_parameters(self, rays: torch.Tensor, target_lr: torch.Tensor, rng=None, lr: Optional[float] = None,
-                            target_sr: Optional[torch.Tensor] = None, far: Optional[float] = None):
+    def _main_loss_grads(self, out, rays, target_lr, target_sr, far):
+        """Loss terms + dL/d(outputs) of the main batch through nsr_loss_epilogue."""
         r = self.r
-        gc, gf = self.forward_backward(rays, target_lr, rng, target_sr=target_sr, far=far)
+        if any(self.lam_dvar) and far is None:
+            far = float(rays[0, 7])
+        terms, grads = [], {}
+        for w, net in enumerate(("coarse", "fine")):
+            e = r.loss_epilogue(out[f"{net}_comp_rgbs"], target_lr, self.s, self.lam[w],
+                                hr_depth=out[f"{net}_depth"] if self.lam_dvar[w] else None, lambda_var=self.lam_var[w],
+                                lambda_depth_var=self.lam_dvar[w], far=far or 0.0, target_hr=target_sr)
+            terms.append(e["metrics"])
+            grads[f"{net}_comp_rgbs"] = e["g_rgb"]
+            if "g_depth" in e:
+                grads[f"{net}_depth"] = e["g_depth"]
+        self.last_terms = torch.stack(terms)
+        self.last_metrics = torch.cat([terms[0][:2], terms[1][:2]])
+        return grads
+
+    def _forward_backward_with_ref(self, rays, target_lr, rng, target_sr, far, ref_rays, ref_rgbs, ref_rng):
+        r = self.r
+        if ref_rgbs is None or ref_rays.shape[0] != ref_rgbs.shape[0] or ref_rays.shape[0] % (self.s * self.s):
+            raise NsrError(1, "ref_rays / ref_rgbs must have the same number of rows, a multiple of downscale^2")
+        ws_main = r.new_train_workspace(rays.shape[0])           # two forwards are in flight before the first backward
+        ws_ref = r.new_train_workspace(ref_rays.shape[0])
+        out = r.render_train(rays, rng, want_weights=False, ws=ws_main)
+        out_ref = r.render_train(ref_rays, ref_rng, want_weights=False, ws=ws_ref)
+        grads = self._main_loss_grads(out, rays, target_lr, target_sr, far)
+        ref_terms, ref_grads = [], {}
+        for net in ("coarse", "fine"):                            # mse(out_ref_*_comp_rgbs, data_ref_rgbs) / s^2
+            e = r.loss_epilogue(out_ref[f"{net}_comp_rgbs"], None, self.s, 0.0, target_hr=ref_rgbs, lambda_hr=1.0 / (self.s * self.s))
+            ref_terms.append(e["metrics"][4])
+            ref_grads[f"{net}_comp_rgbs"] = e["g_rgb"]
+        self.last_ref_terms = torch.stack(ref_terms)
+        gc, gf = r.backward(rays, rng, grads, ws=ws_main)
+        gc2, gf2 = r.backward(ref_rays, ref_rng, ref_grads, ws=ws_ref)
+        return gc.add_(gc2), gf.add_(gf2)                        # autograd's accumulation over the two forward graphs
+
+    def optimize_parameters(self, rays: torch.Tensor, target_lr: torch.Tensor, rng=None, lr: Optional[float] = None,
+                            target_sr: Optional[torch.Tensor] = None, far: Optional[float] = None,
+                            ref_rays: Optional[torch.Tensor] = None, ref_rgbs: Optional[torch.Tensor] = None, ref_rng=None):
+        r = self.r
+        gc, gf = self.forward_backward(rays, target_lr, rng, target_sr=target_sr, far=far, ref_rays=ref_rays, ref_rgbs=ref_rgbs,
+                                       ref_rng=ref_rng)
         if self.group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
                                       and torch.distributed.get_world_size() > 1):
             from .parallel import allreduce_mean_

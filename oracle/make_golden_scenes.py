@@ -143,11 +143,14 @@ def build_llff(LLFF) -> dict:
         meta = dict(img_wh=list(img_wh), torch=torch.__version__, cases=[])
         for tag, kw in (("ndc_lanc_s2", dict(downscale=2, ds_method="lanc")),
                         ("ndc_avg_s3_sr", dict(downscale=3, ds_method="avg", sisr_path=os.path.join(root, "sisr"))),
-                        ("spheric_lanc_s2", dict(downscale=2, ds_method="lanc", spheric_poses=True))):
+                        ("spheric_lanc_s2", dict(downscale=2, ds_method="lanc", spheric_poses=True)),
+                        ("ndc_unified_dir_s2", dict(downscale=2, ds_method="lanc", unified_dir=True)),
+                        ("spheric_corner_pixels_s3", dict(downscale=3, ds_method="avg", spheric_poses=True, use_pixel_centers=False))):
             opt = dataset_opt(dataset_root=root, img_wh=img_wh, **kw)
             ref = LLFF(opt, "train")
             s = opt.downscale
-            mine = S.load_llff_scene(root, img_wh, spheric_poses=opt.spheric_poses, sisr_path=opt.sisr_path)
+            mine = S.load_llff_scene(root, img_wh, spheric_poses=opt.spheric_poses, sisr_path=opt.sisr_path,
+                                     use_pixel_centers=opt.use_pixel_centers, unified_dir=opt.unified_dir)
             # ---- the pin: scene-level quantities bit-equal ----
             assert mine.focal == ref.focal and mine.val_idx == int(np.argmin(np.linalg.norm(ref.poses[..., 3], axis=1)))
             assert np.array_equal(mine.poses, ref.poses), np.abs(mine.poses - ref.poses).max()
@@ -165,7 +168,8 @@ def build_llff(LLFF) -> dict:
                 assert np.array_equal(np.concatenate(sr), ref.all_rgbs_sr.numpy()), tag
             # rays: the oracle's restatement of the dataset path (pinned in raygen.npz) on my poses
             rays = torch.cat([O.build_frame_rays(torch.from_numpy(mine.poses[i]).float(), img_wh[1], img_wh[0], mine.focal, s,
-                                                 mine.near, mine.far, mine.ndc).view(-1, s * s, 8)
+                                                 mine.near, mine.far, mine.ndc, mine.use_pixel_centers,
+                                                 mine.unified_dir).view(-1, s * s, 8)
                               for i in mine.train_indices()], 0)
             assert torch.equal(rays, ref.all_rays), (tag, float((rays - ref.all_rays).abs().max()))
             test = LLFF(opt, "test")
@@ -183,7 +187,8 @@ def build_llff(LLFF) -> dict:
             arrays[f"{tag}/val_rays"], arrays[f"{tag}/val_rgbs"] = vs["rays"].numpy(), vs["rgbs"].numpy()
             arrays[f"{tag}/val_rgbs_ori"] = vs["rgbs_ori"].numpy()
             meta["cases"].append(dict(tag=tag, downscale=s, ds_method=opt.ds_method, spheric_poses=opt.spheric_poses,
-                                      sisr=bool(opt.sisr_path), focal=float(ref.focal), val_idx=int(mine.val_idx),
+                                      sisr=bool(opt.sisr_path), use_pixel_centers=opt.use_pixel_centers,
+                                      unified_dir=opt.unified_dir, focal=float(ref.focal), val_idx=int(mine.val_idx),
                                       near=mine.near, far=mine.far))
     arrays["meta_json"] = np.frombuffer(json.dumps(meta).encode(), np.uint8)
     return arrays

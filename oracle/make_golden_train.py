@@ -53,6 +53,10 @@ FIXTURES = {
                                        "--sisr_path", "/nonexistent/sisr", "--grad_clip_val", "0.1"],
                                  cfg=dict(noise_std=1.0, downscale=4),
                                  tcfg=dict(use_var_loss=True, use_depth_var_loss=True, grad_clip_val=0.1)),
+    # reference-view term (--with_ref, :321-324,369-372): a second forward over 40 sub-pixel rays of the reference image
+    "train_step_with_ref": dict(n_lr=32, s=2, rays="llff", seeds=(21, 8), rng_seed=31, n_ref=40,
+                                args=["--noise_std", "1.0", "--with_ref", "--use_var_loss"],
+                                cfg=dict(noise_std=1.0), tcfg=dict(use_var_loss=True)),
 }
 
 
@@ -89,6 +93,9 @@ def build(name: str, spec: dict) -> dict:
     tg = torch.Generator().manual_seed(spec["rng_seed"] + 1)
     target = torch.rand(spec["n_lr"], 3, generator=tg)
     target_sr = torch.rand(n, 3, generator=tg) if spec.get("sisr") else None
+    n_ref = spec.get("n_ref", 0)
+    ref_rays = O.synthetic_rays(n_ref, seed=4000 + spec["seeds"][0], kind=spec["rays"]) if n_ref else None
+    ref_rgbs = torch.rand(n_ref, 3, generator=tg) if n_ref else None
 
     state = T.TrainState(pc, pf)
     g = torch.Generator().manual_seed(spec["rng_seed"])
@@ -96,13 +103,16 @@ def build(name: str, spec: dict) -> dict:
     arrays = {"rays": rays.numpy(), "target": target.numpy()}
     if target_sr is not None:
         arrays["target_sr"] = target_sr.numpy()
+    if n_ref:
+        arrays["ref_rays"], arrays["ref_rgbs"] = ref_rays.numpy(), ref_rgbs.numpy()
     meta = dict(name=name, cfg=spec["cfg"], tcfg=spec["tcfg"], seeds=list(spec["seeds"]), s=s,
                 reference_args=spec["args"], torch=torch.__version__, steps=[])
     ref_params = lambda: [p for p in model.netCoarse.parameters()] + [p for p in model.netFine.parameters()]
     for step in range(2):
         # ---- reference iteration ----
         model.set_input({"rays": rays.clone(), "rgbs": target.clone(),
-                         **({"rgbs_sr": target_sr.clone()} if target_sr is not None else {})})
+                         **({"rgbs_sr": target_sr.clone()} if target_sr is not None else {}),
+                         **({"ref_rays": ref_rays.clone(), "ref_rgbs": ref_rgbs.clone()} if n_ref else {})})
         model.optimize_parameters()
         ref_grads = [p.grad.detach().clone() for p in ref_params()]
         ref_losses = dict(coarse_mse=model.loss_coarse_mse.detach(), fine_mse=model.loss_fine_mse.detach(),
@@ -115,20 +125,28 @@ def build(name: str, spec: dict) -> dict:
                               fine_depth_var=model.loss_fine_depth_var.detach())
         if target_sr is not None:
             ref_losses.update(coarse_mse_sr=model.loss_coarse_mse_sr.detach(), fine_mse_sr=model.loss_fine_mse_sr.detach())
+        if n_ref:
+            ref_losses.update(ref_coarse_mse=model.loss_ref_coarse_mse.detach(), ref_fine_mse=model.loss_ref_fine_mse.detach())
         # ---- oracle iteration on the same draws ----
         rng = O.RenderRng.draw(n, cfg, g)
+        ref_rng = O.RenderRng.draw(n_ref, cfg, g) if n_ref else None
         if step == 0:   # fp64 floor of the gradients at the initial weights
-            _, gc32, gf32, _ = T.loss_and_grads(state.pc, state.pf, rays, target, cfg, tcfg, rng, s, target_sr=target_sr)
+            refkw = dict(ref_rays=ref_rays, ref_rgbs=ref_rgbs, ref_rng=ref_rng) if n_ref else {}
+            _, gc32, gf32, _ = T.loss_and_grads(state.pc, state.pf, rays, target, cfg, tcfg, rng, s, target_sr=target_sr, **refkw)
             d = lambda t: None if t is None else t.double()
             rng64 = O.RenderRng(d(rng.u_coarse), d(rng.noise_coarse), d(rng.u_fine), d(rng.noise_fine))
+            refkw64 = dict(ref_rays=ref_rays.double(), ref_rgbs=ref_rgbs.double(),
+                           ref_rng=O.RenderRng(d(ref_rng.u_coarse), d(ref_rng.noise_coarse), d(ref_rng.u_fine),
+                                               d(ref_rng.noise_fine))) if n_ref else {}
             _, gc64, gf64, _ = T.loss_and_grads({k: v.double() for k, v in state.pc.items()},
                                                 {k: v.double() for k, v in state.pf.items()},
                                                 rays.double(), target.double(), cfg, tcfg, rng64, s,
-                                                target_sr=None if target_sr is None else target_sr.double())
+                                                target_sr=None if target_sr is None else target_sr.double(), **refkw64)
             rel = lambda a, b: float(torch.linalg.vector_norm(a.double() - b) / (torch.linalg.vector_norm(b) + 1e-30))
             meta["fp64_floor_rel_l2"] = dict(
                 coarse={k: rel(gc32[k], gc64[k]) for k in gc32}, fine={k: rel(gf32[k], gf64[k]) for k in gf32})
-        losses, grads = T.optimize_parameters(state, rays, target, cfg, tcfg, rng, s, target_sr=target_sr)
+        losses, grads = T.optimize_parameters(state, rays, target, cfg, tcfg, rng, s, target_sr=target_sr,
+                                              ref_rays=ref_rays, ref_rgbs=ref_rgbs, ref_rng=ref_rng)
         # ---- the pin ----
         for k in ref_losses:
             assert torch.equal(ref_losses[k], losses[k]), (name, step, k, float(ref_losses[k]), float(losses[k]))
@@ -140,6 +158,9 @@ def build(name: str, spec: dict) -> dict:
             t = getattr(rng, f)
             if t is not None:
                 arrays[f"rng{step}_{f}"] = t.numpy()
+            t = getattr(ref_rng, f) if n_ref else None
+            if t is not None:
+                arrays[f"refrng{step}_{f}"] = t.numpy()
         summarize(grads, f"grad{step}", arrays)
         summarize(state.param_list(), f"param{step}", arrays)
         meta["steps"].append({k: float(v) for k, v in losses.items()})

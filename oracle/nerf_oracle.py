@@ -319,15 +319,22 @@ def ndc_rays(H: int, W: int, focal: float, near: float, o: Tensor, d: Tensor):
 
 
 def build_frame_rays(c2w: Tensor, H: int, W: int, focal: float, s: int,
-                     near: float, far: float, ndc: bool = False) -> Tensor:
+                     near: float, far: float, ndc: bool = False, use_pixel_centers: bool = True,
+                     unified_dir: bool = False) -> Tensor:
     """HR raster of rays for one pose, grouped LR-pixel-major / sub-pixel-minor.
 
     Follows the test branch of data/blender_downX_dataset.py:207-215 (ndc=False:
     cat(o, d, near, far)) and data/llff_downX_dataset.py:473-490 (ndc=True:
     get_ndc_rays at near=1.0, then near=0 far=1), then the einops grouping
     '(h s1) (w s2) c -> (h w) (s1 s2) c' and the flatten of
-    models/nerf_downX_model.py:247.  Returns [H*W, 8]."""
-    dirs = ray_directions(H, W, focal)
+    models/nerf_downX_model.py:247.  Returns [H*W, 8].
+    ``unified_dir`` (data/llff_downX_dataset.py:273-277): directions from the (H/s, W/s) raster with focal // s,
+    each repeated over its s x s sub-pixels ('h w c -> (h s1) (w s2) c')."""
+    if unified_dir:
+        dirs = ray_directions(H // s, W // s, focal // s, use_pixel_centers)
+        dirs = dirs.repeat_interleave(s, dim=0).repeat_interleave(s, dim=1)
+    else:
+        dirs = ray_directions(H, W, focal, use_pixel_centers)
     o, d = rays_from_pose(dirs, c2w)
     if ndc:
         o, d = ndc_rays(H, W, focal, 1.0, o, d)

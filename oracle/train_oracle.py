@@ -10,8 +10,8 @@ Restates, with plain torch CPU ops, what the reference does in one ``optimize_pa
   comp_low_res_output()           :326-353  (s x s box average of the composite colours)
   calculate_losses()              :355-388  (lambda_c * MSE(coarse_lr, target) + lambda_f * MSE(fine_lr, target),
                                              PSNR of both; + the sub-pixel variance terms :331-335,349-353,
-                                             374-378 and the SR-target term :364-367; the ref-ray term is the
-                                             same MSE on a second ray batch and stays with the caller)
+                                             374-378, the SR-target term :364-367 and the reference-view term
+                                             :321-324,369-372 (a second forward over ``data_ref_rays``))
   loss_tot.backward()             :390-396  (torch autograd through exactly the ops nerf_oracle restates;
                                              the fine z-values use coarse_weights.detach(), :302)
   clip_grad_norm_/clip_grad_value_:403-407
@@ -62,14 +62,20 @@ class TrainConfig:
 def loss_and_grads(pc: Dict[str, Tensor], pf: Dict[str, Tensor], rays: Tensor, target_lr: Tensor,
                    cfg: O.RenderConfig, tcfg: TrainConfig, rng: Optional[O.RenderRng] = None,
                    s: int = 2, z_fine_override: Optional[Tensor] = None, extras: Optional[dict] = None,
-                   target_sr: Optional[Tensor] = None):
+                   target_sr: Optional[Tensor] = None, ref_rays: Optional[Tensor] = None, ref_rgbs: Optional[Tensor] = None,
+                   ref_rng: Optional[O.RenderRng] = None, ref_z_fine_override: Optional[Tensor] = None):
     """One forward + backward.  Returns (losses dict, grads_coarse dict, grads_fine dict, outputs dict).
     target_lr: [N/s^2, 3].  target_sr: [N, 3] or None = ``data_rgbs_sr`` (``--sisr_path``, :364-367).
+    ref_rays [M, 8] / ref_rgbs [M, 3] (``--with_ref``, :321-324, :369-372): sub-pixel rays of the reference view with
+    their HR colours; rendered by a second forward after the main one (so its train-mode draws come second).
     Gradients are None-free: parameters the loss does not reach get zeros
     (the reference leaves .grad = None for them; Adam then skips the parameter)."""
     pc_r = {k: v.detach().clone().requires_grad_(True) for k, v in pc.items()}
     pf_r = {k: v.detach().clone().requires_grad_(True) for k, v in pf.items()}
     out = O.forward_rays(pc_r, pf_r, rays, cfg, rng, z_fine_override=z_fine_override, extras=extras)
+    out_ref = None
+    if ref_rays is not None:                                                  # :321-324
+        out_ref = O.forward_rays(pc_r, pf_r, ref_rays, cfg, ref_rng, z_fine_override=ref_z_fine_override)
     # comp_low_res_output (:326-353).  The ops are created in the reference's order: autograd sums the branches
     # that meet at one output in reverse creation order, and fp32 addition of three terms is not associative.
     n_lr = target_lr.shape[0]
@@ -102,6 +108,10 @@ def loss_and_grads(pc: Dict[str, Tensor], pf: Dict[str, Tensor], rays: Tensor, t
         losses["coarse_mse_sr"] = torch.nn.functional.mse_loss(c_rgb_ori, target_sr)
         losses["fine_mse_sr"] = torch.nn.functional.mse_loss(f_rgb_ori, target_sr)
         tot = tot + (losses["coarse_mse_sr"] + losses["fine_mse_sr"])
+    if out_ref is not None:                                                   # :369-372
+        losses["ref_coarse_mse"] = torch.nn.functional.mse_loss(out_ref["coarse_comp_rgbs"], ref_rgbs) / (s ** 2)
+        losses["ref_fine_mse"] = torch.nn.functional.mse_loss(out_ref["fine_comp_rgbs"], ref_rgbs) / (s ** 2)
+        tot = tot + (losses["ref_coarse_mse"] + losses["ref_fine_mse"])
     if tcfg.use_var_loss:                                                     # :374-375
         tot = tot + (tcfg.lambda_coarse_var * losses["coarse_var"] + tcfg.lambda_fine_var * losses["fine_var"])
     if tcfg.use_depth_var_loss:                                               # :376-378
@@ -197,10 +207,12 @@ class TrainState:
 
 def optimize_parameters(state: TrainState, rays: Tensor, target_lr: Tensor, cfg: O.RenderConfig,
                         tcfg: TrainConfig, rng: Optional[O.RenderRng], s: int = 2, lr: Optional[float] = None,
-                        z_fine_override: Optional[Tensor] = None, target_sr: Optional[Tensor] = None):
+                        z_fine_override: Optional[Tensor] = None, target_sr: Optional[Tensor] = None,
+                        ref_rays: Optional[Tensor] = None, ref_rgbs: Optional[Tensor] = None,
+                        ref_rng: Optional[O.RenderRng] = None):
     """One full reference training iteration on ``state`` (in place).  Returns (losses, grads list)."""
     losses, gc, gf, _ = loss_and_grads(state.pc, state.pf, rays, target_lr, cfg, tcfg, rng, s, z_fine_override,
-                                       target_sr=target_sr)
+                                       target_sr=target_sr, ref_rays=ref_rays, ref_rgbs=ref_rgbs, ref_rng=ref_rng)
     grads = [gc[k] for k in state.pc] + [gf[k] for k in state.pf]
     clip_grads(grads, tcfg)
     state.step += 1

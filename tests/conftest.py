@@ -58,10 +58,16 @@ class TrainFixture:
         self.rays = torch.from_numpy(z["rays"])
         self.target = torch.from_numpy(z["target"])
         self.target_sr = torch.from_numpy(z["target_sr"]) if "target_sr" in z.files else None   # data_rgbs_sr (--sisr_path)
-        self.rng = []
+        # --with_ref: the reference-view batch (data_ref_rays / data_ref_rgbs) and its own train-mode draws
+        self.ref_rays = torch.from_numpy(z["ref_rays"]) if "ref_rays" in z.files else None
+        self.ref_rgbs = torch.from_numpy(z["ref_rgbs"]) if "ref_rgbs" in z.files else None
+        self.rng, self.ref_rng = [], []
         for step in range(2):
             get = lambda f: torch.from_numpy(z[f"rng{step}_{f}"]) if f"rng{step}_{f}" in z.files else None
             self.rng.append(O.RenderRng(get("u_coarse"), get("noise_coarse"), get("u_fine"), get("noise_fine")))
+            getr = lambda f: torch.from_numpy(z[f"refrng{step}_{f}"]) if f"refrng{step}_{f}" in z.files else None
+            self.ref_rng.append(None if self.ref_rays is None else
+                                O.RenderRng(getr("u_coarse"), getr("noise_coarse"), getr("u_fine"), getr("noise_fine")))
         sd = self.meta["seeds"]
         self.p_coarse = O.make_mlp_params(self.cfg, sd[0])
         self.p_fine = O.make_mlp_params(self.cfg, sd[1])

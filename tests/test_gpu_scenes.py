@@ -30,7 +30,8 @@ def test_llff_train_buffers_match_reference_dataset(tmp_path):
     for case in meta["cases"]:
         tag, s = case["tag"], case["downscale"]
         sc = S.load_llff_scene(str(tmp_path), meta["img_wh"], spheric_poses=case["spheric_poses"],
-                               sisr_path=os.path.join(str(tmp_path), "sisr") if case["sisr"] else None)
+                               sisr_path=os.path.join(str(tmp_path), "sisr") if case["sisr"] else None,
+                               use_pixel_centers=case["use_pixel_centers"], unified_dir=case["unified_dir"])
         buf = sc.train_buffers(r, s, case["ds_method"], with_sr=case["sisr"])
         ref = torch.from_numpy(z[f"{tag}/all_rays"])
         assert buf["rays"].shape == ref.shape and buf["rays"].is_cuda

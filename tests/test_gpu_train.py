@@ -221,7 +221,7 @@ def test_clip_and_adam_against_torch():
 
 
 @pytest.mark.parametrize("s,n_lr,terms", [(2, 777, "all"), (4, 1001, "all"), (3, 50, "all"), (2, 70001, "var"), (2, 300, "sr"),
-                                          (2, 300, "mse"), (1, 64, "sr")])
+                                          (2, 300, "mse"), (1, 64, "sr"), (2, 300, "ref"), (4, 33, "ref")])
 def test_loss_epilogue_against_autograd(s, n_lr, terms):
     """nsr_loss_epilogue: every term of calculate_losses (box average + lambda*MSE + PSNR, sub-pixel variance of colour
     and of depth/far, SISR MSE) and the gradient to the HR outputs, against torch autograd over the reference's
@@ -233,14 +233,18 @@ def test_loss_epilogue_against_autograd(s, n_lr, terms):
     hr = torch.rand(n, 3, generator=g, dtype=torch.float64, requires_grad=True)
     depth = (2 + 4 * torch.rand(n, generator=g, dtype=torch.float64)).requires_grad_(True)
     tgt = torch.rand(n_lr, 3, generator=g, dtype=torch.float64)
-    tgt_hr = torch.rand(n, 3, generator=g, dtype=torch.float64) if terms in ("all", "sr") else None
+    tgt_hr = torch.rand(n, 3, generator=g, dtype=torch.float64) if terms in ("all", "sr", "ref") else None
     lam, lam_v, lam_d, far = 0.7, (0.02 if terms in ("all", "var") else 0.0), (0.05 if terms in ("all", "var") else 0.0), 6.0
+    lam_hr = 1.0 / (s * s) if terms == "ref" else 1.0        # --with_ref batch: no LR target, HR MSE / s^2
     lr_ref = O.box_average(hr, s)
-    mse = torch.nn.functional.mse_loss(lr_ref, tgt)
-    tot = mse * lam
-    ref = {"mse": float(mse * lam), "psnr": float(-10 * torch.log10(mse)), "var": 0.0, "dvar": 0.0, "sr": 0.0}
+    if terms == "ref":
+        tot, ref = 0.0, {"mse": 0.0, "psnr": 0.0, "var": 0.0, "dvar": 0.0, "sr": 0.0}
+    else:
+        mse = torch.nn.functional.mse_loss(lr_ref, tgt)
+        tot = mse * lam
+        ref = {"mse": float(mse * lam), "psnr": float(-10 * torch.log10(mse)), "var": 0.0, "dvar": 0.0, "sr": 0.0}
     if tgt_hr is not None:
-        sr = torch.nn.functional.mse_loss(hr, tgt_hr)
+        sr = torch.nn.functional.mse_loss(hr, tgt_hr) * lam_hr
         tot = tot + sr
         ref["sr"] = float(sr)
     if lam_v:
@@ -253,7 +257,8 @@ def test_loss_epilogue_against_autograd(s, n_lr, terms):
         ref["dvar"] = float(dv)
     tot.backward()
     f = lambda t: None if t is None else t.detach().float().to(DEV)
-    e = r.loss_epilogue(f(hr), f(tgt), s, lam, hr_depth=f(depth), lambda_var=lam_v, lambda_depth_var=lam_d, far=far, target_hr=f(tgt_hr))
+    e = r.loss_epilogue(f(hr), None if terms == "ref" else f(tgt), s, lam, hr_depth=f(depth), lambda_var=lam_v, lambda_depth_var=lam_d,
+                        far=far, target_hr=f(tgt_hr), lambda_hr=lam_hr)
     torch.cuda.synchronize()
     m = e["metrics"].cpu()
     assert torch.allclose(e["lr_rgb"].cpu().double(), lr_ref.detach(), rtol=0, atol=5e-7)
@@ -272,6 +277,8 @@ def test_loss_epilogue_against_autograd(s, n_lr, terms):
             r.loss_epilogue(f(hr), f(tgt), 1, 1.0, lambda_var=0.01)
     with pytest.raises(NsrError):
         r.loss_epilogue(f(hr), f(tgt), s, 1.0, lambda_depth_var=0.01, far=6.0)
+    with pytest.raises(NsrError):
+        r.loss_epilogue(f(hr), None, s, 1.0)                      # no target at all
     r.close()
 
 
@@ -286,13 +293,16 @@ def _trainer_kwargs(fx):
                 lambda_fine_depth_var=t.lambda_fine_depth_var if t.use_depth_var_loss else 0.0)
 
 
-def _oracle_grads(fx, z_f, rng, dtype=torch.float32):
+def _oracle_grads(fx, z_f, rng, dtype=torch.float32, ref_z_f=None):
     cast = lambda t: None if t is None else t.to(dtype)
-    rr = None if rng is None else O.RenderRng(cast(rng.u_coarse), cast(rng.noise_coarse), cast(rng.u_fine), cast(rng.noise_fine))
+    conv = lambda g: None if g is None else O.RenderRng(cast(g.u_coarse), cast(g.noise_coarse), cast(g.u_fine), cast(g.noise_fine))
+    rr = conv(rng)
     pc = {k: v.to(dtype) for k, v in fx.p_coarse.items()}
     pf = {k: v.to(dtype) for k, v in fx.p_fine.items()}
     return T.loss_and_grads(pc, pf, fx.rays.to(dtype), fx.target.to(dtype), fx.cfg, fx.tcfg, rr, fx.s, z_fine_override=z_f.to(dtype),
-                            target_sr=None if fx.target_sr is None else fx.target_sr.to(dtype))
+                            target_sr=None if fx.target_sr is None else fx.target_sr.to(dtype),
+                            ref_rays=cast(fx.ref_rays), ref_rgbs=cast(fx.ref_rgbs), ref_rng=conv(fx.ref_rng[0]),
+                            ref_z_fine_override=cast(ref_z_f))
 
 
 @pytest.mark.parametrize("prec", ["bf16x3"])
@@ -306,12 +316,16 @@ def test_gradients_against_oracle_autograd(name, prec):
     rays = fx.rays.to(DEV)
     out = r.render_train(rays, rng, want_z_fine=True)
     z_f = out["z_fine"].cpu()
-    gc, gf = tr.forward_backward(rays, fx.target.to(DEV), rng, target_sr=None if fx.target_sr is None else fx.target_sr.to(DEV),
-                                 far=float(fx.rays[0, 7]))
+    dev = lambda t: None if t is None else t.to(DEV)
+    ref_rng, ref_z_f = rng_dict(fx.ref_rng[0]), None
+    if fx.ref_rays is not None:             # --with_ref: the second forward is teacher-forced on its own CUDA z-values too
+        ref_z_f = r.render_train(dev(fx.ref_rays), ref_rng, want_z_fine=True)["z_fine"].cpu()
+    gc, gf = tr.forward_backward(rays, fx.target.to(DEV), rng, target_sr=dev(fx.target_sr), far=float(fx.rays[0, 7]),
+                                 ref_rays=dev(fx.ref_rays), ref_rgbs=dev(fx.ref_rgbs), ref_rng=ref_rng)
     torch.cuda.synchronize()
     assert torch.isfinite(gc).all() and torch.isfinite(gf).all()
-    losses, oc, of, _ = _oracle_grads(fx, z_f, fx.rng[0])
-    _, oc64, of64, _ = _oracle_grads(fx, z_f, fx.rng[0], torch.float64)
+    losses, oc, of, _ = _oracle_grads(fx, z_f, fx.rng[0], ref_z_f=ref_z_f)
+    _, oc64, of64, _ = _oracle_grads(fx, z_f, fx.rng[0], torch.float64, ref_z_f=ref_z_f)
     m = tr.last_metrics.cpu()
     assert float(m[0]) == pytest.approx(float(losses["coarse_mse"]), rel=2e-3)
     assert float(m[2]) == pytest.approx(float(losses["fine_mse"]), rel=2e-3)
@@ -323,7 +337,13 @@ def test_gradients_against_oracle_autograd(name, prec):
                 if key in losses:
                     _report(test="loss_terms", fixture=name, term=key, got=float(lt[w, col]), oracle=float(losses[key]))
                     assert float(lt[w, col]) == pytest.approx(float(losses[key]), rel=5e-3), (key, float(lt[w, col]), float(losses[key]))
-        assert float(lt[0, 5] + lt[1, 5]) == pytest.approx(float(losses["tot"]), rel=3e-3)
+        tot = float(lt[0, 5] + lt[1, 5])
+        if fx.ref_rays is not None:
+            rt = tr.last_ref_terms.cpu()
+            assert float(rt[0]) == pytest.approx(float(losses["ref_coarse_mse"]), rel=5e-3)
+            assert float(rt[1]) == pytest.approx(float(losses["ref_fine_mse"]), rel=5e-3)
+            tot += float(rt.sum())
+        assert tot == pytest.approx(float(losses["tot"]), rel=3e-3)
     worst = 0.0
     for net, flat, ref32, ref64 in (("coarse", gc, oc, oc64), ("fine", gf, of, of64)):
         off = 0

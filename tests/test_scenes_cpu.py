@@ -17,12 +17,13 @@ from oracle import ref_shim
 
 def _llff_case(root, meta, case):
     return S.load_llff_scene(root, meta["img_wh"], spheric_poses=case["spheric_poses"],
-                             sisr_path=os.path.join(root, "sisr") if case["sisr"] else None)
+                             sisr_path=os.path.join(root, "sisr") if case["sisr"] else None,
+                             use_pixel_centers=case["use_pixel_centers"], unified_dir=case["unified_dir"])
 
 
 def test_llff_scene_matches_reference_dataset(tmp_path):
     z, meta = materialize_scene("scene_llff", str(tmp_path))
-    assert len(meta["cases"]) == 3
+    assert len(meta["cases"]) == 5
     for case in meta["cases"]:
         tag, s = case["tag"], case["downscale"]
         sc = _llff_case(str(tmp_path), meta, case)
@@ -51,7 +52,7 @@ def test_llff_scene_matches_reference_dataset(tmp_path):
         # the ray buffers: the oracle's dataset-path restatement on the loader's poses == the reference's all_rays
         w, h = sc.img_wh
         rays = torch.cat([O.build_frame_rays(torch.from_numpy(sc.poses[i]).float(), h, w, sc.focal, s, sc.near, sc.far,
-                                             sc.ndc).view(-1, s * s, 8) for i in sc.train_indices()], 0)
+                                             sc.ndc, sc.use_pixel_centers, sc.unified_dir).view(-1, s * s, 8) for i in sc.train_indices()], 0)
         assert torch.allclose(rays, torch.from_numpy(z[f"{tag}/all_rays"]), rtol=1e-6, atol=1e-6)
 
 

@@ -17,7 +17,8 @@ def test_train_oracle_reproduces_golden(name):
     state = T.TrainState(fx.p_coarse, fx.p_fine)
     for step in range(2):
         losses, grads = T.optimize_parameters(state, fx.rays, fx.target, fx.cfg, fx.tcfg, fx.rng[step], fx.s,
-                                              target_sr=fx.target_sr)
+                                              target_sr=fx.target_sr, ref_rays=fx.ref_rays, ref_rgbs=fx.ref_rgbs,
+                                              ref_rng=fx.ref_rng[step])
         ref = fx.meta["steps"][step]
         for k, v in ref.items():
             assert abs(float(losses[k]) - v) <= 1e-5 * abs(v) + 1e-7, (step, k, float(losses[k]), v)
