@@ -242,19 +242,19 @@ def test_loss_epilogue_against_autograd(s, n_lr, terms):
     else:
         mse = torch.nn.functional.mse_loss(lr_ref, tgt)
         tot = mse * lam
-        ref = {"mse": float(mse * lam), "psnr": float(-10 * torch.log10(mse)), "var": 0.0, "dvar": 0.0, "sr": 0.0}
+        ref = {"mse": float(mse.detach() * lam), "psnr": float(-10 * torch.log10(mse.detach())), "var": 0.0, "dvar": 0.0, "sr": 0.0}
     if tgt_hr is not None:
         sr = torch.nn.functional.mse_loss(hr, tgt_hr) * lam_hr
         tot = tot + sr
-        ref["sr"] = float(sr)
+        ref["sr"] = float(sr.detach())
     if lam_v:
         v = T.subpixel_variance_sum(hr, n_lr, s)
         tot = tot + lam_v * v
-        ref["var"] = float(v)
+        ref["var"] = float(v.detach())
     if lam_d:
         dv = T.subpixel_variance_sum(depth, n_lr, s, far)
         tot = tot + lam_d * dv
-        ref["dvar"] = float(dv)
+        ref["dvar"] = float(dv.detach())
     tot.backward()
     f = lambda t: None if t is None else t.detach().float().to(DEV)
     e = r.loss_epilogue(f(hr), None if terms == "ref" else f(tgt), s, lam, hr_depth=f(depth), lambda_var=lam_v, lambda_depth_var=lam_d,
