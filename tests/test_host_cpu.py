@@ -38,6 +38,37 @@ def test_config_struct_matches_header():
     assert C.sizeof(_lib.NsrConfig) == 4 * (len(fields) - 1) + 4 * 8
 
 
+def test_header_is_plain_c_and_struct_sizes_match_the_binding(tmp_path):
+    """include/nsr.h must compile as C99 on its own (it is what a cgo / JNI / ctypes maintainer binds), and every
+    struct the ctypes stub mirrors must have the same size and field offsets as the C compiler's."""
+    import shutil
+    import subprocess
+    from nerf_sr_b200 import _lib
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    structs = {"NsrConfig": _lib.NsrConfig, "NsrRng": _lib.NsrRng, "NsrOutputs": _lib.NsrOutputs, "NsrPassOutputs": _lib.NsrPassOutputs,
+               "NsrOutGrads": _lib.NsrOutGrads, "NsrLossTerms": _lib.NsrLossTerms, "NsrRayGen": _lib.NsrRayGen}
+    lines = ['#include "nsr.h"', "#include <stdio.h>", "#include <stddef.h>", "int main(void) {"]
+    for name, cls in structs.items():
+        lines.append(f'  printf("{name} %zu", sizeof({name}));')
+        for field, _ in cls._fields_:
+            lines.append(f'  printf(" %zu", offsetof({name}, {field}));')
+        lines.append('  printf("\\n");')
+    lines += ["  return 0;", "}"]
+    src = os.path.join(str(tmp_path), "abi.c")
+    open(src, "w").write("\n".join(lines))
+    exe = os.path.join(str(tmp_path), "abi")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), src, "-o", exe], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.strip().splitlines()
+    assert len(out) == len(structs)
+    for line in out:
+        name, size, *offsets = line.split()
+        cls = structs[name]
+        assert int(size) == C.sizeof(cls), name
+        assert [int(o) for o in offsets] == [getattr(cls, f).offset for f, _ in cls._fields_], name
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
 def test_no_cpu_fallback():
     _build()
