@@ -401,6 +401,28 @@ class Trainer:
     def state_dict(self, which: int) -> Dict[str, torch.Tensor]:
         return dict(zip(self.names, self.params[which]))
 
+    def save_networks(self, save_dir: str, epoch) -> None:
+        """``<epoch>_net_Coarse.pth`` / ``<epoch>_net_Fine.pth`` in the reference's format (models/base_model.py:181-196)."""
+        from .checkpoints import save_networks
+        save_networks(save_dir, epoch, self.state_dict(0), self.state_dict(1))
+
+    def load_networks(self, save_dir: str, epoch, keys: Optional[str] = None) -> None:
+        """Overwrite the master parameters from a checkpoint written by this class or by the reference
+        (models/base_model.py:198-219; ``keys``: ``--init_weights_keys``) and re-pack the tensor-core weight images.
+        Adam moments and the step count are kept (the reference does not checkpoint them either)."""
+        from .checkpoints import load_networks
+        for w, sd in enumerate(load_networks(save_dir, epoch, keys)):
+            have = dict(zip(self.names, self.params[w]))
+            for k, v in sd.items():
+                if k not in have:
+                    raise NsrError(1, f"unexpected key {k!r} in checkpoint")
+                if tuple(v.shape) != tuple(have[k].shape):
+                    raise NsrError(1, f"{k}: checkpoint shape {tuple(v.shape)} != {tuple(have[k].shape)}")
+                have[k].copy_(v.to(have[k].device, torch.float32))
+            if keys is None and len(sd) != len(have):
+                raise NsrError(1, f"checkpoint has {len(sd)} tensors, the architecture {len(have)}")
+            self.r.load_params(w, self.params[w])
+
     def draw_rng(self, n_rays: int, generator: Optional[torch.Generator] = None) -> Dict[str, torch.Tensor]:
         """The reference's train-mode draws, in its order (models/utils.py:41, :210, :73, :210)."""
         c = self.r.cfg

@@ -471,6 +471,34 @@ def test_trainer_with_all_loss_terms_tracks_the_reference():
     r.close()
 
 
+def test_trainer_checkpoint_roundtrip(tmp_path):
+    """save_networks after a step, load into a fresh Trainer: identical renders; a shape mismatch is refused."""
+    from nerf_sr_b200 import NsrError, Trainer
+    from nerf_sr_b200 import checkpoints as K
+    fx = TrainFixture("train_step_blender")
+    r = _renderer(fx.cfg, fx.p_coarse, fx.p_fine)
+    tr = Trainer(r, fx.p_coarse, fx.p_fine, downscale=fx.s)
+    rays, tgt = fx.rays.to(DEV), fx.target.to(DEV)
+    tr.optimize_parameters(rays, tgt, rng_dict(fx.rng[0]), lr=K.LrSchedule().lr)
+    want = {k: v.clone() for k, v in r.forward_rays(rays).items()}
+    tr.save_networks(str(tmp_path), 3)
+    assert K.latest_epoch(str(tmp_path)) == 3
+    sd_c, sd_f = K.load_networks(str(tmp_path), 3)
+    assert all(torch.equal(sd_c[k], tr.state_dict(0)[k].cpu()) for k in sd_c) and not torch.equal(sd_c["sigma.weight"], fx.p_coarse["sigma.weight"])
+    r2 = _renderer(fx.cfg, fx.p_coarse, fx.p_fine)
+    tr2 = Trainer(r2, fx.p_coarse, fx.p_fine, downscale=fx.s)
+    tr2.load_networks(str(tmp_path), 3)
+    got = r2.forward_rays(rays)
+    for k in want:
+        assert torch.equal(got[k], want[k]), k
+    bad = dict(sd_c)
+    bad["sigma.weight"] = torch.zeros(1, 128)
+    K.save_networks(str(tmp_path), 4, bad, sd_f)
+    with pytest.raises(NsrError):
+        tr2.load_networks(str(tmp_path), 4)
+    r.close(); r2.close()
+
+
 def test_training_reduces_the_loss_on_a_fixed_batch():
     from nerf_sr_b200 import Trainer
     cfg = O.RenderConfig(white_bkgd=True)
