@@ -1,6 +1,6 @@
 """GPU diagnostic: detailed per-stage error statistics of the CUDA path against the golden
 fixtures (max abs error, tolerance-violation fraction).  Not a test: prints, never asserts, so
-one gpurun call shows everything.  Usage: python tools/gpu_diag.py [precision ...]"""
+one gpurun call shows everything.  Usage: python tests/diag_parity.py [precision ...]"""
 import os
 import sys
 import time

@@ -116,3 +116,25 @@ def test_pose_paths_match_reference_golden():
     assert np.allclose(centered, z["centered"], rtol=0, atol=1e-13) and np.allclose(avg, z["avg"], rtol=0, atol=1e-14)
     c2, a2 = P.center_poses(centered)              # centring is idempotent: the average of centred poses is the identity frame
     assert np.allclose(a2[:, :3], np.eye(3), atol=1e-12) and np.allclose(a2[:, 3], 0, atol=1e-12)
+
+
+def test_oracle_is_imported_only_by_the_checkers():
+    """oracle/ is test infrastructure: nothing under nerf_sr_b200/ or tools/ may import it, and bench.py only inside its
+    baseline arms (cpu_baseline / --impl reference / the torch-on-GPU reference port)."""
+    pat = re.compile(r"^\s*(from\s+oracle\b|import\s+oracle\b)", re.M)
+    for sub in ("nerf_sr_b200", "tools"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, sub)):
+            for f in files:
+                if f.endswith(".py"):
+                    src = open(os.path.join(dirpath, f)).read()
+                    assert not pat.search(src), os.path.join(dirpath, f)
+    bench = open(os.path.join(ROOT, "bench.py")).read()
+    top_level = [m for m in pat.finditer(bench) if not m.group(0).startswith((" ", "\t"))]
+    assert not top_level, "bench.py imports the oracle at module level"
+    import ast
+    tree = ast.parse(bench)
+    allowed = {"cpu_reference_rate", "torch_gpu_reference_rate", "oracle_train_rate", "run_reference", "run_reference_train"}
+    for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
+        uses = any(isinstance(n, ast.ImportFrom) and (n.module or "").split(".")[0] == "oracle" for n in ast.walk(fn))
+        if uses:
+            assert fn.name in allowed, f"bench.py:{fn.name} imports the oracle outside a baseline arm"

@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 from nerf_sr_b200 import Renderer
-from oracle import nerf_oracle as O
+from nerf_sr_b200 import synthetic as O      # input generation only (seeded rays / kaiming weights)
 
 prec = sys.argv[1] if len(sys.argv) > 1 else "bf16x3"
 dev = torch.device("cuda:0")
