@@ -316,7 +316,7 @@ def run_train(args, rank, world, local):
                                  "from HBM (58 KB per point) and are HBM-bound, profiles/r01_train_*.md"},
             "clocks": sampler.summary(),
         }
-        if world == 1:
+        if world == 1 and args.torch_gpu_port:
             try:
                 line["torch_gpu_reference_port"] = {
                     "value": oracle_train_rate(cfg, pc, pf, rays_cpu, target_cpu, f"cuda:{local}", TRAIN_N_LR, 3), "unit": "rays/s",
@@ -324,13 +324,13 @@ def run_train(args, rank, world, local):
                             "fp32, allow_tf32 off, 2048 rays per step; not the product path"}
             except Exception as e:
                 line["torch_gpu_reference_port"] = {"unavailable": str(e)[:200]}
-            if not args.no_cpu_baseline:
-                ncpu = os.cpu_count() or 1
-                torch.set_num_threads(min(ncpu, 32))
-                rate = oracle_train_rate(cfg, pc, pf, rays_cpu, target_cpu, "cpu", 64, 3)
-                line["cpu_baseline"] = {"value": rate, "unit": "rays/s", "cores": min(ncpu, 32), "host_cores": ncpu, "kind": "port",
-                                        "sample": "256 rays (64 LR pixels) per step, median of 3 full iterations of the oracle port "
-                                                  "(torch CPU autograd + Adam)"}
+        if world == 1 and not args.no_cpu_baseline:
+            ncpu = os.cpu_count() or 1
+            torch.set_num_threads(min(ncpu, 32))
+            rate = oracle_train_rate(cfg, pc, pf, rays_cpu, target_cpu, "cpu", 64, 3)
+            line["cpu_baseline"] = {"value": rate, "unit": "rays/s", "cores": min(ncpu, 32), "host_cores": ncpu, "kind": "port",
+                                    "sample": "256 rays (64 LR pixels) per step, median of 3 full iterations of the oracle port "
+                                              "(torch CPU autograd + Adam)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -345,6 +345,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16x3", choices=["fp32_simt", "bf16x3", "fp16x3", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--torch-gpu-port", action="store_true",
+                    help="also time the reference's PyTorch op sequence (oracle port) on this GPU -- an informational baseline, "
+                         "off by default so that the default arm executes oracle/ only in its cpu_baseline leg")
     ap.add_argument("--workload", default="render", choices=["render", "train"],
                     help="render = the headline metric (BASELINE configs[1]); train = the training iteration (configs[2] shape)")
     args = ap.parse_args()
@@ -487,7 +490,7 @@ def main():
                          "algorithmic_bytes_per_launch": n * (32 + 4 * (N_COARSE + N_IMPORTANCE) + 20)},
             "clocks": sampler.summary(),
         }
-        if world == 1:
+        if world == 1 and args.torch_gpu_port:
             try:
                 line["torch_gpu_reference_port"] = {
                     "value": torch_gpu_reference_rate(cfg, pc, pf, rays), "unit": "rays/s",
