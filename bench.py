@@ -482,7 +482,10 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": "k_tc_pass (fine pass, S=128)" if args.precision != "fp32_simt" else "k_simt_mlp",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "peak_kind": f"{pk_kind} cuBLAS bf16 sustained", "issued_frac": (3 if "x3" in args.precision else 1) * achieved / peak,
+                         "peak_kind": f"{pk_kind} cuBLAS bf16 sustained (each launch runs ~47 ms inside a back-to-back series: the "
+                                      "power-limited regime the sustained figure describes)",
+                         "issued_frac": (3 if "x3" in args.precision else 1) * achieved / peak,
+                         "burst_peak": pk["bf16_tflops"], "frac_vs_burst_peak": achieved / pk["bf16_tflops"],
                          "flop_per_launch": fine_flops, "ms_per_launch": fine_ms,
                          # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu --set full capture
                          # (profiles/r01_k_tc_pass_ncu_full.md); not re-measured per run
