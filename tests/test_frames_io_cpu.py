@@ -92,3 +92,25 @@ def test_png_and_npz_equal_the_reference_savers(tmp_path):
     assert np.array_equal(_decode_cv2(os.path.join(ref_dir, "3-fine-ori.png")), _decode_cv2(os.path.join(my_dir, "3-fine-ori.png")))
     assert np.array_equal(np.load(os.path.join(ref_dir, "3-fine-depth-ori.npz"))["arr_0"],
                           np.load(os.path.join(my_dir, "3-fine-depth-ori.npz"))["arr_0"])
+
+
+def test_png_roundtrip_property():
+    """Arbitrary shapes and contents (hypothesis): what PIL decodes is what was encoded."""
+    import io
+    from hypothesis import given, settings, strategies as st
+    from PIL import Image
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.integers(1, 40), st.integers(1, 40), st.booleans(), st.integers(0, 2 ** 31 - 1), st.sampled_from(["noise", "flat", "ramp"]))
+    def check(h, w, colour, seed, kind):
+        g = np.random.default_rng(seed)
+        shape = (h, w, 3) if colour else (h, w)
+        if kind == "noise":
+            img = g.integers(0, 256, shape, dtype=np.uint8)
+        elif kind == "flat":
+            img = np.full(shape, g.integers(0, 256), dtype=np.uint8)
+        else:
+            img = (np.arange(int(np.prod(shape))) % 256).astype(np.uint8).reshape(shape)
+        got = np.asarray(Image.open(io.BytesIO(F.encode_png(img))))
+        assert got.shape == img.shape and np.array_equal(got, img)
+    check()

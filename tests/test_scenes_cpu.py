@@ -135,3 +135,37 @@ def test_llff_loader_equals_live_reference_dataset(tmp_path):
     assert np.array_equal(sc.poses, ref.poses) and np.array_equal(sc.bounds, ref.bounds) and sc.focal == ref.focal
     lr = np.concatenate([S.load_image_targets(sc.image_paths[i], sc.img_wh, 2, "avg")[0] for i in sc.train_indices()])
     assert np.array_equal(lr, ref.all_rgbs.numpy())
+
+
+def test_colmap_reader_roundtrips_a_written_model(tmp_path):
+    """Every field the loaders use survives write -> read for several camera models, name orders and track lengths."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import make_golden_scenes as M
+    for seed, n_img, n_pts, model in ((1, 3, 5, 0), (2, 9, 40, 1), (3, 4, 0, 4), (4, 2, 17, 10)):
+        g = np.random.default_rng(seed)
+        cams, images, points = M.synth_colmap(g, n_img, n_pts, 64, 48)
+        n_params = S.CAMERA_MODELS[model][1]
+        cams[0].update(model=model, params=list(g.random(n_params)))
+        d = os.path.join(str(tmp_path), f"m{seed}")
+        M.write_colmap(d, cams, images, points)
+        got_c = S.read_cameras_binary(os.path.join(d, "cameras.bin"))
+        assert list(got_c) == [1] and got_c[1].model == S.CAMERA_MODELS[model][0] and np.array_equal(got_c[1].params, cams[0]["params"])
+        got_i = S.read_images_binary(os.path.join(d, "images.bin"))
+        assert [im.name for im in got_i] == [im["name"] for im in images]
+        for a, b in zip(got_i, images):
+            assert a.id == b["id"] and a.camera_id == 1 and np.array_equal(a.qvec, b["q"]) and np.array_equal(a.tvec, b["t"])
+        xyz, tracks = S.read_points3d_binary(os.path.join(d, "points3D.bin"))
+        assert xyz.shape == (n_pts, 3)
+        for k, p in enumerate(points):
+            assert np.array_equal(xyz[k], p["xyz"]) and list(tracks[k]) == [i for i, _ in p["track"]]
+
+
+def test_qvec_to_rotmat_is_a_rotation_for_unit_quaternions():
+    g = np.random.default_rng(0)
+    for _ in range(20):
+        q = g.standard_normal(4)
+        q /= np.linalg.norm(q)
+        R = S.qvec_to_rotmat(q)
+        assert np.allclose(R @ R.T, np.eye(3), atol=1e-12) and np.linalg.det(R) == pytest.approx(1.0, abs=1e-12)
+        assert np.allclose(S.qvec_to_rotmat(-q), R, atol=1e-15)          # q and -q are the same rotation
