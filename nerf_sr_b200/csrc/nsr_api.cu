@@ -418,6 +418,11 @@ extern "C" int nsr_destroy(NsrHandle* h) {
   cudaFree(h->d_jet);
   cudaFree(h->frame_rays);
   if (h->frame_ev) cudaEventDestroy(h->frame_ev);
+  for (int k = 0; k < 2; ++k) {
+    if (h->dw_st[k]) cudaStreamDestroy(h->dw_st[k]);
+    if (h->dw_done[k]) cudaEventDestroy(h->dw_done[k]);
+  }
+  if (h->dw_fork) cudaEventDestroy(h->dw_fork);
   for (int i = 0; i < 2; ++i) {
     if (h->pin_in[i]) cudaFreeHost(h->pin_in[i]);
     if (h->pin_out[i]) cudaFreeHost(h->pin_out[i]);

@@ -74,6 +74,11 @@ struct NsrHandle_ {
   size_t frame_rays_cap = 0;
   cudaEvent_t frame_ev = nullptr;
   std::vector<std::pair<void*, int64_t>> train_stash;   // workspaces filled by nsr_render_train -> n_rays
+  // nsr_backward: the 13 dW GEMMs of a net are independent of each other; they are spread over the caller's stream and
+  // these two library-owned ones (event fork / join around them) so that one launch's tail overlaps the next one's ramp
+  cudaStream_t dw_st[2] = {nullptr, nullptr};
+  cudaEvent_t dw_fork = nullptr;
+  cudaEvent_t dw_done[2] = {nullptr, nullptr};
 };
 
 namespace nsr {

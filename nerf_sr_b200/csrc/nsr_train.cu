@@ -1207,6 +1207,8 @@ struct DwPlanner {
   NsrHandle_* h; cudaStream_t st; long long n_tiles; char* part_base; size_t region; int launch_idx = 0;
   RedArgs red{};
   cudaError_t err = cudaSuccess;
+  cudaStream_t fan[3] = {nullptr, nullptr, nullptr};   // streams the launches rotate over (n_fan = 1: all on st)
+  int n_fan = 1;
   struct JobSpec { const uint8_t* a_img; int a_cpt, blk0, blk1; int row0, rows; long long dst; int ld, col0; long long bias_dst; };
   void launch(const uint8_t* b_img, int b_cpt, int b_chunk0, int nB, int cols, const JobSpec* js, int n_jobs) {
     if (err != cudaSuccess) return;
@@ -1230,7 +1232,7 @@ struct DwPlanner {
       R.row0 = js[j].row0; R.rows = js[j].rows; R.cols = cols; R.ld = js[j].ld; R.col0 = js[j].col0;
       R.dst = js[j].dst; R.bias_dst = js[j].bias_dst;
     }
-    err = launch_dw(h, a, n_jobs, st);
+    err = launch_dw(h, a, n_jobs, n_fan > 1 ? fan[launch_idx % n_fan] : st);
     ++launch_idx;
   }
 };
@@ -1306,6 +1308,20 @@ static int backward_net(NsrHandle_* h, int which, const float* rays, int64_t n, 
   // ---- dW GEMMs ----
   DwPlanner P{h, st, tiles, ws + L.part, L.part_region};
   P.red.grad = grad_flat;
+  // The GEMMs below only read the stash / dZ images and write disjoint partial regions: fork them over three streams
+  // (the caller's and two library-owned ones) and join before the reduction.  Debug flag 4 keeps them on one stream.
+  const bool fan_out = !(h->debug_flags & 4);
+  if (fan_out) {
+    for (int k = 0; k < 2; ++k) {
+      if (!h->dw_st[k]) NSR_TCUDA(h, cudaStreamCreateWithFlags(&h->dw_st[k], cudaStreamNonBlocking));
+      if (!h->dw_done[k]) NSR_TCUDA(h, cudaEventCreateWithFlags(&h->dw_done[k], cudaEventDisableTiming));
+    }
+    if (!h->dw_fork) NSR_TCUDA(h, cudaEventCreateWithFlags(&h->dw_fork, cudaEventDisableTiming));
+    NSR_TCUDA(h, cudaEventRecord(h->dw_fork, st));
+    for (int k = 0; k < 2; ++k) NSR_TCUDA(h, cudaStreamWaitEvent(h->dw_st[k], h->dw_fork, 0));
+    P.fan[0] = st; P.fan[1] = h->dw_st[0]; P.fan[2] = h->dw_st[1];
+    P.n_fan = 3;
+  }
   using JS = DwPlanner::JobSpec;
   const int ld_dir = h->cfg.no_dir ? 256 : 256 + h->rp.ch_dir;
   {   // rgb.0: dW = dHead[:,1:4]^T . dir_act, db
@@ -1341,6 +1357,12 @@ static int backward_net(NsrHandle_* h, int which, const float* rays, int64_t n, 
     } else {
       const JS js[2] = {{dz, 4, 0, 1, 0, 128, off[pw], 256, 0, off[pb]}, {dz, 4, 2, 3, 0, 128, off[pw] + 128 * 256, 256, 0, off[pb] + 128}};
       P.launch(h_layer(Lyr - 1), 4, 0, 4, 256, js, 2);
+    }
+  }
+  if (fan_out) {      // join (also on the error path below: the aux streams must not run past this call's stream order)
+    for (int k = 0; k < 2; ++k) {
+      NSR_TCUDA(h, cudaEventRecord(h->dw_done[k], h->dw_st[k]));
+      NSR_TCUDA(h, cudaStreamWaitEvent(st, h->dw_done[k], 0));
     }
   }
   if (P.err != cudaSuccess) return tfail(h, NSR_ERR_CUDA, std::string("dW launch: ") + cudaGetErrorString(P.err));

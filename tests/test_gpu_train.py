@@ -711,3 +711,32 @@ def test_fused_dx_chain_equals_layerwise_kernels():
     assert torch.isfinite(gc1).all() and torch.isfinite(gf1).all()
     assert e1 < 1e-6 and e2 < 1e-6, (e1, e2)
     r.close()
+
+
+def test_dw_stream_fan_out_is_bit_identical_and_stream_ordered():
+    """nsr_backward spreads a net's independent dW GEMMs over three streams (fork / join by events).  The result must be
+    bit-identical to the single-stream order (debug flag 4) -- same kernels, fixed-order reduction -- also when the call
+    is issued on a non-default stream with work queued right behind it, repeatedly (join really orders the consumers)."""
+    from nerf_sr_b200 import Trainer
+    cfg = O.RenderConfig(noise_std=1.0)
+    pc, pf = O.make_mlp_params(cfg, 21), O.make_mlp_params(cfg, 8)
+    r = _renderer(cfg, pc, pf)
+    tr = Trainer(r, pc, pf, downscale=2)
+    n_lr = 300
+    rays = O.synthetic_rays(n_lr * 4, 9, "llff").to(DEV)
+    tgt = torch.rand(n_lr, 3, generator=torch.Generator().manual_seed(4)).to(DEV)
+    rng = tr.draw_rng(rays.shape[0], torch.Generator(device=DEV).manual_seed(1))
+    r.lib.nsr_debug_set_flags(r._h, 4)
+    gc0, gf0 = tr.forward_backward(rays, tgt, rng)
+    gc0, gf0 = gc0.clone(), gf0.clone()
+    r.lib.nsr_debug_set_flags(r._h, 0)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream(torch.device(DEV))
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(5):
+            gc, gf = tr.forward_backward(rays, tgt, rng)
+            sc, sf = gc.clone(), gf.clone()             # consumers queued immediately behind the join
+            assert torch.equal(sc, gc0) and torch.equal(sf, gf0)
+    side.synchronize()
+    r.close()

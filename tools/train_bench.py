@@ -19,6 +19,7 @@ def main():
     cfg = RenderConfig(noise_std=1.0)
     pc, pf = make_mlp_params(cfg, 21), make_mlp_params(cfg, 8)
     r = Renderer(cfg, dev, precision=prec)
+    r.lib.nsr_debug_set_flags(r._h, int(os.environ.get("NSR_DEBUG_FLAGS", "0")))    # e.g. 4: dW GEMMs on one stream
     tr = Trainer(r, pc, pf, downscale=2)
     rays = synthetic_rays(n_lr * 4, 5, "llff").to(dev)
     tgt = torch.rand(n_lr, 3, device=dev)
