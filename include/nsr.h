@@ -314,7 +314,9 @@ NSR_API int nsr_render_train(NsrHandle* h, const float* rays, int64_t n_rays, in
 /* Replaces: loss_tot.backward() through forward_rays (models/nerf_downX_model.py:390-396): given
  * dL/d(outputs), writes dL/d(parameters) of netCoarse / netFine as flat fp32 buffers (state_dict order,
  * nsr_grad_numel elements each; overwritten, not accumulated).  rays / rng: the ones passed to
- * nsr_render_train (only the sigma noise is read). */
+ * nsr_render_train (only the sigma noise is read).  Stream-ordered on `stream` like every other call; internally the
+ * independent weight-gradient GEMMs of a net are spread over `stream` and two library-owned streams, forked and joined
+ * by events inside the call (nothing runs past the point where work queued on `stream` after this call may start). */
 NSR_API int nsr_backward(NsrHandle* h, const float* rays, int64_t n_rays, int ray_stride, const NsrRng* rng,
                          const NsrOutGrads* g, float* grad_coarse, float* grad_fine, void* train_ws,
                          size_t train_ws_bytes, NsrStream stream);
