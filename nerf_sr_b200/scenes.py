@@ -17,13 +17,15 @@ are produced by ``nsr_generate_rays`` straight into HBM, 48 bytes of pose up per
     load_image_targets            image -> (LR target, grouped HR target) (:311-330; blender :104-121,139-147)
     Scene.train_buffers           the reference's all_rays / all_rgbs / all_rgbs_ori (/ all_rgbs_sr) buffers, on the device
     Scene.frame_rays              one frame's rays (val / test / test_train samples, :473-494)
+    center_crop_lr_indices        the Blender 'train_crop' window (data/blender_downX_dataset.py:123-150)
+    append_viewdir                the vanilla datasets' 11-column rows (data/llff_dataset.py:337-341)
 
 Image decoding and resampling are PIL's (the reference's own third-party dependency for exactly this:
 ``Image.open(..).convert('RGB').resize(.., Image.LANCZOS)``); nothing here touches the oracle.  Results are pinned
 to the reference's dataset classes in tests/golden/scene_*.npz (oracle/make_golden_scenes.py).
 
 Not mirrored (the reference path stays): ``--rand_dir`` (per-dataset random sub-pixel jitter from numpy's global RNG) and
-the 'gan' / 'reg_patch' / 'train_crop' sampling modes."""
+the 'gan' / 'reg_patch' random-patch sampling modes."""
 from __future__ import annotations
 
 import json
@@ -202,21 +204,30 @@ class Scene:
         return renderer.generate_rays(np.asarray(pose, dtype=np.float32), h, w, self.focal, s, self.ndc, self.near, self.far,
                                       use_pixel_centers=self.use_pixel_centers, unified_dir=self.unified_dir)
 
-    def train_buffers(self, renderer, s: int, ds_method: str = "lanc", include_val: bool = False, with_sr: bool = False):
+    def train_buffers(self, renderer, s: int, ds_method: str = "lanc", include_val: bool = False, with_sr: bool = False,
+                      precrop_frac: Optional[float] = None):
         """The reference's training buffers on the renderer's device: ``rays`` [n, s*s, 8] (all_rays), ``rgbs`` [n, 3]
         (all_rgbs, the LR targets), ``rgbs_ori`` [n, s*s, 3] (all_rgbs_ori) and, ``with_sr``, ``rgbs_sr`` [n, s*s, 3]
         (all_rgbs_sr), n = images x (H/s) x (W/s).  Rays are generated on the device per pose; targets are decoded on the
-        host (PIL) and uploaded once."""
+        host (PIL) and uploaded once.  ``precrop_frac``: the Blender 'train_crop' split (``--precrop_frac``,
+        data/blender_downX_dataset.py:123-150): only the LR pixels of the central window are kept."""
         import torch
         w, h = self.img_wh
+        keep = None if precrop_frac is None else center_crop_lr_indices(self.img_wh, s, precrop_frac)
+        keep_dev = None if keep is None else torch.from_numpy(keep).to(renderer.device)
         rays, rgbs, rgbs_ori, rgbs_sr = [], [], [], []
         for i in self.train_indices(include_val):
-            rays.append(self.frame_rays(renderer, self.poses[i], s).view(-1, s * s, 8))
+            r = self.frame_rays(renderer, self.poses[i], s).view(-1, s * s, 8)
             lr, hr = load_image_targets(self.image_paths[i], self.img_wh, s, ds_method, rgba=self.rgba)
+            sr = load_sr_target(self.sr_image_paths[i], self.img_wh, s) if with_sr else None
+            if keep is not None:
+                r, lr, hr = r[keep_dev], lr[keep], hr[keep]
+                sr = None if sr is None else sr[keep]
+            rays.append(r)
             rgbs.append(torch.from_numpy(lr))
             rgbs_ori.append(torch.from_numpy(hr))
             if with_sr:
-                rgbs_sr.append(torch.from_numpy(load_sr_target(self.sr_image_paths[i], self.img_wh, s)))
+                rgbs_sr.append(torch.from_numpy(sr))
         dev = renderer.device
         out = {"rays": torch.cat(rays, 0), "rgbs": torch.cat(rgbs, 0).to(dev), "rgbs_ori": torch.cat(rgbs_ori, 0).to(dev)}
         if with_sr:
@@ -242,6 +253,35 @@ class Scene:
         frames (see nerf_sr_b200.frames.save_test_sweep for the files the reference writes from them)."""
         w, h = self.img_wh
         return renderer.render_path(self.test_poses(split, n_poses), h, w, self.focal, s, self.ndc, self.near, self.far, **kw)
+
+
+def center_crop_lr_indices(img_wh: Sequence[int], s: int, precrop_frac: float = 0.5) -> np.ndarray:
+    """Row-major indices of the LR pixels inside the Blender 'train_crop' window (data/blender_downX_dataset.py:123-131):
+    the reference crops the LR image to rows ``H_lr//2 +- int(H_lr//2 * frac)`` (columns likewise) and the HR image / rays to
+    ``H//2 +- int(H//2 * frac)`` before grouping.  The two windows describe the same pixels only when the HR one is exactly s x
+    the LR one (true for the reference's sizes); anything else would pair rays with the wrong targets, so it is refused.
+    (The reference's own reshape additionally only works for frac = 0.5, where the window is half the frame.)"""
+    w, h = int(img_wh[0]), int(img_wh[1])
+    if w % s or h % s:
+        raise ValueError(f"img_wh {tuple(img_wh)} is not divisible by downscale {s}")
+    w_lr, h_lr = w // s, h // s
+    dh_lr, dw_lr = int(h_lr // 2 * precrop_frac), int(w_lr // 2 * precrop_frac)
+    dh, dw = int(h // 2 * precrop_frac), int(w // 2 * precrop_frac)
+    r0, c0 = h_lr // 2 - dh_lr, w_lr // 2 - dw_lr
+    if (h // 2 - dh, w // 2 - dw, 2 * dh, 2 * dw) != (s * r0, s * c0, s * 2 * dh_lr, s * 2 * dw_lr):
+        raise ValueError(f"precrop window of the {w}x{h} rays is not {s}x the window of the {w_lr}x{h_lr} targets")
+    if dh_lr < 1 or dw_lr < 1:
+        raise ValueError("empty precrop window")
+    rows = np.arange(r0, r0 + 2 * dh_lr)[:, None]
+    cols = np.arange(c0, c0 + 2 * dw_lr)[None, :]
+    return (rows * w_lr + cols).reshape(-1).astype(np.int64)
+
+
+def append_viewdir(rays):
+    """[N, 8] -> [N, 11]: the vanilla datasets' row layout (o, d, near, far, viewdir = d; data/llff_dataset.py:337-341,
+    data/blender_dataset.py), read by ``NeRFModel.forward_rays`` at columns 8:11 (models/nerf_model.py:213)."""
+    import torch
+    return torch.cat([rays, rays[:, 3:6]], 1)
 
 
 def take_batch(buffers, index):

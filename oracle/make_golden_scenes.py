@@ -197,7 +197,7 @@ def build_llff(LLFF) -> dict:
 def build_blender(Blender) -> dict:
     g = np.random.default_rng(21)
     arrays = {}
-    img_wh = (12, 12)
+    img_wh = (16, 16)
     with tempfile.TemporaryDirectory() as root:
         meta = dict(img_wh=list(img_wh), torch=torch.__version__, cases=[])
         for split, n in (("train", 3), ("test", 2)):
@@ -237,6 +237,22 @@ def build_blender(Blender) -> dict:
             arrays[f"{tag}/test1_rays"], arrays[f"{tag}/test1_rgbs"] = ts["rays"].numpy(), ts["rgbs"].numpy()
             arrays[f"{tag}/test1_rgbs_ori"] = ts["rgbs_ori"].numpy()
             meta["cases"].append(dict(tag=tag, downscale=s, ds_method=opt.ds_method, focal=float(ref.focal)))
+        # the 'train_crop' split (--precrop_frac 0.5): central window of targets and rays
+        opt = dataset_opt(dataset_root=root, img_wh=img_wh, downscale=2, ds_method="lanc", precrop_frac=0.5)
+        ref = Blender(opt, "train_crop")
+        mine = S.load_blender_scene(root, "train_crop", img_wh)
+        keep = S.center_crop_lr_indices(img_wh, 2, 0.5)
+        lr, hr, rays = [], [], []
+        for p_img, pose in zip(mine.image_paths, mine.poses):
+            a, b = S.load_image_targets(p_img, img_wh, 2, "lanc", rgba=True)
+            lr.append(a[keep]), hr.append(b[keep])
+            rays.append(O.build_frame_rays(torch.from_numpy(pose).float(), img_wh[1], img_wh[0], mine.focal, 2, 2.0, 6.0,
+                                           False).view(-1, 4, 8)[torch.from_numpy(keep)])
+        assert np.array_equal(np.concatenate(lr), ref.all_rgbs.numpy()) and np.array_equal(np.concatenate(hr), ref.all_rgbs_ori.numpy())
+        assert torch.equal(torch.cat(rays, 0), ref.all_rays)
+        arrays["crop_lanc_s2/all_rays"], arrays["crop_lanc_s2/all_rgbs"] = ref.all_rays.numpy(), ref.all_rgbs.numpy()
+        arrays["crop_lanc_s2/all_rgbs_ori"] = ref.all_rgbs_ori.numpy()
+        meta["crop"] = dict(tag="crop_lanc_s2", downscale=2, ds_method="lanc", precrop_frac=0.5, n_keep=int(keep.size))
     arrays["meta_json"] = np.frombuffer(json.dumps(meta).encode(), np.uint8)
     return arrays
 

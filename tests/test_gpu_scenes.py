@@ -62,6 +62,14 @@ def test_blender_train_buffers_match_reference_dataset(tmp_path):
         te = S.load_blender_scene(str(tmp_path), "test", meta["img_wh"])
         rays = te.frame_rays(r, te.poses[1], s)
         assert torch.allclose(rays.cpu(), torch.from_numpy(z[f"{tag}/test1_rays"]).reshape(-1, 8), rtol=1e-5, atol=1e-5)
+    crop = meta["crop"]                                    # the 'train_crop' split: central window, gathered on the device
+    sc = S.load_blender_scene(str(tmp_path), "train_crop", meta["img_wh"])
+    buf = sc.train_buffers(r, crop["downscale"], crop["ds_method"], precrop_frac=crop["precrop_frac"])
+    ref = torch.from_numpy(z["crop_lanc_s2/all_rays"])
+    assert buf["rays"].shape == ref.shape and torch.allclose(buf["rays"].cpu(), ref, rtol=1e-5, atol=1e-5)
+    assert np.array_equal(buf["rgbs"].cpu().numpy(), z["crop_lanc_s2/all_rgbs"])
+    assert np.array_equal(buf["rgbs_ori"].cpu().numpy(), z["crop_lanc_s2/all_rgbs_ori"])
+    assert S.append_viewdir(buf["rays"].reshape(-1, 8)).shape[1] == 11
     r.close()
 
 

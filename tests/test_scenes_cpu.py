@@ -72,6 +72,32 @@ def test_blender_scene_matches_reference_dataset(tmp_path):
         assert te.test_poses("test") is te.poses and len(te.poses) == 2
     with pytest.raises(ValueError):
         S.load_blender_scene(str(tmp_path), "train", (12, 8))
+    # the 'train_crop' split: central window of targets and (oracle-built) rays == the reference's cropped buffers
+    crop = meta["crop"]
+    sc = S.load_blender_scene(str(tmp_path), "train_crop", meta["img_wh"])
+    keep = S.center_crop_lr_indices(sc.img_wh, crop["downscale"], crop["precrop_frac"])
+    assert keep.size == crop["n_keep"] == 16 and keep[0] == 2 * 8 + 2 and keep[-1] == 5 * 8 + 5
+    lr, hr, rays = [], [], []
+    for p_img, pose in zip(sc.image_paths, sc.poses):
+        a, b = S.load_image_targets(p_img, sc.img_wh, 2, "lanc", rgba=True)
+        lr.append(a[keep]), hr.append(b[keep])
+        rays.append(O.build_frame_rays(torch.from_numpy(pose).float(), 16, 16, sc.focal, 2, 2.0, 6.0, False).view(-1, 4, 8)[torch.from_numpy(keep)])
+    assert np.array_equal(np.concatenate(lr), z["crop_lanc_s2/all_rgbs"]) and np.array_equal(np.concatenate(hr), z["crop_lanc_s2/all_rgbs_ori"])
+    assert torch.allclose(torch.cat(rays, 0), torch.from_numpy(z["crop_lanc_s2/all_rays"]), rtol=1e-6, atol=1e-6)
+
+
+def test_center_crop_window_rules():
+    assert S.center_crop_lr_indices((400, 400), 2, 0.5).size == 100 * 100            # the reference's Blender size
+    assert S.center_crop_lr_indices((800, 800), 4, 0.5).size == 100 * 100
+    with pytest.raises(ValueError, match="not 2x the window"):
+        S.center_crop_lr_indices((12, 12), 2, 0.5)       # LR window 2x2 but HR window 6x6: the reference's buffers would disagree
+    with pytest.raises(ValueError, match="divisible"):
+        S.center_crop_lr_indices((15, 15), 2, 0.5)
+    with pytest.raises(ValueError):
+        S.center_crop_lr_indices((16, 16), 2, 0.0)
+    rays = torch.arange(24, dtype=torch.float32).view(3, 8)
+    r11 = S.append_viewdir(rays)
+    assert r11.shape == (3, 11) and torch.equal(r11[:, :8], rays) and torch.equal(r11[:, 8:], rays[:, 3:6])
 
 
 def test_colmap_parsers_reject_damaged_files(tmp_path):
