@@ -235,6 +235,15 @@ class Scene:
         return out
 
 
+    def ref_buffers(self, renderer, s: int, ref_idx: int = 0):
+        """``--with_ref`` (data/llff_downX_dataset.py:288-293, 331-332, 357-358): the reference view's rays and HR colours,
+        ``ref_rays`` [n_lr, s*s, 8] / ``ref_rgbs`` [n_lr, s*s, 3], from which every training sample draws one LR pixel's
+        sub-pixel group (``take_batch`` with a random index gives the flattened [B*s*s, .] batch ``Trainer`` takes)."""
+        import torch
+        _, hr = load_image_targets(self.image_paths[ref_idx], self.img_wh, s, "lanc", rgba=self.rgba)
+        return {"ref_rays": self.frame_rays(renderer, self.poses[ref_idx], s).view(-1, s * s, 8),
+                "ref_rgbs": torch.from_numpy(hr).to(renderer.device)}
+
     def val_sample(self, renderer, s: int, index: Optional[int] = None):
         """The reference's 'val' / 'test_train' sample of image ``index`` (default: the held-out val image): device
         ``rays`` [H*W, 8], ``rgbs`` [H*W/s^2, 3] (always the s x s mean of the HR image, data/llff_downX_dataset.py:499-507)
