@@ -101,6 +101,14 @@ def test_scene_to_training_step_and_test_frame(tmp_path):
         assert np.isfinite(float(tr.last_terms[:, 5].sum()))
     last = probe()
     assert np.isfinite(first) and last < first, (first, last)
+    # --with_ref: the reference view's sub-pixel groups feed the second forward of the iteration
+    ref = sc.ref_buffers(r, s)
+    assert ref["ref_rays"].shape == (12 * 9, s * s, 8) and ref["ref_rgbs"].shape == (12 * 9, s * s, 3)
+    rb = S.take_batch(ref, torch.arange(0, 10, device=DEV))
+    b = S.take_batch(buf, torch.arange(0, 64, device=DEV))
+    tr.optimize_parameters(b["rays"], b["rgbs"], tr.draw_rng(b["rays"].shape[0], g), target_sr=b["rgbs_sr"], far=sc.far,
+                           ref_rays=rb["ref_rays"], ref_rgbs=rb["ref_rgbs"], ref_rng=tr.draw_rng(rb["ref_rays"].shape[0], g))
+    assert torch.isfinite(tr.last_ref_terms).all() and float(tr.last_ref_terms.sum()) > 0
     w, h = sc.img_wh
     frames = list(sc.render_sweep(r, s, n_poses=2))
     assert len(frames) == 2 and tuple(frames[0]["fine_pred_ori"].shape) == (h, 2 * w, 3)
