@@ -7,6 +7,8 @@ boundaries at multiples of s*s, weights are replicated, results stay rank-local 
 the [P,90] point tensor around every call (models/networks.py:54-69) -- not reproduced.
 Training's only collective is the gradient all-reduce of DDP (models/networks.py:72-86): one flat
 4.77 MB fp32 bucket, mean over ranks -- `allreduce_mean_` below (NCCL on GPUs, gloo in the CPU tests).
+Training batches are sharded the way the reference's DDP loader does it (data/__init__.py:94-113:
+`DistributedSampler(seed=opt.seed)` + per-rank batch = batch_size / n_gpus): `epoch_indices` / `rank_batches` below.
 One process per GPU; torch.distributed is used for plumbing only."""
 from __future__ import annotations
 
@@ -68,3 +70,45 @@ def allreduce_mean_(tensors: Sequence[torch.Tensor], group: Optional[dist.Proces
         n = t.numel()
         t.copy_(flat[off:off + n].view_as(t))
         off += n
+
+
+def epoch_indices(n_samples: int, world_size: int, rank: int, epoch: int = 0, seed: int = 0, shuffle: bool = True,
+                  drop_last: bool = False) -> torch.Tensor:
+    """The sample indices rank `rank` visits in `epoch`: torch.utils.data.DistributedSampler's rule, which the
+    reference's DDP loader uses over the LR-pixel buffers (data/__init__.py:94-101).  One permutation per epoch from
+    `seed + epoch` (identical on every rank), padded by wrapping around to a multiple of the world size (or truncated with
+    `drop_last`), then rank r takes every world_size-th entry starting at r -- disjoint shards that cover the set."""
+    if not 0 <= rank < world_size:
+        raise ValueError(f"rank {rank} outside world of {world_size}")
+    if shuffle:
+        g = torch.Generator()
+        g.manual_seed(seed + epoch)
+        idx = torch.randperm(n_samples, generator=g)
+    else:
+        idx = torch.arange(n_samples)
+    if drop_last and n_samples % world_size:
+        total = (n_samples // world_size) * world_size
+        idx = idx[:total]
+    else:
+        total = ((n_samples + world_size - 1) // world_size) * world_size
+        pad = total - n_samples
+        if pad:
+            reps = (pad + n_samples - 1) // n_samples
+            idx = torch.cat([idx, idx.repeat(reps)[:pad]])
+    return idx[rank:total:world_size]
+
+
+def rank_batches(n_samples: int, batch_size: int, world_size: int, rank: int, epoch: int = 0, seed: int = 0,
+                 shuffle: bool = True, keep_last: bool = False):
+    """Per-rank batches of one epoch: the global `batch_size` must divide by the world size (the reference asserts it,
+    data/__init__.py:94-96); every rank steps through its `epoch_indices` in chunks of batch_size / world_size, dropping the
+    ragged last chunk unless `keep_last` (`--keep_last`).  Yields LongTensors for `scenes.take_batch`."""
+    if batch_size % world_size:
+        raise ValueError(f"batch_size {batch_size} is not divisible by the number of ranks {world_size}")
+    per_rank = batch_size // world_size
+    idx = epoch_indices(n_samples, world_size, rank, epoch, seed, shuffle)
+    for lo in range(0, idx.numel(), per_rank):
+        chunk = idx[lo:lo + per_rank]
+        if chunk.numel() < per_rank and not keep_last:
+            return
+        yield chunk
