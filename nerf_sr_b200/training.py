@@ -291,6 +291,22 @@ for _f in (train_layout, stash_activation, stash_mask, relu_bits, new_train_work
     setattr(Renderer, _f.__name__, _f)
 
 
+def frozen_slices(names: Sequence[str], numels: Sequence[int], fix_layers: Optional[str]) -> List[tuple]:
+    """[lo, hi) ranges of the flat gradient that belong to parameters whose name matches the reference's ``--fix_layers``
+    regular expression (``re.match`` on ``named_parameters()`` names, models/base_model.py:96-103: those parameters get
+    ``requires_grad = False``, so they receive no gradient, stay out of the clipping norm and are skipped by Adam)."""
+    import re
+    out, off = [], 0
+    for n, k in zip(names, numels):
+        if fix_layers and re.match(fix_layers, n):
+            if out and out[-1][1] == off:
+                out[-1] = (out[-1][0], off + int(k))
+            else:
+                out.append((off, off + int(k)))
+        off += int(k)
+    return out
+
+
 def unflatten_grads(flat: torch.Tensor, shapes: Sequence[Sequence[int]]) -> List[torch.Tensor]:
     out, off = [], 0
     for s in shapes:
@@ -371,9 +387,12 @@ class Trainer:
                  lr: float = 5e-4, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8, lambda_coarse_mse: float = 1.0,
                  lambda_fine_mse: float = 1.0, grad_clip_val: float = 0.0, grad_clip_type: str = "norm", downscale: int = 2,
                  group=None, lambda_coarse_var: float = 0.0, lambda_fine_var: float = 0.0, lambda_coarse_depth_var: float = 0.0,
-                 lambda_fine_depth_var: float = 0.0):
+                 lambda_fine_depth_var: float = 0.0, fix_layers: Optional[str] = None):
         """lambda_*_var / lambda_*_depth_var: the reference's ``--lambda_*`` values when ``--use_var_loss`` /
-        ``--use_depth_var_loss`` are given (models/nerf_downX_model.py:107-112), 0 (default) otherwise."""
+        ``--use_depth_var_loss`` are given (models/nerf_downX_model.py:107-112), 0 (default) otherwise.
+        fix_layers: the reference's ``--fix_layers`` regex; matching parameters of both nets are frozen: their gradient
+        slices are zeroed before the all-reduce / clipping / Adam, which leaves parameter and moments untouched (Adam with
+        an identically zero gradient history is the identity) -- the effect of ``requires_grad = False``."""
         self.r = renderer
         dev = renderer.device
         names = state_dict_order(renderer.cfg.D)
@@ -395,6 +414,7 @@ class Trainer:
         self.group = group
         self.last_metrics: Optional[torch.Tensor] = None
         self.last_grads = None
+        self._frozen = frozen_slices(names, [int(renderer.lib.nsr_param_numel(renderer._h, i)) for i in range(len(names))], fix_layers)
         for w in (0, 1):
             renderer.load_params(w, self.params[w])
 
@@ -500,6 +520,9 @@ class Trainer:
         r = self.r
         gc, gf = self.forward_backward(rays, target_lr, rng, target_sr=target_sr, far=far, ref_rays=ref_rays, ref_rgbs=ref_rgbs,
                                        ref_rng=ref_rng)
+        for lo, hi in self._frozen:                    # --fix_layers
+            gc[lo:hi].zero_()
+            gf[lo:hi].zero_()
         if self.group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
                                       and torch.distributed.get_world_size() > 1):
             from .parallel import allreduce_mean_

@@ -95,6 +95,32 @@ def test_sharded_gradients_average_to_the_full_batch():
         assert torch.allclose(avg, gf[k], rtol=1e-4, atol=1e-7 + 1e-4 * float(gf[k].abs().max())), k
 
 
+def test_frozen_slices_follow_the_fix_layers_regex():
+    from nerf_sr_b200.training import frozen_slices
+    from nerf_sr_b200.renderer import state_dict_order
+    cfg = O.RenderConfig()
+    names = state_dict_order(cfg.D)
+    shapes = O.make_mlp_params(cfg, 1)
+    numels = [shapes[n].numel() for n in names]
+    assert frozen_slices(names, numels, None) == [] and frozen_slices(names, numels, "nothing") == []
+    sl = frozen_slices(names, numels, r"xyz_encoding_[1-4]\.")
+    assert sl == [(0, sum(numels[:8]))]                              # layers 1-4 (weight + bias each) are contiguous: merged
+    sl = frozen_slices(names, numels, r"(sigma|rgb)")
+    offs = [sum(numels[:i]) for i in range(len(names) + 1)]
+    want = [(offs[names.index("sigma.weight")], offs[names.index("sigma.bias") + 1]),
+            (offs[names.index("rgb.0.weight")], offs[names.index("rgb.0.bias") + 1])]
+    # sigma.* and rgb.* are adjacent in state_dict order -> one merged range; otherwise two
+    assert sl == ([(want[0][0], want[1][1])] if want[0][1] == want[1][0] else want)
+    # re.match anchors at the start, like the reference: 'encoding' alone matches nothing
+    assert frozen_slices(names, numels, "encoding") == []
+    # the mirror of requires_grad=False: Adam on an identically zero gradient never moves a parameter
+    p, m, v = [torch.randn(5)], [torch.zeros(5)], [torch.zeros(5)]
+    before = p[0].clone()
+    for step in (1, 2, 3):
+        T.adam_step(p, [torch.zeros(5)], m, v, step, 1e-3)
+    assert torch.equal(p[0], before) and not m[0].any() and not v[0].any()
+
+
 def test_training_host_helpers():
     from nerf_sr_b200 import training as TR
     flat = torch.arange(10.)
