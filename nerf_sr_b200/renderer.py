@@ -373,8 +373,8 @@ Renderer.render_path = _render_path
 def patch_model(model, precision: str = "bf16x3"):
     """Rebind ``forward_rays`` of a reference NeRFDownXModel / NeRFModel instance to the CUDA path
     (the one-line hook of INTEGRATION.md).  Keeps self.near / self.far (consumed by depth2im,
-    models/nerf_downX_model.py:422) without the reference's per-chunk device sync: they are read
-    once per distinct ray tensor.  With grad enabled the outputs are autograd-connected to the
+    models/nerf_downX_model.py:422): they are read once per forward_rays call -- and a call can take a
+    whole frame, where the reference reads them (and synchronises) once per 4096-ray chunk.  With grad enabled the outputs are autograd-connected to the
     parameters of netCoarse / netFine through training.RenderFunction (CUDA backward), so the
     reference's loss_tot.backward() / optimizer.step() run unchanged; option sets the backward does
     not cover (precisions other than bf16x3, N_importance == 0, --no_dir) keep the reference path in train mode."""
@@ -391,10 +391,8 @@ def patch_model(model, precision: str = "bf16x3"):
             return reference_forward_rays(rays)
         if not grad_mode:
             renderer.sync_from_modules(self.netCoarse, self.netFine)
-        if getattr(self, "_nsr_nearfar_src", None) is not rays.untyped_storage().data_ptr():
-            nf = rays[0, 6:8].cpu().numpy()
-            self.near, self.far = nf[0:1], nf[1:2]
-            self._nsr_nearfar_src = rays.untyped_storage().data_ptr()
+        nf = rays[0, 6:8].cpu().numpy()            # one 8-byte read per call (the reference: one per 4096-ray chunk, :284)
+        self.near, self.far = nf[0:1], nf[1:2]
         rng = None
         if self.randomized:
             n = rays.shape[0]
