@@ -373,6 +373,23 @@ def module_params_in_order(net) -> List[torch.Tensor]:
     return [named[n] for n in state_dict_order(D)]
 
 
+def trainer_kwargs_from_opt(opt) -> Dict[str, object]:
+    """The ``Trainer`` arguments for a reference option namespace (options/train_options.py:28-55,
+    models/nerf_model.py lambda flags, models/nerf_downX_model.py:107-112): learning rate and Adam beta1, loss weights
+    (the variance weights count only when their ``--use_*`` switch is on), clipping, ``--downscale``, ``--fix_layers``."""
+    g = lambda name, default: getattr(opt, name, default)
+    return dict(
+        lr=g("lr", 5e-4), beta1=g("beta1", 0.9),
+        lambda_coarse_mse=g("lambda_coarse_mse", 1.0), lambda_fine_mse=g("lambda_fine_mse", 1.0),
+        grad_clip_val=g("grad_clip_val", 0.0) or 0.0, grad_clip_type=g("grad_clip_type", "norm"),
+        downscale=g("downscale", 1),
+        lambda_coarse_var=g("lambda_coarse_var", 0.01) if g("use_var_loss", False) else 0.0,
+        lambda_fine_var=g("lambda_fine_var", 0.01) if g("use_var_loss", False) else 0.0,
+        lambda_coarse_depth_var=g("lambda_coarse_depth_var", 0.01) if g("use_depth_var_loss", False) else 0.0,
+        lambda_fine_depth_var=g("lambda_fine_depth_var", 0.01) if g("use_depth_var_loss", False) else 0.0,
+        fix_layers=g("fix_layers", None))
+
+
 # ---- the fused training iteration -----------------------------------------------------------------------
 class Trainer:
     """The reference's ``optimize_parameters`` (models/nerf_downX_model.py:398-408) on the device.

@@ -157,3 +157,31 @@ def test_draw_rng_follows_the_reference_order_and_shapes():
     assert torch.equal(rng["u_coarse"], ref.u_coarse) and torch.equal(rng["noise_fine"], ref.noise_fine)
     r.cfg.noise_std = 0.0
     assert list(tr.draw_rng(4, g)) == ["u_coarse", "u_fine"]
+
+
+def test_trainer_kwargs_from_a_reference_style_opt():
+    opt = types.SimpleNamespace(lr=1e-3, beta1=0.8, lambda_coarse_mse=0.5, lambda_fine_mse=1.0, grad_clip_val=0.05, grad_clip_type="value",
+                                downscale=4, use_var_loss=True, lambda_coarse_var=0.02, lambda_fine_var=0.03, use_depth_var_loss=False,
+                                lambda_coarse_depth_var=0.07, lambda_fine_depth_var=0.07, fix_layers=r"dir_")
+    kw = TR.trainer_kwargs_from_opt(opt)
+    assert kw == dict(lr=1e-3, beta1=0.8, lambda_coarse_mse=0.5, lambda_fine_mse=1.0, grad_clip_val=0.05, grad_clip_type="value", downscale=4,
+                      lambda_coarse_var=0.02, lambda_fine_var=0.03, lambda_coarse_depth_var=0.0, lambda_fine_depth_var=0.0, fix_layers=r"dir_")
+    r = FakeRenderer()
+    tr = TR.Trainer(r, PC, PF, **kw)                                  # every key is a Trainer argument
+    assert tr.lam == (0.5, 1.0) and tr.lam_var == (0.02, 0.03) and tr.lam_dvar == (0.0, 0.0) and tr.s == 4 and tr.clip_type == "value"
+    assert tr._frozen and tr.beta1 == 0.8
+    # defaults of a bare namespace = the reference's defaults with every optional term off
+    kw0 = TR.trainer_kwargs_from_opt(types.SimpleNamespace())
+    assert kw0["lr"] == 5e-4 and kw0["lambda_coarse_var"] == 0.0 and kw0["grad_clip_val"] == 0.0 and kw0["fix_layers"] is None
+
+
+def test_trainer_kwargs_from_the_live_reference_options():
+    from oracle import ref_shim
+    if not ref_shim.reference_available():
+        pytest.skip("reference tree only exists in the build container")
+    _, opt = ref_shim.load_reference_model("nerf_downX", ["--use_var_loss", "--lambda_fine_var", "0.5", "--grad_clip_val", "0.1",
+                                                          "--downscale", "2", "--lr", "2e-4"], train=True)
+    kw = TR.trainer_kwargs_from_opt(opt)
+    assert kw["lr"] == 2e-4 and kw["beta1"] == opt.beta1 and kw["downscale"] == 2 and kw["grad_clip_val"] == 0.1
+    assert kw["lambda_coarse_var"] == opt.lambda_coarse_var == 0.01 and kw["lambda_fine_var"] == 0.5
+    assert kw["lambda_coarse_depth_var"] == 0.0 and kw["lambda_coarse_mse"] == opt.lambda_coarse_mse
