@@ -370,15 +370,20 @@ Renderer.render_test_pose = _render_test_pose
 Renderer.render_path = _render_path
 
 
-def patch_model(model, precision: str = "bf16x3"):
+def patch_model(model, precision: str = "bf16x3", whole_frame: bool = True):
     """Rebind ``forward_rays`` of a reference NeRFDownXModel / NeRFModel instance to the CUDA path
     (the one-line hook of INTEGRATION.md).  Keeps self.near / self.far (consumed by depth2im,
     models/nerf_downX_model.py:422): they are read once per forward_rays call -- and a call can take a
     whole frame, where the reference reads them (and synchronises) once per 4096-ray chunk.  With grad enabled the outputs are autograd-connected to the
     parameters of netCoarse / netFine through training.RenderFunction (CUDA backward), so the
     reference's loss_tot.backward() / optimizer.step() run unchanged; option sets the backward does
-    not cover (precisions other than bf16x3, N_importance == 0, --no_dir) keep the reference path in train mode."""
+    not cover (precisions other than bf16x3, N_importance == 0, --no_dir) keep the reference path in train mode.
+    whole_frame: raise ``opt.ray_chunk`` so that the reference's ``chunk_batch(self.forward_rays, opt.ray_chunk, rays)``
+    (models/nerf_downX_model.py:318, utils/utils.py:130-152) hands a whole frame to one call -- the chunking only exists to
+    bound the [P, 90] intermediates of the PyTorch path, which this path never materialises; the stitched result is the same."""
     import types
+    if whole_frame and hasattr(model.opt, "ray_chunk"):
+        model.opt.ray_chunk = max(int(model.opt.ray_chunk), 1 << 30)
     vo = 8 if type(model).__name__ == "NeRFModel" else 3
     renderer = Renderer(model.opt, device=model.device, precision=precision, viewdir_offset=vo)
     reference_forward_rays = model.forward_rays

@@ -87,3 +87,13 @@ def test_option_sets_without_a_cuda_backward_keep_the_reference_path_under_autog
 def test_vanilla_model_reads_the_view_direction_from_column_8(fake_renderer):
     R.patch_model(_model("NeRFModel"))
     assert fake_renderer[-1] == ("init", "bf16x3", 8)                    # models/nerf_model.py:213: rays[:, 8:11]
+
+
+def test_whole_frame_lifts_the_ray_chunk(fake_renderer):
+    m = _model(ray_chunk=4096)
+    R.patch_model(m)
+    assert m.opt.ray_chunk >= 1 << 30                                   # chunk_batch now makes one call per frame
+    m2 = _model(ray_chunk=4096)
+    R.patch_model(m2, whole_frame=False)
+    assert m2.opt.ray_chunk == 4096
+    R.patch_model(_model())                                              # an opt without ray_chunk is left alone
