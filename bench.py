@@ -308,7 +308,7 @@ def run_train(args, rank, world, local):
                     "d2h_bytes_per_step": 16, "api": "Trainer.optimize_parameters (pinned host batch in, losses out)"},
             "gpu_launches": int(launches),
             "final_loss": [float(x) for x in host_metrics.tolist()],
-            "roofline": {"bound": "hbm", "kernel": "whole step (k_tc_pass stash variant, k_tg_dx, k_tg_dw; see DESIGN.md section 11)",
+            "roofline": {"bound": "hbm", "kernel": "whole step (k_tc_pass stash variant, k_tg_dxchain, k_tg_dw; see DESIGN.md section 11)",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "peak_kind": f"{pk_kind} cuBLAS bf16 sustained", "issued_frac": 3 * achieved / peak,
                          "flop_per_step": flop_step, "traffic": None,
