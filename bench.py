@@ -337,6 +337,41 @@ def run_train(args, rank, world, local):
     r.close()
 
 
+def render_roofline(precision: str, n: int, steps: int, dev_ms: float, fine_ms: float, pk: dict, pk_kind: str) -> dict:
+    """The `roofline` object of the render line (pure: unit-tested on CPU).
+
+    Dominant kernel = k_tc_pass, launched twice per step (coarse pass S=64, fine pass S=128; 99.9 % of the step's device
+    time, profiles/r01_launch_list.md).  `achieved` = the algorithmic FLOP of those two launches (1 186 816 FLOP
+    per point x (64 + 128) points per ray) over the step time measured with CUDA events INSIDE the timed region, so the
+    denominator is the SUSTAINED measured peak (a kernel timed inside a long step).  The fine pass timed ALONE (its own
+    event pair per launch) is reported next to it, against both the sustained and the burst peak.
+    n: rays per step per GPU; dev_ms: device time of all `steps` steps (max over ranks; it also holds the step's two
+    k_box_average launches, < 0.1 %); fine_ms: one fine-pass launch."""
+    step_flops = n * (N_COARSE + N_COARSE + N_IMPORTANCE) * FLOP_PER_POINT
+    achieved = step_flops * steps / (dev_ms / 1e3) / 1e12
+    fine_flops = n * (N_COARSE + N_IMPORTANCE) * FLOP_PER_POINT
+    fine_achieved = fine_flops / (fine_ms / 1e3) / 1e12
+    peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+    split = 3 if "x3" in precision else 1
+    tc = precision != "fp32_simt"
+    return {
+        "bound": "tensor", "kernel": "k_tc_pass (coarse S=64 + fine S=128 launches of one step)" if tc else "k_simt_mlp",
+        "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+        "peak_kind": f"{pk_kind} cuBLAS bf16 sustained (kernel timed inside the timed region of back-to-back steps)",
+        "issued_frac": split * achieved / peak,
+        "flop_per_launch": step_flops / 2, "ms_per_launch": dev_ms / steps / 2,
+        "launches_per_step": 2,
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the two launches of one ncu --set full
+        # capture (profiles/r01_k_tc_pass_ncu_full.md: 37.6 MB coarse, 93.5 MB fine); not re-measured per run
+        "traffic": (37557504 + 93537024) // 2 if tc else None,
+        # per ray: coarse launch 32 B rays in + 20 B results + 512 B fine z-values out; fine launch 32 B + 512 B in + 20 B out
+        "algorithmic_bytes_per_launch": n * (32 + 4 * (N_COARSE + N_IMPORTANCE) + 20),
+        "fine_pass_alone": {"achieved": fine_achieved, "flop_per_launch": fine_flops, "ms_per_launch": fine_ms,
+                            "frac_vs_sustained_peak": fine_achieved / peak, "burst_peak": pk["bf16_tflops"],
+                            "frac_vs_burst_peak": fine_achieved / pk["bf16_tflops"], "traffic": 93537024 if tc else None},
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -465,9 +500,6 @@ def main():
         pk, pk_kind = peaks()
         total_rays = n * world * args.steps
         value = total_rays / (dev_ms / 1e3)
-        fine_flops = n * (N_COARSE + N_IMPORTANCE) * FLOP_PER_POINT
-        achieved = fine_flops / (fine_ms / 1e3) / 1e12
-        peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
         line = {
             "metric": "rays/sec (64+128 samples, 2x SS)", "value": value, "unit": "rays/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
@@ -480,17 +512,7 @@ def main():
             "e2e": {"value": total_rays / (e2e_ms / 1e3), "unit": "rays/s", "h2d_bytes_per_step": n * rays.shape[1] * 4,
                     "d2h_bytes_per_step": (n // (SS * SS)) * 4 * 4, "api": "nsr_render_host (pinned host rays in, LR rgb+depth out)"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "k_tc_pass (fine pass, S=128)" if args.precision != "fp32_simt" else "k_simt_mlp",
-                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "peak_kind": f"{pk_kind} cuBLAS bf16 sustained (each launch runs ~47 ms inside a back-to-back series: the "
-                                      "power-limited regime the sustained figure describes)",
-                         "issued_frac": (3 if "x3" in args.precision else 1) * achieved / peak,
-                         "burst_peak": pk["bf16_tflops"], "frac_vs_burst_peak": achieved / pk["bf16_tflops"],
-                         "flop_per_launch": fine_flops, "ms_per_launch": fine_ms,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu --set full capture
-                         # (profiles/r01_k_tc_pass_ncu_full.md); not re-measured per run
-                         "traffic": 93537024 if args.precision != "fp32_simt" else None,
-                         "algorithmic_bytes_per_launch": n * (32 + 4 * (N_COARSE + N_IMPORTANCE) + 20)},
+            "roofline": render_roofline(args.precision, n, args.steps, dev_ms, fine_ms, pk, pk_kind),
             "clocks": sampler.summary(),
         }
         if world == 1 and args.torch_gpu_port:

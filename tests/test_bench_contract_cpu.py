@@ -49,3 +49,27 @@ def test_product_arm_fails_loudly_without_a_gpu():
     p = _run("--steps", "1", timeout=120)
     assert p.returncode != 0 and p.stdout.strip() == ""
     assert "no GPU visible" in p.stderr and "no CPU fallback" in p.stderr
+
+
+def test_render_roofline_object():
+    """The roofline object of the product arm (pure function): algorithmic FLOP of the step's two k_tc_pass launches over
+    the event-timed step, against the sustained measured peak; the fine pass timed alone next to it."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_module", BENCH)
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    pk = {"bf16_tflops": 1652.1, "bf16_tflops_sustained": 1386.6, "hbm_gbs": 6550.7}
+    r = b.render_roofline("bf16x3", 160000, 10, 708.297, 47.049, pk, "measured")     # the numbers of profiles/r01_bench_bf16x3.json
+    assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and r["peak"] == 1386.6 and r["launches_per_step"] == 2
+    assert r["flop_per_launch"] * 2 == 160000 * 192 * 1186816                          # 227.87 MFLOP per ray (SURVEY.md 8d)
+    assert r["achieved"] == pytest.approx(r["flop_per_launch"] / (r["ms_per_launch"] / 1e3) / 1e12)
+    assert r["achieved"] == pytest.approx(514.74, rel=1e-3) and r["frac"] == pytest.approx(r["achieved"] / 1386.6)
+    assert r["issued_frac"] == pytest.approx(3 * r["frac"]) and r["traffic"] == (37557504 + 93537024) // 2
+    assert r["algorithmic_bytes_per_launch"] == 160000 * 564
+    f = r["fine_pass_alone"]
+    assert f["flop_per_launch"] == 160000 * 128 * 1186816 and f["achieved"] == pytest.approx(516.6, rel=1e-3)
+    assert f["frac_vs_burst_peak"] == pytest.approx(f["achieved"] / 1652.1) and f["frac_vs_sustained_peak"] == pytest.approx(f["achieved"] / 1386.6)
+    s = b.render_roofline("fp32_simt", 160000, 2, 2400.0, 800.0, {"bf16_tflops": 1590.0}, "fallback")   # no sustained figure
+    assert s["kernel"] == "k_simt_mlp" and s["traffic"] is None and s["peak"] == 1590.0 and s["issued_frac"] == pytest.approx(s["frac"])
+    import json
+    json.dumps(r), json.dumps(s)
