@@ -138,3 +138,15 @@ def test_oracle_is_imported_only_by_the_checkers():
         uses = any(isinstance(n, ast.ImportFrom) and (n.module or "").split(".")[0] == "oracle" for n in ast.walk(fn))
         if uses:
             assert fn.name in allowed, f"bench.py:{fn.name} imports the oracle outside a baseline arm"
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    """No silent fallback when libnsr_b200.so is absent: importing the binding with a bad path raises, naming the build step."""
+    import subprocess
+    import sys
+    code = ("import nerf_sr_b200._lib as L\n"
+            "try:\n    L.load()\nexcept ImportError as e:\n    print('IMPORT_ERROR', e)\nelse:\n    print('LOADED')\n")
+    env = dict(os.environ, NSR_LIB_PATH=os.path.join(str(tmp_path), "nowhere", "libnsr_b200.so"))
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, env=env, timeout=300)
+    assert p.returncode == 0, p.stderr[-1500:]
+    assert "IMPORT_ERROR" in p.stdout and "no CPU or PyTorch fallback" in p.stdout and "build" in p.stdout
