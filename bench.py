@@ -296,9 +296,6 @@ def run_train(args, rank, world, local):
         pk, pk_kind = peaks()
         total = n * world * args.steps
         value = total / (dev_ms / 1e3)
-        flop_step = n * (N_COARSE + N_COARSE + N_IMPORTANCE) * FLOP_PER_POINT * 3      # forward + 2x backward
-        achieved = flop_step * args.steps / (dev_ms / 1e3) / 1e12
-        peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
         line = {
             "metric": "training rays/sec (64+128 samples, 2x SS; forward + backward + Adam)", "value": value, "unit": "rays/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
@@ -308,12 +305,7 @@ def run_train(args, rank, world, local):
                     "d2h_bytes_per_step": 16, "api": "Trainer.optimize_parameters (pinned host batch in, losses out)"},
             "gpu_launches": int(launches),
             "final_loss": [float(x) for x in host_metrics.tolist()],
-            "roofline": {"bound": "hbm", "kernel": "whole step (k_tc_pass stash variant, k_tg_dxchain, k_tg_dw; see DESIGN.md section 11)",
-                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "peak_kind": f"{pk_kind} cuBLAS bf16 sustained", "issued_frac": 3 * achieved / peak,
-                         "flop_per_step": flop_step, "traffic": None,
-                         "note": "algorithmic FLOP of the step against the tensor peak; the backward GEMM kernels stream their operands "
-                                 "from HBM (58 KB per point) and are HBM-bound, profiles/r01_train_*.md"},
+            "roofline": train_roofline(n, args.steps, dev_ms, pk, pk_kind),
             "clocks": sampler.summary(),
         }
         if world == 1 and args.torch_gpu_port:
@@ -335,6 +327,37 @@ def run_train(args, rank, world, local):
     if world > 1:
         dist.destroy_process_group()
     r.close()
+
+
+# HBM bytes one point (one sample of one ray) costs in a training iteration, by design (every operand of
+# the backward GEMMs is a bf16 hi/lo "tile image" written once and read once):
+#   forward stash written   enc 256 + h_1..h_8, feat 9 x 1024 + dir 512 + ReLU bits 256 + raw 16 + z 4            = 10 260
+#   k_render_bwd            reads raw 16, z 4, dir 512, noise 4; writes dHead 256, dZ_dir 512, encdir 256, d sigma 4 =  1 564
+#   k_tg_dxchain            reads dZ_dir 512, ReLU bits 256, d sigma 4; writes the nine dZ images 9 x 1024           =  9 988
+#   k_tg_dw (13 GEMMs)      both operands once: rgb 768, dir 1536, dir-enc 768, final+sigma 2304, L8,7,6,4,3,2 6 x 2048,
+#                           L5 2048, L5-enc 1280, L1 1280                                                            = 22 272
+TRAIN_BYTES_PER_POINT = 10260 + 1564 + 9988 + 22272
+
+
+def train_roofline(n: int, steps: int, dev_ms: float, pk: dict, pk_kind: str) -> dict:
+    """The `roofline` object of the training line (pure: unit-tested on CPU).  The iteration is HBM-bound by construction,
+    so the bound is the measured copy bandwidth: achieved = algorithmic bytes of the step (TRAIN_BYTES_PER_POINT x points;
+    the per-CTA dW partials, ~1 GB per step independent of the batch, are NOT counted) / event-timed step time.  The
+    tensor-side view (algorithmic FLOP = 3 x forward) is kept beside it.  n: rays per step per GPU; dev_ms: all steps."""
+    points = n * (N_COARSE + N_COARSE + N_IMPORTANCE)
+    step_bytes = points * TRAIN_BYTES_PER_POINT
+    gbs = step_bytes * steps / (dev_ms / 1e3) / 1e9
+    flop_step = points * FLOP_PER_POINT * 3                     # forward + 2x backward (SURVEY.md 8d)
+    tflops = flop_step * steps / (dev_ms / 1e3) / 1e12
+    tpeak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+    return {
+        "bound": "hbm", "kernel": "whole step (k_tc_pass stash variant, k_render_bwd, k_tg_dxchain, k_tg_dw; DESIGN.md section 11)",
+        "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+        "peak_kind": f"{pk_kind} copy bandwidth", "bytes_per_step": step_bytes, "bytes_per_point": TRAIN_BYTES_PER_POINT,
+        "traffic": None,
+        "tensor": {"achieved": tflops, "peak": tpeak, "unit": "TFLOP/s", "frac": tflops / tpeak, "issued_frac": 3 * tflops / tpeak,
+                   "flop_per_step": flop_step, "peak_kind": f"{pk_kind} cuBLAS bf16 sustained"},
+    }
 
 
 def render_roofline(precision: str, n: int, steps: int, dev_ms: float, fine_ms: float, pk: dict, pk_kind: str) -> dict:

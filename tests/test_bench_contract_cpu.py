@@ -73,3 +73,20 @@ def test_render_roofline_object():
     assert s["kernel"] == "k_simt_mlp" and s["traffic"] is None and s["peak"] == 1590.0 and s["issued_frac"] == pytest.approx(s["frac"])
     import json
     json.dumps(r), json.dumps(s)
+
+
+def test_train_roofline_object():
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("bench_module2", BENCH)
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    assert b.TRAIN_BYTES_PER_POINT == 44084
+    pk = {"bf16_tflops": 1652.1, "bf16_tflops_sustained": 1386.6, "hbm_gbs": 6550.7}
+    r = b.train_roofline(2048, 20, 20 * 4.8617, pk, "measured")                      # profiles/r01_bench_train_1gpu.json
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["peak"] == 6550.7 and r["traffic"] is None
+    assert r["bytes_per_step"] == 2048 * 192 * 44084 and r["achieved"] == pytest.approx(r["bytes_per_step"] / 4.8617e-3 / 1e9)
+    assert r["frac"] == pytest.approx(0.5443, rel=1e-3)
+    t = r["tensor"]
+    assert t["flop_per_step"] == 2048 * 192 * 1186816 * 3 and t["frac"] == pytest.approx(t["achieved"] / 1386.6) and t["issued_frac"] == pytest.approx(3 * t["frac"])
+    json.dumps(r)
