@@ -370,34 +370,122 @@ Renderer.render_test_pose = _render_test_pose
 Renderer.render_path = _render_path
 
 
+class _LazyNearFar:
+    """``self.near`` / ``self.far`` of the reference model (models/nerf_downX_model.py:284: ``near[0].cpu().numpy()``,
+    shape-(1,) numpy arrays read by depth2im :422 and the depth-variance loss :351) without the reference's blocking
+    device read per forward_rays call: the 8 bytes are copied to pinned memory on the render stream and the event is
+    waited on only when somebody reads the attribute."""
+
+    def __init__(self):
+        self._pinned = None
+        self._event = None
+        self._override = {}
+
+    def capture(self, rays: torch.Tensor):
+        self._override.clear()
+        if rays.device.type != "cuda":
+            self._pinned, self._event = rays[0, 6:8].detach().float().clone(), None
+            return
+        if self._pinned is None or not self._pinned.is_pinned():
+            self._pinned = torch.empty(2, dtype=torch.float32).pin_memory()
+        if self._event is not None:
+            self._event.synchronize()          # the previous copy must have landed before the slot is reused
+        self._pinned.copy_(rays[0, 6:8].detach(), non_blocking=True)
+        self._event = torch.cuda.Event()
+        self._event.record(torch.cuda.current_stream(rays.device))
+
+    def get(self, i: int):
+        if i in self._override:
+            return self._override[i]
+        if self._pinned is None:
+            raise AttributeError("near / far are set by the first forward_rays call")
+        if self._event is not None:
+            self._event.synchronize()
+        return self._pinned[i:i + 1].numpy().copy()
+
+    def set(self, i: int, v):
+        self._override[i] = v
+
+
+def _install_lazy_near_far(model) -> _LazyNearFar:
+    """Give ``model`` lazily evaluated ``near`` / ``far`` attributes (a per-instance subclass with two properties; the
+    class name is kept, assignments by other code -- the reference's own forward_rays on the fallback path -- still work)."""
+    lazy = _LazyNearFar()
+    cls = type(model)
+    sub = type(cls.__name__, (cls,), {
+        "near": property(lambda self: lazy.get(0), lambda self, v: lazy.set(0, v)),
+        "far": property(lambda self: lazy.get(1), lambda self, v: lazy.set(1, v)),
+        "__module__": cls.__module__})
+    for k in ("near", "far"):
+        model.__dict__.pop(k, None)
+    model.__class__ = sub
+    return lazy
+
+
+def _ddp_group(net):
+    """The process group of a DistributedDataParallel wrapper (models/networks.py:72-86), else None."""
+    try:
+        from torch.nn.parallel import DistributedDataParallel as DDP
+    except Exception:                           # pragma: no cover
+        return None
+    if isinstance(net, DDP) and torch.distributed.is_initialized() and torch.distributed.get_world_size(net.process_group) > 1:
+        return net.process_group
+    return None
+
+
 def patch_model(model, precision: str = "bf16x3", whole_frame: bool = True):
     """Rebind ``forward_rays`` of a reference NeRFDownXModel / NeRFModel instance to the CUDA path
-    (the one-line hook of INTEGRATION.md).  Keeps self.near / self.far (consumed by depth2im,
-    models/nerf_downX_model.py:422): they are read once per forward_rays call -- and a call can take a
-    whole frame, where the reference reads them (and synchronises) once per 4096-ray chunk.  With grad enabled the outputs are autograd-connected to the
-    parameters of netCoarse / netFine through training.RenderFunction (CUDA backward), so the
-    reference's loss_tot.backward() / optimizer.step() run unchanged; option sets the backward does
-    not cover (precisions other than bf16x3, N_importance == 0, --no_dir) keep the reference path in train mode.
-    whole_frame: raise ``opt.ray_chunk`` so that the reference's ``chunk_batch(self.forward_rays, opt.ray_chunk, rays)``
-    (models/nerf_downX_model.py:318, utils/utils.py:130-152) hands a whole frame to one call -- the chunking only exists to
-    bound the [P, 90] intermediates of the PyTorch path, which this path never materialises; the stitched result is the same."""
+    (the one-line hook of INTEGRATION.md).
+
+    * ``self.near`` / ``self.far`` (depth2im, models/nerf_downX_model.py:422; depth-variance loss :351) keep the reference's
+      value and type but are read lazily (``_LazyNearFar``): no device sync per call, where the reference has one per
+      4096-ray chunk (:284).
+    * With grad enabled the outputs are autograd-connected to the parameters of netCoarse / netFine through
+      training.RenderFunction (CUDA backward), so the reference's ``loss_tot.backward()`` / ``optimizer.step()`` run
+      unchanged.  When the nets are wrapped in DistributedDataParallel (``--accelerator ddp``, models/networks.py:72-86) the
+      backward averages the two flat gradient buffers over the DDP process group -- what DDP's reducer would have done had
+      its ``forward`` been called -- so every rank steps with the same gradients.
+    * Option sets the library refuses (``nsr_create`` -> NSR_ERR_UNSUPPORTED) leave the model untouched (one warning);
+      option sets only the backward does not cover (precisions other than bf16x3, N_importance == 0, --no_dir) keep the
+      reference path in train mode, chunked by the ORIGINAL ``opt.ray_chunk``.
+    * whole_frame: raise ``opt.ray_chunk`` so that the reference's ``chunk_batch(self.forward_rays, opt.ray_chunk, rays)``
+      (models/nerf_downX_model.py:318, utils/utils.py:130-152) hands a whole frame to one call -- the chunking only exists to
+      bound the [P, 90] intermediates of the PyTorch path, which this path never materialises; the stitched result is the same."""
     import types
-    if whole_frame and hasattr(model.opt, "ray_chunk"):
-        model.opt.ray_chunk = max(int(model.opt.ray_chunk), 1 << 30)
+    import warnings
     vo = 8 if type(model).__name__ == "NeRFModel" else 3
-    renderer = Renderer(model.opt, device=model.device, precision=precision, viewdir_offset=vo)
+    try:
+        renderer = Renderer(model.opt, device=model.device, precision=precision, viewdir_offset=vo)
+    except NsrError as e:
+        if e.code != 2:
+            raise
+        warnings.warn(f"nerf_sr_b200.patch_model: option set not supported by the CUDA path ({e}); "
+                      "the reference forward_rays stays in place", RuntimeWarning, stacklevel=2)
+        model._nsr_renderer = None
+        return model
+    reference_chunk = int(getattr(model.opt, "ray_chunk", 4096))
+    if whole_frame and hasattr(model.opt, "ray_chunk"):
+        model.opt.ray_chunk = max(reference_chunk, 1 << 30)
     reference_forward_rays = model.forward_rays
+    lazy = _install_lazy_near_far(model)
 
     train_capable = (precision == "bf16x3" and renderer.n_importance > 0 and not renderer.cfg.no_dir)
 
-    def forward_rays(self, rays):
-        grad_mode = torch.is_grad_enabled() and any(p.requires_grad for p in self.netCoarse.parameters())
-        if grad_mode and not train_capable:
+    def reference_path(rays):
+        # the PyTorch path needs its chunking back (utils/utils.py:130-152) when whole_frame lifted opt.ray_chunk
+        if rays.shape[0] <= reference_chunk:
             return reference_forward_rays(rays)
+        parts = [reference_forward_rays(rays[i:i + reference_chunk]) for i in range(0, rays.shape[0], reference_chunk)]
+        return {k: torch.cat([p[k] for p in parts], 0) for k in parts[0]}
+
+    def forward_rays(self, rays):
+        grad_mode = torch.is_grad_enabled() and any(
+            p.requires_grad for net in (self.netCoarse, self.netFine) for p in net.parameters())
+        if grad_mode and not train_capable:
+            return reference_path(rays)
         if not grad_mode:
             renderer.sync_from_modules(self.netCoarse, self.netFine)
-        nf = rays[0, 6:8].cpu().numpy()            # one 8-byte read per call (the reference: one per 4096-ray chunk, :284)
-        self.near, self.far = nf[0:1], nf[1:2]
+        lazy.capture(rays)                         # 8 bytes, asynchronous (the reference: a blocking read per chunk, :284)
         rng = None
         if self.randomized:
             n = rays.shape[0]
@@ -412,7 +500,10 @@ def patch_model(model, precision: str = "bf16x3", whole_frame: bool = True):
         if grad_mode:
             from . import training as T
             pcs, pfs = T.module_params_in_order(self.netCoarse), T.module_params_in_order(self.netFine)
-            outs = T.RenderFunction.apply(renderer, rays, rng, len(pcs), *pcs, *pfs)
+            group = _ddp_group(self.netCoarse)
+            if group is None:
+                group = _ddp_group(self.netFine)
+            outs = T.RenderFunction.apply(renderer, rays, rng, len(pcs), group, *pcs, *pfs)
             renderer._param_versions = [None, None]          # the images now hold the training weights
             return dict(zip(T.OUT_KEYS, outs))
         return renderer.forward_rays(rays, rng)

@@ -320,20 +320,24 @@ def unflatten_grads(flat: torch.Tensor, shapes: Sequence[Sequence[int]]) -> List
 class RenderFunction(torch.autograd.Function):
     """forward_rays whose outputs are connected to the parameters of netCoarse / netFine.
 
-    apply(renderer, rays, rng_dict_or_None, n_coarse_params, *params) -> the 8 tensors of OUT_KEYS.
+    apply(renderer, rays, rng_dict_or_None, n_coarse_params, ddp_group_or_None, *params) -> the 8 tensors of OUT_KEYS.
     The backward hands dL/d(comp_rgbs, depth, opacity) to the CUDA library and returns per-parameter
-    gradients (views of the two flat buffers)."""
+    gradients (views of the two flat buffers).  ``ddp_group``: the process group of the DistributedDataParallel
+    wrappers around the nets (models/networks.py:72-86).  This function reads the raw parameters, so DDP's own
+    ``forward`` -- the only place its reducer is armed -- never runs; the backward therefore does the reducer's job
+    itself: one all-reduce (mean) of the two flat gradient buffers over that group."""
 
     @staticmethod
-    def forward(ctx, renderer: Renderer, rays: torch.Tensor, rng, n_coarse: int, *params: torch.Tensor):
+    def forward(ctx, renderer: Renderer, rays: torch.Tensor, rng, n_coarse: int, ddp_group, *params: torch.Tensor):
         with torch.no_grad():
             renderer.load_params(0, params[:n_coarse])
             renderer.load_params(1, params[n_coarse:])
-            ws = new_train_workspace(renderer, rays.shape[0])     # private: several forwards may precede their backwards
+            ws = renderer.new_train_workspace(rays.shape[0])      # private: several forwards may precede their backwards
             out = renderer.render_train(rays, rng, ws=ws)
         ctx.renderer, ctx.rays, ctx.rng, ctx.ws = renderer, rays, rng, ws
         ctx.shapes = [tuple(p.shape) for p in params]
         ctx.n_coarse = n_coarse
+        ctx.ddp_group = ddp_group
         ctx.set_materialize_grads(False)
         outs = tuple(out[k] for k in OUT_KEYS)
         ctx.mark_non_differentiable(outs[3], outs[7])
@@ -344,9 +348,12 @@ class RenderFunction(torch.autograd.Function):
         grads = dict(zip(OUT_KEYS, gouts))
         gc, gf = ctx.renderer.backward(ctx.rays, ctx.rng, grads, ws=ctx.ws)
         ctx.ws = None                                             # release the stash
+        if ctx.ddp_group is not None:
+            from .parallel import allreduce_mean_
+            allreduce_mean_([gc, gf], ctx.ddp_group)
         nc = ctx.n_coarse
         pg = unflatten_grads(gc, ctx.shapes[:nc]) + unflatten_grads(gf, ctx.shapes[nc:])
-        return (None, None, None, None, *pg)
+        return (None, None, None, None, None, *pg)
 
 
 def _load_params(self: Renderer, which: int, params: Sequence[torch.Tensor]):

@@ -1,10 +1,13 @@
 """Import the UNMODIFIED reference (cwchenwang/NeRF-SR) in the build container.
 
 TEST INFRASTRUCTURE ONLY (see oracle/nerf_oracle.py header).  /root/reference
-does not exist on the GPU box, so nothing in the ``-m gpu`` tests, ``smoke()``
-or ``bench.py`` may import this module; it is used by ``oracle/make_golden.py``
-and by the CPU-only test that re-pins the oracle when the reference tree is
-present.
+does not exist on the GPU box; ``smoke()`` and ``bench.py`` never import this
+module.  It is used by ``oracle/make_golden*.py``, by the CPU-only test that
+re-pins the oracle when the reference tree is present, and by
+``tests/test_gpu_reference_model.py``, which runs the reference's own model
+class under ``patch_model`` on the B200 from the git-ignored copy that
+``tools/stage_reference.py`` packs into ``baseline/_ref/NeRF-SR.tar.gz`` (the
+tests skip when no archive travelled).
 
 The reference does not import as-is here: numpy 2.x
 dropped ``numpy.lib.shape_base``, ``dominate`` and ``imageio`` are absent, and
@@ -19,7 +22,34 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("NSR_REFERENCE_ROOT", "/root/reference")
+_ARCHIVE = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref", "NeRF-SR.tar.gz")
+
+
+def _resolve_root() -> str:
+    env = os.environ.get("NSR_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isfile("/root/reference/models/nerf_downX_model.py"):
+        return "/root/reference"
+    if os.path.isfile(_ARCHIVE):                      # the GPU box: unpack the staged archive once per process tree
+        import hashlib
+        import tarfile
+        import tempfile
+        tag = hashlib.sha1(open(_ARCHIVE, "rb").read()).hexdigest()[:12]
+        dst = os.path.join(tempfile.gettempdir(), f"nsr_reference_{tag}")
+        if not os.path.isfile(os.path.join(dst, "models", "nerf_downX_model.py")):
+            tmp = tempfile.mkdtemp(prefix="nsr_reference_")
+            with tarfile.open(_ARCHIVE) as tar:
+                tar.extractall(tmp, filter="data")
+            try:
+                os.rename(tmp, dst)
+            except OSError:                           # another process won the race
+                pass
+        return dst
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _resolve_root()
 
 
 def reference_available() -> bool:

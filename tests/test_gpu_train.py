@@ -379,7 +379,7 @@ def test_autograd_function_matches_trainer_and_reference_adam():
     pfs = [torch.nn.Parameter(fx.p_fine[n].clone().to(DEV)) for n in names]
     rng = rng_dict(fx.rng[0])
     rays, tgt = fx.rays.to(DEV), fx.target.to(DEV)
-    outs = dict(zip(OUT_KEYS, RenderFunction.apply(r, rays, rng, len(pcs), *pcs, *pfs)))
+    outs = dict(zip(OUT_KEYS, RenderFunction.apply(r, rays, rng, len(pcs), None, *pcs, *pfs)))
     lr_c = O.box_average(outs["coarse_comp_rgbs"], fx.s)
     lr_f = O.box_average(outs["fine_comp_rgbs"], fx.s)
     loss = torch.nn.functional.mse_loss(lr_c, tgt) + torch.nn.functional.mse_loss(lr_f, tgt)
@@ -635,8 +635,8 @@ def test_two_forwards_in_flight_and_stash_guard():
     def grads(order):
         for p in pcs + pfs:
             p.grad = None
-        oa = dict(zip(OUT_KEYS, RenderFunction.apply(r, ra, None, len(pcs), *pcs, *pfs)))
-        ob = dict(zip(OUT_KEYS, RenderFunction.apply(r, rb, None, len(pcs), *pcs, *pfs)))
+        oa = dict(zip(OUT_KEYS, RenderFunction.apply(r, ra, None, len(pcs), None, *pcs, *pfs)))
+        ob = dict(zip(OUT_KEYS, RenderFunction.apply(r, rb, None, len(pcs), None, *pcs, *pfs)))
         la, lb = oa["fine_comp_rgbs"].square().mean() + oa["coarse_comp_rgbs"].mean(), ob["fine_comp_rgbs"].mean()
         if order == "joint":
             (la + lb).backward()

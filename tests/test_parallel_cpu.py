@@ -106,3 +106,82 @@ def test_rank_batches_follow_the_ddp_loader():
         list(rank_batches(n, 66, 4, 0))
     with pytest.raises(ValueError):
         epoch_indices(10, 2, 2)
+
+
+# ---- patch_model under DistributedDataParallel (the reference's --accelerator ddp, models/networks.py:72-86) ----
+class _TinyNet(torch.nn.Module):
+    """Parameter names of the reference's VanillaMLP with D=1 (models/networks.py:149-180), tiny shapes."""
+
+    def __init__(self):
+        super().__init__()
+        nn = torch.nn
+        self.xyz_encoding_1 = nn.Sequential(nn.Linear(3, 4), nn.ReLU(True))
+        self.xyz_encoding_final = nn.Linear(4, 4)
+        self.dir_encoding = nn.Sequential(nn.Linear(4, 2), nn.ReLU(True))
+        self.sigma = nn.Linear(4, 1)
+        self.rgb = nn.Sequential(nn.Linear(2, 3), nn.Sigmoid())
+
+
+class _RecordingRenderer:
+    """Stand-in for the CUDA renderer: outputs depend on nothing, the 'backward' returns rank-dependent flat gradients."""
+
+    def __init__(self, opt, device=None, precision="bf16x3", viewdir_offset=3):
+        import types
+        self.n_importance, self.cfg = opt.N_importance, types.SimpleNamespace(no_dir=0)
+        self._param_versions = [None, None]
+        self.numel = None
+
+    def load_params(self, which, params):
+        self.numel = sum(p.numel() for p in params)
+
+    def new_train_workspace(self, n):
+        return torch.empty(1)
+
+    def render_train(self, rays, rng, ws=None):
+        n = rays.shape[0]
+        from nerf_sr_b200.training import OUT_KEYS
+        return {k: torch.zeros(n, 3 if "rgbs" in k else (4 if "weights" in k else 1)).squeeze(-1) for k in OUT_KEYS}
+
+    def backward(self, rays, rng, grads, ws=None):
+        r = dist.get_rank()
+        return torch.full((self.numel,), float(r + 1)), torch.full((self.numel,), float(10 * (r + 1)))
+
+
+def _ddp_worker(rank, world, port, q):
+    import types
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    from nerf_sr_b200 import renderer as R
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        R.Renderer = _RecordingRenderer
+        torch.manual_seed(0)
+        m = type("NeRFDownXModel", (), {})()
+        m.opt = types.SimpleNamespace(N_coarse=4, N_importance=4, noise_std=0.0, ray_chunk=4096)
+        m.device, m.randomized = "cpu", False
+        m.netCoarse, m.netFine = DDP(_TinyNet()), DDP(_TinyNet())
+        m.forward_rays = lambda rays: None
+        R.patch_model(m)
+        out = m.forward_rays(torch.rand(6, 8))
+        (out["coarse_comp_rgbs"].sum() + out["fine_comp_rgbs"].sum()).backward()
+        gc = torch.cat([p.grad.reshape(-1) for p in m.netCoarse.parameters()])
+        gf = torch.cat([p.grad.reshape(-1) for p in m.netFine.parameters()])
+        q.put((rank, float(gc.min()), float(gc.max()), float(gf.min()), float(gf.max())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_patch_model_averages_gradients_over_the_ddp_group():
+    """RenderFunction bypasses DDP.forward, so its backward must do the reducer's all-reduce: both ranks
+    end with the MEAN of the rank-local gradients (1.5 / 15), not their own (1 / 10 and 2 / 20)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, 1.5, 1.5, 15.0, 15.0), (1, 1.5, 1.5, 15.0, 15.0)], res

@@ -97,3 +97,70 @@ def test_whole_frame_lifts_the_ray_chunk(fake_renderer):
     R.patch_model(m2, whole_frame=False)
     assert m2.opt.ray_chunk == 4096
     R.patch_model(_model())                                              # an opt without ray_chunk is left alone
+
+
+def test_unsupported_option_set_keeps_the_reference_path(monkeypatch):
+    """SURVEY 8b / INTEGRATION.md: nsr_create -> NSR_ERR_UNSUPPORTED leaves the model untouched, with one warning."""
+    class Refusing:
+        def __init__(self, *a, **k):
+            raise R.NsrError(2, "D=3 is not supported")
+
+    monkeypatch.setattr(R, "Renderer", Refusing)
+    m = _model(ray_chunk=4096)
+    ref = m.forward_rays
+    with pytest.warns(RuntimeWarning, match="reference forward_rays stays"):
+        assert R.patch_model(m) is m
+    assert m.forward_rays is ref and m.opt.ray_chunk == 4096 and m._nsr_renderer is None
+
+    class Broken:
+        def __init__(self, *a, **k):
+            raise R.NsrError(5, "CUDA error")
+
+    monkeypatch.setattr(R, "Renderer", Broken)
+    with pytest.raises(R.NsrError):                                      # anything else is a real failure: not swallowed
+        R.patch_model(_model())
+
+
+def test_near_far_are_lazy_and_assignable(fake_renderer):
+    m = R.patch_model(_model())
+    with pytest.raises(AttributeError):
+        m.near                                                           # nothing rendered yet
+    rays = torch.rand(4, 8)
+    rays[0, 6], rays[0, 7] = 2.0, 6.0
+    with torch.no_grad():
+        m.forward_rays(rays)
+    assert type(m).__name__ == "NeRFDownXModel"                          # the per-instance subclass keeps the class name
+    assert m.near.dtype.name == "float32" and m.far.shape == (1,)
+    m.far = 6.5                                                          # e.g. a harness replacing the array by a scalar
+    assert m.far == 6.5 and float(m.near[0]) == 2.0
+    with torch.no_grad():
+        m.forward_rays(rays)
+    assert float(m.far[0]) == 6.0                                        # a new call refreshes both
+
+
+def test_reference_fallback_in_train_mode_is_chunked_by_the_original_ray_chunk(fake_renderer):
+    m = _model(ray_chunk=3, N_importance=0)                              # coarse-only: no CUDA backward -> reference path
+    seen = []
+
+    def ref(rays):
+        seen.append(rays.shape[0])
+        return {"coarse_comp_rgbs": rays[:, :3] * 2}
+    m.forward_rays = ref
+    R.patch_model(m)
+    assert m.opt.ray_chunk >= 1 << 30
+    rays = torch.rand(8, 8)
+    out = m.forward_rays(rays)                                           # grad enabled, parameters require grad
+    assert seen == [3, 3, 2] and torch.equal(out["coarse_comp_rgbs"], rays[:, :3] * 2)
+
+
+def test_grad_mode_looks_at_both_nets(fake_renderer, monkeypatch):
+    """--fix_layers may freeze all of netCoarse: the fine net still needs the autograd path."""
+    from nerf_sr_b200 import training as T
+    m = R.patch_model(_model())
+    for p in m.netCoarse.parameters():
+        p.requires_grad_(False)
+    called = []
+    monkeypatch.setattr(T, "module_params_in_order", lambda net: list(net.parameters()))
+    monkeypatch.setattr(T.RenderFunction, "apply", staticmethod(lambda *a: called.append(a) or tuple(range(8))))
+    out = m.forward_rays(torch.rand(4, 8))
+    assert called and set(out) == set(T.OUT_KEYS)
