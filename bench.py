@@ -10,6 +10,11 @@ line is printed by rank 0.  `value` times the device-resident path (rays already
 the host-buffer call (pinned rays in, LR rgb+depth out, copies inside the timed region),
 `roofline` the dominant kernel (fine pass) against the measured tensor peak, `cpu_baseline` the
 oracle port (the reference's algorithm, torch CPU ops) on a bounded sample of the same workload.
+The same line carries what BASELINE.json's other configs ask for, measured at every N the driver runs:
+`strong` = ONE frame of configs[4] (762 048 rays) and of configs[3] (640 000 rays, 4x4 SS) held in rank 0's
+pinned host memory, ray-sharded over the N ranks (H2D on rank 0, NCCL scatter, render, box average, NCCL
+gather, D2H on rank 0 -- all inside the timed region); `train` = configs[2] at the reference's DDP shape
+(2048 rays per step IN TOTAL, 2048 / N per rank, gradient all-reduce inside the timed region).
 """
 from __future__ import annotations
 
@@ -41,6 +46,16 @@ def peaks():
         d = json.load(open(p))
         return d, "measured"
     return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0}, "fallback"
+
+
+def ncu_traffic(kernel: str, field: str):
+    """profiles/r02_ncu_traffic.json (written from this round's `ncu --set full` capture by tools/ncu_summary.py):
+    {kernel: {mean_bytes_per_launch, fine_bytes_per_launch, source}}.  None when no capture of this round is committed."""
+    p = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+    try:
+        return json.load(open(p)).get(kernel, {}).get(field)
+    except Exception:
+        return None
 
 
 class ClockSampler(threading.Thread):
@@ -384,15 +399,154 @@ def render_roofline(precision: str, n: int, steps: int, dev_ms: float, fine_ms: 
         "issued_frac": split * achieved / peak,
         "flop_per_launch": step_flops / 2, "ms_per_launch": dev_ms / steps / 2,
         "launches_per_step": 2,
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the two launches of one ncu --set full
-        # capture (profiles/r01_k_tc_pass_ncu_full.md: 37.6 MB coarse, 93.5 MB fine); not re-measured per run
-        "traffic": (37557504 + 93537024) // 2 if tc else None,
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch: NOT measurable inside this process (it needs ncu
+        # replays); taken from this round's committed `ncu --set full` capture when it exists, with its provenance
+        "traffic": ncu_traffic("k_tc_pass", "mean_bytes_per_launch") if tc else None,
+        "traffic_source": ncu_traffic("k_tc_pass", "source") if tc else None,
         # per ray: coarse launch 32 B rays in + 20 B results + 512 B fine z-values out; fine launch 32 B + 512 B in + 20 B out
         "algorithmic_bytes_per_launch": n * (32 + 4 * (N_COARSE + N_IMPORTANCE) + 20),
         "fine_pass_alone": {"achieved": fine_achieved, "flop_per_launch": fine_flops, "ms_per_launch": fine_ms,
                             "frac_vs_sustained_peak": fine_achieved / peak, "burst_peak": pk["bf16_tflops"],
-                            "frac_vs_burst_peak": fine_achieved / pk["bf16_tflops"], "traffic": 93537024 if tc else None},
+                            "frac_vs_burst_peak": fine_achieved / pk["bf16_tflops"],
+                            "traffic": ncu_traffic("k_tc_pass", "fine_bytes_per_launch") if tc else None},
     }
+
+
+
+# ------------------------------------------------------------------------------------------------
+# `strong`: one frame, ray-sharded over the ranks (BASELINE configs[3] / configs[4])
+# ------------------------------------------------------------------------------------------------
+STRONG_FRAMES = {
+    # name: (rays, s, kind, white_bkgd)
+    "C5_llff_1008x756_s2": (1008 * 756, 2, "llff", False),
+    "C4_blender_800x800_s4": (800 * 800, 4, "blender", True),
+}
+
+
+def run_strong(r_by_cfg, rank, world, dev, steps, warmup):
+    """One frame per step, held in rank 0's PINNED HOST memory; per step and inside the timed region: rank 0 uploads the
+    frame (H2D), NCCL scatters contiguous ray shards (boundaries at multiples of s*s: parallel.shard_bounds), every
+    rank renders its shard (no collective in the render) and box-averages it, NCCL gathers LR rgb+depth on rank 0,
+    rank 0 copies the LR frame to pinned host memory (D2H).  Device-timed with CUDA events on every rank's stream,
+    max over ranks.  Returns {frame: {...}} on every rank (identical after the MAX all-reduce)."""
+    import torch.distributed as dist
+    from nerf_sr_b200 import synthetic as S
+    from nerf_sr_b200.parallel import shard_bounds
+    out = {}
+    for name, (n, s, kind, white) in STRONG_FRAMES.items():
+        r = r_by_cfg(white, s)
+        ss = s * s
+        bounds = shard_bounds(n, world, ss)
+        lo, hi = bounds[rank]
+        mx = max(b[1] - b[0] for b in bounds)
+        if rank == 0:
+            frame_pin = S.synthetic_rays(n, 4242, kind).pin_memory()
+            frame_dev = torch.empty(world * mx, 8, device=dev)             # shard-padded layout for the scatter
+            lr_pin = torch.empty(n // ss, 4).pin_memory()
+            gathered = [torch.empty(mx // ss, 4, device=dev) for _ in range(world)]
+        shard = torch.empty(mx, 8, device=dev)
+        lr = torch.empty(mx // ss, 4, device=dev)
+
+        def one_frame():
+            if rank == 0:
+                if world == 1:
+                    shard.copy_(frame_pin, non_blocking=True)
+                else:
+                    for g, (a, b) in enumerate(bounds):                          # H2D straight into the scatter layout
+                        frame_dev[g * mx: g * mx + (b - a)].copy_(frame_pin[a:b], non_blocking=True)
+            if world > 1:
+                dist.scatter(shard, list(frame_dev.view(world, mx, 8).unbind(0)) if rank == 0 else None, src=0)
+            o = r.forward_rays(shard[: hi - lo], want_weights=False)
+            lr[: (hi - lo) // ss, :3] = r.box_average(o["fine_comp_rgbs"], s)
+            lr[: (hi - lo) // ss, 3:] = r.box_average(o["fine_depth"], s)
+            if world > 1:
+                dist.gather(lr, gathered if rank == 0 else None, dst=0)
+                if rank == 0:
+                    for g, (a, b) in enumerate(bounds):
+                        lr_pin[a // ss: b // ss].copy_(gathered[g][: (b - a) // ss], non_blocking=True)
+            elif rank == 0:
+                lr_pin.copy_(lr[: n // ss], non_blocking=True)
+
+        for _ in range(max(1, warmup // 2)):
+            one_frame()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        a.record()
+        for _ in range(steps):
+            one_frame()
+        b.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        t = torch.tensor([a.elapsed_time(b), wall * 1e3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, wall_ms = float(t[0]) / steps, float(t[1]) / steps
+        if rank == 0:
+            assert bool(torch.isfinite(lr_pin).all())
+        out[name] = {"rays": n, "s": s, "rays_per_rank": [b_ - a_ for a_, b_ in bounds], "ms_per_frame": ms,
+                     "wall_ms_per_frame": wall_ms, "value": n / (ms / 1e3), "unit": "rays/s",
+                     "h2d_bytes_per_frame": n * 32, "d2h_bytes_per_frame": (n // ss) * 16,
+                     "nccl_bytes_per_frame": 0 if world == 1 else (world - 1) * (mx * 32 + (mx // ss) * 16),
+                     "timed": "CUDA events on each rank's stream around K whole frames (H2D on rank 0, scatter, render, box "
+                              "average, gather, D2H on rank 0), max over ranks"}
+    return out
+
+
+def run_train_ddp(rank, world, dev, steps, warmup):
+    """BASELINE configs[2] at the reference's DDP shape (data/__init__.py:94-99: per-rank batch = batch_size / n_gpus):
+    512 LR pixels x 2x2 SS = 2048 rays per step IN TOTAL, 2048 / N per rank; forward (train mode) + LR loss + backward +
+    gradient all-reduce (mean over ranks) + Adam + re-pack, device-timed with the all-reduce inside the region."""
+    import torch.distributed as dist
+    from nerf_sr_b200 import Renderer, Trainer
+    from nerf_sr_b200.parallel import shard_bounds
+    cfg, pc, pf, rays_cpu, target_cpu = train_inputs(0)                   # every rank derives the same global batch
+    lo, hi = shard_bounds(rays_cpu.shape[0], world, SS * SS)[rank]
+    rays, target = rays_cpu[lo:hi].to(dev), target_cpu[lo // (SS * SS): hi // (SS * SS)].to(dev)
+    r = Renderer(cfg, dev, precision="bf16x3")
+    tr = Trainer(r, pc, pf, downscale=SS)
+    gen = torch.Generator(device=dev).manual_seed(rank)
+    n = rays.shape[0]
+    for _ in range(max(3, warmup)):
+        tr.optimize_parameters(rays, target, tr.draw_rng(n, gen))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = r.launch_count
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        tr.optimize_parameters(rays, target, tr.draw_rng(n, gen))
+    b.record()
+    torch.cuda.synchronize()
+    launches = r.launch_count - launches0
+    # the collective alone, same buffers, same stream (event-timed): what it adds to the step
+    ar_ms = 0.0
+    if world > 1:
+        gc, gf = tr.last_grads
+        c, d = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        c.record()
+        for _ in range(20):
+            tr.allreduce_grads(gc, gf)
+        d.record()
+        torch.cuda.synchronize()
+        ar_ms = c.elapsed_time(d) / 20
+    t = torch.tensor([a.elapsed_time(b) / steps, ar_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ar_ms = float(t[0]), float(t[1])
+    res = {"rays_per_step_total": rays_cpu.shape[0], "rays_per_step_per_gpu": n, "ms_per_step": ms,
+           "value": rays_cpu.shape[0] / (ms / 1e3), "unit": "rays/s", "scaling": "strong",
+           "allreduce_ms": ar_ms, "allreduce_bytes": 2 * int(r.lib.nsr_grad_numel(r._h)) * 4,
+           "allreduce_impl": tr.allreduce_impl if world > 1 else None,
+           "gpu_launches_per_step": launches / steps,
+           "final_loss": [float(x) for x in tr.last_metrics.tolist()],
+           "timed": "CUDA events around K optimize_parameters calls (gradient all-reduce inside), max over ranks"}
+    r.close()
+    return res
 
 
 def main():
@@ -403,9 +557,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16x3", choices=["fp32_simt", "bf16x3", "fp16x3", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--torch-gpu-port", action="store_true",
-                    help="also time the reference's PyTorch op sequence (oracle port) on this GPU -- an informational baseline, "
-                         "off by default so that the default arm executes oracle/ only in its cpu_baseline leg")
+    ap.add_argument("--no-torch-gpu-port", dest="torch_gpu_port", action="store_false",
+                    help="skip timing the reference's PyTorch op sequence (oracle port, fp32, TF32 off) on this GPU -- the "
+                         "same-GPU 'before' number (BASELINE.md section 3), measured by default on rank 0 at N=1 (~0.3 s)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the `strong` / `train` / `e2e_full` / weights-variant sub-objects")
+    ap.set_defaults(torch_gpu_port=True)
     ap.add_argument("--workload", default="render", choices=["render", "train"],
                     help="render = the headline metric (BASELINE configs[1]); train = the training iteration (configs[2] shape)")
     args = ap.parse_args()
@@ -469,9 +625,43 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed(fn, steps, flush_l2=True):
+        """K calls of fn, each between its own CUDA event pair on the launching stream (L2 flushed in between)."""
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        torch.cuda.synchronize()
+        for s_, e_ in ev:
+            if flush_l2:
+                flush.fill_(1)
+            s_.record()
+            fn()
+            e_.record()
+        torch.cuda.synchronize()
+        return sum(s_.elapsed_time(e_) for s_, e_ in ev) / steps
+
+    # what the reference's test() consumes per frame (models/nerf_downX_model.py:326-353,418-450): HR `_ori` rgb + depth and
+    # their LR box averages, for the coarse and the fine net -- through the public Renderer API, pinned host buffers
+    n_lr = n // (SS * SS)
+    full_pin = {f"{net}_{k}": torch.empty(rows, c).pin_memory() for net in ("coarse", "fine")
+                for k, rows, c in (("rgb_ori", n, 3), ("depth_ori", n, 1), ("rgb", n_lr, 3), ("depth", n_lr, 1))}
+    rays_stage = torch.empty_like(rays)
+
+    def step_e2e_full():
+        rays_stage.copy_(rays_pinned, non_blocking=True)
+        o = r.forward_rays(rays_stage, want_weights=False)
+        for net in ("coarse", "fine"):
+            rgb, dep = o[f"{net}_comp_rgbs"], o[f"{net}_depth"]
+            full_pin[f"{net}_rgb_ori"].copy_(rgb, non_blocking=True)
+            full_pin[f"{net}_depth_ori"].copy_(dep.view(-1, 1), non_blocking=True)
+            full_pin[f"{net}_rgb"].copy_(r.box_average(rgb, SS), non_blocking=True)
+            full_pin[f"{net}_depth"].copy_(r.box_average(dep, SS), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
     for _ in range(args.warmup):
         step_device()
         r.render_frame_host(rays_pinned, SS)
+    if not args.no_extras:
+        step_e2e_full()
+        r.forward_rays(rays, want_weights=True)
     torch.cuda.synchronize()
 
     # ---- device-resident throughput -----------------------------------------------------
@@ -504,6 +694,8 @@ def main():
     torch.cuda.synchronize()
     fine_ms = sum(s.elapsed_time(e) for s, e in kev) / args.steps
 
+    sm_mhz_in_kernel = r.kernel_clock_mhz()      # clock64 / globaltimer stamps of the last fine-pass launch (CTA 0)
+
     # ---- end to end through the host-buffer call -----------------------------------------
     barrier()
     t0 = time.perf_counter()
@@ -511,13 +703,43 @@ def main():
         rgb, depth = r.render_frame_host(rays_pinned, SS)
     barrier()
     e2e_s = time.perf_counter() - t0
+
+    # ---- variants: the full 8-key dict (weights maps included), and the e2e call returning what test() consumes ----
+    ww_ms = full_s = 0.0
+    if not args.no_extras:
+        ww_ms = timed(lambda: r.forward_rays(rays, want_weights=True), args.steps)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e_full()
+        barrier()
+        full_s = time.perf_counter() - t0
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3, fine_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms, e2e_s * 1e3, fine_ms, ww_ms, full_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, fine_ms = (float(x) for x in t.tolist())
+    dev_ms, e2e_ms, fine_ms, ww_ms, full_ms = (float(x) for x in t.tolist())
+
+    # ---- BASELINE configs[3] / [4] (one frame sharded over the ranks) and configs[2] at the DDP shape ----
+    strong = train_ddp = None
+    if not args.no_extras and args.precision == "bf16x3":
+        cache = {}
+
+        def r_by_cfg(white, s):
+            from nerf_sr_b200 import synthetic as S
+            if (white, s) not in cache:
+                c2 = S.RenderConfig(white_bkgd=white, N_coarse=N_COARSE, N_importance=N_IMPORTANCE, downscale=s)
+                rr = Renderer(c2, dev, precision=args.precision)
+                rr.load_state_dict(0, pc)
+                rr.load_state_dict(1, pf)
+                cache[(white, s)] = rr
+            return cache[(white, s)]
+        strong = run_strong(r_by_cfg, rank, world, dev, max(2, min(args.steps, 5)), args.warmup)
+        for rr in cache.values():
+            rr.close()
+        train_ddp = run_train_ddp(rank, world, dev, max(10, args.steps), args.warmup)
 
     if rank == 0:
         pk, pk_kind = peaks()
@@ -536,8 +758,24 @@ def main():
                     "d2h_bytes_per_step": (n // (SS * SS)) * 4 * 4, "api": "nsr_render_host (pinned host rays in, LR rgb+depth out)"},
             "gpu_launches": int(launches),
             "roofline": render_roofline(args.precision, n, args.steps, dev_ms, fine_ms, pk, pk_kind),
-            "clocks": sampler.summary(),
+            "clocks": {**sampler.summary(), "sm_mhz_in_kernel": sm_mhz_in_kernel,
+                       "sm_mhz_in_kernel_how": "clock64 / globaltimer deltas stamped by CTA 0 of the last fine-pass launch"},
         }
+        if not args.no_extras:
+            line["with_weights"] = {
+                "value": n * world / (ww_ms / 1e3), "unit": "rays/s", "ms_per_step": ww_ms,
+                "what": "forward_rays(want_weights=True): the reference's full 8-key dict incl. coarse_weights [N,64] and "
+                        "fine_weights [N,128] (768 more bytes written per ray); no box average",
+                "bytes_written_per_step": n * (2 * 20 + 4 * (N_COARSE + N_COARSE + N_IMPORTANCE))}
+            line["e2e_full"] = {
+                "value": total_rays / (full_ms / 1e3), "unit": "rays/s", "h2d_bytes_per_step": n * rays.shape[1] * 4,
+                "d2h_bytes_per_step": 2 * (n * 16 + n_lr * 16),
+                "api": "Renderer.forward_rays + box_average, pinned host rays in; HR `_ori` rgb+depth and LR rgb+depth of the "
+                       "coarse AND the fine net out (what the reference's test() consumes, models/nerf_downX_model.py:326-353)"}
+        if strong is not None:
+            line["strong"] = strong
+        if train_ddp is not None:
+            line["train"] = train_ddp
         if world == 1 and args.torch_gpu_port:
             try:
                 line["torch_gpu_reference_port"] = {
@@ -551,7 +789,10 @@ def main():
             line["cpu_baseline"] = {"value": rate, "unit": "rays/s", "cores": getattr(cpu_reference_rate, "threads", os.cpu_count() or 1),
                                     "host_cores": os.cpu_count() or 1, "kind": "port",
                                     "sample": "4096 rays of the frame (one ray_chunk), median of 3, oracle port of the reference "
-                                              "(torch CPU), thread count calibrated over {all, 1/2, 32, 16}"}
+                                              "(torch CPU), thread count calibrated over {all, 1/2, 32, 16}",
+                                    "note": "kind=port: oracle/nerf_oracle.py, a restatement pinned BIT-EQUAL to the unmodified "
+                                            "reference in the build container (oracle/make_golden*.py); the reference tree itself "
+                                            "is not a bench dependency"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -393,6 +393,34 @@ NSR_API int nsr_debug_set_trace(NsrHandle* h, long long* device_buffer);
 /* Debug: timing-experiment switches (bit 0: weight producer skips its bulk copies -> WRONG results). */
 NSR_API int nsr_debug_set_flags(NsrHandle* h, int flags);
 
+/*
+ * Data-parallel gradient all-reduce (the only collective of the path).  Replaces the bucketed NCCL
+ * all-reduce + division by the world size that DistributedDataParallel performs during loss_tot.backward()
+ * (models/networks.py:72-86; per-rank batch = batch_size / n_gpus, data/__init__.py:94-99).
+ * One process per GPU.  Every rank creates a comm of the same size; its buffer (`nsr_comm_buffer`, device memory owned
+ * by the comm) is where nsr_backward should write the flat gradients (grad_coarse = buffer, grad_fine = buffer + numel).
+ * Ranks exchange the 64-byte handles of nsr_comm_export by any means (torch.distributed.all_gather_object in
+ * nerf_sr_b200/parallel.py) and map each other's buffers with nsr_comm_connect_ipc (CUDA IPC, NVLink peer access).
+ * nsr_comm_allreduce_mean is then ONE kernel on `stream`: in place, mean over ranks, summed in fixed rank order, so the
+ * result is bit-identical on every rank.  Every rank must call it the same number of times (it is a collective); it
+ * synchronises with the peers on the device only, never with the host.
+ * nsr_comm_connect_ptrs wires comms that live in ONE process (several handles on one or more devices: tests).
+ */
+typedef struct NsrComm_ NsrComm;   /* opaque */
+NSR_API int nsr_comm_create(NsrHandle* h, int rank, int world, int64_t n_floats, NsrComm** out);
+NSR_API int nsr_comm_destroy(NsrComm* c);
+NSR_API float* nsr_comm_buffer(NsrComm* c);                 /* device pointer, >= n_floats floats, zero padded */
+NSR_API int64_t nsr_comm_buffer_floats(const NsrComm* c);   /* padded length */
+NSR_API int nsr_comm_export(NsrComm* c, void* handle_out64);
+NSR_API int nsr_comm_connect_ipc(NsrComm* c, const void* handles64, int n_handles);   /* world x 64 bytes, rank order */
+NSR_API int nsr_comm_connect_ptrs(NsrComm* c, void* const* peer_buffers, int n);      /* same-process peers */
+NSR_API int nsr_comm_allreduce_mean(NsrComm* c, NsrStream stream);
+
+/* Debug: (clock64, globaltimer ns) stamped by CTA 0 at entry and at exit of the most recent fused-pass kernel
+ * (k_tc_pass) of this handle -> out4_host = {clk0, ns0, clk1, ns1}; (clk1-clk0)/(ns1-ns0) GHz is the SM clock the
+ * kernel actually ran at.  Synchronises `stream` (a measurement aid, not part of the render path). */
+NSR_API int nsr_debug_kernel_clock(NsrHandle* h, int64_t* out4_host, NsrStream stream);
+
 /* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 NSR_API int64_t nsr_launch_count(const NsrHandle* h);
 

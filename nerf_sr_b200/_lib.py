@@ -109,6 +109,16 @@ SIGNATURES = {
     "nsr_debug_set_trace": (C.c_int, [C.c_void_p, C.c_void_p]),
     "nsr_debug_set_flags": (C.c_int, [C.c_void_p, C.c_int]),
     "nsr_launch_count": (C.c_int64, [C.c_void_p]),
+    # data-parallel gradient all-reduce over peer-mapped memory (nsr_comm.cu)
+    "nsr_comm_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_void_p)]),
+    "nsr_comm_destroy": (C.c_int, [C.c_void_p]),
+    "nsr_comm_buffer": (C.c_void_p, [C.c_void_p]),
+    "nsr_comm_buffer_floats": (C.c_int64, [C.c_void_p]),
+    "nsr_comm_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "nsr_comm_connect_ipc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "nsr_comm_connect_ptrs": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int]),
+    "nsr_comm_allreduce_mean": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "nsr_debug_kernel_clock": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
 }
 
 _lib = None

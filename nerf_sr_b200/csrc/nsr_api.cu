@@ -384,6 +384,9 @@ extern "C" int nsr_create(const NsrConfig* cfg, NsrHandle** out_handle) {
   if (e == cudaSuccess) e = cudaMalloc(&h->d_tables, sizeof(SampleTables));
   if (e == cudaSuccess) e = cudaMalloc(&h->d_partials, 1024 * sizeof(double));
   if (e == cudaSuccess) e = cudaMemcpy(h->d_tables, &T, sizeof(T), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_clk, 4 * sizeof(long long));
+  if (e == cudaSuccess) e = cudaMemset(h->d_clk, 0, 4 * sizeof(long long));
+  if (e == cudaSuccess && c.precision != NSR_PREC_FP32_SIMT) e = tc_init(h);
   if (e == cudaSuccess) e = cudaMalloc(&h->d_jet, sizeof(kJetLut));
   if (e == cudaSuccess) e = cudaMemcpy(h->d_jet, kJetLut, sizeof(kJetLut), cudaMemcpyHostToDevice);
   const size_t blob = simt_blob_floats(h);
@@ -416,8 +419,10 @@ extern "C" int nsr_destroy(NsrHandle* h) {
   cudaFree(h->d_tables);
   cudaFree(h->d_partials);
   cudaFree(h->d_jet);
+  cudaFree(h->d_clk);
   cudaFree(h->frame_rays);
   if (h->frame_ev) cudaEventDestroy(h->frame_ev);
+  for (int w = 0; w < 2; ++w) if (h->pack_ev[w]) cudaEventDestroy(h->pack_ev[w]);
   for (int k = 0; k < 2; ++k) {
     if (h->dw_st[k]) cudaStreamDestroy(h->dw_st[k]);
     if (h->dw_done[k]) cudaEventDestroy(h->dw_done[k]);
@@ -450,6 +455,15 @@ extern "C" int nsr_debug_set_flags(NsrHandle* h, int flags) {
   return NSR_OK;
 }
 extern "C" int64_t nsr_launch_count(const NsrHandle* h) { return h ? h->launches.load() : 0; }
+extern "C" int nsr_debug_kernel_clock(NsrHandle* h, int64_t* out4_host, NsrStream stream) {
+  if (!h || !out4_host) return NSR_ERR_INVALID_ARG;
+  NSR_CUDA(h, cudaSetDevice(h->cfg.device));
+  NSR_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream));
+  long long v[4];
+  NSR_CUDA(h, cudaMemcpy(v, h->d_clk, sizeof(v), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 4; ++i) out4_host[i] = (int64_t)v[i];
+  return NSR_OK;
+}
 
 extern "C" int nsr_pack_weights(NsrHandle* h, int which, const float* const* param_ptrs, int n_params,
                                 NsrStream stream) {
@@ -470,6 +484,11 @@ extern "C" int nsr_pack_weights(NsrHandle* h, int which, const float* const* par
     NSR_CUDA(h, train_pack_wt(h, which, reinterpret_cast<const float* const*>(h->net[which].tc_consts + 8192), st));
   }
   h->net[which].packed = true;
+  // The host-buffer pipeline (nsr_render_host / nsr_render_pose_host) runs on library-owned non-blocking streams: order it
+  // behind this pack (and behind whatever the caller enqueued on `stream` before it, e.g. the upload of the tensors)
+  if (!h->pack_ev[which]) NSR_CUDA(h, cudaEventCreateWithFlags(&h->pack_ev[which], cudaEventDisableTiming));
+  NSR_CUDA(h, cudaEventRecord(h->pack_ev[which], st));
+  h->pack_pending[which] = true;
   return NSR_OK;
 }
 
@@ -770,6 +789,17 @@ static int ensure_host_state(NsrHandle_* h, int64_t chunk, int stride) {
   return NSR_OK;
 }
 
+// nsr_pack_weights is asynchronous on the CALLER's stream; the frame pipeline below runs on hs[0..1].  Make both wait for the
+// most recent pack of each net (stream-ordered, no host sync).
+static int wait_for_packs(NsrHandle_* h) {
+  for (int w = 0; w < 2; ++w) {
+    if (!h->pack_pending[w]) continue;
+    for (int i = 0; i < 2; ++i) NSR_CUDA(h, cudaStreamWaitEvent(h->hs[i], h->pack_ev[w], 0));
+    h->pack_pending[w] = false;
+  }
+  return NSR_OK;
+}
+
 // Chunked, double-buffered frame render.  Rays come either from host memory (staged through pinned
 // buffers, H2D inside the pipeline) or from a device buffer the caller filled on stream hs[0]
 // (rays_dev != null: nsr_render_pose_host generates them on the device).
@@ -781,6 +811,8 @@ static int render_frame_pipeline(NsrHandle* h, const float* rays_host, const flo
   chunk -= chunk % ss;
   if (chunk > n_rays) chunk = n_rays;
   rc = ensure_host_state(h, chunk, ray_stride);
+  if (rc) return rc;
+  rc = wait_for_packs(h);
   if (rc) return rc;
   const bool fine = h->cfg.n_importance > 0;
   const int64_t n_chunks = (n_rays + chunk - 1) / chunk;
@@ -862,6 +894,8 @@ extern "C" int nsr_render_pose_host(NsrHandle* h, const float* c2w_host, int H, 
     NSR_CUDA(h, cudaMalloc(&h->frame_rays, (size_t)n_rays * 8 * sizeof(float)));
     h->frame_rays_cap = (size_t)n_rays * 8;
   }
+  rc = wait_for_packs(h);
+  if (rc) return rc;
   rc = nsr_generate_rays(h, c2w_host, H, W, focal, s, ndc, near_plane, far_plane, h->frame_rays, h->hs[0]);
   if (rc) return rc;
   if (!h->frame_ev) NSR_CUDA(h, cudaEventCreateWithFlags(&h->frame_ev, cudaEventDisableTiming));

@@ -54,6 +54,7 @@ struct NsrHandle_ {
   nsr::SampleTables h_tables;
   double* d_partials = nullptr;     // [1024] block partial sums for nsr_lr_metrics
   uint32_t* d_jet = nullptr;        // [256] packed COLORMAP_JET entries (nsr_assemble_frame)
+  long long* d_clk = nullptr;       // [4] (clock64, globaltimer) at entry / exit of CTA 0 of the last k_tc_pass launch
   nsr::NetImages net[2];
   std::vector<int64_t> param_numel;
   int sm_count = 0;
@@ -73,6 +74,9 @@ struct NsrHandle_ {
   float* frame_rays = nullptr;      // nsr_render_pose_host: device rays of one frame
   size_t frame_rays_cap = 0;
   cudaEvent_t frame_ev = nullptr;
+  // nsr_pack_weights records an event on the caller's stream; the host-buffer pipeline's own streams wait for it
+  cudaEvent_t pack_ev[2] = {nullptr, nullptr};
+  bool pack_pending[2] = {false, false};
   std::vector<std::pair<void*, int64_t>> train_stash;   // workspaces filled by nsr_render_train -> n_rays
   // nsr_backward: the 13 dW GEMMs of a net are independent of each other; they are spread over the caller's stream and
   // these two library-owned ones (event fork / join around them) so that one launch's tail overlaps the next one's ramp
@@ -103,6 +107,7 @@ constexpr int kcTotal = 3080 + 128 * 28;
 bool tc_supported(const NsrConfig& cfg, std::string* why);
 size_t tc_image_bytes(const NsrHandle_* h);
 cudaError_t tc_pack(NsrHandle_* h, int which, const float* const* params, cudaStream_t st);
+cudaError_t tc_init(NsrHandle_* h);     // per-function attributes (dynamic shared memory opt-in), once per handle
 // Fused pass: sampling/encoding -> MLP -> compositing (-> resampling).
 //   z_in   : [N,S] or null (coarse pass computes z itself; u_jitter optional)
 //   z_next : [N, S+n_imp] or null; written when do_resample

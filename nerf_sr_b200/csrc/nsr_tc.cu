@@ -235,6 +235,9 @@ struct TcKernelArgs {
   uint8_t* stash_dir;   // [n_tiles][2][32 KB]         dir layer output (post-ReLU, 128 wide)
   uint32_t* stash_mask; // [8][n_tiles][128][8]        ReLU masks of h_1..h_8, one bit per activation
   float* z_out;         // [N,S] z-values actually used (coarse pass computes them on the fly), or null
+  // SM-clock probe: CTA 0 stamps (clock64, globaltimer ns) at kernel entry and exit -> clk[0..3]; the ratio of the
+  // deltas is the SM clock the kernel actually ran at (nsr_debug_kernel_clock; bench.py's `clocks.sm_mhz_in_kernel`)
+  long long* clk;
 };
 
 // ---------------------------------------------------------------------------
@@ -773,6 +776,11 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_tc_pass(const TcKernelArgs a)
   if (sm_base & 1023u) { if (threadIdx.x == 0) printf("[nsr_tc] dynamic smem base %u not 1024-aligned\n", sm_base); __trap(); }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long my_tiles = (a.n_tiles > blockIdx.x) ? (a.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  if (a.clk && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
+    a.clk[0] = clock64(); a.clk[1] = (long long)ns;
+  }
 
   if (threadIdx.x == 0) {
     const uint32_t bar = sm_base + kSmBar;
@@ -821,6 +829,27 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_tc_pass(const TcKernelArgs a)
   if (warp == kMmaWarp) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
   }
+  if (a.clk && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
+    a.clk[2] = clock64(); a.clk[3] = (long long)ns;
+  }
+}
+
+// The opt-in to > 48 KB of dynamic shared memory is a per-function, per-device attribute: set once at nsr_create
+// (not on every launch).
+cudaError_t tc_init(NsrHandle_* h) {
+  cudaError_t e = cudaSuccess;
+  auto set = [&](void (*k)(const TcKernelArgs)) {
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTcBytes);
+  };
+  switch (h->cfg.precision) {
+    case NSR_PREC_BF16X3_TC: set(k_tc_pass<1, 3, true>); set(k_tc_pass<1, 3, false>); break;
+    case NSR_PREC_FP16X3_TC: set(k_tc_pass<0, 3, true>); set(k_tc_pass<0, 3, false>); break;
+    case NSR_PREC_BF16_TC: set(k_tc_pass<1, 1, false>); break;
+    default: break;
+  }
+  return e;
 }
 
 cudaError_t tc_pass(NsrHandle_* h, int which, const TcPassArgs& p, cudaStream_t st) {
@@ -846,8 +875,7 @@ cudaError_t tc_pass(NsrHandle_* h, int which, const TcPassArgs& p, cudaStream_t 
     case NSR_PREC_BF16_TC: if (stash) return cudaErrorInvalidValue; kern = k_tc_pass<1, 1, false>; break;
     default: return cudaErrorInvalidValue;
   }
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTcBytes);
-  if (e != cudaSuccess) return e;
+  a.clk = h->d_clk;
   kern<<<grid, kThreadsTc, kSmemTcBytes, st>>>(a);
   h->launches += 1;
   return cudaGetLastError();

@@ -159,7 +159,7 @@ struct RenderBwdArgs {
   const float* raw;      // [N,S,4]  rgb after the colour activation, raw sigma (VanillaMLP output)
   const float* noise;    // [N,S] or null
   int S;
-  const float* g_rgb;    // [N,3] dL/d comp_rgb (required)
+  const float* g_rgb;    // [N,3] dL/d comp_rgb, or null
   const float* g_depth;  // [N] or null
   const float* g_opacity;// [N] or null
   const float* w_rgb;    // [3][128] fp32
@@ -197,7 +197,7 @@ k_render_bwd(const RenderBwdArgs a) {
     const bool valid = ray < a.n_rays;
     float gr = 0.f, gg = 0.f, gb = 0.f, gd = 0.f, go = 0.f;
     if (valid) {
-      gr = a.g_rgb[ray * 3]; gg = a.g_rgb[ray * 3 + 1]; gb = a.g_rgb[ray * 3 + 2];
+      if (a.g_rgb) { gr = a.g_rgb[ray * 3]; gg = a.g_rgb[ray * 3 + 1]; gb = a.g_rgb[ray * 3 + 2]; }
       if (a.g_depth) gd = a.g_depth[ray];
       if (a.g_opacity) go = a.g_opacity[ray];
       const float4* r4 = reinterpret_cast<const float4*>(a.raw) + ray * S;
@@ -1475,14 +1475,15 @@ extern "C" int nsr_backward(NsrHandle* h, const float* rays, int64_t n_rays, int
   const NsrRng none{};
   const NsrRng& R = rng ? *rng : none;
   const int64_t numel = nsr_grad_numel(h);
-  if (g->coarse_comp_rgbs) {
+  // a net takes part as soon as ANY of its outputs carries a gradient (depth / opacity regularisers without a colour term)
+  if (g->coarse_comp_rgbs || g->coarse_depth || g->coarse_opacity) {
     rc = backward_net(h, 0, rays, n_rays, ray_stride, R.noise_coarse, g->coarse_comp_rgbs, g->coarse_depth, g->coarse_opacity,
                       grad_coarse, ws, L, st);
     if (rc) return rc;
   } else {
     NSR_TCUDA(h, cudaMemsetAsync(grad_coarse, 0, (size_t)numel * sizeof(float), st));
   }
-  if (g->fine_comp_rgbs) {
+  if (g->fine_comp_rgbs || g->fine_depth || g->fine_opacity) {
     rc = backward_net(h, 1, rays, n_rays, ray_stride, R.noise_fine, g->fine_comp_rgbs, g->fine_depth, g->fine_opacity,
                       grad_fine, ws, L, st);
     if (rc) return rc;

@@ -57,19 +57,108 @@ def render_sharded(render_fn: Callable[[torch.Tensor], Sequence[torch.Tensor]], 
     return full, bounds
 
 
+def _allreduce_mean_flat_(flat: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -> None:
+    """Mean over ranks of ONE flat tensor, in place, with as few launches as the backend allows: NCCL averages inside
+    the collective (ncclAvg); gloo has no AVG, so SUM then one division."""
+    if dist.get_backend(group) == "nccl":
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
+    else:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat /= dist.get_world_size(group)
+
+
 def allreduce_mean_(tensors: Sequence[torch.Tensor], group: Optional[dist.ProcessGroup] = None) -> None:
-    """DDP-equivalent gradient averaging: flatten into ONE bucket (2 x 595 844 fp32 = 4.77 MB for the
-    coarse+fine nets), one all-reduce, scatter back in place."""
+    """DDP-equivalent gradient averaging of arbitrary tensors (the autograd bridge hands over two separately allocated
+    flat buffers): flatten into ONE bucket (2 x 595 844 fp32 = 4.77 MB for the coarse+fine nets), one all-reduce,
+    scatter back in place.  `Trainer` does not come through here: its gradients already live in one bucket
+    (`make_grad_reducer`)."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return
+    if len(tensors) == 1 and tensors[0].is_contiguous():
+        _allreduce_mean_flat_(tensors[0].view(-1), group)
+        return
     flat = torch.cat([t.reshape(-1) for t in tensors])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    flat /= dist.get_world_size(group)
+    _allreduce_mean_flat_(flat, group)
     off = 0
     for t in tensors:
         n = t.numel()
         t.copy_(flat[off:off + n].view_as(t))
         off += n
+
+
+class _DevicePointer:
+    """Zero-copy view of library-owned device memory as a torch tensor (``torch.as_tensor`` reads this protocol)."""
+
+    def __init__(self, ptr: int, n_floats: int):
+        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+class TorchGradReducer:
+    """The flat gradient bucket in ordinary device memory, averaged with ONE torch.distributed collective
+    (NCCL: ncclAvg, no extra elementwise launch; gloo in the CPU tests)."""
+
+    def __init__(self, n_floats: int, device, group=None):
+        self.group = group
+        self.buffer = torch.zeros(n_floats, device=device, dtype=torch.float32)
+        self.impl = f"torch.distributed all_reduce on one flat bucket ({dist.get_backend(group)}" + \
+                    (", ncclAvg)" if dist.get_backend(group) == "nccl" else ", sum + divide)")
+
+    def allreduce_mean_(self) -> None:
+        _allreduce_mean_flat_(self.buffer, self.group)
+
+    def close(self) -> None:
+        pass
+
+
+class P2PGradReducer:
+    """The flat gradient bucket in libnsr_b200's symmetric memory, averaged by the library's own one-kernel all-reduce over
+    NVLink peer loads / stores (nsr_comm_allreduce_mean, csrc/nsr_comm.cu).  torch.distributed only carries the 64-byte
+    CUDA IPC handles at construction; the collective itself is a single kernel launch on the current stream and its
+    result is bit-identical on every rank (fixed summation order)."""
+
+    def __init__(self, renderer, n_floats: int, group=None):
+        import ctypes as C
+        self.r, self.group = renderer, group
+        lib = renderer.lib
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        c = C.c_void_p()
+        renderer._check(lib.nsr_comm_create(renderer._h, rank, world, n_floats, C.byref(c)))
+        self._c = c
+        mine = (C.c_char * 64)()
+        renderer._check(lib.nsr_comm_export(c, mine))
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(mine), group=group)           # plumbing only: 64 bytes per rank
+        blob = b"".join(handles)
+        renderer._check(lib.nsr_comm_connect_ipc(c, blob, world))
+        self.buffer = torch.as_tensor(_DevicePointer(int(lib.nsr_comm_buffer(c)), int(lib.nsr_comm_buffer_floats(c))),
+                                      device=renderer.device)
+        dist.barrier(group=group)                                            # everyone mapped everyone before first use
+        self.impl = "nsr_comm_allreduce_mean: one kernel, two-shot over CUDA-IPC peer memory (NVLink ld/st), fixed rank order"
+
+    def allreduce_mean_(self) -> None:
+        self.r._check(self.r.lib.nsr_comm_allreduce_mean(self._c, self.r._stream()))
+
+    def close(self) -> None:
+        if getattr(self, "_c", None):
+            self.buffer = None
+            self.r.lib.nsr_comm_destroy(self._c)
+            self._c = None
+
+
+def make_grad_reducer(renderer, n_floats: int, group=None, mode: str = "auto"):
+    """The gradient bucket + its all-reduce for `Trainer`.  mode: "p2p" | "nccl" | "auto" (p2p when the process group is NCCL
+    on CUDA devices, else the torch.distributed collective).  The environment variable NSR_ALLREDUCE overrides "auto"."""
+    import os
+    if mode == "auto":
+        mode = os.environ.get("NSR_ALLREDUCE", "auto")
+    backend = dist.get_backend(group)
+    if mode == "auto":
+        mode = "p2p" if (backend == "nccl" and renderer.device.type == "cuda") else "nccl"
+    if mode == "p2p":
+        return P2PGradReducer(renderer, n_floats, group)
+    if mode == "nccl":
+        return TorchGradReducer(n_floats, renderer.device, group)
+    raise ValueError(f"unknown all-reduce mode {mode!r}")
 
 
 def epoch_indices(n_samples: int, world_size: int, rank: int, epoch: int = 0, seed: int = 0, shuffle: bool = True,

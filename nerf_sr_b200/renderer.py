@@ -126,6 +126,14 @@ class Renderer:
     def launch_count(self) -> int:
         return int(self.lib.nsr_launch_count(self._h))
 
+    def kernel_clock_mhz(self) -> Optional[float]:
+        """SM clock (MHz) the most recent fused-pass kernel ran at, from clock64 / globaltimer stamps taken by CTA 0 at
+        kernel entry and exit (nsr_debug_kernel_clock).  Synchronises the current stream."""
+        v = (C.c_int64 * 4)()
+        self._check(self.lib.nsr_debug_kernel_clock(self._h, v, self._stream()))
+        dns = v[3] - v[1]
+        return None if dns <= 0 else 1e3 * (v[2] - v[0]) / dns
+
     # -- weights -----------------------------------------------------------------
     def load_state_dict(self, which: int, state_dict: Mapping[str, torch.Tensor]):
         """which: 0 = netCoarse, 1 = netFine.  Accepts the reference's state_dict (optionally with a

@@ -87,9 +87,10 @@ def render_train(self: Renderer, rays: torch.Tensor, rng=None, want_weights: boo
 
 
 def backward(self: Renderer, rays: torch.Tensor, rng, grads: Mapping[str, Optional[torch.Tensor]],
-             ws: Optional[torch.Tensor] = None):
+             ws: Optional[torch.Tensor] = None, out: Optional[Sequence[torch.Tensor]] = None):
     """dL/d(outputs) -> (grad_coarse_flat, grad_fine_flat): flat fp32 gradients in state_dict order.
-    ``ws``: the stash buffer the matching render_train filled (default: the renderer-owned one)."""
+    ``ws``: the stash buffer the matching render_train filled (default: the renderer-owned one).
+    ``out``: (grad_coarse, grad_fine) buffers to fill (e.g. the two halves of one flat all-reduce bucket)."""
     rays = self._f32(rays)
     n, stride = rays.shape
     g = NsrOutGrads()
@@ -105,8 +106,14 @@ def backward(self: Renderer, rays: torch.Tensor, rng, grads: Mapping[str, Option
             raise NsrError(2, f"gradient w.r.t. {k} is not supported (the reference's losses never use it)")
     r = _rng_struct(self, rng, keep)
     numel = int(self.lib.nsr_grad_numel(self._h))
-    gc = torch.empty(numel, device=self.device, dtype=torch.float32)
-    gf = torch.empty(numel, device=self.device, dtype=torch.float32)
+    if out is not None:
+        gc, gf = out
+        for t in (gc, gf):
+            if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != numel or t.device != self.device:
+                raise NsrError(1, f"backward(out=...) needs two contiguous fp32 buffers of {numel} elements on {self.device}")
+    else:
+        gc = torch.empty(numel, device=self.device, dtype=torch.float32)
+        gf = torch.empty(numel, device=self.device, dtype=torch.float32)
     if ws is None:
         ws = _train_workspace(self, n)
     self._check(self.lib.nsr_backward(self._h, rays.data_ptr(), n, stride, C.byref(r) if r is not None else None, C.byref(g),
@@ -115,14 +122,14 @@ def backward(self: Renderer, rays: torch.Tensor, rng, grads: Mapping[str, Option
 
 
 def lr_loss_grad(self: Renderer, hr_rgb: torch.Tensor, target_lr: torch.Tensor, s: int, lam: float = 1.0,
-                 want_grad: bool = True):
+                 want_grad: bool = True, metrics_out: Optional[torch.Tensor] = None):
     """(lr_rgb [n_lr,3], metrics [2] = (lam*mse, psnr), g_hr [n_lr*s*s,3] = d(lam*mse)/d(hr_rgb))."""
     hr_rgb, target_lr = self._f32(hr_rgb), self._f32(target_lr)
     n_lr = target_lr.shape[0]
     if hr_rgb.shape[0] != n_lr * s * s:
         raise NsrError(1, f"hr_rgb has {hr_rgb.shape[0]} rows, expected {n_lr}*{s}*{s}")
     lr = torch.empty(n_lr, 3, device=self.device, dtype=torch.float32)
-    m = torch.empty(2, device=self.device, dtype=torch.float32)
+    m = metrics_out if metrics_out is not None else torch.empty(2, device=self.device, dtype=torch.float32)
     g = torch.empty_like(hr_rgb) if want_grad else None
     self._check(self.lib.nsr_lr_loss_grad(self._h, hr_rgb.data_ptr(), target_lr.data_ptr(), n_lr, s, float(lam), lr.data_ptr(),
                                           m.data_ptr(), g.data_ptr() if g is not None else None, self._stream()))
@@ -411,8 +418,12 @@ class Trainer:
                  lr: float = 5e-4, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8, lambda_coarse_mse: float = 1.0,
                  lambda_fine_mse: float = 1.0, grad_clip_val: float = 0.0, grad_clip_type: str = "norm", downscale: int = 2,
                  group=None, lambda_coarse_var: float = 0.0, lambda_fine_var: float = 0.0, lambda_coarse_depth_var: float = 0.0,
-                 lambda_fine_depth_var: float = 0.0, fix_layers: Optional[str] = None):
-        """lambda_*_var / lambda_*_depth_var: the reference's ``--lambda_*`` values when ``--use_var_loss`` /
+                 lambda_fine_depth_var: float = 0.0, fix_layers: Optional[str] = None, allreduce: str = "auto"):
+        """allreduce: how the gradient bucket is averaged over the ranks of ``group`` (DDP semantics, models/networks.py:72-86):
+        "p2p" = libnsr_b200's own one-kernel all-reduce over peer-mapped memory (nsr_comm_allreduce_mean: NVLink loads /
+        stores, fixed rank order -> bit-identical on every rank), "nccl" = one ncclAvg all-reduce on the flat bucket,
+        "auto" = p2p on CUDA with NCCL, else the torch.distributed fallback (gloo in the CPU tests).
+        lambda_*_var / lambda_*_depth_var: the reference's ``--lambda_*`` values when ``--use_var_loss`` /
         ``--use_depth_var_loss`` are given (models/nerf_downX_model.py:107-112), 0 (default) otherwise.
         fix_layers: the reference's ``--fix_layers`` regex; matching parameters of both nets are frozen: their gradient
         slices are zeroed before the all-reduce / clipping / Adam, which leaves parameter and moments untouched (Adam with
@@ -438,6 +449,22 @@ class Trainer:
         self.group = group
         self.last_metrics: Optional[torch.Tensor] = None
         self.last_grads = None
+        # ONE flat gradient bucket [coarse | fine] (2 x 595 844 fp32 = 4.77 MB): nsr_backward's reduction kernel writes the
+        # two halves in place, the data-parallel all-reduce works on the whole bucket (no cat / copy-back launches).  With
+        # more than one rank the bucket lives in the reducer's symmetric (peer-mapped) memory.
+        self._numel = numel
+        self._reducer = None
+        self.allreduce_impl = None
+        world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            world = torch.distributed.get_world_size(group)
+        if world > 1:
+            from .parallel import make_grad_reducer
+            self._reducer = make_grad_reducer(renderer, 2 * numel, group, allreduce)
+            self.allreduce_impl = self._reducer.impl
+            self._gflat = self._reducer.buffer
+        else:
+            self._gflat = torch.empty(2 * numel, device=dev, dtype=torch.float32)
         self._frozen = frozen_slices(names, [int(renderer.lib.nsr_param_numel(renderer._h, i)) for i in range(len(names))], fix_layers)
         for w in (0, 1):
             renderer.load_params(w, self.params[w])
@@ -479,9 +506,24 @@ class Trainer:
             rng["noise_fine"] = torch.randn(n_rays, c.n_coarse + c.n_importance, device=dev, generator=generator)
         return rng
 
+    def grad_views(self):
+        """(grad_coarse, grad_fine): the two halves of the flat all-reduce bucket."""
+        return self._gflat[: self._numel], self._gflat[self._numel: 2 * self._numel]
+
+    def allreduce_grads(self, gc: torch.Tensor, gf: torch.Tensor) -> None:
+        """Average (gc, gf) over the ranks in place.  One collective on the flat bucket when they are its halves."""
+        if self._reducer is None:
+            return
+        a, b = self.grad_views()
+        if gc.data_ptr() == a.data_ptr() and gf.data_ptr() == b.data_ptr():
+            self._reducer.allreduce_mean_()
+        else:
+            from .parallel import allreduce_mean_
+            allreduce_mean_([gc, gf], self.group)
+
     def forward_backward(self, rays: torch.Tensor, target_lr: torch.Tensor, rng=None, target_sr: Optional[torch.Tensor] = None,
                          far: Optional[float] = None, ref_rays: Optional[torch.Tensor] = None,
-                         ref_rgbs: Optional[torch.Tensor] = None, ref_rng=None):
+                         ref_rgbs: Optional[torch.Tensor] = None, ref_rng=None, out: Optional[Sequence[torch.Tensor]] = None):
         """forward + loss + backward; returns (grad_coarse_flat, grad_fine_flat), sets last_metrics.
         ``target_sr`` [N,3]: the SISR supervision ``data_rgbs_sr`` (``--sisr_path``).  ``far``: the reference's
         ``self.far`` for the depth-variance term (default: read from ``rays[0, 7]`` like the reference -- one host sync;
@@ -492,14 +534,15 @@ class Trainer:
         batch's) whose HR colours enter the loss as MSE / s^2; ``last_ref_terms`` [2] holds the two terms."""
         r = self.r
         if ref_rays is not None:
-            return self._forward_backward_with_ref(rays, target_lr, rng, target_sr, far, ref_rays, ref_rgbs, ref_rng)
-        out = r.render_train(rays, rng, want_weights=False)
+            return self._forward_backward_with_ref(rays, target_lr, rng, target_sr, far, ref_rays, ref_rgbs, ref_rng, out)
+        o = r.render_train(rays, rng, want_weights=False)
         if target_sr is not None or any(self.lam_var) or any(self.lam_dvar):
-            return r.backward(rays, rng, self._main_loss_grads(out, rays, target_lr, target_sr, far))
-        _, mc, g_c = r.lr_loss_grad(out["coarse_comp_rgbs"], target_lr, self.s, self.lam[0])
-        _, mf, g_f = r.lr_loss_grad(out["fine_comp_rgbs"], target_lr, self.s, self.lam[1])
-        self.last_metrics = torch.cat([mc, mf])
-        return r.backward(rays, rng, {"coarse_comp_rgbs": g_c, "fine_comp_rgbs": g_f})
+            return r.backward(rays, rng, self._main_loss_grads(o, rays, target_lr, target_sr, far), out=out)
+        m = torch.empty(4, device=r.device, dtype=torch.float32)
+        _, _, g_c = r.lr_loss_grad(o["coarse_comp_rgbs"], target_lr, self.s, self.lam[0], metrics_out=m[0:2])
+        _, _, g_f = r.lr_loss_grad(o["fine_comp_rgbs"], target_lr, self.s, self.lam[1], metrics_out=m[2:4])
+        self.last_metrics = m
+        return r.backward(rays, rng, {"coarse_comp_rgbs": g_c, "fine_comp_rgbs": g_f}, out=out)
 
     def _main_loss_grads(self, out, rays, target_lr, target_sr, far):
         """Loss terms + dL/d(outputs) of the main batch through nsr_loss_epilogue."""
@@ -519,7 +562,7 @@ class Trainer:
         self.last_metrics = torch.cat([terms[0][:2], terms[1][:2]])
         return grads
 
-    def _forward_backward_with_ref(self, rays, target_lr, rng, target_sr, far, ref_rays, ref_rgbs, ref_rng):
+    def _forward_backward_with_ref(self, rays, target_lr, rng, target_sr, far, ref_rays, ref_rgbs, ref_rng, grad_out=None):
         r = self.r
         if ref_rgbs is None or ref_rays.shape[0] != ref_rgbs.shape[0] or ref_rays.shape[0] % (self.s * self.s):
             raise NsrError(1, "ref_rays / ref_rgbs must have the same number of rows, a multiple of downscale^2")
@@ -534,7 +577,7 @@ class Trainer:
             ref_terms.append(e["metrics"][4])
             ref_grads[f"{net}_comp_rgbs"] = e["g_rgb"]
         self.last_ref_terms = torch.stack(ref_terms)
-        gc, gf = r.backward(rays, rng, grads, ws=ws_main)
+        gc, gf = r.backward(rays, rng, grads, ws=ws_main, out=grad_out)
         gc2, gf2 = r.backward(ref_rays, ref_rng, ref_grads, ws=ws_ref)
         return gc.add_(gc2), gf.add_(gf2)                        # autograd's accumulation over the two forward graphs
 
@@ -543,14 +586,11 @@ class Trainer:
                             ref_rays: Optional[torch.Tensor] = None, ref_rgbs: Optional[torch.Tensor] = None, ref_rng=None):
         r = self.r
         gc, gf = self.forward_backward(rays, target_lr, rng, target_sr=target_sr, far=far, ref_rays=ref_rays, ref_rgbs=ref_rgbs,
-                                       ref_rng=ref_rng)
+                                       ref_rng=ref_rng, out=self.grad_views())
         for lo, hi in self._frozen:                    # --fix_layers
             gc[lo:hi].zero_()
             gf[lo:hi].zero_()
-        if self.group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
-                                      and torch.distributed.get_world_size() > 1):
-            from .parallel import allreduce_mean_
-            allreduce_mean_([gc, gf], self.group)       # one 4.77 MB bucket (DDP: models/networks.py:72-86)
+        self.allreduce_grads(gc, gf)                    # one 4.77 MB bucket, one kernel (DDP: models/networks.py:72-86)
         coef, clip_value = None, 0.0
         if self.clip_val > 0:
             if self.clip_type == "norm":

@@ -66,23 +66,29 @@ def _linear(x: Tensor, p: Dict[str, Tensor], name: str) -> Tensor:
     return torch.nn.functional.linear(x, p[name + ".weight"], p[name + ".bias"])
 
 
-def mlp_forward(p: Dict[str, Tensor], x: Tensor, cfg: RenderConfig, acts: Optional[list] = None) -> Tensor:
+def mlp_forward(p: Dict[str, Tensor], x: Tensor, cfg: RenderConfig, acts: Optional[list] = None,
+                relu_masks: Optional[Sequence[Tensor]] = None) -> Tensor:
     """[P, ch_pos+ch_dir] -> [P,4] = (rgb after colour activation, raw sigma).
     models/networks.py:199-224.  ``acts`` (a list) receives the intermediate tensors
-    [h_1, ..., h_D, feat, dir_act] for the training-stash tests."""
+    [h_1, ..., h_D, feat, dir_act] for the training-stash tests.
+    ``relu_masks`` (test harness only; None = the reference's path, untouched): D + 1 boolean tensors [P, W] / [P, W/2]
+    that REPLACE the sign test of the D trunk ReLUs and of the dir layer's ReLU (y = pre * mask) -- "mask teacher
+    forcing": the gradient then flows through exactly the units another implementation's forward kept active, so
+    a gradient comparison is not polluted by ReLU decisions that flip on pre-activations of ~1e-5."""
     ch_pos, ch_dir = cfg.ch_pos, cfg.ch_dir
     in_xyz, in_dir = torch.split(x, [ch_pos, ch_dir], dim=-1)      # :199
     h = in_xyz
+    act = (lambda pre, i: torch.relu(pre)) if relu_masks is None else (lambda pre, i: pre * relu_masks[i].to(pre.dtype))
     for i in range(cfg.D):                                           # :202-205
         if i in cfg.skips:
             h = torch.cat([in_xyz, h], -1)                           # :204
-        h = torch.relu(_linear(h, p, f"xyz_encoding_{i+1}.0"))
+        h = act(_linear(h, p, f"xyz_encoding_{i+1}.0"), i)
         if acts is not None:
             acts.append(h)
     sigma = _linear(h, p, "sigma")                                   # :207
     feat = _linear(h, p, "xyz_encoding_final")                       # :211 (no act)
     d_in = feat if cfg.no_dir else torch.cat([feat, in_dir], -1)     # :213-216
-    d = torch.relu(_linear(d_in, p, "dir_encoding.0"))               # :221
+    d = act(_linear(d_in, p, "dir_encoding.0"), cfg.D)               # :221
     if acts is not None:
         acts += [feat, d]
     rgb = _linear(d, p, "rgb.0")                                     # :222
@@ -177,11 +183,11 @@ def resample_along_rays(o: Tensor, d: Tensor, z: Tensor, weights: Tensor,
 # (models/nerf_downX_model.py:260-278, models/utils.py:199-212)
 # --------------------------------------------------------------------------
 def render_pass(p: Dict[str, Tensor], xyz: Tensor, dir_enc: Tensor, z: Tensor,
-                cfg: RenderConfig, noise: Optional[Tensor]):
+                cfg: RenderConfig, noise: Optional[Tensor], relu_masks: Optional[Sequence[Tensor]] = None):
     n_rays, n_s = xyz.shape[:2]
     enc = posenc(xyz.reshape(-1, 3), cfg.deg_pos, cfg.no_xyz, cfg.no_logscale)
     d = dir_enc.repeat_interleave(n_s, dim=0)                        # ray-major, :266
-    raw = mlp_forward(p, torch.cat([enc, d], -1), cfg).view(n_rays, n_s, 4)
+    raw = mlp_forward(p, torch.cat([enc, d], -1), cfg, relu_masks=relu_masks).view(n_rays, n_s, 4)
     rgb, sigma = raw[..., :3], raw[..., 3]
     if cfg.gamma_correct:                                            # :271-276
         rgb = torch.pow(rgb, 1 / 2.2)
@@ -222,7 +228,8 @@ def forward_rays(p_coarse: Dict[str, Tensor], p_fine: Dict[str, Tensor],
                  rays: Tensor, cfg: RenderConfig,
                  rng: Optional[RenderRng] = None,
                  z_fine_override: Optional[Tensor] = None,
-                 extras: Optional[dict] = None) -> Dict[str, Tensor]:
+                 extras: Optional[dict] = None,
+                 relu_masks: Optional[Tuple[Optional[Sequence[Tensor]], Optional[Sequence[Tensor]]]] = None) -> Dict[str, Tensor]:
     """rays [N, 8|11] = (o3, d3, near, far[, viewdir3]) -> the reference's
     8-key dict.  ``rng=None`` is eval mode.  ``z_fine_override`` teacher-forces
     the fine pass (parity protocol ii).  ``extras`` (a
@@ -233,8 +240,9 @@ def forward_rays(p_coarse: Dict[str, Tensor], p_fine: Dict[str, Tensor],
     dir_enc = posenc(rays[:, vo:vo + 3], cfg.deg_dir, cfg.no_xyz, cfg.no_logscale)  # :286
     rng = rng or RenderRng()
     z, xyz = sample_along_rays(o, d, near, far, cfg.N_coarse, cfg.lindisp, rng.u_coarse)
+    rm = relu_masks or (None, None)        # (coarse, fine) mask teacher forcing, see mlp_forward
     c_rgb, c_depth, c_opa, c_w, raw_c = render_pass(p_coarse, xyz, dir_enc, z, cfg,
-                                                    rng.noise_coarse)
+                                                    rng.noise_coarse, rm[0])
     out = {"coarse_comp_rgbs": c_rgb, "coarse_depth": c_depth,
            "coarse_opacity": c_opa, "coarse_weights": c_w}           # :293-298
     if extras is not None:
@@ -246,7 +254,7 @@ def forward_rays(p_coarse: Dict[str, Tensor], p_fine: Dict[str, Tensor],
         else:
             z_f, xyz_f = z_fine_override, cast_rays(o, d, z_fine_override)
         f_rgb, f_depth, f_opa, f_w, raw_f = render_pass(p_fine, xyz_f, dir_enc, z_f, cfg,
-                                                        rng.noise_fine)
+                                                        rng.noise_fine, rm[1])
         out.update({"fine_comp_rgbs": f_rgb, "fine_depth": f_depth,
                     "fine_opacity": f_opa, "fine_weights": f_w})
         if extras is not None:

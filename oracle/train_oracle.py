@@ -63,7 +63,8 @@ def loss_and_grads(pc: Dict[str, Tensor], pf: Dict[str, Tensor], rays: Tensor, t
                    cfg: O.RenderConfig, tcfg: TrainConfig, rng: Optional[O.RenderRng] = None,
                    s: int = 2, z_fine_override: Optional[Tensor] = None, extras: Optional[dict] = None,
                    target_sr: Optional[Tensor] = None, ref_rays: Optional[Tensor] = None, ref_rgbs: Optional[Tensor] = None,
-                   ref_rng: Optional[O.RenderRng] = None, ref_z_fine_override: Optional[Tensor] = None):
+                   ref_rng: Optional[O.RenderRng] = None, ref_z_fine_override: Optional[Tensor] = None,
+                   relu_masks=None):
     """One forward + backward.  Returns (losses dict, grads_coarse dict, grads_fine dict, outputs dict).
     target_lr: [N/s^2, 3].  target_sr: [N, 3] or None = ``data_rgbs_sr`` (``--sisr_path``, :364-367).
     ref_rays [M, 8] / ref_rgbs [M, 3] (``--with_ref``, :321-324, :369-372): sub-pixel rays of the reference view with
@@ -72,7 +73,7 @@ def loss_and_grads(pc: Dict[str, Tensor], pf: Dict[str, Tensor], rays: Tensor, t
     (the reference leaves .grad = None for them; Adam then skips the parameter)."""
     pc_r = {k: v.detach().clone().requires_grad_(True) for k, v in pc.items()}
     pf_r = {k: v.detach().clone().requires_grad_(True) for k, v in pf.items()}
-    out = O.forward_rays(pc_r, pf_r, rays, cfg, rng, z_fine_override=z_fine_override, extras=extras)
+    out = O.forward_rays(pc_r, pf_r, rays, cfg, rng, z_fine_override=z_fine_override, extras=extras, relu_masks=relu_masks)
     out_ref = None
     if ref_rays is not None:                                                  # :321-324
         out_ref = O.forward_rays(pc_r, pf_r, ref_rays, cfg, ref_rng, z_fine_override=ref_z_fine_override)

@@ -64,7 +64,9 @@ def test_render_roofline_object():
     assert r["flop_per_launch"] * 2 == 160000 * 192 * 1186816                          # 227.87 MFLOP per ray
     assert r["achieved"] == pytest.approx(r["flop_per_launch"] / (r["ms_per_launch"] / 1e3) / 1e12)
     assert r["achieved"] == pytest.approx(514.74, rel=1e-3) and r["frac"] == pytest.approx(r["achieved"] / 1386.6)
-    assert r["issued_frac"] == pytest.approx(3 * r["frac"]) and r["traffic"] == (37557504 + 93537024) // 2
+    # `traffic` is never a hard-coded constant: it is this round's committed ncu capture (profiles/r02_ncu_traffic.json) or null
+    assert r["issued_frac"] == pytest.approx(3 * r["frac"]) and r["traffic"] == b.ncu_traffic("k_tc_pass", "mean_bytes_per_launch")
+    assert (r["traffic"] is None) == (r["traffic_source"] is None)
     assert r["algorithmic_bytes_per_launch"] == 160000 * 564
     f = r["fine_pass_alone"]
     assert f["flop_per_launch"] == 160000 * 128 * 1186816 and f["achieved"] == pytest.approx(516.6, rel=1e-3)

@@ -46,6 +46,35 @@ def _dev(t):
     return None if t is None else t.cuda()
 
 
+def _report(**rec):
+    import json
+    import os
+    from conftest import ROOT
+    d = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(d, exist_ok=True)
+    with open(os.path.join(d, "r02_parity.jsonl"), "a") as fh:
+        fh.write(json.dumps(rec) + "\n")
+
+
+_FP64 = {}
+
+
+def _fp64_reference(fx):
+    """The oracle in fp64 on cuda:0 for a golden fixture (same weights, rays and train-mode draws): the 'exact' answer
+    both the reference's fp32 output (the fixture) and ours are measured against."""
+    if fx.name not in _FP64:
+        dev = torch.device("cuda:0")
+        d = lambda t: None if t is None else t.to(dev).double()
+        rng = None
+        if fx.rng is not None:
+            rng = O.RenderRng(d(fx.rng.u_coarse), d(fx.rng.noise_coarse), d(fx.rng.u_fine), d(fx.rng.noise_fine))
+        with torch.no_grad():
+            out = O.forward_rays({k: d(v) for k, v in fx.p_coarse.items()}, {k: d(v) for k, v in fx.p_fine.items()},
+                                 d(fx.rays), fx.cfg, rng)
+        _FP64[fx.name] = {k: v.cpu() for k, v in out.items()}
+    return _FP64[fx.name]
+
+
 @pytest.mark.parametrize("prec", PRECISIONS)
 @pytest.mark.parametrize("name", golden_names())
 def test_forward_rays_against_reference_golden(name, prec, load_fixture):
@@ -63,11 +92,20 @@ def test_forward_rays_against_reference_golden(name, prec, load_fixture):
     if fx.cfg.N_importance == 0:
         assert "fine_comp_rgbs" not in out
         return
-    # (iii) end to end: bounded by the reference's own fp32-vs-fp64 disagreement on this fixture
+    # (iii) end to end.  Fine sample positions are an ill-conditioned function of the coarse weights, so the
+    # bound is the reference's OWN fp32-vs-fp64 disagreement on this fixture ("floor", recomputed here with the oracle in
+    # fp64 on the GPU): we must be as close to the exact answer as the reference's arithmetic is (+1 point), and no
+    # further from the reference's fp32 output than two independent fp32-grade evaluations can be (2 x floor + 1 point).
+    ref64 = _fp64_reference(fx)
     for k in ("fine_comp_rgbs", "fine_depth", "fine_opacity", "fine_weights"):
-        mx, viol = O.tolerance_violations(out[k].cpu(), fx.out[k])
-        floor = fx.meta["fp64_floor"][k]["viol"]
-        assert viol <= 2.0 * floor + 0.06, (k, mx, viol, floor)
+        got = out[k].cpu()
+        mx, viol = O.tolerance_violations(got, fx.out[k])
+        _, floor = O.tolerance_violations(fx.out[k], ref64[k])
+        _, v64 = O.tolerance_violations(got, ref64[k])
+        _report(test="e2e_fine", fixture=name, prec=prec, key=k, max_abs=mx, viol_vs_ref32=viol, viol_vs_fp64=v64, floor=floor,
+                floor_in_fixture=fx.meta["fp64_floor"][k]["viol"])
+        assert v64 <= floor + 0.01, (k, v64, floor)
+        assert viol <= 2.0 * floor + 0.01, (k, mx, viol, floor)
         assert torch.isfinite(out[k]).all()
     r.close()
 
@@ -85,7 +123,8 @@ def test_teacher_forced_passes_and_mlp_output(name, prec, load_fixture):
                    ("weights", "coarse_weights")):
         mx, viol = O.tolerance_violations(pc[kl].cpu(), fx.out[kr])
         assert viol == 0.0, (kl, mx, viol)
-    mx, viol = O.tolerance_violations(pc["raw"].cpu(), fx.raw_coarse, rtol=1e-3, atol=2e-4)
+    mx, viol = O.tolerance_violations(pc["raw"].cpu(), fx.raw_coarse, rtol=1e-3, atol=1e-4)     # north_star tolerance
+    _report(test="raw_mlp", fixture=name, prec=prec, net="coarse", max_abs=mx, viol=viol)
     assert viol == 0.0, ("raw_coarse", mx, viol)
     if fx.cfg.N_importance > 0:
         nzf = _dev(fx.rng.noise_fine) if fx.rng is not None else None
@@ -93,7 +132,8 @@ def test_teacher_forced_passes_and_mlp_output(name, prec, load_fixture):
         for kl, kr in FINE_MAP:
             mx, viol = O.tolerance_violations(pf[kl].cpu(), fx.out[kr])
             assert viol == 0.0, (kl, mx, viol)
-        mx, viol = O.tolerance_violations(pf["raw"].cpu(), fx.raw_fine, rtol=1e-3, atol=2e-4)
+        mx, viol = O.tolerance_violations(pf["raw"].cpu(), fx.raw_fine, rtol=1e-3, atol=1e-4)
+        _report(test="raw_mlp", fixture=name, prec=prec, net="fine", max_abs=mx, viol=viol)
         assert viol == 0.0, ("raw_fine", mx, viol)
     r.close()
 
@@ -252,6 +292,46 @@ def test_patch_model_rebinds_forward_rays_on_a_reference_lookalike(load_fixture)
     m._nsr_renderer.close()
 
 
+def test_host_pipeline_is_ordered_behind_pack_weights(load_fixture):
+    """nsr_pack_weights is asynchronous on the caller's stream while nsr_render_host /
+    nsr_render_pose_host run on library-owned streams; a pack immediately followed by a host render must see the NEW
+    weights, with no host synchronisation in between."""
+    from nerf_sr_b200 import Renderer
+    fx = load_fixture("eval_blender")
+    dev = torch.device("cuda:0")
+    rays = O.synthetic_rays(4 * 5000, 5, "blender")
+    pose = torch.tensor([[1.0, 0, 0, 0.1], [0, 1, 0, -0.2], [0, 0, 1, 4.0]])
+    other_c, other_f = O.make_mlp_params(fx.cfg, 31), O.make_mlp_params(fx.cfg, 34)
+    want = Renderer(fx.cfg, dev, precision="bf16x3")
+    want.load_state_dict(0, other_c)
+    want.load_state_dict(1, other_f)
+    torch.cuda.synchronize()
+    rgb_want, depth_want = want.render_frame_host(rays, 2)
+    prgb_want, _ = want.render_pose_host(pose, 64, 64, 80.0, 2)
+    r = _renderer(fx, "bf16x3")
+    r.render_frame_host(rays, 2)                     # creates the library streams, old weights
+    busy = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(3):
+        for _ in range(8):
+            busy.fill_(1)                            # keep the caller's stream busy so that the pack is still queued
+        r.load_state_dict(0, other_c)
+        r.load_state_dict(1, other_f)
+        rgb, depth = r.render_frame_host(rays, 2)
+        assert torch.equal(rgb, rgb_want) and torch.equal(depth, depth_want)
+        for _ in range(8):
+            busy.fill_(2)
+        r.load_state_dict(0, fx.p_coarse)
+        r.load_state_dict(1, fx.p_fine)
+        for _ in range(8):
+            busy.fill_(3)
+        r.load_state_dict(0, other_c)
+        r.load_state_dict(1, other_f)
+        prgb, _ = r.render_pose_host(pose, 64, 64, 80.0, 2)
+        assert torch.equal(prgb, prgb_want)
+    r.close()
+    want.close()
+
+
 @pytest.mark.parametrize("prec", PRECISIONS)
 @pytest.mark.parametrize("n", [1, 2, 3, 129])
 def test_tiny_and_ragged_batches(n, prec, load_fixture):
@@ -368,9 +448,16 @@ def test_against_oracle_run_on_the_gpu(prec, load_fixture):
     for k in COARSE_KEYS:
         mx, viol = O.tolerance_violations(out[k].cpu(), ref[k].cpu())
         assert viol == 0.0, (k, mx, viol)
+    d = lambda p: {k: v.double() for k, v in p.items()}
+    with torch.no_grad():
+        ref64 = O.forward_rays(d(pc), d(pf), rays.double(), fx.cfg)
     for k in ("fine_comp_rgbs", "fine_depth", "fine_weights"):
         mx, viol = O.tolerance_violations(out[k].cpu(), ref[k].cpu())
-        assert viol <= 0.06, (k, mx, viol)
+        _, floor = O.tolerance_violations(ref[k].cpu(), ref64[k].cpu())
+        _, v64 = O.tolerance_violations(out[k].cpu(), ref64[k].cpu())
+        _report(test="e2e_fine_gpu_oracle", prec=prec, key=k, max_abs=mx, viol_vs_ref32=viol, viol_vs_fp64=v64, floor=floor)
+        assert v64 <= floor + 0.01, (k, v64, floor)
+        assert viol <= 2.0 * floor + 0.01, (k, mx, viol, floor)
     r.close()
 
 

@@ -47,9 +47,12 @@ class FakeRenderer:
         return {k: torch.rand(n, 3) if "rgbs" in k else torch.rand(n) for k in
                 ("coarse_comp_rgbs", "coarse_depth", "coarse_opacity", "fine_comp_rgbs", "fine_depth", "fine_opacity")}
 
-    def lr_loss_grad(self, hr, tgt, s, lam):
+    def lr_loss_grad(self, hr, tgt, s, lam, want_grad=True, metrics_out=None):
         self.calls.append(("lr_loss_grad", s, lam))
-        return torch.zeros(tgt.shape[0], 3), torch.tensor([lam * 0.5, 3.0]), torch.ones_like(hr)
+        m = torch.tensor([lam * 0.5, 3.0])
+        if metrics_out is not None:
+            metrics_out.copy_(m)
+        return torch.zeros(tgt.shape[0], 3), m, torch.ones_like(hr)
 
     def loss_epilogue(self, hr, tgt, s, lam, hr_depth=None, lambda_var=0.0, lambda_depth_var=0.0, far=0.0, target_hr=None,
                       want_grad=True, lambda_hr=1.0):
@@ -60,8 +63,12 @@ class FakeRenderer:
             out["g_depth"] = torch.ones(hr.shape[0])
         return out
 
-    def backward(self, rays, rng, grads, ws=None):
+    def backward(self, rays, rng, grads, ws=None, out=None):
         self.calls.append(("backward", rays.shape[0], tuple(sorted(grads)), ws is not None))
+        if out is not None:
+            out[0].fill_(1.0)
+            out[1].fill_(2.0)
+            return out
         return torch.ones(TOTAL), torch.full((TOTAL,), 2.0)
 
     def clip_coef(self, a, b, max_norm):
