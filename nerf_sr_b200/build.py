@@ -13,7 +13,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libnsr_b200.so")
 SOURCES = ["nsr_api.cu", "nsr_simt.cu", "nsr_tc.cu", "nsr_train.cu", "nsr_comm.cu"]
-HEADERS = ["nsr_internal.h", "nsr_device.cuh", "nsr_tc_ptx.cuh", "nsr_jet_lut.h", os.path.join(ROOT, "include", "nsr.h")]
+HEADERS = ["nsr_internal.h", "nsr_device.cuh", "nsr_tc_ptx.cuh", "nsr_tc_mma.cuh", "nsr_jet_lut.h", os.path.join(ROOT, "include", "nsr.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-diag-suppress", "177"]
 

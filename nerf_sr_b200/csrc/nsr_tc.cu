@@ -33,6 +33,7 @@
 // (models/rendering.py:89-111) and resample_along_rays (models/utils.py:47-95).
 #include "nsr_internal.h"
 #include "nsr_tc_ptx.cuh"
+#include "nsr_tc_mma.cuh"
 
 namespace nsr {
 
@@ -40,9 +41,7 @@ namespace nsr {
 // compile-time geometry
 // ---------------------------------------------------------------------------
 constexpr int kTile = 128;                  // points per tile (UMMA M)
-constexpr int kStageBytes = 32768;          // 128 rows x 64 k x 2 B, hi then lo
-constexpr int kPlaneBytes = 16384;
-constexpr int kRing = 4;
+// (kStageBytes = 32768, kPlaneBytes = 16384, kRing = 4: nsr_tc_mma.cuh)
 constexpr int kStagesPerTile = 72;
 constexpr int kWarpsFront = 4, kWarpsEpi = 8;
 constexpr int kThreadsTc = 32 * (2 + kWarpsFront + kWarpsEpi);   // 448
@@ -73,18 +72,7 @@ constexpr int kSmBar = kSmScratch + 2 * 320 * 4;
 constexpr int kSmTmemPtr = kSmBar + 32 * 8;
 constexpr int kSmemTcBytes = kSmTmemPtr + 16;
 
-// barrier indices
-enum {
-  B_WFULL = 0,            // [4] weights landed (tx)
-  B_WEMPTY = 4,           // [4] stage consumed (tcgen05.commit)
-  B_ACCFULL = 8,          // [2] accumulator half complete (commit)
-  B_AFREE = 10,           // [2] A operand k chunk 0 / 1 no longer read by this layer (commit)
-  B_AREADY = 12,          // [4] epilogue finished 64-column quarter q: acc quarter drained, A k chunk q written
-  B_ENCFULL = 16,         // [2] front-end produced tile inputs
-  B_COMPREADY = 18,       // epilogue staged the tile's per-sample (rgb, sigma) for compositing
-  B_COMPDONE = 19,        // front-end finished compositing the staged tile
-  B_COUNT = 20
-};
+// (barrier indices B_*: nsr_tc_mma.cuh)
 
 // ---------------------------------------------------------------------------
 // weight image: stage table shared by the packer and (by construction) the MMA
@@ -278,89 +266,14 @@ __device__ __forceinline__ void producer_role(const TcKernelArgs& a, uint32_t sm
 // L2-L4 and L6-L9 share one body each (stage-index phase 2 and 4 mod 8).
 // The stage ORDER is build_stage_table()'s (the weight image is laid out in issue order).
 // ---------------------------------------------------------------------------
-struct MmaCtx {
-  uint32_t sm_base, bar, idesc;
-};
-
-// 12 (or 4) MMAs of one weight stage with A from TMEM.  N8 = stage index mod 8 (compile time).
-template <int PASSES, int N8>
-__device__ __forceinline__ void mma_stage_ts(const MmaCtx& c, int half, int chunk, bool first, bool wait_next) {
-  constexpr uint64_t HI = (64ull << 32) | (1ull << 46) | (2ull << 61);   // SBO=1024, version 1, SWIZZLE_128B
-  constexpr int slot = N8 & 3;
-  constexpr int nslot = (N8 + 1) & 3, npar = ((N8 + 1) >> 2) & 1;
-  const uint32_t wlo = ((c.sm_base + kSmRing + slot * kStageBytes) >> 4) | (1u << 16);
-  const uint32_t d = 128u * half;
-  const uint32_t a_hi = 256u + 32u * chunk;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const uint64_t bh = HI | (uint64_t)(wlo + 2u * k), bl = HI | (uint64_t)(wlo + 1024u + 2u * k);
-    mma_ts(d, a_hi + 8u * k, bh, c.idesc, (k == 0 && first) ? 0u : 1u);
-    if (PASSES == 3) { mma_ts(d, a_hi + 128u + 8u * k, bh, c.idesc, 1u); mma_ts(d, a_hi + 8u * k, bl, c.idesc, 1u); }
-    // the NEXT stage's weights are waited for here, hidden behind this stage's queued MMAs
-    if (k == 1 && wait_next) { mbar_wait(c.bar + 8 * (B_WFULL + nslot), npar); tc_fence_after(); }
-  }
-  tc_commit(c.bar + 8 * (B_WEMPTY + slot));
-}
-
-// Same with A = the tile's encoded inputs in shared memory (first layer and skip layer).
-template <int PASSES, int N8>
-__device__ __forceinline__ void mma_stage_ss(const MmaCtx& c, uint32_t enc, int half, bool wait_next) {
-  constexpr uint64_t HI = (64ull << 32) | (1ull << 46) | (2ull << 61);
-  constexpr int slot = N8 & 3;
-  constexpr int nslot = (N8 + 1) & 3, npar = ((N8 + 1) >> 2) & 1;
-  const uint32_t wlo = ((c.sm_base + kSmRing + slot * kStageBytes) >> 4) | (1u << 16);
-  const uint32_t elo = (enc >> 4) | (1u << 16);
-  const uint32_t d = 128u * half;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const uint64_t bh = HI | (uint64_t)(wlo + 2u * k), bl = HI | (uint64_t)(wlo + 1024u + 2u * k);
-    const uint64_t eh = HI | (uint64_t)(elo + 2u * k), el = HI | (uint64_t)(elo + 1024u + 2u * k);
-    mma_ss(d, eh, bh, c.idesc, k == 0 ? 0u : 1u);      // an encoding chunk always opens its half
-    if (PASSES == 3) { mma_ss(d, el, bh, c.idesc, 1u); mma_ss(d, eh, bl, c.idesc, 1u); }
-    if (k == 1 && wait_next) { mbar_wait(c.bar + 8 * (B_WFULL + nslot), npar); tc_fence_after(); }
-  }
-  tc_commit(c.bar + 8 * (B_WEMPTY + slot));
-}
-
-__device__ __forceinline__ void mma_wait_ready(const MmaCtx& c, int q, uint32_t gpar) {
-  mbar_wait(c.bar + 8 * (B_AREADY + q), gpar);
-}
-
-// A 256x256 trunk layer (optionally with the 64-wide encoding chunk in front: the skip layer).
-// P = stage index of the layer's first stage mod 8.  gpar = parity of the previous layer's A_READY.
-// Schedule (accumulator halves n0/n1 = column quarters {0,1}/{2,3}; k chunk c of the A operand =
-// quarter c of the previous layer's accumulator):
-//   n0: [enc] c0 (needs quarters 0,1 drained + A chunk 0), c1, c2 (A chunk 2), c3 (A chunk 3) -> ACC_FULL[0]
-//   n1: [enc] c0 -> A_FREE[0], c1 -> A_FREE[1], c2, c3                                        -> ACC_FULL[1]
-// so every quarter-epilogue has >= 1536 cycles of MMA work to hide behind.
-template <int PASSES, int P, bool SKIP>
-__device__ __forceinline__ void mma_layer(const MmaCtx& c, uint32_t enc, uint32_t gpar) {
-  constexpr int E = SKIP ? 1 : 0;
-  mma_wait_ready(c, 0, gpar); mma_wait_ready(c, 1, gpar); tc_fence_after();
-  if (SKIP) mma_stage_ss<PASSES, (P + 0) & 7>(c, enc, 0, true);
-  mma_stage_ts<PASSES, (P + E + 0) & 7>(c, 0, 0, !SKIP, true);
-  mma_stage_ts<PASSES, (P + E + 1) & 7>(c, 0, 1, false, true);
-  mma_wait_ready(c, 2, gpar); tc_fence_after();
-  mma_stage_ts<PASSES, (P + E + 2) & 7>(c, 0, 2, false, true);
-  mma_wait_ready(c, 3, gpar); tc_fence_after();
-  mma_stage_ts<PASSES, (P + E + 3) & 7>(c, 0, 3, false, true);
-  tc_commit(c.bar + 8 * (B_ACCFULL + 0));
-  if (SKIP) mma_stage_ss<PASSES, (P + E + 4) & 7>(c, enc, 1, true);
-  mma_stage_ts<PASSES, (P + 2 * E + 4) & 7>(c, 1, 0, !SKIP, true);
-  tc_commit(c.bar + 8 * (B_AFREE + 0));
-  mma_stage_ts<PASSES, (P + 2 * E + 5) & 7>(c, 1, 1, false, true);
-  tc_commit(c.bar + 8 * (B_AFREE + 1));
-  mma_stage_ts<PASSES, (P + 2 * E + 6) & 7>(c, 1, 2, false, true);
-  mma_stage_ts<PASSES, (P + 2 * E + 7) & 7>(c, 1, 3, false, true);
-  tc_commit(c.bar + 8 * (B_ACCFULL + 1));
-}
+// (MmaCtx, mma_stage_ts / mma_stage_ss, mma_layer: nsr_tc_mma.cuh -- shared with the backward dX chain, nsr_train.cu)
 
 template <int PASSES>
 __device__ __forceinline__ void mma_role(const TcKernelArgs& a, uint8_t* sm, uint32_t sm_base, uint32_t tmem,
                                          uint32_t idesc, long long my_tiles) {
   (void)sm; (void)tmem;            // TMEM base is 0 (checked at kernel start)
   if (!elect_one()) return;
-  const MmaCtx c{sm_base, sm_base + kSmBar, idesc};
+  const MmaCtx c{sm_base + kSmRing, sm_base + kSmBar, idesc};
   if (my_tiles > 0) { mbar_wait(c.bar + 8 * (B_WFULL + 0), 0); tc_fence_after(); }   // first stage's weights
 #pragma unroll 1
   for (long long it = 0; it < my_tiles; ++it) {

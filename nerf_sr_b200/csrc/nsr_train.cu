@@ -32,6 +32,7 @@
 
 #include "nsr_internal.h"
 #include "nsr_tc_ptx.cuh"
+#include "nsr_tc_mma.cuh"
 
 namespace nsr {
 
@@ -39,43 +40,47 @@ constexpr int kT = 128;               // points per tile
 constexpr int kChunk = 32768;         // one 64-feature chunk of a tile image: hi plane | lo plane
 constexpr int kPlane = 16384;
 constexpr int kNumDxLayers = 9;       // dir, final, L8..L2
-constexpr int kWtChunkBytes = 65536;  // transposed-weight chunk: 256 rows x 64 k, hi 32 KB | lo 32 KB
-constexpr int kWtChunks = 2 + 8 * 4;
+constexpr int kWtStages = 4 + 8 * 8;  // transposed-weight ring stages per tile (32 KB each), see build_wt_table
 constexpr int kMaxSplit = 148;
 constexpr int kDwLaunchesPerNet = 14;   // 13 used: rgb, dir, dir-enc, final+sigma, L8..L2 (7), L5-enc, L1
 
 __host__ __device__ inline size_t img_off(int row, int j) { return (size_t)row * 128 + (size_t)((j ^ (row & 7)) << 4); }
 
 // ---------------------------------------------------------------------------
-// transposed weight images for the dX GEMMs (B operand: rows = input feature n, K = output feature)
+// transposed weight images for the dX GEMMs (B operand: rows = input feature n, K = output feature), laid out as the
+// 32 KB ring STAGES of the fused chain in consumption order (nsr_tc_mma.cuh): stage (layer, half h, chunk c) = rows
+// [128 h, 128 h + 128) x the 64 k-values of chunk c, hi plane 16 KB | lo plane 16 KB, K-major SWIZZLE_128B.
+// Per layer the order is h0: c0 .. c(nkc-1), then h1: c0 .. c(nkc-1); layer 0 (dir) has nkc = 2, the others 4.
 // ---------------------------------------------------------------------------
-struct WtLayer { int param, n_out, ld, col0, chunk0; };
+struct WtLayer { int param, n_out, ld, col0, stage0; };
 struct WtTable { WtLayer l[kNumDxLayers]; };
 
 static WtTable build_wt_table(int ch_dir, bool no_dir) {
   WtTable T{};
   int c = 0;
-  T.l[0] = WtLayer{18, 128, no_dir ? 256 : 256 + ch_dir, 0, c}; c += 2;     // dir_encoding.0 (feat part)
-  T.l[1] = WtLayer{16, 256, 256, 0, c}; c += 4;                              // xyz_encoding_final
+  T.l[0] = WtLayer{18, 128, no_dir ? 256 : 256 + ch_dir, 0, c}; c += 4;     // dir_encoding.0 (feat part): 2 halves x 2 chunks
+  T.l[1] = WtLayer{16, 256, 256, 0, c}; c += 8;                              // xyz_encoding_final
   for (int i = 0; i < 7; ++i) {                                              // L8 .. L2
     const int L = 8 - i;
     const bool skip = (L == 5);
-    T.l[2 + i] = WtLayer{2 * (L - 1), 256, skip ? 319 : 256, skip ? 63 : 0, c}; c += 4;
+    T.l[2 + i] = WtLayer{2 * (L - 1), 256, skip ? 319 : 256, skip ? 63 : 0, c}; c += 8;
   }
   return T;
 }
 
 template <int FMT>
 __global__ void k_pack_wt(WtTable T, const float* const* __restrict__ params, uint8_t* __restrict__ image) {
-  // one thread per (chunk, row n, 16-byte chunk j)
-  const int total = kWtChunks * 256 * 8;
+  // one thread per (stage, row r, 16-byte chunk j)
+  const int total = kWtStages * 128 * 8;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    const int cg = idx / 2048, n = (idx / 8) % 256, j = idx % 8;
+    const int st = idx / 1024, r = (idx / 8) % 128, j = idx % 8;
     int li = 0;
 #pragma unroll
-    for (int t = 1; t < kNumDxLayers; ++t) if (cg >= T.l[t].chunk0) li = t;
+    for (int t = 1; t < kNumDxLayers; ++t) if (st >= T.l[t].stage0) li = t;
     const WtLayer L = T.l[li];
-    const int c = cg - L.chunk0;
+    const int nkc = L.n_out / 64;
+    const int s_in = st - L.stage0, h = s_in / nkc, c = s_in % nkc;
+    const int n = 128 * h + r;                                     // input feature of the forward layer = output column here
     const float* W = params[L.param];
     __align__(16) uint16_t hi[8];
     __align__(16) uint16_t lo[8];
@@ -85,13 +90,13 @@ __global__ void k_pack_wt(WtTable T, const float* const* __restrict__ params, ui
       const float v = W[(int64_t)o * L.ld + L.col0 + n];
       Split<FMT>::apply1(v, hi[e], lo[e]);
     }
-    uint8_t* dst = image + (size_t)cg * kWtChunkBytes + img_off(n, j);
+    uint8_t* dst = image + (size_t)st * kChunk + img_off(r, j);
     *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hi);
-    *reinterpret_cast<uint4*>(dst + 32768) = *reinterpret_cast<const uint4*>(lo);
+    *reinterpret_cast<uint4*>(dst + kPlane) = *reinterpret_cast<const uint4*>(lo);
   }
 }
 
-size_t train_wt_bytes() { return (size_t)kWtChunks * kWtChunkBytes; }
+size_t train_wt_bytes() { return (size_t)kWtStages * kChunk; }
 
 cudaError_t train_pack_wt(NsrHandle_* h, int which, const float* const* params_dev, cudaStream_t st) {
   const WtTable T = build_wt_table(h->rp.ch_dir, h->cfg.no_dir != 0);
@@ -405,7 +410,7 @@ __device__ __forceinline__ void gemm_epilogue_free(uint32_t tmem) {
 // ---------------------------------------------------------------------------
 struct DxArgs {
   const uint8_t* a_img; int nkc;        // [n_tiles][nkc][32 KB]   dZ of this layer (K = its output features)
-  const uint8_t* wt_img;                // [nkc][64 KB]            transposed weights (rows = input features)
+  const uint8_t* wt_img;                // [2][nkc][32 KB]         this layer's stages of the transposed-weight image (half, chunk)
   uint8_t* out_img;                     // [n_tiles][4][32 KB]     dZ of the previous layer
   const uint32_t* mask_bits;            // [n_tiles][128][8]       ReLU mask gating the output, or null
   const float* dsig; const float* wsig; // rank-1 term of the sigma head (final layer only), or null
@@ -466,8 +471,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_tg_dx(const DxArgs a) {
           const uint32_t dst = sm_base + kSmSlots + slot * kSlotBytes;
           mbar_expect_tx(full, kSlotBytes);
           bulk_copy_g2s(dst, a.a_img + ((size_t)tile * a.nkc + c) * kChunk, kChunk, full);
-          bulk_copy_g2s(dst + 32768, a.wt_img + (size_t)c * kWtChunkBytes, 32768, full);
-          bulk_copy_g2s(dst + 65536, a.wt_img + (size_t)c * kWtChunkBytes + 32768, 32768, full);
+          for (int hf = 0; hf < 2; ++hf) {      // 256-row hi plane at +32 KB, lo plane at +64 KB: rows [128 hf, +128) from stage (hf, c)
+            const uint8_t* stg = a.wt_img + ((size_t)hf * a.nkc + c) * kChunk;
+            bulk_copy_g2s(dst + 32768 + hf * kPlane, stg, kPlane, full);
+            bulk_copy_g2s(dst + 65536 + hf * kPlane, stg + kPlane, kPlane, full);
+          }
         }
       }
     }
@@ -568,36 +576,70 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_tg_dx(const DxArgs a) {
 // ---------------------------------------------------------------------------
 // k_tg_dxchain: the whole dX chain of one net, fused per 128-point tile (dir -> final -> L8 .. L2).
 //
-// Same on-chip dataflow as the forward pass (nsr_tc.cu): the gradient of a layer's input never leaves the SM
-// between layers -- the epilogue writes it back into TMEM as the next layer's A operand (hi/lo planes, TS-form
-// MMAs) -- and the transposed weights stream through a shared-memory ring from L2.  HBM sees only what the dW
-// GEMMs need afterwards: each layer's dZ image written once (256-bit stores), the 1-bit ReLU masks read once.
-// This removes, per point and layer, the 1 KB re-read of dZ and half of the per-SM operand ingest that bound the
-// layer-by-layer k_tg_dx (profiles/r01_train_ncu_full.md).
-//   warp 0: producer   (a 6-slot ring of 32 KB entries: per tile the two dZ_dir chunks and, for each of the 34
-//                       transposed-weight chunks, its hi plane and its lo plane -- 70 entries; a freed entry has two
-//                       chunks' worth of MMA time to refill, which a 2 x 64 KB ring did not give)
-//   warp 1: MMA issue  (M=128 N=256 K=16 kind::f16, 3 MMAs per product; layer 0 SS, layers 1..8 TS)
-//   warps 2-17: epilogue (4 per TMEM lane quarter, 64 accumulator columns each)
+// Same on-chip dataflow AND the same issue schedule as the forward pass (nsr_tc.cu, shared code in nsr_tc_mma.cuh): the
+// gradient of a layer's input never leaves the SM between layers -- the epilogue writes it back into TMEM as the next
+// layer's A operand (hi/lo planes, TS-form MMAs) -- and the transposed weights stream through a 4-slot ring of 32 KB
+// stages from L2.  HBM sees only what the dW GEMMs need afterwards: each layer's dZ image written once, the 1-bit ReLU
+// masks read once.
+//
+// Schedule (round 2; round 1 issued N = 256 over the whole accumulator and only then ran the epilogue: tensor pipe 32 %
+// active, 13.1 k cycles per tile-layer of which 6.1 k were MMAs).  The 256-column accumulator is two N = 128 halves; per
+// layer the MMA lane issues half n0 over k-chunks c0..c3, then n1; the epilogue handles 64-column quarters q0..q3:
+//   M(l+1, n0, c) needs quarter c of layer l's epilogue (A_READY[c]: accumulator quarter drained, A chunk c rewritten);
+//   E(l, q) needs its accumulator half (ACC_FULL) and A chunk q no longer read by layer l (A_FREE);
+// so every quarter-epilogue has >= 1536 cycles of queued MMAs to hide behind, and the dZ image stores (the reason this
+// kernel exists for HBM) are issued AFTER the A_READY arrive, off the MMA lane's critical path.
+//   warps 0-7  epilogue  (warp & 3 = TMEM lane quarter, warp >> 2 = 32-column half of the 64-column quarter)
+//   warp  8    producer  (per tile: the dZ_dir tile, 64 KB, into its own buffer; then 68 weight stages through the ring)
+//   warp  9    MMA issue (one elected lane; layer 0 SS-form from the dZ_dir buffer, layers 1..8 TS-form)
+// A tile has 68 = 8 * 8 + 4 stages and 9 layers, so ring parities alternate between even and odd tiles: two instances of
+// the tile body (stage phase P0 = 0 / 4); per-layer barrier parities are runtime (layer counter g).
 // TMEM: [0,256) fp32 accumulator, [256,384) A hi plane, [384,512) A lo plane.
 // ---------------------------------------------------------------------------
 struct ChainArgs {
   const uint8_t* dzdir;     // [n_tiles][2][32 KB]
-  const uint8_t* wt;        // 34 chunks x 64 KB in consumption order (build_wt_table)
+  const uint8_t* wt;        // kWtStages x 32 KB in consumption order (build_wt_table)
   uint8_t* dz;              // [9][n_tiles][4][32 KB]: 0 = d feat, 1 = dZ_8, ..., 8 = dZ_1
   const uint32_t* mask;     // [8][n_tiles][128][8]: ReLU bits of h_1..h_8
   const float* dsig; const float* wsig;
   long long n_tiles;
 };
-constexpr int kChainThreads = 576;
-constexpr int kChainEpiWarps = 16;
-constexpr int kChSlots = 6;
-constexpr int kChRing = 0;                          // 6 x 32 KB
-constexpr int kChAux = kChSlots * kChunk;           // 196608: w_sigma
+constexpr int kChEpiWarps = 8;
+constexpr int kChProducerWarp = kChEpiWarps;          // warp 8
+constexpr int kChMmaWarp = kChEpiWarps + 1;           // warp 9 (highest id: the arbiter favours it)
+constexpr int kChainThreads = 32 * (kChEpiWarps + 2);
+constexpr int kChRing = 0;                            // 4 x 32 KB weight stages
+constexpr int kChDz = kRing * kStageBytes;            // 131072: the tile's dZ_dir image, 2 chunks x 32 KB
+constexpr int kChAux = kChDz + 2 * kChunk;            // 196608: w_sigma (1 KB)
 constexpr int kChBar = kChAux + 1024;
-constexpr int kChTmem = kChBar + 16 * 8;
+constexpr int kChTmem = kChBar + 32 * 8;
 constexpr int kSmemChainBytes = kChTmem + 16;
-enum { C_FULL = 0, C_EMPTY = 6, C_ACCFULL = 12, C_AREADY = 13 };
+constexpr int C_DZFULL = 16, C_DZEMPTY = 17;          // (indices 0..15: B_WFULL .. B_AREADY of nsr_tc_mma.cuh)
+static_assert(kStageBytes == kChunk && kPlaneBytes == kPlane, "ring stage == tile-image chunk");
+
+// One tile of the MMA lane.  P0 = stage index of the tile's first stage mod 8 (0 for even tiles, 4 for odd ones).
+template <int P0>
+__device__ __forceinline__ void chain_tile_mma(const MmaCtx& c, uint32_t dz, uint32_t dz_par, uint32_t g0, bool last_tile) {
+  // ---- layer 0 (dir layer, K = 128 = 2 chunks), A = the dZ_dir tile in shared memory
+  mbar_wait(c.bar + 8 * C_DZFULL, dz_par);
+  tc_fence_after();
+  const uint32_t gp = (g0 - 1u) & 1u;                 // A_READY parity of the previous tile's last layer
+  if (g0 > 0) { mma_wait_ready(c, 0, gp); mma_wait_ready(c, 1, gp); tc_fence_after(); }      // accumulator half 0 drained
+  mma_stage_ss<3, (P0 + 0) & 7>(c, dz, 0, true, true);
+  mma_stage_ss<3, (P0 + 1) & 7>(c, dz + kChunk, 0, true, false);
+  tc_commit(c.bar + 8 * (B_ACCFULL + 0));
+  if (g0 > 0) { mma_wait_ready(c, 2, gp); mma_wait_ready(c, 3, gp); tc_fence_after(); }      // half 1 drained
+  mma_stage_ss<3, (P0 + 2) & 7>(c, dz, 1, true, true);
+  tc_commit(c.bar + 8 * (B_AFREE + 0));
+  mma_stage_ss<3, (P0 + 3) & 7>(c, dz + kChunk, 1, true, false);
+  tc_commit(c.bar + 8 * (B_AFREE + 1));
+  tc_commit(c.bar + 8 * (B_ACCFULL + 1));
+  tc_commit(c.bar + 8 * C_DZEMPTY);                   // the dZ_dir buffer may be refilled for the next tile
+  // ---- layers 1..8 (final, L8 .. L2): K = 256, A = the previous layer's masked gradient in TMEM
+#pragma unroll 1
+  for (uint32_t l = 1; l <= 8; ++l)
+    mma_layer<3, (P0 + 4) & 7, false>(c, 0u, (g0 + l - 1u) & 1u, !(last_tile && l == 8));
+}
 
 template <int FMT>
 __global__ void __launch_bounds__(kChainThreads, 1) k_tg_dxchain(const ChainArgs a) {
@@ -610,140 +652,126 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_tg_dxchain(const ChainArgs
   if (sm_base & 1023u) { if (threadIdx.x == 0) printf("[nsr_train] dynamic smem base %u not 1024-aligned\n", sm_base); __trap(); }
   const uint32_t bar = sm_base + kChBar;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kChSlots; ++i) { mbar_init(bar + 8 * (C_FULL + i), 1); mbar_init(bar + 8 * (C_EMPTY + i), 1); }
-    mbar_init(bar + 8 * C_ACCFULL, 1); mbar_init(bar + 8 * C_AREADY, kChainEpiWarps);
+    for (int i = 0; i < kRing; ++i) { mbar_init(bar + 8 * (B_WFULL + i), 1); mbar_init(bar + 8 * (B_WEMPTY + i), 1); }
+    mbar_init(bar + 8 * (B_ACCFULL + 0), 1); mbar_init(bar + 8 * (B_ACCFULL + 1), 1);
+    mbar_init(bar + 8 * (B_AFREE + 0), 1); mbar_init(bar + 8 * (B_AFREE + 1), 1);
+    for (int q4 = 0; q4 < 4; ++q4) mbar_init(bar + 8 * (B_AREADY + q4), kChEpiWarps);
+    mbar_init(bar + 8 * C_DZFULL, 1); mbar_init(bar + 8 * C_DZEMPTY, 1);
     fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == kChMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sm_base + kChTmem), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + kChTmem);
+  // all 512 columns are ours (one CTA per SM): the base is column 0, which the shared issue code assumes (checked)
+  if (*reinterpret_cast<volatile uint32_t*>(sm + kChTmem) != 0u) {
+    if (threadIdx.x == 0) printf("[nsr_train] unexpected TMEM base %u\n", *reinterpret_cast<volatile uint32_t*>(sm + kChTmem));
+    __trap();
+  }
+  const uint32_t tmem = 0u;
 
-  if (warp == 0) {
+  if (warp == kChProducerWarp) {
     if (elect_one()) {
       uint32_t slot = 0, par = 0;
-      auto push = [&](const uint8_t* src) {
-        mbar_wait(bar + 8 * (C_EMPTY + slot), par ^ 1u);
-        const uint32_t full = bar + 8 * (C_FULL + slot);
-        mbar_expect_tx(full, kChunk);
-        bulk_copy_g2s(sm_base + kChRing + slot * kChunk, src, kChunk, full);
-        if (++slot == kChSlots) { slot = 0; par ^= 1u; }
-      };
       for (long long it = 0; it < my_tiles; ++it) {
         const long long tile = blockIdx.x + it * (long long)gridDim.x;
-        for (int cg = 0; cg < kWtChunks; ++cg) {
-          if (cg < 2) push(a.dzdir + ((size_t)tile * 2 + cg) * kChunk);        // layer 0: its A chunk first
-          push(a.wt + (size_t)cg * kWtChunkBytes);                             // hi plane (256 rows x 128 B)
-          push(a.wt + (size_t)cg * kWtChunkBytes + 32768);                     // lo plane
+        mbar_wait(bar + 8 * C_DZEMPTY, (uint32_t)((it & 1) ^ 1));          // layer 0 of the previous tile is done with the buffer
+        mbar_expect_tx(bar + 8 * C_DZFULL, 2 * kChunk);
+        bulk_copy_g2s(sm_base + kChDz, a.dzdir + (size_t)tile * 2 * kChunk, 2 * kChunk, bar + 8 * C_DZFULL);
+#pragma unroll 1
+        for (int s = 0; s < kWtStages; ++s) {
+          mbar_wait(bar + 8 * (B_WEMPTY + slot), par ^ 1u);
+          const uint32_t full = bar + 8 * (B_WFULL + slot);
+          mbar_expect_tx(full, kStageBytes);
+          bulk_copy_g2s(sm_base + kChRing + slot * kStageBytes, a.wt + (size_t)s * kStageBytes, kStageBytes, full);
+          if (++slot == kRing) { slot = 0; par ^= 1u; }
         }
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
+  } else if (warp == kChMmaWarp) {
     if (elect_one()) {
-      const uint32_t idesc = gemm_idesc(FMT, 128, 256, 0, 0);
-      uint32_t slot = 0, par = 0, g = 0;
-      auto take = [&]() -> uint32_t {          // wait for the next ring entry, return its smem address
-        mbar_wait(bar + 8 * (C_FULL + slot), par);
-        const uint32_t addr = sm_base + kChRing + slot * kChunk;
-        if (++slot == kChSlots) { slot = 0; par ^= 1u; }
-        return addr;
-      };
+      const MmaCtx c{sm_base + kChRing, bar, umma_idesc(FMT, 128, 128)};
+      if (my_tiles > 0) { mbar_wait(bar + 8 * (B_WFULL + 0), 0); tc_fence_after(); }      // the first stage's weights
+#pragma unroll 1
       for (long long it = 0; it < my_tiles; ++it) {
-        for (int l = 0; l < 9; ++l, ++g) {
-          if (g > 0) { mbar_wait(bar + 8 * C_AREADY, (g - 1) & 1u); tc_fence_after(); }    // accumulator drained, A planes written
-          const int nkc = (l == 0) ? 2 : 4;
-          for (int c = 0; c < nkc; ++c) {
-            const uint32_t s0 = slot;
-            const uint32_t sa = (l == 0) ? take() : 0u;
-            const uint32_t sh = take(), sl = take();
-            tc_fence_after();
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t bh = kmajor_desc(sh + 32 * k), bl = kmajor_desc(sl + 32 * k);
-              const uint32_t acc = (c | k) ? 1u : 0u;
-              if (l == 0) {
-                const uint64_t ah = kmajor_desc(sa + 32 * k), al = kmajor_desc(sa + kPlane + 32 * k);
-                mma_ss(tmem, ah, bh, idesc, acc);
-                mma_ss(tmem, al, bh, idesc, 1u);
-                mma_ss(tmem, ah, bl, idesc, 1u);
-              } else {
-                const uint32_t ah = tmem + 256u + 32u * (uint32_t)c + 8u * (uint32_t)k;
-                mma_ts(tmem, ah, bh, idesc, acc);
-                mma_ts(tmem, ah + 128u, bh, idesc, 1u);
-                mma_ts(tmem, ah, bl, idesc, 1u);
-              }
-            }
-            uint32_t f = s0;                    // release the entries this chunk used
-            for (int i = 0; i < (l == 0 ? 3 : 2); ++i) { tc_commit(bar + 8 * (C_EMPTY + f)); if (++f == kChSlots) f = 0; }
-          }
-          tc_commit(bar + 8 * C_ACCFULL);
-        }
+        const uint32_t g0 = 9u * (uint32_t)it;
+        const bool last = it + 1 == my_tiles;
+        if (it & 1) chain_tile_mma<4>(c, sm_base + kChDz, 1u, g0, last);
+        else chain_tile_mma<0>(c, sm_base + kChDz, 0u, g0, last);
       }
     }
     __syncwarp();
   } else {
-    const int q = warp & 3, part = (warp - 2) >> 2;          // part: 64-column slice of the 256 accumulator columns
+    const int q = warp & 3, hh = warp >> 2;
     const int row = 32 * q + lane, r7 = lane & 7;
     const uint32_t tlane = tmem + ((uint32_t)(32 * q) << 16);
     const float* wsig = reinterpret_cast<const float*>(sm + kChAux);
     uint32_t g = 0;
+#pragma unroll 1
     for (long long it = 0; it < my_tiles; ++it) {
       const long long tile = blockIdx.x + it * (long long)gridDim.x;
       const float ds = a.dsig[tile * kT + row];
 #pragma unroll 1
       for (int l = 0; l < 9; ++l, ++g) {
-        uint32_t mb[2] = {0xffffffffu, 0xffffffffu};
-        if (l >= 1) {      // output of step l is the gradient w.r.t. h_{9-l}: gate with that layer's ReLU bits
-          const uint2 m = *reinterpret_cast<const uint2*>(a.mask + (((size_t)(8 - l) * (size_t)a.n_tiles + (size_t)tile) * kT + row) * 8 + 2 * part);
-          mb[0] = m.x; mb[1] = m.y;
+        // output of step l >= 1 is the gradient w.r.t. h_{9-l}: gate it with that layer's ReLU bits (this thread's row,
+        // mask word 2 q4 + hh of the 8 covers columns [64 q4 + 32 hh, +32))
+        uint32_t mq[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+        if (l >= 1) {
+          const uint4* mp = reinterpret_cast<const uint4*>(a.mask + (((size_t)(8 - l) * (size_t)a.n_tiles + (size_t)tile) * kT + row) * 8);
+          const uint4 m0 = mp[0], m1 = mp[1];
+          mq[0] = hh ? m0.y : m0.x; mq[1] = hh ? m0.w : m0.z; mq[2] = hh ? m1.y : m1.x; mq[3] = hh ? m1.w : m1.z;
         }
         uint8_t* orow = a.dz + (((size_t)l * (size_t)a.n_tiles + (size_t)tile) * 4) * kChunk + (size_t)row * 128;
-        mbar_wait(bar + 8 * C_ACCFULL, g & 1u);
-        tc_fence_after();
-#pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          const int col0 = 64 * part + 32 * b;
+#pragma unroll 1
+        for (int q4 = 0; q4 < 4; ++q4) {
+          // every barrier is waited for in every layer (one phase per layer: nobody can fall two phases behind)
+          if (q4 == 0) { mbar_wait(bar + 8 * (B_ACCFULL + 0), g & 1u); mbar_wait(bar + 8 * (B_AFREE + 0), g & 1u); }
+          else if (q4 == 1) mbar_wait(bar + 8 * (B_AFREE + 1), g & 1u);
+          else if (q4 == 2) mbar_wait(bar + 8 * (B_ACCFULL + 1), g & 1u);
+          tc_fence_after();
+          const int col0 = 64 * q4 + 32 * hh;
           uint32_t r[32];
           TMEM_LD32(tlane + (uint32_t)col0, r);
           tc_wait_ld();
           uint32_t whi[16], wlo[16];
+          const uint32_t mb = mq[q4];
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
             float v0 = __uint_as_float(r[2 * e]), v1 = __uint_as_float(r[2 * e + 1]);
             if (l == 1) { v0 = fmaf(ds, wsig[col0 + 2 * e], v0); v1 = fmaf(ds, wsig[col0 + 2 * e + 1], v1); }
-            if (!((mb[b] >> (2 * e)) & 1u)) v0 = 0.f;
-            if (!((mb[b] >> (2 * e + 1)) & 1u)) v1 = 0.f;
+            if (!((mb >> (2 * e)) & 1u)) v0 = 0.f;
+            if (!((mb >> (2 * e + 1)) & 1u)) v1 = 0.f;
             Split<FMT>::apply(v0, v1, whi[e], wlo[e]);
           }
           if (l < 8) {       // next layer's A operand (hi and lo planes), two k-values per TMEM column
             TMEM_ST16(tlane + 256u + (uint32_t)(col0 / 2), whi);
             TMEM_ST16(tlane + 384u + (uint32_t)(col0 / 2), wlo);
+            tc_wait_st();
           }
-          uint8_t* gp = orow + (size_t)(col0 >> 6) * kChunk;
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar + 8 * (B_AREADY + q4));
+          // the layer's dZ image (what the dW GEMMs read), 32 bytes per store -- after the arrive: the MMA lane moves on
+          uint8_t* gp = orow + (size_t)q4 * kChunk;
 #pragma unroll
           for (int t2 = 0; t2 < 2; ++t2) {
             const int e = 8 * t2;
-            store_chunk_pair(gp, 2 * b + t2, r7, make_uint4(whi[e], whi[e + 1], whi[e + 2], whi[e + 3]),
+            store_chunk_pair(gp, 2 * hh + t2, r7, make_uint4(whi[e], whi[e + 1], whi[e + 2], whi[e + 3]),
                              make_uint4(whi[e + 4], whi[e + 5], whi[e + 6], whi[e + 7]));
-            store_chunk_pair(gp + kPlane, 2 * b + t2, r7, make_uint4(wlo[e], wlo[e + 1], wlo[e + 2], wlo[e + 3]),
+            store_chunk_pair(gp + kPlane, 2 * hh + t2, r7, make_uint4(wlo[e], wlo[e + 1], wlo[e + 2], wlo[e + 3]),
                              make_uint4(wlo[e + 4], wlo[e + 5], wlo[e + 6], wlo[e + 7]));
           }
         }
-        tc_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar + 8 * C_AREADY);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+  if (warp == kChMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
 // ---------------------------------------------------------------------------
@@ -1275,7 +1303,7 @@ static int backward_net(NsrHandle_* h, int which, const float* rays, int64_t n, 
   }
 
   const WtTable WT = build_wt_table(h->rp.ch_dir, h->cfg.no_dir != 0);
-  auto wt = [&](int idx) { return net.wt_image + (size_t)WT.l[idx].chunk0 * kWtChunkBytes; };
+  auto wt = [&](int idx) { return net.wt_image + (size_t)WT.l[idx].stage0 * kChunk; };
   // dz(i): i = 0 d feat, 1 dZ_8, ..., 8 dZ_1 (each [tiles][4 chunks])
   auto dzi = [&](int i) { return (uint8_t*)(ws + L.dz) + (size_t)i * (size_t)tiles * 4 * kChunk; };
 
@@ -1664,7 +1692,7 @@ extern "C" int nsr_debug_dx(NsrHandle* h, int which, int layer_idx, const void* 
   const WtTable WT = build_wt_table(h->rp.ch_dir, h->cfg.no_dir != 0);
   DxArgs a{};
   a.a_img = (const uint8_t*)a_img; a.nkc = WT.l[layer_idx].n_out / 64;
-  a.wt_img = h->net[which].wt_image + (size_t)WT.l[layer_idx].chunk0 * kWtChunkBytes;
+  a.wt_img = h->net[which].wt_image + (size_t)WT.l[layer_idx].stage0 * kChunk;
   a.out_img = (uint8_t*)out_img; a.mask_bits = (const uint32_t*)mask_bits; a.dsig = dsig; a.wsig = wsig;
   a.n_tiles = (n_rows + kT - 1) / kT;
   NSR_TCUDA(h, launch_dx(h, a, (cudaStream_t)stream));

@@ -127,11 +127,16 @@ def sample_along_rays(o: Tensor, d: Tensor, near: Tensor, far: Tensor, n: int,
 # a10: alpha compositing   (models/rendering.py:89-111)
 # --------------------------------------------------------------------------
 def composite(rgb: Tensor, sigma: Tensor, z: Tensor, white_bkgd: bool,
-              sigma_activation: str = "relu"):
+              sigma_activation: str = "relu", sigma_mask: Optional[Tensor] = None):
+    """``sigma_mask`` (test harness only, None = the reference's path): replaces the sign test of relu(sigma) the same way
+    mlp_forward's ``relu_masks`` do.  The LAST sample has delta = 1e10, so alpha_last jumps between 0 and 1 with the sign of
+    sigma_last: the one genuinely discontinuous decision of the compositing stage."""
     eps = 1e-10
     deltas = z[:, 1:] - z[:, :-1]                                    # :90
     deltas = torch.cat([deltas, 1e10 * torch.ones_like(deltas[:, :1])], -1)
-    if sigma_activation == "relu":                                   # :70-73
+    if sigma_activation == "relu" and sigma_mask is not None:
+        act = sigma * sigma_mask.to(sigma.dtype)
+    elif sigma_activation == "relu":                                 # :70-73
         act = torch.relu(sigma)
     else:
         act = torch.log(1 + torch.exp(sigma - 1))
@@ -187,13 +192,16 @@ def render_pass(p: Dict[str, Tensor], xyz: Tensor, dir_enc: Tensor, z: Tensor,
     n_rays, n_s = xyz.shape[:2]
     enc = posenc(xyz.reshape(-1, 3), cfg.deg_pos, cfg.no_xyz, cfg.no_logscale)
     d = dir_enc.repeat_interleave(n_s, dim=0)                        # ray-major, :266
+    sigma_mask = None
+    if relu_masks is not None and len(relu_masks) > cfg.D + 1:       # optional last entry: [N, S] mask of relu(sigma)
+        sigma_mask, relu_masks = relu_masks[cfg.D + 1], relu_masks[: cfg.D + 1]
     raw = mlp_forward(p, torch.cat([enc, d], -1), cfg, relu_masks=relu_masks).view(n_rays, n_s, 4)
     rgb, sigma = raw[..., :3], raw[..., 3]
     if cfg.gamma_correct:                                            # :271-276
         rgb = torch.pow(rgb, 1 / 2.2)
     if noise is not None and cfg.noise_std > 0:                      # utils.py:209-210
         sigma = sigma + noise * cfg.noise_std
-    return composite(rgb, sigma, z, cfg.white_bkgd, cfg.sigma_activation) + (raw,)
+    return composite(rgb, sigma, z, cfg.white_bkgd, cfg.sigma_activation, sigma_mask) + (raw,)
 
 
 @dataclass

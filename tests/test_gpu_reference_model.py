@@ -18,7 +18,7 @@ import os
 import pytest
 import torch
 
-from conftest import ROOT
+from conftest import ROOT, e2e_bounds
 from oracle import nerf_oracle as O
 from oracle import ref_shim
 
@@ -101,9 +101,20 @@ def test_real_reference_model_inference_unpatched_vs_patched(kind, s, white, hw,
         assert got[k].shape == ref[k].shape and got[k].dtype == ref[k].dtype, k
         mx, v = O.tolerance_violations(got[k].float().cpu(), ref[k].float().cpu())
         rec["keys"][k] = {"max_abs": mx, "viol": v}
-    # coarse stage (HR *_ori and box-averaged LR attributes): within tolerance everywhere
+    # coarse stage (HR *_ori and box-averaged LR attributes): within tolerance everywhere -- except on a ray whose LAST coarse
+    # sample has sigma within 1e-4 of zero: delta_last = 1e10 makes alpha_last a step function of sign(sigma_last)
+    # (models/rendering.py:91-98), the one discontinuous decision of the coarse stage (tests/test_gpu_frame_parity.py)
+    with torch.no_grad():
+        ex = {}
+        O.forward_rays({k: v.to("cuda:0") for k, v in pc.items()}, {k: v.to("cuda:0") for k, v in pf.items()}, rays.view(-1, 8).to("cuda:0"), cfg, extras=ex)
+    well = (ex["raw_coarse"][:, -1, 3].abs() >= 1e-4).cpu()
+    rec["ill_conditioned_rays_coarse"] = int((~well).sum())
+    well_lr = well.view(n_lr, s * s).all(1)
     for k in ("coarse_comp_rgbs", "coarse_comp_rgbs_ori", "coarse_depth", "coarse_depth_ori", "coarse_opacity", "coarse_weights"):
-        assert rec["keys"][k]["viol"] == 0.0, (k, rec["keys"][k])
+        w = well if got[k].shape[0] == well.shape[0] else well_lr
+        _, v = O.tolerance_violations(got[k].float().cpu()[w], ref[k].float().cpu()[w])
+        assert v == 0.0, (k, rec["keys"][k], rec["ill_conditioned_rays_coarse"])
+    assert rec["ill_conditioned_rays_coarse"] <= 3
     # fine stage end to end: ill-conditioned -> fp64 floor of the oracle on the same rays
     dev = torch.device("cuda:0")
     flat = rays.view(-1, 8).to(dev)
@@ -116,8 +127,9 @@ def test_real_reference_model_inference_unpatched_vs_patched(kind, s, white, hw,
         _, v64 = O.tolerance_violations(got[src].cpu().reshape(ref64[k].shape), ref64[k].cpu())
         rec["keys"][src]["floor_fp32_vs_fp64"] = floor
         rec["keys"][src]["viol_vs_fp64"] = v64
-        assert v64 <= floor + 0.01, (src, rec["keys"][src])
-        assert rec["keys"][src]["viol"] <= 2 * floor + 0.01, (src, rec["keys"][src])
+        b64, b32 = e2e_bounds(floor, n_lr * s * s, "bf16x3")
+        assert v64 <= b64, (src, rec["keys"][src], b64)
+        assert rec["keys"][src]["viol"] <= b32, (src, rec["keys"][src], b32)
     rec["psnr_fine_lr_image_db"] = _psnr(got["fine_comp_rgbs"], ref["fine_comp_rgbs"])
     rec["psnr_fine_vis_db"] = _psnr(got["vis_fine_pred_img"], ref["vis_fine_pred_img"])
     rec["loss_fine_psnr"] = [float(ref["loss_fine_psnr"]), float(got["loss_fine_psnr"])]

@@ -372,7 +372,8 @@ def test_gradients_with_relu_masks_teacher_forced(name):
     """VERDICT r1 weak #1 / ADVICE: isolate the GEMM + compositing backward from ReLU decisions.  The free-running test
     above attributes its 1e-2-level first-layer residual to ReLU masks that flip on ~1e-5 pre-activation differences;
     here the oracle's autograd is run with the masks the CUDA forward actually stashed (8 trunk layers + the dir layer of
-    both nets), so every gradient must sit at the arithmetic floor: rel-L2 <= 3 x (fp32-vs-fp64 oracle) + 1e-3."""
+    both nets) and with the CUDA forward's relu(sigma) decisions, so every gradient must sit at the arithmetic floor:
+    rel-L2 <= 3 x (fp32-vs-fp64 oracle) + 2e-4 (measured: 2e-6 .. 3e-5)."""
     from nerf_sr_b200 import Trainer
     fx = TrainFixture(name)
     r = _renderer(fx.cfg, fx.p_coarse, fx.p_fine, "bf16x3")
@@ -383,7 +384,17 @@ def test_gradients_with_relu_masks_teacher_forced(name):
     z_f = r.render_train(rays, rng, want_z_fine=True)["z_fine"].cpu()
     gc, gf = tr.forward_backward(rays, fx.target.to(DEV), rng, far=float(fx.rays[0, 7]))
     torch.cuda.synchronize()
-    masks = tuple([r.stash_mask(n, w, l).cpu() for l in range(1, 9)] + [(r.stash_activation(n, w, 10) > 0).cpu()] for w in (0, 1))
+    masks = [[r.stash_mask(n, w, l).cpu() for l in range(1, 9)] + [(r.stash_activation(n, w, 10) > 0).cpu()] for w in (0, 1)]
+    # ... and the sign decisions of relu(sigma) in the compositing (the last sample's delta is 1e10: alpha jumps 0 <-> 1):
+    # sigma as the CUDA forward computed it (the non-stash kernel is bit-identical, test_stash_matches_oracle_activations)
+    z_c = r.sample_along_rays(rays, rng["u_coarse"].to(DEV) if (rng and rng.get("u_coarse") is not None) else None)
+    for w, z, nk in ((0, z_c, "noise_coarse"), (1, z_f.to(DEV), "noise_fine")):
+        nz = rng.get(nk).to(DEV) if (rng and rng.get(nk) is not None and fx.cfg.noise_std > 0) else None
+        sig = r.render_pass(w, rays, z, nz, want_raw=True)["raw"][..., 3]
+        if nz is not None:
+            sig = sig + nz * fx.cfg.noise_std
+        masks[w].append((sig > 0).cpu())
+    masks = tuple(masks)
 
     def oracle(dtype):
         cast = lambda t: None if t is None else t.to(dtype)
