@@ -427,14 +427,10 @@ __device__ __forceinline__ void frontend_role(const TcKernelArgs& a, uint8_t* sm
       const int sw = (j ^ (t & 7)) << 4;
       *reinterpret_cast<uint4*>(row_hi + sw) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
       *reinterpret_cast<uint4*>(row_lo + sw) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-    }
-    if (STASH) {   // the same swizzled row image -> global stash, 32 bytes per store (re-read from smem: own writes)
-      uint8_t* g = a.stash_enc + (size_t)tile * kStageBytes + t * 128;
-#pragma unroll
-      for (int pr = 0; pr < 4; ++pr) {
-        const int pos = 32 * pr;
-        stg256(g + pos, *reinterpret_cast<const uint4*>(row_hi + pos), *reinterpret_cast<const uint4*>(row_hi + pos + 16));
-        stg256(g + kPlaneBytes + pos, *reinterpret_cast<const uint4*>(row_lo + pos), *reinterpret_cast<const uint4*>(row_lo + pos + 16));
+      if (STASH) {   // the same 16-byte pieces -> the tile image in HBM (lanes = consecutive points: 512 B per warp store)
+        uint8_t* g = a.stash_enc + (size_t)tile * kStageBytes + img2_off(t, j);
+        stg128(g, hi[0], hi[1], hi[2], hi[3]);
+        stg128(g + kPlaneBytes, lo[0], lo[1], lo[2], lo[3]);
       }
     }
     TR(5002);
@@ -491,8 +487,8 @@ __device__ __forceinline__ void frontend_role(const TcKernelArgs& a, uint8_t* sm
 // 32 columns of each:  acc + bias (+ReLU) (-> sigma-head partial) -> hi/lo split -> A operand planes.
 template <int FMT, int PASSES, bool SIGMA, bool STASH>
 __device__ __forceinline__ void epi_layer(int L, float relu_floor, uint32_t g, uint32_t bar, uint32_t tlane,
-                                          uint32_t cst_addr, int hh, int lane, float& sig_p,
-                                          uint8_t* stash_row, uint32_t* mask_row TR_PARAMS) {
+                                          uint32_t cst_addr, int hh, int lane, float& sig_p, int row,
+                                          uint8_t* stash_chunks, uint32_t* mask_row TR_PARAMS) {
   const uint32_t bias_addr = cst_addr + 4u * (uint32_t)((L - 1) * 256);   // L9 -> kcBiasFinal
 #pragma unroll 1
   for (int q4 = 0; q4 < 4; ++q4) {
@@ -526,24 +522,21 @@ __device__ __forceinline__ void epi_layer(int L, float relu_floor, uint32_t g, u
     }
     TMEM_ST16(tlane + 256u + (uint32_t)(col0 / 2), whi);
     if (PASSES == 3) TMEM_ST16(tlane + 384u + (uint32_t)(col0 / 2), wlo);
-    if (STASH) {   // this thread's 32 activations of layer L -> the layer's tile image (row = tile row)
-      uint8_t* gp = stash_row + (size_t)q4 * kStageBytes;        // k chunk = 64-column quarter
-      const int r7 = lane & 7;                                   // tile row = 32*quarter + lane
-#pragma unroll
-      for (int t2 = 0; t2 < 2; ++t2) {                           // 16-byte chunks (4hh + 2 t2, + 1): one 32-byte store each
-        const int e = 8 * t2;
-        store_chunk_pair(gp, 2 * hh + t2, r7, make_uint4(whi[e], whi[e + 1], whi[e + 2], whi[e + 3]),
-                         make_uint4(whi[e + 4], whi[e + 5], whi[e + 6], whi[e + 7]));
-        store_chunk_pair(gp + kPlaneBytes, 2 * hh + t2, r7, make_uint4(wlo[e], wlo[e + 1], wlo[e + 2], wlo[e + 3]),
-                         make_uint4(wlo[e + 4], wlo[e + 5], wlo[e + 6], wlo[e + 7]));
-      }
-      if (mask_row) mask_row[2 * q4 + hh] = relu_bits;          // columns [64 q4 + 32 hh, +32)
-    }
     TR(100 * L + 10 * q4 + 3);
     tc_wait_st();
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(bar + 8 * (B_AREADY + q4));
+    if (STASH) {   // this thread's 32 activations of layer L -> the layer's tile image, AFTER the arrive (the MMA lane is
+                   // already released); four 16-byte pieces per plane, each a 512-byte contiguous warp store
+      uint8_t* gp = stash_chunks + (size_t)q4 * kStageBytes + img2_off(row, 4 * hh);      // k chunk = 64-column quarter
+#pragma unroll
+      for (int t2 = 0; t2 < 4; ++t2) {
+        stg128(gp + 1024 * t2, whi[4 * t2], whi[4 * t2 + 1], whi[4 * t2 + 2], whi[4 * t2 + 3]);
+        stg128(gp + kPlaneBytes + 1024 * t2, wlo[4 * t2], wlo[4 * t2 + 1], wlo[4 * t2 + 2], wlo[4 * t2 + 3]);
+      }
+      if (mask_row) mask_row[2 * q4 + hh] = relu_bits;          // columns [64 q4 + 32 hh, +32)
+    }
     TR(100 * L + 10 * q4 + 4);
   }
 }
@@ -613,15 +606,15 @@ __device__ __forceinline__ void epilogue_role(const TcKernelArgs& a, uint8_t* sm
       // the previous tile's tail goes here, behind this tile's first layer: the MMA lane is already
       // busy with L2 while the heads' activations are finished and staged
       if (L == 2 && it >= 1) tile_tail(it - 1, sig_prev, rgb_prev[0], rgb_prev[1], rgb_prev[2]);
-      uint8_t* stash_row = nullptr;
+      uint8_t* stash_chunks = nullptr;
       uint32_t* mask_row = nullptr;
       if (STASH) {
         const size_t lt = (size_t)(L - 1) * (size_t)a.n_tiles + (size_t)(first_tile + it * (long long)tile_stride);
-        stash_row = a.stash_h + lt * (size_t)(4 * kStageBytes) + (size_t)row * 128;
+        stash_chunks = a.stash_h + lt * (size_t)(4 * kStageBytes);
         if (L <= 8) mask_row = a.stash_mask + (lt * 128 + (size_t)row) * 8;
       }
-      if (L == 8) epi_layer<FMT, PASSES, true, STASH>(L, 0.f, g, bar, tlane, sm_base + kSmConst, hh, lane, sig_p, stash_row, mask_row TR_ARGS);   // + sigma head
-      else epi_layer<FMT, PASSES, false, STASH>(L, L <= 8 ? 0.f : -INFINITY, g, bar, tlane, sm_base + kSmConst, hh, lane, sig_p, stash_row, mask_row TR_ARGS);
+      if (L == 8) epi_layer<FMT, PASSES, true, STASH>(L, 0.f, g, bar, tlane, sm_base + kSmConst, hh, lane, sig_p, row, stash_chunks, mask_row TR_ARGS);   // + sigma head
+      else epi_layer<FMT, PASSES, false, STASH>(L, L <= 8 ? 0.f : -INFINITY, g, bar, tlane, sm_base + kSmConst, hh, lane, sig_p, row, stash_chunks, mask_row TR_ARGS);
     }
     // ---- layer 10: dir layer (N=128, accumulator half 0) + rgb head ----
     float rgb_p[3] = {0.f, 0.f, 0.f};
@@ -657,15 +650,12 @@ __device__ __forceinline__ void epilogue_role(const TcKernelArgs& a, uint8_t* sm
             Split<FMT>::apply(v2, v3, dhi[j / 2 + 1], dlo[j / 2 + 1]);
           }
         }
-        if (STASH) {   // dir layer activations (post-ReLU) -> tile image, chunk hh, 16-B chunks 4c .. 4c+3
-          uint8_t* gp = a.stash_dir + ((size_t)(first_tile + it * (long long)tile_stride) * 2 + (size_t)hh) * (size_t)kStageBytes + (size_t)row * 128;
+        if (STASH) {   // dir layer activations (post-ReLU) -> tile image, chunk hh, 16-byte pieces j = 4c .. 4c+3
+          uint8_t* gp = a.stash_dir + ((size_t)(first_tile + it * (long long)tile_stride) * 2 + (size_t)hh) * (size_t)kStageBytes + img2_off(row, 4 * c);
 #pragma unroll
-          for (int t2 = 0; t2 < 2; ++t2) {
-            const int e = 8 * t2;
-            store_chunk_pair(gp, 2 * c + t2, row & 7, make_uint4(dhi[e], dhi[e + 1], dhi[e + 2], dhi[e + 3]),
-                             make_uint4(dhi[e + 4], dhi[e + 5], dhi[e + 6], dhi[e + 7]));
-            store_chunk_pair(gp + kPlaneBytes, 2 * c + t2, row & 7, make_uint4(dlo[e], dlo[e + 1], dlo[e + 2], dlo[e + 3]),
-                             make_uint4(dlo[e + 4], dlo[e + 5], dlo[e + 6], dlo[e + 7]));
+          for (int t2 = 0; t2 < 4; ++t2) {
+            stg128(gp + 1024 * t2, dhi[4 * t2], dhi[4 * t2 + 1], dhi[4 * t2 + 2], dhi[4 * t2 + 3]);
+            stg128(gp + kPlaneBytes + 1024 * t2, dlo[4 * t2], dlo[4 * t2 + 1], dlo[4 * t2 + 2], dlo[4 * t2 + 3]);
           }
         }
       }

@@ -142,6 +142,23 @@ __device__ __forceinline__ void store_chunk_pair(uint8_t* row_base, int pair, in
   stg256(row_base + pos, swp ? c_odd : c_even, swp ? c_even : c_odd);
 }
 
+// ---- "tile image": how activations / gradients that the backward GEMMs consume live in HBM (nsr_train.cu) ----
+// Per 128-point tile and 64-feature chunk: a hi plane (16 KB) then a lo plane (16 KB) of 16-bit values.  Inside a plane
+// the unit is the 16-byte piece (8 consecutive features j of one point), ordered  [64-point half][j = 0..7][point & 63]:
+//   offset(row, j) = (row >> 6) * 8192 + j * 1024 + (row & 63) * 16.
+// Why: (1) a warp whose lanes are 32 consecutive points stores one piece per lane = 512 contiguous bytes = four full 128-byte
+// lines per instruction (round 1's row-major swizzled image took 32 half-used sectors per instruction and made the stash /
+// dZ stores, not the tensor pipe, the limiter of the forward-with-stash and of the dX chain); (2) a 64-point half of a plane
+// is 8 KB contiguous, so the dW GEMMs fetch their stages with the same bulk copies as before; (3) it is a canonical
+// no-swizzle UMMA operand both ways: MN-major (dW: points = K; 8-point groups 128 B apart = LBO, 8-feature groups 1 KB
+// apart = SBO) and, with the two halves of a j-block placed side by side in shared memory, K-major (dX: points = M).
+__host__ __device__ inline size_t img2_off(int row, int j) {
+  return (size_t)(row >> 6) * 8192 + (size_t)j * 1024 + (size_t)(row & 63) * 16;
+}
+__device__ __forceinline__ void stg128(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 // ---- hi/lo split of two fp32 values into packed 16-bit pairs (even k in the low half) ----
 template <int FMT> struct Split;
 template <> struct Split<1> {   // bf16

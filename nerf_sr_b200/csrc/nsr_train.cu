@@ -44,7 +44,9 @@ constexpr int kWtStages = 4 + 8 * 8;  // transposed-weight ring stages per tile 
 constexpr int kMaxSplit = 148;
 constexpr int kDwLaunchesPerNet = 14;   // 13 used: rgb, dir, dir-enc, final+sigma, L8..L2 (7), L5-enc, L1
 
-__host__ __device__ inline size_t img_off(int row, int j) { return (size_t)row * 128 + (size_t)((j ^ (row & 7)) << 4); }
+// K-major SWIZZLE_128B rows (the WEIGHT stages: 128-byte rows, 16-byte chunks XOR-swizzled with the row index)
+__host__ __device__ inline size_t sw128_off(int row, int j) { return (size_t)row * 128 + (size_t)((j ^ (row & 7)) << 4); }
+// (activation / gradient TILE IMAGES use img2_off, nsr_tc_ptx.cuh)
 
 // ---------------------------------------------------------------------------
 // transposed weight images for the dX GEMMs (B operand: rows = input feature n, K = output feature), laid out as the
@@ -90,7 +92,7 @@ __global__ void k_pack_wt(WtTable T, const float* const* __restrict__ params, ui
       const float v = W[(int64_t)o * L.ld + L.col0 + n];
       Split<FMT>::apply1(v, hi[e], lo[e]);
     }
-    uint8_t* dst = image + (size_t)st * kChunk + img_off(r, j);
+    uint8_t* dst = image + (size_t)st * kChunk + sw128_off(r, j);
     *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hi);
     *reinterpret_cast<uint4*>(dst + kPlane) = *reinterpret_cast<const uint4*>(lo);
   }
@@ -128,7 +130,7 @@ __global__ void k_pack_image(const float* __restrict__ src, long long n_rows, in
       const float v = (p < n_rows && k < ld) ? src[p * ld + k] : 0.f;
       Split<FMT>::apply1(v, hi[e], lo[e]);
     }
-    uint8_t* dst = image + (size_t)tc * kChunk + img_off(row, j);
+    uint8_t* dst = image + (size_t)tc * kChunk + img2_off(row, j);
     *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hi);
     *reinterpret_cast<uint4*>(dst + kPlane) = *reinterpret_cast<const uint4*>(lo);
   }
@@ -147,7 +149,7 @@ __global__ void k_unpack_image(const uint8_t* __restrict__ image, long long n_ro
     const int k = (int)(idx % ld);
     const long long tile = p / kT;
     const int row = (int)(p % kT), c = k / 64, j = (k % 64) / 8, e = k % 8;
-    const uint8_t* s = image + (size_t)(tile * cpt + c) * kChunk + img_off(row, j) + 2 * e;
+    const uint8_t* s = image + (size_t)(tile * cpt + c) * kChunk + img2_off(row, j) + 2 * e;
     const uint16_t hi = *reinterpret_cast<const uint16_t*>(s), lo = *reinterpret_cast<const uint16_t*>(s + kPlane);
     dst[idx] = half_to_float<FMT>(hi) + half_to_float<FMT>(lo);
   }
@@ -287,56 +289,53 @@ k_render_bwd(const RenderBwdArgs a) {
       const long long tile = p >> 7;
       const int row = (int)(p & 127);
       a.dsig[p] = dsg;
-      const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
-      {   // dHead: (d sigma, d r, d g, d b, 0...) in the first 16-byte chunk
+      // the three image rows of this point: 16-byte pieces j = 0..7 of each 64-feature chunk, lanes = consecutive points
+      // (one 512-byte contiguous warp store per piece and plane)
+      {   // dHead: (d sigma, d r, d g, d b, 0...) in piece 0
         uint32_t h0, l0, h1, l1;
         Split<FMT>::apply(dsg, drgb[0], h0, l0);
         Split<FMT>::apply(drgb[1], drgb[2], h1, l1);
-        uint8_t* g = a.dhead + (size_t)tile * kChunk + (size_t)row * 128;
+        uint8_t* g = a.dhead + (size_t)tile * kChunk + img2_off(row, 0);
 #pragma unroll
-        for (int pr = 0; pr < 4; ++pr) {
-          store_chunk_pair(g, pr, row & 7, pr == 0 ? make_uint4(h0, h1, 0u, 0u) : zero4, zero4);
-          store_chunk_pair(g + kPlane, pr, row & 7, pr == 0 ? make_uint4(l0, l1, 0u, 0u) : zero4, zero4);
+        for (int j = 0; j < 8; ++j) {
+          stg128(g + 1024 * j, j == 0 ? h0 : 0u, j == 0 ? h1 : 0u, 0u, 0u);
+          stg128(g + kPlane + 1024 * j, j == 0 ? l0 : 0u, j == 0 ? l1 : 0u, 0u, 0u);
         }
       }
       {   // encdir: the ray's 27 encoded view-direction channels (+ zero pad to 64)
-        uint8_t* g = a.encdir + (size_t)tile * kChunk + (size_t)row * 128;
+        uint8_t* g = a.encdir + (size_t)tile * kChunk + img2_off(row, 0);
 #pragma unroll
-        for (int pr = 0; pr < 4; ++pr) {
-          uint32_t hi[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u}, lo[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-          if (pr < 2 && valid) {
+        for (int j = 0; j < 8; ++j) {
+          uint32_t hi[4] = {0u, 0u, 0u, 0u}, lo[4] = {0u, 0u, 0u, 0u};
+          if (j < 4 && valid) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) Split<FMT>::apply(senc[16 * pr + 2 * q], senc[16 * pr + 2 * q + 1], hi[q], lo[q]);
+            for (int q = 0; q < 4; ++q) Split<FMT>::apply(senc[8 * j + 2 * q], senc[8 * j + 2 * q + 1], hi[q], lo[q]);
           }
-          store_chunk_pair(g, pr, row & 7, make_uint4(hi[0], hi[1], hi[2], hi[3]), make_uint4(hi[4], hi[5], hi[6], hi[7]));
-          store_chunk_pair(g + kPlane, pr, row & 7, make_uint4(lo[0], lo[1], lo[2], lo[3]), make_uint4(lo[4], lo[5], lo[6], lo[7]));
+          stg128(g + 1024 * j, hi[0], hi[1], hi[2], hi[3]);
+          stg128(g + kPlane + 1024 * j, lo[0], lo[1], lo[2], lo[3]);
         }
       }
       // dZ_dir = (d rgb_pre . W_rgb) masked by the dir layer's ReLU (networks.py:221-222)
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
-        uint8_t* g = a.dzdir + (size_t)(tile * 2 + c) * kChunk + (size_t)row * 128;
-        const uint8_t* m = a.stash_dir + (size_t)(tile * 2 + c) * kChunk;
+        uint8_t* g = a.dzdir + (size_t)(tile * 2 + c) * kChunk + img2_off(row, 0);
+        const uint8_t* m = a.stash_dir + (size_t)(tile * 2 + c) * kChunk + img2_off(row, 0);
 #pragma unroll 2
-        for (int pr = 0; pr < 4; ++pr) {
-          uint32_t hi[8], lo[8];
+        for (int j = 0; j < 8; ++j) {
+          uint32_t hi[4], lo[4];
+          const uint4 mk = *reinterpret_cast<const uint4*>(m + 1024 * j);        // hi plane of the stashed activation: != 0 <=> active
+          const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
 #pragma unroll
-          for (int jj = 0; jj < 2; ++jj) {
-            const int j = 2 * pr + jj;
-            const uint4 mk = *reinterpret_cast<const uint4*>(m + img_off(row, j));
-            const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int n = 64 * c + 8 * j + 2 * q;
-              float d0 = drgb[0] * swr[n] + drgb[1] * swr[128 + n] + drgb[2] * swr[256 + n];
-              float d1 = drgb[0] * swr[n + 1] + drgb[1] * swr[128 + n + 1] + drgb[2] * swr[256 + n + 1];
-              if ((mw[q] & 0x7fffu) == 0u) d0 = 0.f;
-              if ((mw[q] & 0x7fff0000u) == 0u) d1 = 0.f;
-              Split<FMT>::apply(d0, d1, hi[4 * jj + q], lo[4 * jj + q]);
-            }
+          for (int q = 0; q < 4; ++q) {
+            const int n = 64 * c + 8 * j + 2 * q;
+            float d0 = drgb[0] * swr[n] + drgb[1] * swr[128 + n] + drgb[2] * swr[256 + n];
+            float d1 = drgb[0] * swr[n + 1] + drgb[1] * swr[128 + n + 1] + drgb[2] * swr[256 + n + 1];
+            if ((mw[q] & 0x7fffu) == 0u) d0 = 0.f;
+            if ((mw[q] & 0x7fff0000u) == 0u) d1 = 0.f;
+            Split<FMT>::apply(d0, d1, hi[q], lo[q]);
           }
-          store_chunk_pair(g, pr, row & 7, make_uint4(hi[0], hi[1], hi[2], hi[3]), make_uint4(hi[4], hi[5], hi[6], hi[7]));
-          store_chunk_pair(g + kPlane, pr, row & 7, make_uint4(lo[0], lo[1], lo[2], lo[3]), make_uint4(lo[4], lo[5], lo[6], lo[7]));
+          stg128(g + 1024 * j, hi[0], hi[1], hi[2], hi[3]);
+          stg128(g + kPlane + 1024 * j, lo[0], lo[1], lo[2], lo[3]);
         }
       }
     }
@@ -366,6 +365,27 @@ __device__ __forceinline__ uint64_t kmajor_desc(uint32_t saddr) {
 __device__ __forceinline__ uint64_t mnmajor_desc(uint32_t saddr, uint32_t lbo_bytes) {
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) | (64ull << 32) |
          (1ull << 46) | (2ull << 61);
+}
+// The same two views over a TILE IMAGE held in shared memory (img2 layout, no swizzle; canonical forms per CUTLASS
+// make_umma_desc, in 16-byte units):
+//   MN-major ((1,n),(8,k)):((X,SBO),(1,LBO)): 8 points of one 8-feature group are 128 contiguous bytes; the next 8 points
+//            follow at LBO = 128 B, the next 8-feature group at SBO = 1024 B (a 64-point half: [j][64 points][16 B]; the
+//            64-feature blocks of an operand are placed 8 KB apart, so the group stride is uniform across blocks)
+//   K-major  ((8,n),2):((1,SBO),LBO): 8 points x 16 B contiguous; next 8 points at SBO = 128 B, the second 8-k piece of a
+//            K = 16 step at LBO = 2048 B (a full tile: [j][128 points][16 B], the two halves of a j-block side by side)
+__device__ __forceinline__ uint64_t img_mn_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ uint64_t img_k_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(2048u >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
+}
+// Copy one chunk PLANE (16 KB in HBM: [half][j][64 points]) into the K-major arrangement [j][128 points] (16 x 1 KB pieces).
+__device__ __forceinline__ void copy_plane_kmajor(uint32_t dst, const uint8_t* src, uint32_t bar) {
+#pragma unroll 1
+  for (int i = 0; i < 16; ++i) {
+    const int half = i >> 3, j = i & 7;
+    bulk_copy_g2s(dst + j * 2048 + half * 1024, src + half * 8192 + j * 1024, 1024, bar);
+  }
 }
 __host__ __device__ constexpr uint32_t gemm_idesc(int fmt, int M, int N, int a_mn, int b_mn) {
   return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
@@ -470,7 +490,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_tg_dx(const DxArgs a) {
           const uint32_t full = bar + 8 * (G_FULL + slot);
           const uint32_t dst = sm_base + kSmSlots + slot * kSlotBytes;
           mbar_expect_tx(full, kSlotBytes);
-          bulk_copy_g2s(dst, a.a_img + ((size_t)tile * a.nkc + c) * kChunk, kChunk, full);
+          const uint8_t* asrc = a.a_img + ((size_t)tile * a.nkc + c) * kChunk;
+          copy_plane_kmajor(dst, asrc, full);                     // hi plane -> [j][128 points]
+          copy_plane_kmajor(dst + kPlane, asrc + kPlane, full);   // lo plane
           for (int hf = 0; hf < 2; ++hf) {      // 256-row hi plane at +32 KB, lo plane at +64 KB: rows [128 hf, +128) from stage (hf, c)
             const uint8_t* stg = a.wt_img + ((size_t)hf * a.nkc + c) * kChunk;
             bulk_copy_g2s(dst + 32768 + hf * kPlane, stg, kPlane, full);
@@ -496,7 +518,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_tg_dx(const DxArgs a) {
           const uint32_t sa = sm_base + kSmSlots + slot * kSlotBytes;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint64_t ah = kmajor_desc(sa + 32 * k), al = kmajor_desc(sa + kPlane + 32 * k);
+            const uint64_t ah = img_k_desc(sa + 4096 * k), al = img_k_desc(sa + kPlane + 4096 * k);
             const uint64_t bh = kmajor_desc(sa + 32768 + 32 * k), bl = kmajor_desc(sa + 65536 + 32 * k);
             mma_ss(d, ah, bh, idesc, (c | k) ? 1u : 0u);
             mma_ss(d, al, bh, idesc, 1u);
@@ -513,7 +535,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_tg_dx(const DxArgs a) {
     const int row = 32 * q + lane, r7 = lane & 7;
     const uint32_t tlane = tmem + ((uint32_t)(32 * q) << 16);
     const float* wsig = reinterpret_cast<const float*>(sm + kSmDxAux);
-    const uint32_t stage_row = sm_base + kSmDxStage + (uint32_t)row * 128u;
+    const uint32_t stage_row = sm_base + kSmDxStage + (uint32_t)img2_off(row, 0);
     const bool issuer = (warp == 2 && lane == 0);
     for (long long it = 0; it < my_tiles; ++it) {
       const uint32_t buf = (uint32_t)(it & 1);
@@ -552,9 +574,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_tg_dx(const DxArgs a) {
             if (!((mb >> (col + 1)) & 1u)) v1 = 0.f;
             Split<FMT>::apply(v0, v1, hi[e], lo[e]);
           }
-          const uint32_t sw = (uint32_t)((((cc & 1) * 4 + jj) ^ r7) << 4);
-          sts128(stage_row + sw, hi[0], hi[1], hi[2], hi[3]);
-          sts128(stage_row + kPlane + sw, lo[0], lo[1], lo[2], lo[3]);
+          const uint32_t pj = (uint32_t)(((cc & 1) * 4 + jj) * 1024);     // piece j of the chunk
+          sts128(stage_row + pj, hi[0], hi[1], hi[2], hi[3]);
+          sts128(stage_row + kPlane + pj, lo[0], lo[1], lo[2], lo[3]);
         }
         if (cc & 1) {             // chunk complete: hand it to the bulk-copy engine
           fence_proxy_async();
@@ -603,6 +625,9 @@ struct ChainArgs {
   const uint32_t* mask;     // [8][n_tiles][128][8]: ReLU bits of h_1..h_8
   const float* dsig; const float* wsig;
   long long n_tiles;
+  int debug_flags;          // timing experiments (WRONG results): 8 = skip the dZ image stores, 16 = skip the mask loads,
+                            // 32 = the weight producer re-arms the ring without copying (stale weights)
+  long long* clk;           // SM-clock probe of CTA 0 (see TcKernelArgs::clk), or null
 };
 constexpr int kChEpiWarps = 8;
 constexpr int kChProducerWarp = kChEpiWarps;          // warp 8
@@ -610,12 +635,35 @@ constexpr int kChMmaWarp = kChEpiWarps + 1;           // warp 9 (highest id: the
 constexpr int kChainThreads = 32 * (kChEpiWarps + 2);
 constexpr int kChRing = 0;                            // 4 x 32 KB weight stages
 constexpr int kChDz = kRing * kStageBytes;            // 131072: the tile's dZ_dir image, 2 chunks x 32 KB
-constexpr int kChAux = kChDz + 2 * kChunk;            // 196608: w_sigma (1 KB)
+constexpr int kChStage = kChDz + 2 * kChunk;          // 196608: 32 KB staging chunk for the dZ image bulk stores
+constexpr int kChAux = kChStage + kChunk;             // 229376: w_sigma (1 KB)
 constexpr int kChBar = kChAux + 1024;
 constexpr int kChTmem = kChBar + 32 * 8;
 constexpr int kSmemChainBytes = kChTmem + 16;
+static_assert(kSmemChainBytes <= 227 * 1024, "chain smem budget");
 constexpr int C_DZFULL = 16, C_DZEMPTY = 17;          // (indices 0..15: B_WFULL .. B_AREADY of nsr_tc_mma.cuh)
 static_assert(kStageBytes == kChunk && kPlaneBytes == kPlane, "ring stage == tile-image chunk");
+
+// Layer-0 stage of the chain: A = one 64-k chunk of the tile's dZ_dir image in shared memory (K-major view of the tile-image
+// layout, img_k_desc), B = a weight stage of the ring (K-major SWIZZLE_128B).  Mirrors mma_stage_ss (nsr_tc_mma.cuh).
+template <int N8>
+__device__ __forceinline__ void chain_stage_ss(const MmaCtx& c, uint32_t a_chunk, int half, bool first) {
+  constexpr uint64_t HI = (64ull << 32) | (1ull << 46) | (2ull << 61);
+  constexpr int slot = N8 & 3;
+  constexpr int nslot = (N8 + 1) & 3, npar = ((N8 + 1) >> 2) & 1;
+  const uint32_t wlo = ((c.ring + slot * kStageBytes) >> 4) | (1u << 16);
+  const uint32_t d = 128u * half;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint64_t bh = HI | (uint64_t)(wlo + 2u * k), bl = HI | (uint64_t)(wlo + 1024u + 2u * k);
+    const uint64_t ah = img_k_desc(a_chunk + 4096u * k), al = img_k_desc(a_chunk + kPlane + 4096u * k);
+    mma_ss(d, ah, bh, c.idesc, (k == 0 && first) ? 0u : 1u);
+    mma_ss(d, al, bh, c.idesc, 1u);
+    mma_ss(d, ah, bl, c.idesc, 1u);
+    if (k == 1) { mbar_wait(c.bar + 8 * (B_WFULL + nslot), npar); tc_fence_after(); }     // next stage's weights
+  }
+  tc_commit(c.bar + 8 * (B_WEMPTY + slot));
+}
 
 // One tile of the MMA lane.  P0 = stage index of the tile's first stage mod 8 (0 for even tiles, 4 for odd ones).
 template <int P0>
@@ -625,13 +673,13 @@ __device__ __forceinline__ void chain_tile_mma(const MmaCtx& c, uint32_t dz, uin
   tc_fence_after();
   const uint32_t gp = (g0 - 1u) & 1u;                 // A_READY parity of the previous tile's last layer
   if (g0 > 0) { mma_wait_ready(c, 0, gp); mma_wait_ready(c, 1, gp); tc_fence_after(); }      // accumulator half 0 drained
-  mma_stage_ss<3, (P0 + 0) & 7>(c, dz, 0, true, true);
-  mma_stage_ss<3, (P0 + 1) & 7>(c, dz + kChunk, 0, true, false);
+  chain_stage_ss<(P0 + 0) & 7>(c, dz, 0, true);
+  chain_stage_ss<(P0 + 1) & 7>(c, dz + kChunk, 0, false);
   tc_commit(c.bar + 8 * (B_ACCFULL + 0));
   if (g0 > 0) { mma_wait_ready(c, 2, gp); mma_wait_ready(c, 3, gp); tc_fence_after(); }      // half 1 drained
-  mma_stage_ss<3, (P0 + 2) & 7>(c, dz, 1, true, true);
+  chain_stage_ss<(P0 + 2) & 7>(c, dz, 1, true);
   tc_commit(c.bar + 8 * (B_AFREE + 0));
-  mma_stage_ss<3, (P0 + 3) & 7>(c, dz + kChunk, 1, true, false);
+  chain_stage_ss<(P0 + 3) & 7>(c, dz + kChunk, 1, false);
   tc_commit(c.bar + 8 * (B_AFREE + 1));
   tc_commit(c.bar + 8 * (B_ACCFULL + 1));
   tc_commit(c.bar + 8 * C_DZEMPTY);                   // the dZ_dir buffer may be refilled for the next tile
@@ -648,6 +696,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_tg_dxchain(const ChainArgs
   const uint32_t sm_base = smem_u32(sm);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long my_tiles = (a.n_tiles > blockIdx.x) ? (a.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  if (a.clk && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
+    a.clk[0] = clock64(); a.clk[1] = (long long)ns;
+  }
   for (int i = threadIdx.x; i < 256; i += kChainThreads) reinterpret_cast<float*>(sm + kChAux)[i] = a.wsig[i];
   if (sm_base & 1023u) { if (threadIdx.x == 0) printf("[nsr_train] dynamic smem base %u not 1024-aligned\n", sm_base); __trap(); }
   const uint32_t bar = sm_base + kChBar;
@@ -680,13 +733,17 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_tg_dxchain(const ChainArgs
         const long long tile = blockIdx.x + it * (long long)gridDim.x;
         mbar_wait(bar + 8 * C_DZEMPTY, (uint32_t)((it & 1) ^ 1));          // layer 0 of the previous tile is done with the buffer
         mbar_expect_tx(bar + 8 * C_DZFULL, 2 * kChunk);
-        bulk_copy_g2s(sm_base + kChDz, a.dzdir + (size_t)tile * 2 * kChunk, 2 * kChunk, bar + 8 * C_DZFULL);
+        for (int cp = 0; cp < 4; ++cp)                                     // (chunk, plane): 16 KB each -> [j][128 points]
+          copy_plane_kmajor(sm_base + kChDz + cp * kPlane, a.dzdir + (size_t)tile * 2 * kChunk + (size_t)cp * kPlane, bar + 8 * C_DZFULL);
 #pragma unroll 1
         for (int s = 0; s < kWtStages; ++s) {
           mbar_wait(bar + 8 * (B_WEMPTY + slot), par ^ 1u);
           const uint32_t full = bar + 8 * (B_WFULL + slot);
-          mbar_expect_tx(full, kStageBytes);
-          bulk_copy_g2s(sm_base + kChRing + slot * kStageBytes, a.wt + (size_t)s * kStageBytes, kStageBytes, full);
+          if ((a.debug_flags & 32) && (it > 0 || s >= kRing)) { mbar_arrive(full); }
+          else {
+            mbar_expect_tx(full, kStageBytes);
+            bulk_copy_g2s(sm_base + kChRing + slot * kStageBytes, a.wt + (size_t)s * kStageBytes, kStageBytes, full);
+          }
           if (++slot == kRing) { slot = 0; par ^= 1u; }
         }
       }
@@ -707,9 +764,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_tg_dxchain(const ChainArgs
     __syncwarp();
   } else {
     const int q = warp & 3, hh = warp >> 2;
-    const int row = 32 * q + lane, r7 = lane & 7;
+    const int row = 32 * q + lane;
     const uint32_t tlane = tmem + ((uint32_t)(32 * q) << 16);
     const float* wsig = reinterpret_cast<const float*>(sm + kChAux);
+    const uint32_t stage_row = sm_base + kChStage + (uint32_t)img2_off(row, 0);
+    const bool issuer = (warp == 0 && lane == 0);
     uint32_t g = 0;
 #pragma unroll 1
     for (long long it = 0; it < my_tiles; ++it) {
@@ -720,12 +779,12 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_tg_dxchain(const ChainArgs
         // output of step l >= 1 is the gradient w.r.t. h_{9-l}: gate it with that layer's ReLU bits (this thread's row,
         // mask word 2 q4 + hh of the 8 covers columns [64 q4 + 32 hh, +32))
         uint32_t mq[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-        if (l >= 1) {
+        if (l >= 1 && !(a.debug_flags & 16)) {
           const uint4* mp = reinterpret_cast<const uint4*>(a.mask + (((size_t)(8 - l) * (size_t)a.n_tiles + (size_t)tile) * kT + row) * 8);
           const uint4 m0 = mp[0], m1 = mp[1];
           mq[0] = hh ? m0.y : m0.x; mq[1] = hh ? m0.w : m0.z; mq[2] = hh ? m1.y : m1.x; mq[3] = hh ? m1.w : m1.z;
         }
-        uint8_t* orow = a.dz + (((size_t)l * (size_t)a.n_tiles + (size_t)tile) * 4) * kChunk + (size_t)row * 128;
+        uint8_t* ochunks = a.dz + (((size_t)l * (size_t)a.n_tiles + (size_t)tile) * 4) * kChunk;
 #pragma unroll 1
         for (int q4 = 0; q4 < 4; ++q4) {
           // every barrier is waited for in every layer (one phase per layer: nobody can fall two phases behind)
@@ -755,23 +814,36 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_tg_dxchain(const ChainArgs
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar + 8 * (B_AREADY + q4));
-          // the layer's dZ image (what the dW GEMMs read), 32 bytes per store -- after the arrive: the MMA lane moves on
-          uint8_t* gp = orow + (size_t)q4 * kChunk;
+          // the layer's dZ image (what the dW GEMMs read) -- after the arrive: the MMA lane has moved on.  The 64-column
+          // quarter of the tile is one 32 KB image chunk: the eight warps lay it out in shared memory (512 contiguous bytes per
+          // warp store) and ONE thread hands it to the bulk-copy engine, which drains it to HBM asynchronously.  (Storing
+          // from registers -- even fully coalesced -- kept every epilogue warp blocked on its own store issue for longer than
+          // the MMA window it has: the chain ran at 347 us per 1024 tiles against 258 us without the stores.)
+          if (a.debug_flags & 8) continue;
+          if (issuer) bulk_store_wait_read();                 // the previous chunk has left shared memory
+          named_bar_sync(3, 32 * kChEpiWarps);
+          const uint32_t sp = stage_row + 4096u * (uint32_t)hh;
 #pragma unroll
-          for (int t2 = 0; t2 < 2; ++t2) {
-            const int e = 8 * t2;
-            store_chunk_pair(gp, 2 * hh + t2, r7, make_uint4(whi[e], whi[e + 1], whi[e + 2], whi[e + 3]),
-                             make_uint4(whi[e + 4], whi[e + 5], whi[e + 6], whi[e + 7]));
-            store_chunk_pair(gp + kPlane, 2 * hh + t2, r7, make_uint4(wlo[e], wlo[e + 1], wlo[e + 2], wlo[e + 3]),
-                             make_uint4(wlo[e + 4], wlo[e + 5], wlo[e + 6], wlo[e + 7]));
+          for (int t2 = 0; t2 < 4; ++t2) {
+            sts128(sp + 1024u * t2, whi[4 * t2], whi[4 * t2 + 1], whi[4 * t2 + 2], whi[4 * t2 + 3]);
+            sts128(sp + kPlane + 1024u * t2, wlo[4 * t2], wlo[4 * t2 + 1], wlo[4 * t2 + 2], wlo[4 * t2 + 3]);
           }
+          fence_proxy_async();
+          named_bar_sync(3, 32 * kChEpiWarps);
+          if (issuer) bulk_store_s2g(ochunks + (size_t)q4 * kChunk, sm_base + kChStage, kChunk);
         }
       }
     }
+    if (issuer) bulk_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
   if (warp == kChMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+  if (a.clk && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
+    a.clk[2] = clock64(); a.clk[3] = (long long)ns;
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -848,8 +920,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_tg_dw(const DwArgs a) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint32_t first = (n | (uint32_t)k) ? 1u : 0u;
-            const uint64_t ah = mnmajor_desc(sa + 2048 * k, 8192), al = mnmajor_desc(sa + 16384 + 2048 * k, 8192);
-            const uint64_t bh = mnmajor_desc(sa + 32768 + 2048 * k, 8192), bl = mnmajor_desc(sa + 65536 + 2048 * k, 8192);
+            const uint64_t ah = img_mn_desc(sa + 256 * k), al = img_mn_desc(sa + 16384 + 256 * k);
+            const uint64_t bh = img_mn_desc(sa + 32768 + 256 * k), bl = img_mn_desc(sa + 65536 + 256 * k);
             mma_ss(tmem, ah, bh, idesc, first);
             mma_ss(tmem, al, bh, idesc, 1u);
             mma_ss(tmem, ah, bl, idesc, 1u);
@@ -1311,7 +1383,7 @@ static int backward_net(NsrHandle_* h, int which, const float* rays, int64_t n, 
   if (!(h->debug_flags & 2)) {
     ChainArgs a{};
     a.dzdir = dzdir; a.wt = net.wt_image; a.dz = dzi(0); a.mask = (const uint32_t*)(ws + L.mask[which]);
-    a.dsig = dsig; a.wsig = net.tc_consts + kcWsig; a.n_tiles = tiles;
+    a.dsig = dsig; a.wsig = net.tc_consts + kcWsig; a.n_tiles = tiles; a.debug_flags = h->debug_flags; a.clk = h->d_clk;
     const int grid = (int)(tiles < h->sm_count ? tiles : h->sm_count);
     if (fmt_of(h) == 1) {
       NSR_TCUDA(h, cudaFuncSetAttribute(k_tg_dxchain<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemChainBytes));
