@@ -4,6 +4,7 @@
 // ray generation.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -341,6 +342,8 @@ extern "C" int nsr_create(const NsrConfig* cfg, NsrHandle** out_handle) {
   if (!h) return fail(nullptr, NSR_ERR_CUDA, "out of host memory");
   h->cfg = c;
   h->sm_count = prop.multiProcessorCount;
+  if (const char* ev = getenv("NSR_TC_CLUSTER")) h->tc_cluster = atoi(ev) == 1 ? 1 : 2;
+  if (h->sm_count % 2) h->tc_cluster = 1;
   RenderParams& rp = h->rp;
   rp.n_coarse = c.n_coarse; rp.n_importance = c.n_importance;
   rp.deg_pos = c.deg_pos; rp.deg_dir = c.deg_dir; rp.no_xyz = c.no_xyz;

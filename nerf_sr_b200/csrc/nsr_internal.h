@@ -61,6 +61,8 @@ struct NsrHandle_ {
   std::atomic<int64_t> launches{0};
   long long* trace_buf = nullptr;
   int debug_flags = 0;
+  int tc_cluster = 2;               // CTAs per cluster of k_tc_pass (2: the pair shares one multicast weight stream;
+                                    // NSR_TC_CLUSTER=1 in the environment switches it off for A/B runs)
   std::string err;
   // nsr_render_host state (library-owned staging)
   cudaStream_t hs[2] = {nullptr, nullptr};

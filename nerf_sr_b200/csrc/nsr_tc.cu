@@ -232,8 +232,15 @@ struct TcKernelArgs {
 // roles
 // ---------------------------------------------------------------------------
 // (executed by the whole warp, warp-uniformly; one elected lane issues)
-__device__ __forceinline__ void producer_role(const TcKernelArgs& a, uint32_t sm_base, long long my_tiles) {
+__device__ __forceinline__ void producer_role(const TcKernelArgs& a, uint32_t sm_base, long long my_tiles, uint32_t crank,
+                                              uint32_t csize) {
   if (!elect_one()) return;       // one elected lane runs the whole loop (uniform registers, see mma_role)
+  // Cluster of 2 (CTA pair): each CTA fetches HALF of every stage (rank 0 the hi plane, rank 1 the lo plane) and the copy is
+  // multicast into both CTAs' rings -- the weight stream L2 -> shared memory is halved.  (Measured, tools/l2_weight_ab.py:
+  // that stream costs no cycles but ~7 % of SM clock under the 1 kW cap.)  Each CTA still expects the full 32 KB on its own
+  // stage barrier; the slot is reused only after BOTH CTAs' MMAs released it (B_WEMPTY counts csize arrivals).
+  const uint16_t mask = (uint16_t)((1u << csize) - 1u);
+  const uint32_t part = kStageBytes / csize, poff = crank * part;
   uint32_t slot = 0, par = 0;
 #pragma unroll 1
   for (long long it = 0; it < my_tiles; ++it) {
@@ -244,7 +251,10 @@ __device__ __forceinline__ void producer_role(const TcKernelArgs& a, uint32_t sm
       if ((a.debug_flags & 1) && (it > 0 || s >= kRing)) { mbar_arrive(full); }
       else {
         mbar_expect_tx(full, kStageBytes);
-        bulk_copy_g2s(sm_base + kSmRing + slot * kStageBytes, a.image + (size_t)s * kStageBytes, kStageBytes, full);
+        const uint32_t dst = sm_base + kSmRing + slot * kStageBytes;
+        const uint8_t* src = a.image + (size_t)s * kStageBytes;
+        if (csize == 1) bulk_copy_g2s(dst, src, kStageBytes, full);
+        else bulk_copy_g2s_mc(dst + poff, src + poff, part, full, mask);
       }
       if (++slot == kRing) { slot = 0; par ^= 1; }
     }
@@ -270,10 +280,10 @@ __device__ __forceinline__ void producer_role(const TcKernelArgs& a, uint32_t sm
 
 template <int PASSES>
 __device__ __forceinline__ void mma_role(const TcKernelArgs& a, uint8_t* sm, uint32_t sm_base, uint32_t tmem,
-                                         uint32_t idesc, long long my_tiles) {
+                                         uint32_t idesc, long long my_tiles, uint32_t csize) {
   (void)sm; (void)tmem;            // TMEM base is 0 (checked at kernel start)
   if (!elect_one()) return;
-  const MmaCtx c{sm_base + kSmRing, sm_base + kSmBar, idesc};
+  const MmaCtx c{sm_base + kSmRing, sm_base + kSmBar, idesc, csize > 1 ? (1u << csize) - 1u : 0u};
   if (my_tiles > 0) { mbar_wait(c.bar + 8 * (B_WFULL + 0), 0); tc_fence_after(); }   // first stage's weights
 #pragma unroll 1
   for (long long it = 0; it < my_tiles; ++it) {
@@ -427,7 +437,7 @@ __device__ __forceinline__ void frontend_role(const TcKernelArgs& a, uint8_t* sm
       const int sw = (j ^ (t & 7)) << 4;
       *reinterpret_cast<uint4*>(row_hi + sw) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
       *reinterpret_cast<uint4*>(row_lo + sw) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-      if (STASH) {   // the same 16-byte pieces -> the tile image in HBM (lanes = consecutive points: 512 B per warp store)
+      if (STASH && tile < a.n_tiles) {   // the same 16-byte pieces -> the tile image in HBM (lanes = consecutive points: 512 B per warp store)
         uint8_t* g = a.stash_enc + (size_t)tile * kStageBytes + img2_off(t, j);
         stg128(g, hi[0], hi[1], hi[2], hi[3]);
         stg128(g + kPlaneBytes, lo[0], lo[1], lo[2], lo[3]);
@@ -527,7 +537,7 @@ __device__ __forceinline__ void epi_layer(int L, float relu_floor, uint32_t g, u
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(bar + 8 * (B_AREADY + q4));
-    if (STASH) {   // this thread's 32 activations of layer L -> the layer's tile image, AFTER the arrive (the MMA lane is
+    if (STASH && stash_chunks) {   // this thread's 32 activations of layer L -> the layer's tile image, AFTER the arrive (the MMA lane is
                    // already released); four 16-byte pieces per plane, each a 512-byte contiguous warp store
       uint8_t* gp = stash_chunks + (size_t)q4 * kStageBytes + img2_off(row, 4 * hh);      // k chunk = 64-column quarter
 #pragma unroll
@@ -608,7 +618,7 @@ __device__ __forceinline__ void epilogue_role(const TcKernelArgs& a, uint8_t* sm
       if (L == 2 && it >= 1) tile_tail(it - 1, sig_prev, rgb_prev[0], rgb_prev[1], rgb_prev[2]);
       uint8_t* stash_chunks = nullptr;
       uint32_t* mask_row = nullptr;
-      if (STASH) {
+      if (STASH && first_tile + it * (long long)tile_stride < a.n_tiles) {      // (a cluster's dummy tile stores nothing)
         const size_t lt = (size_t)(L - 1) * (size_t)a.n_tiles + (size_t)(first_tile + it * (long long)tile_stride);
         stash_chunks = a.stash_h + lt * (size_t)(4 * kStageBytes);
         if (L <= 8) mask_row = a.stash_mask + (lt * 128 + (size_t)row) * 8;
@@ -650,7 +660,7 @@ __device__ __forceinline__ void epilogue_role(const TcKernelArgs& a, uint8_t* sm
             Split<FMT>::apply(v2, v3, dhi[j / 2 + 1], dlo[j / 2 + 1]);
           }
         }
-        if (STASH) {   // dir layer activations (post-ReLU) -> tile image, chunk hh, 16-byte pieces j = 4c .. 4c+3
+        if (STASH && first_tile + it * (long long)tile_stride < a.n_tiles) {   // dir layer activations (post-ReLU) -> tile image, chunk hh, pieces j = 4c .. 4c+3
           uint8_t* gp = a.stash_dir + ((size_t)(first_tile + it * (long long)tile_stride) * 2 + (size_t)hh) * (size_t)kStageBytes + img2_off(row, 4 * c);
 #pragma unroll
           for (int t2 = 0; t2 < 4; ++t2) {
@@ -678,7 +688,11 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_tc_pass(const TcKernelArgs a)
   const uint32_t sm_base = smem_u32(sm);
   if (sm_base & 1023u) { if (threadIdx.x == 0) printf("[nsr_tc] dynamic smem base %u not 1024-aligned\n", sm_base); __trap(); }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long my_tiles = (a.n_tiles > blockIdx.x) ? (a.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  // In a cluster the CTAs share the weight ring stage by stage, so all of them run the SAME number of tiles; a tile index
+  // past the end is a dummy (no valid ray: nothing is read or written for it).
+  const uint32_t csize = cluster_nctarank(), crank = cluster_ctarank();
+  const long long my_tiles = (csize > 1) ? (a.n_tiles + gridDim.x - 1) / gridDim.x
+                                         : ((a.n_tiles > blockIdx.x) ? (a.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
   if (a.clk && blockIdx.x == 0 && threadIdx.x == 0) {
     unsigned long long ns;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
@@ -687,7 +701,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_tc_pass(const TcKernelArgs a)
 
   if (threadIdx.x == 0) {
     const uint32_t bar = sm_base + kSmBar;
-    for (int i = 0; i < kRing; ++i) { mbar_init(bar + 8 * (B_WFULL + i), 1); mbar_init(bar + 8 * (B_WEMPTY + i), 1); }
+    for (int i = 0; i < kRing; ++i) { mbar_init(bar + 8 * (B_WFULL + i), 1); mbar_init(bar + 8 * (B_WEMPTY + i), csize); }
     mbar_init(bar + 8 * (B_ACCFULL + 0), 1); mbar_init(bar + 8 * (B_ACCFULL + 1), 1);
     mbar_init(bar + 8 * (B_AFREE + 0), 1); mbar_init(bar + 8 * (B_AFREE + 1), 1);
     for (int q4 = 0; q4 < 4; ++q4) mbar_init(bar + 8 * (B_AREADY + q4), kWarpsEpi);
@@ -707,6 +721,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_tc_pass(const TcKernelArgs a)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (csize > 1) cluster_sync_all();     // the peer's barriers are initialised before anything is multicast into them
   // All 512 columns are allocated, so the base is lane 0 / column 0; using the literal keeps every
   // TMEM address warp-uniform for the compiler (checked, not assumed).
   if (*reinterpret_cast<volatile uint32_t*>(sm + kSmTmemPtr) != 0u) {
@@ -716,10 +731,10 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_tc_pass(const TcKernelArgs a)
   const uint32_t tmem = 0u;
 
   if (warp == kProducerWarp) {
-    producer_role(a, sm_base, my_tiles);
+    producer_role(a, sm_base, my_tiles, crank, csize);
     __syncwarp();
   } else if (warp == kMmaWarp) {
-    mma_role<PASSES>(a, sm, sm_base, tmem, umma_idesc(FMT, 128, 128), my_tiles);
+    mma_role<PASSES>(a, sm, sm_base, tmem, umma_idesc(FMT, 128, 128), my_tiles, csize);
     __syncwarp();
   } else if (warp < kEpiWarp0) {
     frontend_role<FMT, STASH>(a, sm, sm_base, my_tiles, blockIdx.x, gridDim.x);
@@ -729,6 +744,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_tc_pass(const TcKernelArgs a)
 
   tc_fence_before();
   __syncthreads();
+  if (csize > 1) cluster_sync_all();     // no CTA leaves while a peer's multicast copies / commits may still target it
   if (warp == kMmaWarp) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
   }
@@ -779,7 +795,18 @@ cudaError_t tc_pass(NsrHandle_* h, int which, const TcPassArgs& p, cudaStream_t 
     default: return cudaErrorInvalidValue;
   }
   a.clk = h->d_clk;
-  kern<<<grid, kThreadsTc, kSmemTcBytes, st>>>(a);
+  const int csize = (h->tc_cluster == 2 && a.n_tiles >= 2) ? 2 : 1;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(csize == 2 ? (grid + 1) & ~1 : grid));
+  cfg.blockDim = dim3(kThreadsTc);
+  cfg.dynamicSmemBytes = kSmemTcBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a);
+  if (e != cudaSuccess) return e;
   h->launches += 1;
   return cudaGetLastError();
 }

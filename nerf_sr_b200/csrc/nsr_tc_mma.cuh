@@ -29,7 +29,14 @@ enum {
 
 struct MmaCtx {
   uint32_t ring, bar, idesc;      // shared-memory addresses of the weight ring and of the barrier array; instruction descriptor
+  uint32_t wmask;                 // 0: the ring is private to this CTA; else the cluster's CTA mask -- the weight stages are
+                                  // multicast to all of them, so a slot is free only when EVERY CTA's MMAs have consumed it:
+                                  // the stage-consumed commit arrives on B_WEMPTY of every CTA (barrier count = cluster size)
 };
+__device__ __forceinline__ void ring_release(const MmaCtx& c, int slot) {
+  if (c.wmask) tc_commit_mc(c.bar + 8 * (B_WEMPTY + slot), (uint16_t)c.wmask);
+  else tc_commit(c.bar + 8 * (B_WEMPTY + slot));
+}
 
 // 12 (or 4) MMAs of one weight stage with A from TMEM.  N8 = stage index mod 8 (compile time).
 template <int PASSES, int N8>
@@ -48,7 +55,7 @@ __device__ __forceinline__ void mma_stage_ts(const MmaCtx& c, int half, int chun
     // the NEXT stage's weights are waited for here, hidden behind this stage's queued MMAs
     if (k == 1 && wait_next) { mbar_wait(c.bar + 8 * (B_WFULL + nslot), npar); tc_fence_after(); }
   }
-  tc_commit(c.bar + 8 * (B_WEMPTY + slot));
+  ring_release(c, slot);
 }
 
 // Same with A = the tile's encoded inputs in shared memory (first layer and skip layer).
@@ -68,7 +75,7 @@ __device__ __forceinline__ void mma_stage_ss(const MmaCtx& c, uint32_t enc, int 
     if (PASSES == 3) { mma_ss(d, el, bh, c.idesc, 1u); mma_ss(d, eh, bl, c.idesc, 1u); }
     if (k == 1 && wait_next) { mbar_wait(c.bar + 8 * (B_WFULL + nslot), npar); tc_fence_after(); }
   }
-  tc_commit(c.bar + 8 * (B_WEMPTY + slot));
+  ring_release(c, slot);
 }
 
 __device__ __forceinline__ void mma_wait_ready(const MmaCtx& c, int q, uint32_t gpar) {

@@ -662,7 +662,7 @@ __device__ __forceinline__ void chain_stage_ss(const MmaCtx& c, uint32_t a_chunk
     mma_ss(d, ah, bl, c.idesc, 1u);
     if (k == 1) { mbar_wait(c.bar + 8 * (B_WFULL + nslot), npar); tc_fence_after(); }     // next stage's weights
   }
-  tc_commit(c.bar + 8 * (B_WEMPTY + slot));
+  ring_release(c, slot);
 }
 
 // One tile of the MMA lane.  P0 = stage index of the tile's first stage mod 8 (0 for even tiles, 4 for odd ones).
@@ -751,7 +751,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_tg_dxchain(const ChainArgs
     __syncwarp();
   } else if (warp == kChMmaWarp) {
     if (elect_one()) {
-      const MmaCtx c{sm_base + kChRing, bar, umma_idesc(FMT, 128, 128)};
+      const MmaCtx c{sm_base + kChRing, bar, umma_idesc(FMT, 128, 128), 0u};
       if (my_tiles > 0) { mbar_wait(bar + 8 * (B_WFULL + 0), 0); tc_fence_after(); }      // the first stage's weights
 #pragma unroll 1
       for (long long it = 0; it < my_tiles; ++it) {
