@@ -59,13 +59,41 @@ def ncu_traffic(kernel: str, field: str):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock, power and throttle reasons DURING the timed region (B200_PROFILING.md recipe).  NVML in-process (a sample
+    every ~5 ms, so even a 100 ms timed region is covered); falls back to the nvidia-smi query loop of the recipe."""
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
-        self.index, self.stop_flag, self.rows = index, False, []
+        self.index, self.stop_flag, self.rows, self.how = index, False, [], None
+
+    def _run_nvml(self) -> bool:
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].strip().isdigit() else self.index
+            h = N.nvmlDeviceGetHandleByIndex(phys)
+            mx = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+            reasons_fn = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        except Exception:
+            return False
+        self.how = "nvml, ~5 ms period"
+        while not self.stop_flag:
+            try:
+                r = int(reasons_fn(h))
+                self.rows.append([float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)), mx, N.nvmlDeviceGetPowerUsage(h) / 1e3] +
+                                 [bool(r & bits[n]) for n in self.NAMES])
+            except Exception:
+                pass
+            time.sleep(0.005)
+        return True
 
     def run(self):
+        if self._run_nvml():
+            return
+        self.how = "nvidia-smi, 200 ms period"
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -75,7 +103,7 @@ class ClockSampler(threading.Thread):
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
                 f = [x.strip() for x in out.strip().split(",")]
                 if len(f) >= 7:
-                    self.rows.append(f)
+                    self.rows.append([float(f[0]), float(f[1]), float(f[2])] + [x.lower().startswith("active") for x in f[3:7]])
             except Exception:
                 pass
             time.sleep(0.2)
@@ -83,11 +111,11 @@ class ClockSampler(threading.Thread):
     def summary(self):
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]),
-                "reasons": reasons, "samples": len(self.rows)}
+        sm = sorted(r[0] for r in self.rows)
+        pw = sorted(r[2] for r in self.rows)
+        reasons = [n for i, n in enumerate(self.NAMES) if any(r[3 + i] for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.rows[0][1], "power_w_median": pw[len(pw) // 2],
+                "power_w_max": pw[-1], "reasons": reasons, "samples": len(self.rows), "how": self.how}
 
 
 def make_inputs(seed_offset: int = 0):

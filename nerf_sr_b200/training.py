@@ -195,10 +195,7 @@ def clip_coef(self: Renderer, grad_a: torch.Tensor, grad_b: Optional[torch.Tenso
 def adam_step(self: Renderer, params: Sequence[torch.Tensor], grad_flat: torch.Tensor, exp_avg: torch.Tensor,
               exp_avg_sq: torch.Tensor, step: int, lr: float, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8,
               clip_coef_dev: Optional[torch.Tensor] = None, clip_value: float = 0.0):
-    for p in params:
-        if p.dtype != torch.float32 or not p.is_contiguous() or p.device != self.device:
-            raise NsrError(1, "adam_step needs contiguous fp32 parameters on the renderer's device")
-    arr = (C.c_void_p * len(params))(*[p.data_ptr() for p in params])
+    arr, _ = _checked_param_array(self, params, "adam_step")
     self._check(self.lib.nsr_adam_step(self._h, arr, len(params), grad_flat.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
                                        int(step), float(lr), float(beta1), float(beta2), float(eps),
                                        clip_coef_dev.data_ptr() if clip_coef_dev is not None else None, float(clip_value),
@@ -363,15 +360,33 @@ class RenderFunction(torch.autograd.Function):
         return (None, None, None, None, None, *pg)
 
 
-def _load_params(self: Renderer, which: int, params: Sequence[torch.Tensor]):
-    """nsr_pack_weights straight from a parameter list in state_dict order (no name lookup)."""
+def _checked_param_array(self: Renderer, params: Sequence[torch.Tensor], what: str):
+    """(ctypes pointer array, detached tensors) for a parameter list in state_dict order.  The dtype / layout / size checks
+    run once per distinct list of storages (the training loop passes the same tensors every step: ~50 ctypes calls and a
+    Python loop per call otherwise, which is first-order once a step is ~1 ms of GPU time)."""
+    key = tuple(p.data_ptr() for p in params)
+    cache = self.__dict__.setdefault("_param_arrays", {})
+    hit = cache.get(key)
+    if hit is not None:
+        return hit
     ts = [p.detach() for p in params]
+    if len(ts) != int(self.lib.nsr_param_count(self._h)):
+        raise NsrError(1, f"{what}: expected {int(self.lib.nsr_param_count(self._h))} parameter tensors, got {len(ts)}")
     for i, t in enumerate(ts):
         if t.dtype != torch.float32 or not t.is_contiguous() or t.device != self.device:
-            raise NsrError(1, "parameters must be contiguous fp32 tensors on the renderer's device")
+            raise NsrError(1, f"{what}: parameters must be contiguous fp32 tensors on the renderer's device")
         if t.numel() != self.lib.nsr_param_numel(self._h, i):
-            raise NsrError(1, f"parameter {i}: {tuple(t.shape)} does not match the configured architecture")
+            raise NsrError(1, f"{what}: parameter {i}: {tuple(t.shape)} does not match the configured architecture")
     arr = (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+    if len(cache) > 16:
+        cache.clear()
+    cache[key] = (arr, ts)                    # `ts` keeps the storages alive, so a data_ptr key cannot be recycled
+    return cache[key]
+
+
+def _load_params(self: Renderer, which: int, params: Sequence[torch.Tensor]):
+    """nsr_pack_weights straight from a parameter list in state_dict order (no name lookup)."""
+    arr, ts = _checked_param_array(self, params, "load_params")
     self._check(self.lib.nsr_pack_weights(self._h, which, arr, len(ts), self._stream()))
     self._keep[which] = ts
 
