@@ -381,14 +381,31 @@ def run_train(args, rank, world, local):
 #                           L5 2048, L5-enc 1280, L1 1280                                                            = 22 272
 TRAIN_BYTES_PER_POINT = 10260 + 1564 + 9988 + 22272
 
+# The dW GEMMs are split over the SMs along the points; every split writes an fp32 partial [N][128] (+ 128 bias sums) that
+# k_grad_reduce reads back in a fixed order (deterministic, no atomics).  This traffic does not scale with the batch:
+# (jobs, N) of the 13 GEMMs of a net (csrc/nsr_train.cu backward_net): rgb, dir, dir-enc, final+sigma, L8 L7 L6 L5 L5-enc L4 L3 L2, L1
+DW_GEMMS = [(1, 128), (1, 256), (1, 64), (3, 256)] + [(2, 256)] * 3 + [(2, 256), (2, 64)] + [(2, 256)] * 3 + [(2, 64)]
+
+
+def dw_partial_bytes(n_rays: int, sm_count: int = 148) -> int:
+    """Bytes of dW partials written + read back per training step (both nets), mirroring DwPlanner::launch."""
+    total = 0
+    for s in (N_COARSE, N_COARSE + N_IMPORTANCE):
+        tiles = (n_rays * s + 127) // 128
+        for jobs, n in DW_GEMMS:
+            n_split = max(1, min(sm_count // jobs, (tiles + 3) // 4))
+            total += 2 * jobs * n_split * 128 * (n + 1) * 4
+    return total
+
 
 def train_roofline(n: int, steps: int, dev_ms: float, pk: dict, pk_kind: str) -> dict:
     """The `roofline` object of the training line (pure: unit-tested on CPU).  The iteration is HBM-bound by construction,
-    so the bound is the measured copy bandwidth: achieved = algorithmic bytes of the step (TRAIN_BYTES_PER_POINT x points;
-    the per-CTA dW partials, ~1 GB per step independent of the batch, are NOT counted) / event-timed step time.  The
+    so the bound is the measured copy bandwidth: achieved = bytes the step's design moves (TRAIN_BYTES_PER_POINT x points,
+    PLUS the dW partial sums written and read back, which do not scale with the batch) / event-timed step time.  The
     tensor-side view (algorithmic FLOP = 3 x forward) is kept beside it.  n: rays per step per GPU; dev_ms: all steps."""
     points = n * (N_COARSE + N_COARSE + N_IMPORTANCE)
-    step_bytes = points * TRAIN_BYTES_PER_POINT
+    partial_bytes = dw_partial_bytes(n)
+    step_bytes = points * TRAIN_BYTES_PER_POINT + partial_bytes
     gbs = step_bytes * steps / (dev_ms / 1e3) / 1e9
     flop_step = points * FLOP_PER_POINT * 3                     # forward + 2x backward (SURVEY.md 8d)
     tflops = flop_step * steps / (dev_ms / 1e3) / 1e12
@@ -397,6 +414,7 @@ def train_roofline(n: int, steps: int, dev_ms: float, pk: dict, pk_kind: str) ->
         "bound": "hbm", "kernel": "whole step (k_tc_pass stash variant, k_render_bwd, k_tg_dxchain, k_tg_dw; DESIGN.md section 11)",
         "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
         "peak_kind": f"{pk_kind} copy bandwidth", "bytes_per_step": step_bytes, "bytes_per_point": TRAIN_BYTES_PER_POINT,
+        "dw_partial_bytes_per_step": partial_bytes,
         "traffic": None,
         "tensor": {"achieved": tflops, "peak": tpeak, "unit": "TFLOP/s", "frac": tflops / tpeak, "issued_frac": 3 * tflops / tpeak,
                    "flop_per_step": flop_step, "peak_kind": f"{pk_kind} cuBLAS bf16 sustained"},

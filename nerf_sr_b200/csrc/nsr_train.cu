@@ -847,30 +847,39 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_tg_dxchain(const ChainArgs
 }
 
 // ---------------------------------------------------------------------------
-// k_tg_dw: partial[split][m][n] = sum over this CTA's tiles of A[p][m] * B[p][n]; bias partial = sum A[p][m]
+// k_tg_dw: ALL dW GEMMs of one net in ONE persistent launch (round 2; round 1 launched each of the 13 separately and paid a
+// ramp, a TMEM allocation and a tail per launch: ~5 us x 26 per iteration, first-order at the 256-rays-per-GPU DDP shape).
+// Per GEMM g:  partial[split][n][m] = sum over this CTA's tiles of A[p][m] * B[p][n];  bias partial[split][m] = sum A[p][m].
+// One CTA per SM.  For GEMM g, CTA b works on (job, split) = (b / n_split_g, b % n_split_g) when job < n_jobs_g, exactly
+// the decomposition of the former per-GEMM grids; the GEMMs are independent (they read the stash / dZ images and write
+// disjoint partial regions), so the CTA simply walks the list: the operand ring (2 x 96 KB), its barrier parities and the
+// TMEM allocation carry over from one GEMM to the next, the producer prefetches GEMM g+1 while the epilogue of g drains the
+// accumulator (ACC_FULL / ACC_EMPTY hand it back and forth).  Partials are stored [n][m] so that the 32 lanes of an
+// epilogue warp (= 32 consecutive output rows m) write 128 contiguous bytes per column and k_grad_reduce reads them the
+// same way.
 // ---------------------------------------------------------------------------
 struct DwJob {
   const uint8_t* a_img; int a_cpt;      // A image and its chunks per tile
   int a_blk0, a_blk1;                   // chunk indices giving output rows 0..63 and 64..127
-  float* part;                          // [n_split][128][N]
+  float* part;                          // [n_split][N][128]
   float* part_bias;                     // [n_split][128]
 };
-struct DwArgs {
-  DwJob job[4];
+constexpr int kMaxDwJobs = 3;
+constexpr int kMaxDwGemms = 14;
+struct DwGemm {
+  DwJob job[kMaxDwJobs]; int n_jobs;
   const uint8_t* b_img; int b_cpt; int b_chunk0; int nB;    // N = 64 * nB
-  long long n_tiles; int n_split;
+  int n_split;
 };
+struct DwAllArgs { DwGemm g[kMaxDwGemms]; int n_gemms; long long n_tiles; };
+static_assert(sizeof(DwAllArgs) <= 4000, "kernel parameter space");
 
 template <int FMT>
-__global__ void __launch_bounds__(kGemmThreads, 1) k_tg_dw(const DwArgs a) {
+__global__ void __launch_bounds__(kGemmThreads, 1) k_tg_dw(const DwAllArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* sm = smem_raw;
   const uint32_t sm_base = smem_u32(sm);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const DwJob& J = a.job[blockIdx.y];
-  const int split = blockIdx.x;
-  const long long my_tiles = (a.n_tiles > split) ? (a.n_tiles - split + a.n_split - 1) / a.n_split : 0;
-  const int N = 64 * a.nB;
   {   // a 16-row K-major tile of ones for the bias-gradient MMA
     const uint32_t one2 = (FMT == 1) ? 0x3f803f80u : 0x3c003c00u;
     for (int i = threadIdx.x; i < 512; i += kGemmThreads) reinterpret_cast<uint32_t*>(sm + kSmAux)[i] = one2;
@@ -878,28 +887,42 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_tg_dw(const DwArgs a) {
   }
   const uint32_t tmem = gemm_prologue(sm, sm_base, 4);
   const uint32_t bar = sm_base + kSmGBar;
+  // this CTA's share of GEMM gi (the same arithmetic in every role)
+  auto my_work = [&](const DwGemm& G, int& job, int& split) -> long long {
+    job = (int)blockIdx.x / G.n_split; split = (int)blockIdx.x % G.n_split;
+    if (job >= G.n_jobs) return -1;                                                   // not part of this GEMM
+    return (a.n_tiles > split) ? (a.n_tiles - split + G.n_split - 1) / G.n_split : 0;
+  };
 
   if (warp == 0) {
     if (elect_one()) {
       uint32_t n = 0;
-      const uint32_t bytes = (uint32_t)(4 + 2 * a.nB) * 8192u;
-      for (long long it = 0; it < my_tiles; ++it) {
-        const long long tile = split + it * (long long)a.n_split;
-        for (int half = 0; half < 2; ++half, ++n) {
-          const uint32_t slot = n & 1u, par = (n >> 1) & 1u;
-          mbar_wait(bar + 8 * (G_EMPTY + slot), par ^ 1u);
-          const uint32_t full = bar + 8 * (G_FULL + slot);
-          const uint32_t dst = sm_base + kSmSlots + slot * kSlotBytes;
-          mbar_expect_tx(full, bytes);
-          for (int b = 0; b < 2; ++b) {
-            const uint8_t* src = J.a_img + ((size_t)tile * J.a_cpt + (b ? J.a_blk1 : J.a_blk0)) * kChunk + (size_t)half * 8192;
-            bulk_copy_g2s(dst + b * 8192, src, 8192, full);
-            bulk_copy_g2s(dst + 16384 + b * 8192, src + kPlane, 8192, full);
-          }
-          for (int b = 0; b < a.nB; ++b) {
-            const uint8_t* src = a.b_img + ((size_t)tile * a.b_cpt + a.b_chunk0 + b) * kChunk + (size_t)half * 8192;
-            bulk_copy_g2s(dst + 32768 + b * 8192, src, 8192, full);
-            bulk_copy_g2s(dst + 65536 + b * 8192, src + kPlane, 8192, full);
+#pragma unroll 1
+      for (int gi = 0; gi < a.n_gemms; ++gi) {
+        const DwGemm& G = a.g[gi];
+        int job, split;
+        const long long my_tiles = my_work(G, job, split);
+        if (my_tiles <= 0) continue;
+        const DwJob& J = G.job[job];
+        const uint32_t bytes = (uint32_t)(4 + 2 * G.nB) * 8192u;
+        for (long long it = 0; it < my_tiles; ++it) {
+          const long long tile = split + it * (long long)G.n_split;
+          for (int half = 0; half < 2; ++half, ++n) {
+            const uint32_t slot = n & 1u, par = (n >> 1) & 1u;
+            mbar_wait(bar + 8 * (G_EMPTY + slot), par ^ 1u);
+            const uint32_t full = bar + 8 * (G_FULL + slot);
+            const uint32_t dst = sm_base + kSmSlots + slot * kSlotBytes;
+            mbar_expect_tx(full, bytes);
+            for (int b = 0; b < 2; ++b) {
+              const uint8_t* src = J.a_img + ((size_t)tile * J.a_cpt + (b ? J.a_blk1 : J.a_blk0)) * kChunk + (size_t)half * 8192;
+              bulk_copy_g2s(dst + b * 8192, src, 8192, full);
+              bulk_copy_g2s(dst + 16384 + b * 8192, src + kPlane, 8192, full);
+            }
+            for (int b = 0; b < G.nB; ++b) {
+              const uint8_t* src = G.b_img + ((size_t)tile * G.b_cpt + G.b_chunk0 + b) * kChunk + (size_t)half * 8192;
+              bulk_copy_g2s(dst + 32768 + b * 8192, src, 8192, full);
+              bulk_copy_g2s(dst + 65536 + b * 8192, src + kPlane, 8192, full);
+            }
           }
         }
       }
@@ -907,59 +930,83 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_tg_dw(const DwArgs a) {
     __syncwarp();
   } else if (warp == 1) {
     if (elect_one()) {
-      const uint32_t idesc = gemm_idesc(FMT, 128, N, 1, 1);
       const uint32_t idesc_b = gemm_idesc(FMT, 128, 16, 1, 0);
       const uint64_t ones = kmajor_desc(sm_base + kSmAux);
-      uint32_t n = 0;
-      for (long long it = 0; it < my_tiles; ++it) {
-        for (int half = 0; half < 2; ++half, ++n) {
-          const uint32_t slot = n & 1u, par = (n >> 1) & 1u;
-          mbar_wait(bar + 8 * (G_FULL + slot), par);
-          tc_fence_after();
-          const uint32_t sa = sm_base + kSmSlots + slot * kSlotBytes;
+      uint32_t n = 0, uses = 0;
+#pragma unroll 1
+      for (int gi = 0; gi < a.n_gemms; ++gi) {
+        const DwGemm& G = a.g[gi];
+        int job, split;
+        const long long my_tiles = my_work(G, job, split);
+        if (my_tiles <= 0) continue;
+        const uint32_t idesc = gemm_idesc(FMT, 128, 64 * G.nB, 1, 1);
+        if (uses > 0) { mbar_wait(bar + 8 * (G_ACCEMPTY + 0), (uses - 1u) & 1u); tc_fence_after(); }   // previous GEMM drained
+        for (long long it = 0; it < my_tiles; ++it) {
+          for (int half = 0; half < 2; ++half, ++n) {
+            const uint32_t slot = n & 1u, par = (n >> 1) & 1u;
+            mbar_wait(bar + 8 * (G_FULL + slot), par);
+            tc_fence_after();
+            const uint32_t sa = sm_base + kSmSlots + slot * kSlotBytes;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t first = (n | (uint32_t)k) ? 1u : 0u;
-            const uint64_t ah = img_mn_desc(sa + 256 * k), al = img_mn_desc(sa + 16384 + 256 * k);
-            const uint64_t bh = img_mn_desc(sa + 32768 + 256 * k), bl = img_mn_desc(sa + 65536 + 256 * k);
-            mma_ss(tmem, ah, bh, idesc, first);
-            mma_ss(tmem, al, bh, idesc, 1u);
-            mma_ss(tmem, ah, bl, idesc, 1u);
-            mma_ss(tmem + 256u, ah, ones, idesc_b, first);
-            mma_ss(tmem + 256u, al, ones, idesc_b, 1u);
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t first = (it | (long long)half | (long long)k) ? 1u : 0u;
+              const uint64_t ah = img_mn_desc(sa + 256 * k), al = img_mn_desc(sa + 16384 + 256 * k);
+              const uint64_t bh = img_mn_desc(sa + 32768 + 256 * k), bl = img_mn_desc(sa + 65536 + 256 * k);
+              mma_ss(tmem, ah, bh, idesc, first);
+              mma_ss(tmem, al, bh, idesc, 1u);
+              mma_ss(tmem, ah, bl, idesc, 1u);
+              mma_ss(tmem + 256u, ah, ones, idesc_b, first);
+              mma_ss(tmem + 256u, al, ones, idesc_b, 1u);
+            }
+            tc_commit(bar + 8 * (G_EMPTY + slot));
           }
-          tc_commit(bar + 8 * (G_EMPTY + slot));
         }
+        tc_commit(bar + 8 * (G_ACCFULL + 0));
+        ++uses;
       }
-      tc_commit(bar + 8 * (G_ACCFULL + 0));
     }
     __syncwarp();
   } else {
     const int q = warp & 3;
     const int row = 32 * q + lane;
     const uint32_t tlane = tmem + ((uint32_t)(32 * q) << 16);
-    float* dst = J.part + ((size_t)split * 128 + row) * N;
-    if (my_tiles > 0) {
-      mbar_wait(bar + 8 * (G_ACCFULL + 0), 0u);
-      tc_fence_after();
-    }
+    uint32_t uses = 0;
 #pragma unroll 1
-    for (int cc = 0; cc < 2 * a.nB; ++cc) {
-      uint32_t r[32];
-      if (my_tiles > 0) { TMEM_LD32(tlane + 32u * (uint32_t)cc, r); tc_wait_ld(); }
-      else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) r[i] = 0u;
+    for (int gi = 0; gi < a.n_gemms; ++gi) {
+      const DwGemm& G = a.g[gi];
+      int job, split;
+      const long long my_tiles = my_work(G, job, split);
+      if (my_tiles < 0) continue;
+      const DwJob& J = G.job[job];
+      const int N = 64 * G.nB;
+      float* dst = J.part + (size_t)split * N * 128 + row;              // [n][m]: lanes = consecutive rows m
+      if (my_tiles > 0) {
+        mbar_wait(bar + 8 * (G_ACCFULL + 0), uses & 1u);
+        tc_fence_after();
       }
+#pragma unroll 1
+      for (int cc = 0; cc < 2 * G.nB; ++cc) {
+        uint32_t r[32];
+        if (my_tiles > 0) { TMEM_LD32(tlane + 32u * (uint32_t)cc, r); tc_wait_ld(); }
+        else {
 #pragma unroll
-      for (int i = 0; i < 32; i += 4)
-        *reinterpret_cast<uint4*>(dst + 32 * cc + i) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
-    }
-    {
-      uint32_t r[32];
-      float b = 0.f;
-      if (my_tiles > 0) { TMEM_LD32(tlane + 256u, r); tc_wait_ld(); b = __uint_as_float(r[0]); }
-      J.part_bias[(size_t)split * 128 + row] = b;
+          for (int i = 0; i < 32; ++i) r[i] = 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) dst[(size_t)(32 * cc + i) * 128] = __uint_as_float(r[i]);
+      }
+      {
+        uint32_t r[32];
+        float b = 0.f;
+        if (my_tiles > 0) { TMEM_LD32(tlane + 256u, r); tc_wait_ld(); b = __uint_as_float(r[0]); }
+        J.part_bias[(size_t)split * 128 + row] = b;
+      }
+      if (my_tiles > 0) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar + 8 * (G_ACCEMPTY + 0));         // the accumulator may be overwritten
+        ++uses;
+      }
     }
   }
   gemm_epilogue_free(tmem);
@@ -980,8 +1027,8 @@ __global__ void __launch_bounds__(256) k_grad_reduce(const RedArgs a) {
   const RedJob& J = a.job[blockIdx.y];
   const int total = J.rows * J.cols;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    const int r = idx / J.cols, c = idx % J.cols;
-    const float* p = J.part + (size_t)(J.row0 + r) * J.N + c;
+    const int r = idx % J.rows, c = idx / J.rows;                  // partials are [split][n][m]: lanes walk the rows m
+    const float* p = J.part + (size_t)c * 128 + J.row0 + r;
     const size_t stride = (size_t)128 * J.N;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;       // four independent chains (fixed order: deterministic)
     int k = 0;
@@ -1278,9 +1325,9 @@ static cudaError_t launch_dx(NsrHandle_* h, const DxArgs& a, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-static cudaError_t launch_dw(NsrHandle_* h, const DwArgs& a, int n_jobs, cudaStream_t st) {
-  if (a.n_tiles == 0 || n_jobs == 0) return cudaSuccess;
-  const dim3 grid((unsigned)a.n_split, (unsigned)n_jobs);
+static cudaError_t launch_dw(NsrHandle_* h, const DwAllArgs& a, cudaStream_t st) {
+  if (a.n_tiles == 0 || a.n_gemms == 0) return cudaSuccess;
+  const int grid = h->sm_count < kMaxSplit ? h->sm_count : kMaxSplit;      // persistent: one CTA per SM
   cudaError_t e;
   if (fmt_of(h) == 1) {
     e = cudaFuncSetAttribute(k_tg_dw<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemGemmBytes);
@@ -1302,22 +1349,26 @@ static std::vector<long long> grad_offsets(const NsrHandle_* h) {
   return off;
 }
 
-// Builder for one net's dW launches: collects the reduce jobs while launching the GEMMs.
+// Builder for one net's dW GEMMs: collects them (and the matching reduce jobs); flush() issues the ONE persistent launch.
 struct DwPlanner {
   NsrHandle_* h; cudaStream_t st; long long n_tiles; char* part_base; size_t region; int launch_idx = 0;
   RedArgs red{};
+  DwAllArgs all{};
   cudaError_t err = cudaSuccess;
-  cudaStream_t fan[3] = {nullptr, nullptr, nullptr};   // streams the launches rotate over (n_fan = 1: all on st)
-  int n_fan = 1;
   struct JobSpec { const uint8_t* a_img; int a_cpt, blk0, blk1; int row0, rows; long long dst; int ld, col0; long long bias_dst; };
   void launch(const uint8_t* b_img, int b_cpt, int b_chunk0, int nB, int cols, const JobSpec* js, int n_jobs) {
     if (err != cudaSuccess) return;
-    if (region != 0 && launch_idx >= kDwLaunchesPerNet) { err = cudaErrorInvalidValue; return; }   // partial regions exhausted
-    DwArgs a{};
-    a.b_img = b_img; a.b_cpt = b_cpt; a.b_chunk0 = b_chunk0; a.nB = nB; a.n_tiles = n_tiles;
-    int n_split = h->sm_count / n_jobs;
-    if (n_split > kMaxSplit / n_jobs) n_split = kMaxSplit / n_jobs;
-    if (n_split > n_tiles) n_split = (int)n_tiles;
+    if ((region != 0 && launch_idx >= kDwLaunchesPerNet) || all.n_gemms >= kMaxDwGemms || n_jobs > kMaxDwJobs) {
+      err = cudaErrorInvalidValue; return;                     // partial regions / argument table exhausted
+    }
+    DwGemm& a = all.g[all.n_gemms++];
+    a.b_img = b_img; a.b_cpt = b_cpt; a.b_chunk0 = b_chunk0; a.nB = nB; a.n_jobs = n_jobs;
+    all.n_tiles = n_tiles;
+    const int ctas = h->sm_count < kMaxSplit ? h->sm_count : kMaxSplit;
+    int n_split = ctas / n_jobs;
+    // every split costs one [N][128] fp32 partial (written here, read back by k_grad_reduce) whatever the batch: keep at
+    // least four tiles per split, so small batches (the 256-rays-per-GPU DDP shape) do not drown in partial traffic
+    if ((long long)n_split * 4 > n_tiles) n_split = (int)((n_tiles + 3) / 4);
     if (n_split < 1) n_split = 1;
     a.n_split = n_split;
     const int N = 64 * nB;
@@ -1332,8 +1383,10 @@ struct DwPlanner {
       R.row0 = js[j].row0; R.rows = js[j].rows; R.cols = cols; R.ld = js[j].ld; R.col0 = js[j].col0;
       R.dst = js[j].dst; R.bias_dst = js[j].bias_dst;
     }
-    err = launch_dw(h, a, n_jobs, n_fan > 1 ? fan[launch_idx % n_fan] : st);
     ++launch_idx;
+  }
+  void flush() {
+    if (err == cudaSuccess) err = launch_dw(h, all, st);
   }
 };
 
@@ -1408,20 +1461,6 @@ static int backward_net(NsrHandle_* h, int which, const float* rays, int64_t n, 
   // ---- dW GEMMs ----
   DwPlanner P{h, st, tiles, ws + L.part, L.part_region};
   P.red.grad = grad_flat;
-  // The GEMMs below only read the stash / dZ images and write disjoint partial regions: fork them over three streams
-  // (the caller's and two library-owned ones) and join before the reduction.  Debug flag 4 keeps them on one stream.
-  const bool fan_out = !(h->debug_flags & 4);
-  if (fan_out) {
-    for (int k = 0; k < 2; ++k) {
-      if (!h->dw_st[k]) NSR_TCUDA(h, cudaStreamCreateWithFlags(&h->dw_st[k], cudaStreamNonBlocking));
-      if (!h->dw_done[k]) NSR_TCUDA(h, cudaEventCreateWithFlags(&h->dw_done[k], cudaEventDisableTiming));
-    }
-    if (!h->dw_fork) NSR_TCUDA(h, cudaEventCreateWithFlags(&h->dw_fork, cudaEventDisableTiming));
-    NSR_TCUDA(h, cudaEventRecord(h->dw_fork, st));
-    for (int k = 0; k < 2; ++k) NSR_TCUDA(h, cudaStreamWaitEvent(h->dw_st[k], h->dw_fork, 0));
-    P.fan[0] = st; P.fan[1] = h->dw_st[0]; P.fan[2] = h->dw_st[1];
-    P.n_fan = 3;
-  }
   using JS = DwPlanner::JobSpec;
   const int ld_dir = h->cfg.no_dir ? 256 : 256 + h->rp.ch_dir;
   {   // rgb.0: dW = dHead[:,1:4]^T . dir_act, db
@@ -1459,12 +1498,7 @@ static int backward_net(NsrHandle_* h, int which, const float* rays, int64_t n, 
       P.launch(h_layer(Lyr - 1), 4, 0, 4, 256, js, 2);
     }
   }
-  if (fan_out) {      // join (also on the error path below: the aux streams must not run past this call's stream order)
-    for (int k = 0; k < 2; ++k) {
-      NSR_TCUDA(h, cudaEventRecord(h->dw_done[k], h->dw_st[k]));
-      NSR_TCUDA(h, cudaStreamWaitEvent(st, h->dw_done[k], 0));
-    }
-  }
+  P.flush();
   if (P.err != cudaSuccess) return tfail(h, NSR_ERR_CUDA, std::string("dW launch: ") + cudaGetErrorString(P.err));
   {
     const dim3 grid(128, (unsigned)P.red.n_jobs);     // one element per thread for the 128 x 256 jobs
@@ -1789,6 +1823,7 @@ extern "C" int nsr_debug_dw(NsrHandle* h, const void* a_img, int a_cols, int blk
   P.red.grad = out;
   const DwPlanner::JobSpec js[1] = {{(const uint8_t*)a_img, a_cols / 64, blk0, blk1, 0, 128, 0, b_cols, 0, -1}};
   P.launch((const uint8_t*)b_img, b_cols / 64, 0, b_cols / 64, b_cols, js, 1);
+  P.flush();
   if (P.err != cudaSuccess) return tfail(h, NSR_ERR_CUDA, std::string("dW launch: ") + cudaGetErrorString(P.err));
   k_grad_reduce<<<dim3(32, 1), 256, 0, st>>>(P.red);
   RedArgs rb = P.red;           // second pass: the bias partials into bias_out

@@ -87,8 +87,11 @@ def test_train_roofline_object():
     pk = {"bf16_tflops": 1652.1, "bf16_tflops_sustained": 1386.6, "hbm_gbs": 6550.7}
     r = b.train_roofline(2048, 20, 20 * 4.8617, pk, "measured")                      # profiles/r01_bench_train_1gpu.json
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["peak"] == 6550.7 and r["traffic"] is None
-    assert r["bytes_per_step"] == 2048 * 192 * 44084 and r["achieved"] == pytest.approx(r["bytes_per_step"] / 4.8617e-3 / 1e9)
-    assert r["frac"] == pytest.approx(0.5443, rel=1e-3)
+    # the dW partials (written + read back, independent of the batch) are part of the step's bytes
+    assert r["dw_partial_bytes_per_step"] == b.dw_partial_bytes(2048) and 0.7e9 < r["dw_partial_bytes_per_step"] < 0.9e9
+    assert r["bytes_per_step"] == 2048 * 192 * 44084 + r["dw_partial_bytes_per_step"]
+    assert r["achieved"] == pytest.approx(r["bytes_per_step"] / 4.8617e-3 / 1e9)
+    assert r["frac"] == pytest.approx(r["achieved"] / 6550.7)
     t = r["tensor"]
     assert t["flop_per_step"] == 2048 * 192 * 1186816 * 3 and t["frac"] == pytest.approx(t["achieved"] / 1386.6) and t["issued_frac"] == pytest.approx(3 * t["frac"])
     json.dumps(r)
