@@ -5,7 +5,7 @@ layer that mirrors the reference's ``forward_rays`` / ``render_rays`` interface.
 package does not load the library; constructing a ``Renderer`` does, and fails loudly without it."""
 from ._lib import NsrError, PRECISIONS, LIB_PATH  # noqa: F401
 from .renderer import Renderer, config_from_opt, patch_model, state_dict_order  # noqa: F401
-from .training import RenderFunction, Trainer  # noqa: F401  (also attaches the training seams to Renderer)
+from .training import RenderFunction, Trainer  # noqa: F401
 
 __all__ = ["Renderer", "Trainer", "RenderFunction", "NsrError", "config_from_opt", "patch_model", "state_dict_order",
            "PRECISIONS", "LIB_PATH"]

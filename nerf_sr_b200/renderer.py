@@ -23,6 +23,7 @@ import torch
 
 from . import _lib
 from ._lib import NsrConfig, NsrError, NsrOutputs, NsrPassOutputs, NsrRayGen, NsrRng, PRECISIONS
+from .train_seams import TrainSeams
 
 
 def state_dict_order(D: int = 8):
@@ -67,8 +68,9 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
-class Renderer:
-    """One handle = one (opt, device).  Thread-compatible: use one Renderer per thread/stream."""
+class Renderer(TrainSeams):
+    """One handle = one (opt, device).  Thread-compatible: use one Renderer per thread/stream.
+    The training seams (render_train, backward, adam_step, ...) come from ``TrainSeams`` (train_seams.py)."""
 
     def __init__(self, opt, device: Optional[torch.device] = None, precision: str = "bf16x3",
                  viewdir_offset: int = 3):
@@ -308,74 +310,64 @@ class Renderer:
         self._check(self.lib.nsr_render_host(self._h, rays_host.data_ptr(), n, stride, s, rgb.data_ptr(), depth.data_ptr()))
         return rgb, depth
 
+    def render_pose_host(self, c2w, H: int, W: int, focal: float, s: int = 1, ndc: bool = False,
+                          near: float = 2.0, far: float = 6.0):
+        """One camera pose -> (rgb [H*W/s^2,3], depth [H*W/s^2]) CPU tensors; rays are generated on the
+        device (48 bytes of pose go up instead of 32 bytes per ray)."""
+        c = torch.as_tensor(c2w, dtype=torch.float32).reshape(12).cpu()
+        arr = (C.c_float * 12)(*c.tolist())
+        n_out = (H // s) * (W // s)
+        rgb = torch.empty(n_out, 3, dtype=torch.float32)
+        depth = torch.empty(n_out, dtype=torch.float32)
+        self._check(self.lib.nsr_render_pose_host(self._h, arr, H, W, float(focal), s, int(ndc), float(near), float(far),
+                                                  rgb.data_ptr(), depth.data_ptr()))
+        return rgb, depth
 
-def _render_pose_host(self, c2w, H: int, W: int, focal: float, s: int = 1, ndc: bool = False,
-                      near: float = 2.0, far: float = 6.0):
-    """One camera pose -> (rgb [H*W/s^2,3], depth [H*W/s^2]) CPU tensors; rays are generated on the
-    device (48 bytes of pose go up instead of 32 bytes per ray)."""
-    c = torch.as_tensor(c2w, dtype=torch.float32).reshape(12).cpu()
-    arr = (C.c_float * 12)(*c.tolist())
-    n_out = (H // s) * (W // s)
-    rgb = torch.empty(n_out, 3, dtype=torch.float32)
-    depth = torch.empty(n_out, dtype=torch.float32)
-    self._check(self.lib.nsr_render_pose_host(self._h, arr, H, W, float(focal), s, int(ndc), float(near), float(far),
-                                              rgb.data_ptr(), depth.data_ptr()))
-    return rgb, depth
+    def render_test_pose(self, c2w, H: int, W: int, focal: float, s: int = 2, ndc: bool = False,
+                          near: float = 2.0, far: float = 6.0) -> Dict[str, torch.Tensor]:
+        """One iteration of the reference's test sweep for a camera pose, entirely on the device:
+        dataset __getitem__ (rays for the pose, data/*_downX_dataset.py test branch) -> forward -> comp_low_res_output
+        -> calculate_vis(with_gt=False) (models/nerf_downX_model.py:316-353,418-450).  Returns device tensors:
+        {coarse,fine}_pred_ori  uint8 [H, 2W, 3]      HR [pred | depth] frames
+        {coarse,fine}_pred      uint8 [H/s, 2W/s, 3]  LR (box-averaged) frames
+        {coarse,fine}_depth_mat_ori [H, W], {coarse,fine}_depth_mat [H/s, W/s]   fp32 depth matrices (the *.npz payloads)"""
+        rays = self.generate_rays(c2w, H, W, focal, s=s, ndc=ndc, near=near, far=far)
+        nr, fr = (0.0, 1.0) if ndc else (near, far)              # self.near / self.far = rays[0, 6:8]
+        out = self.forward_rays(rays, want_weights=False)
+        res: Dict[str, torch.Tensor] = {}
+        for name in ("coarse", "fine") if self.n_importance > 0 else ("coarse",):
+            rgb, depth = out[f"{name}_comp_rgbs"], out[f"{name}_depth"]
+            res[f"{name}_pred_ori"], res[f"{name}_depth_mat_ori"] = self.assemble_frame(rgb, depth, H, W, s, nr, fr)
+            lr_rgb, lr_depth = self.box_average(rgb, s), self.box_average(depth, s)
+            res[f"{name}_pred"], res[f"{name}_depth_mat"] = self.assemble_frame(lr_rgb, lr_depth, H // s, W // s, 1, nr, fr)
+        return res
 
-
-Renderer.render_pose_host = _render_pose_host
-
-
-def _render_test_pose(self, c2w, H: int, W: int, focal: float, s: int = 2, ndc: bool = False,
-                      near: float = 2.0, far: float = 6.0) -> Dict[str, torch.Tensor]:
-    """One iteration of the reference's test sweep for a camera pose, entirely on the device:
-    dataset __getitem__ (rays for the pose, data/*_downX_dataset.py test branch) -> forward -> comp_low_res_output
-    -> calculate_vis(with_gt=False) (models/nerf_downX_model.py:316-353,418-450).  Returns device tensors:
-    {coarse,fine}_pred_ori  uint8 [H, 2W, 3]      HR [pred | depth] frames
-    {coarse,fine}_pred      uint8 [H/s, 2W/s, 3]  LR (box-averaged) frames
-    {coarse,fine}_depth_mat_ori [H, W], {coarse,fine}_depth_mat [H/s, W/s]   fp32 depth matrices (the *.npz payloads)"""
-    rays = self.generate_rays(c2w, H, W, focal, s=s, ndc=ndc, near=near, far=far)
-    nr, fr = (0.0, 1.0) if ndc else (near, far)              # self.near / self.far = rays[0, 6:8]
-    out = self.forward_rays(rays, want_weights=False)
-    res: Dict[str, torch.Tensor] = {}
-    for name in ("coarse", "fine") if self.n_importance > 0 else ("coarse",):
-        rgb, depth = out[f"{name}_comp_rgbs"], out[f"{name}_depth"]
-        res[f"{name}_pred_ori"], res[f"{name}_depth_mat_ori"] = self.assemble_frame(rgb, depth, H, W, s, nr, fr)
-        lr_rgb, lr_depth = self.box_average(rgb, s), self.box_average(depth, s)
-        res[f"{name}_pred"], res[f"{name}_depth_mat"] = self.assemble_frame(lr_rgb, lr_depth, H // s, W // s, 1, nr, fr)
-    return res
-
-
-def _render_path(self, poses, H: int, W: int, focal: float, s: int = 2, ndc: bool = False, near: float = 2.0,
-                 far: float = 6.0, keys: Sequence[str] = ("fine_pred", "fine_pred_ori", "fine_depth_mat_ori")):
-    """Test sweep over a pose path (nerf_sr_b200.paths): yields one dict of HOST (pinned) tensors per pose.
-    48 bytes go up per frame; frame k's device-to-host copies overlap frame k+1's render (two pinned slots)."""
-    copy_stream = torch.cuda.Stream(self.device)
-    slots, events, pending = [None, None], [None, None], None
-    for k, c2w in enumerate(poses):
-        res = self.render_test_pose(c2w, H, W, focal, s, ndc, near, far)
-        slot = k & 1
-        if slots[slot] is None:
-            slots[slot] = {n: torch.empty(res[n].shape, dtype=res[n].dtype).pin_memory() for n in keys}
-        done = torch.cuda.Event()
-        copy_stream.wait_stream(torch.cuda.current_stream(self.device))
-        with torch.cuda.stream(copy_stream):
-            for n in keys:
-                res[n].record_stream(copy_stream)
-                slots[slot][n].copy_(res[n], non_blocking=True)
-            done.record(copy_stream)
-        events[slot] = done
+    def render_path(self, poses, H: int, W: int, focal: float, s: int = 2, ndc: bool = False, near: float = 2.0,
+                     far: float = 6.0, keys: Sequence[str] = ("fine_pred", "fine_pred_ori", "fine_depth_mat_ori")):
+        """Test sweep over a pose path (nerf_sr_b200.paths): yields one dict of HOST (pinned) tensors per pose.
+        48 bytes go up per frame; frame k's device-to-host copies overlap frame k+1's render (two pinned slots)."""
+        copy_stream = torch.cuda.Stream(self.device)
+        slots, events, pending = [None, None], [None, None], None
+        for k, c2w in enumerate(poses):
+            res = self.render_test_pose(c2w, H, W, focal, s, ndc, near, far)
+            slot = k & 1
+            if slots[slot] is None:
+                slots[slot] = {n: torch.empty(res[n].shape, dtype=res[n].dtype).pin_memory() for n in keys}
+            done = torch.cuda.Event()
+            copy_stream.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(copy_stream):
+                for n in keys:
+                    res[n].record_stream(copy_stream)
+                    slots[slot][n].copy_(res[n], non_blocking=True)
+                done.record(copy_stream)
+            events[slot] = done
+            if pending is not None:
+                events[pending].synchronize()
+                yield slots[pending]
+            pending = slot
         if pending is not None:
             events[pending].synchronize()
             yield slots[pending]
-        pending = slot
-    if pending is not None:
-        events[pending].synchronize()
-        yield slots[pending]
-
-
-Renderer.render_test_pose = _render_test_pose
-Renderer.render_path = _render_path
 
 
 class _LazyNearFar:
