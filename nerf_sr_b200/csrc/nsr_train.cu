@@ -850,9 +850,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_tg_dxchain(const ChainArgs
 // k_tg_dw: ALL dW GEMMs of one net in ONE persistent launch (round 2; round 1 launched each of the 13 separately and paid a
 // ramp, a TMEM allocation and a tail per launch: ~5 us x 26 per iteration, first-order at the 256-rays-per-GPU DDP shape).
 // Per GEMM g:  partial[split][n][m] = sum over this CTA's tiles of A[p][m] * B[p][n];  bias partial[split][m] = sum A[p][m].
-// One CTA per SM.  For GEMM g, CTA b works on (job, split) = (b / n_split_g, b % n_split_g) when job < n_jobs_g, exactly
-// the decomposition of the former per-GEMM grids; the GEMMs are independent (they read the stash / dZ images and write
-// disjoint partial regions), so the CTA simply walks the list: the operand ring (2 x 96 KB), its barrier parities and the
+// One CTA per SM.  The work items of the launch are (GEMM g, job, split), n_jobs_g x n_split_g per GEMM, numbered GEMM after
+// GEMM; CTA b takes items b, b + grid, ... (at frame-sized batches every GEMM has as many items as there are CTAs, i.e. the
+// decomposition of the former per-GEMM grids; at small batches, where a GEMM has fewer items than SMs, different GEMMs run
+// side by side).  Items are independent (they read the stash / dZ images and write disjoint partial regions), so the CTA
+// simply walks its list: the operand ring (2 x 96 KB), its barrier parities and the
 // TMEM allocation carry over from one GEMM to the next, the producer prefetches GEMM g+1 while the epilogue of g drains the
 // accumulator (ACC_FULL / ACC_EMPTY hand it back and forth).  Partials are stored [n][m] so that the 32 lanes of an
 // epilogue warp (= 32 consecutive output rows m) write 128 contiguous bytes per column and k_grad_reduce reads them the
@@ -870,8 +872,9 @@ struct DwGemm {
   DwJob job[kMaxDwJobs]; int n_jobs;
   const uint8_t* b_img; int b_cpt; int b_chunk0; int nB;    // N = 64 * nB
   int n_split;
+  int item0;                // index of this GEMM's first work item in the launch-wide list
 };
-struct DwAllArgs { DwGemm g[kMaxDwGemms]; int n_gemms; long long n_tiles; };
+struct DwAllArgs { DwGemm g[kMaxDwGemms]; int n_gemms; int n_items; long long n_tiles; };
 static_assert(sizeof(DwAllArgs) <= 4000, "kernel parameter space");
 
 template <int FMT>
@@ -887,10 +890,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_tg_dw(const DwAllArgs a) {
   }
   const uint32_t tmem = gemm_prologue(sm, sm_base, 4);
   const uint32_t bar = sm_base + kSmGBar;
-  // this CTA's share of GEMM gi (the same arithmetic in every role)
-  auto my_work = [&](const DwGemm& G, int& job, int& split) -> long long {
-    job = (int)blockIdx.x / G.n_split; split = (int)blockIdx.x % G.n_split;
-    if (job >= G.n_jobs) return -1;                                                   // not part of this GEMM
+  // work item -> (GEMM, job, split) and its number of tiles (the same arithmetic in every role)
+  auto my_work = [&](int item, int& gi, int& job, int& split) -> long long {
+    gi = 0;
+    while (gi + 1 < a.n_gemms && item >= a.g[gi + 1].item0) ++gi;
+    const DwGemm& G = a.g[gi];
+    const int local = item - G.item0;
+    job = local / G.n_split; split = local % G.n_split;
     return (a.n_tiles > split) ? (a.n_tiles - split + G.n_split - 1) / G.n_split : 0;
   };
 
@@ -898,11 +904,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_tg_dw(const DwAllArgs a) {
     if (elect_one()) {
       uint32_t n = 0;
 #pragma unroll 1
-      for (int gi = 0; gi < a.n_gemms; ++gi) {
-        const DwGemm& G = a.g[gi];
-        int job, split;
-        const long long my_tiles = my_work(G, job, split);
+      for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+        int gi, job, split;
+        const long long my_tiles = my_work(item, gi, job, split);
         if (my_tiles <= 0) continue;
+        const DwGemm& G = a.g[gi];
         const DwJob& J = G.job[job];
         const uint32_t bytes = (uint32_t)(4 + 2 * G.nB) * 8192u;
         for (long long it = 0; it < my_tiles; ++it) {
@@ -934,11 +940,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_tg_dw(const DwAllArgs a) {
       const uint64_t ones = kmajor_desc(sm_base + kSmAux);
       uint32_t n = 0, uses = 0;
 #pragma unroll 1
-      for (int gi = 0; gi < a.n_gemms; ++gi) {
-        const DwGemm& G = a.g[gi];
-        int job, split;
-        const long long my_tiles = my_work(G, job, split);
+      for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+        int gi, job, split;
+        const long long my_tiles = my_work(item, gi, job, split);
         if (my_tiles <= 0) continue;
+        const DwGemm& G = a.g[gi];
         const uint32_t idesc = gemm_idesc(FMT, 128, 64 * G.nB, 1, 1);
         if (uses > 0) { mbar_wait(bar + 8 * (G_ACCEMPTY + 0), (uses - 1u) & 1u); tc_fence_after(); }   // previous GEMM drained
         for (long long it = 0; it < my_tiles; ++it) {
@@ -972,11 +978,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_tg_dw(const DwAllArgs a) {
     const uint32_t tlane = tmem + ((uint32_t)(32 * q) << 16);
     uint32_t uses = 0;
 #pragma unroll 1
-    for (int gi = 0; gi < a.n_gemms; ++gi) {
+    for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+      int gi, job, split;
+      const long long my_tiles = my_work(item, gi, job, split);
       const DwGemm& G = a.g[gi];
-      int job, split;
-      const long long my_tiles = my_work(G, job, split);
-      if (my_tiles < 0) continue;
       const DwJob& J = G.job[job];
       const int N = 64 * G.nB;
       float* dst = J.part + (size_t)split * N * 128 + row;              // [n][m]: lanes = consecutive rows m
@@ -1371,6 +1376,8 @@ struct DwPlanner {
     if ((long long)n_split * 4 > n_tiles) n_split = (int)((n_tiles + 3) / 4);
     if (n_split < 1) n_split = 1;
     a.n_split = n_split;
+    a.item0 = all.n_items;
+    all.n_items += n_jobs * n_split;
     const int N = 64 * nB;
     char* reg = part_base + (size_t)launch_idx * region;
     size_t off = 0;
