@@ -803,6 +803,12 @@ static int wait_for_packs(NsrHandle_* h) {
   return NSR_OK;
 }
 
+// Rays per chunk of the host-buffer pipeline.  The render needs 74 MB/s of rays at 2.3 M rays/s -- three orders of
+// magnitude under PCIe -- so copy/compute overlap buys nothing, while every chunk boundary costs a partly filled last wave
+// and two launches: chunks are as large as the staging buffers reasonably allow (a 160 000-ray frame is ONE chunk; its 5 MB
+// upload takes 0.2 ms of 70), and only frames beyond that are pipelined over the two slots.
+static constexpr int64_t kHostChunkRays = 262144;
+
 // Chunked, double-buffered frame render.  Rays come either from host memory (staged through pinned
 // buffers, H2D inside the pipeline) or from a device buffer the caller filled on stream hs[0]
 // (rays_dev != null: nsr_render_pose_host generates them on the device).
@@ -810,7 +816,7 @@ static int render_frame_pipeline(NsrHandle* h, const float* rays_host, const flo
                                  int ray_stride, int s, float* rgb_host, float* depth_host) {
   int rc = NSR_OK;
   const int ss = s * s;
-  int64_t chunk = 65536;
+  int64_t chunk = kHostChunkRays;
   chunk -= chunk % ss;
   if (chunk > n_rays) chunk = n_rays;
   rc = ensure_host_state(h, chunk, ray_stride);
@@ -886,7 +892,7 @@ extern "C" int nsr_render_pose_host(NsrHandle* h, const float* c2w_host, int H, 
   if (h->cfg.viewdir_offset != 3) return fail(h, NSR_ERR_UNSUPPORTED, "pose rendering produces 8-column rays (NeRFDownXModel layout)");
   NSR_CUDA(h, cudaSetDevice(h->cfg.device));
   const int64_t n_rays = (int64_t)H * W;
-  int64_t chunk = 65536;
+  int64_t chunk = kHostChunkRays;
   chunk -= chunk % (s * s);
   if (chunk > n_rays) chunk = n_rays;
   int rc = ensure_host_state(h, chunk, 8);      // creates the streams / events / staging
