@@ -508,6 +508,8 @@ static WsLayout ws_layout(const NsrHandle_* h, int64_t n) {
   if (h->cfg.precision == NSR_PREC_FP32_SIMT) {
     L.z_c = off; off += align_up((size_t)n * Sc * sizeof(float));
     L.raw = off; off += align_up((size_t)n * Sf * 4 * sizeof(float));
+  } else if (Sf > 128) {      // tensor-core fine pass in MLP-only mode (192 / 256 samples): raw (rgb, sigma) for k_composite
+    L.raw = off; off += align_up((size_t)n * Sf * 4 * sizeof(float));
   }
   L.total = off + 256;
   return L;
@@ -550,6 +552,14 @@ static int run_pass(NsrHandle_* h, int which, const float* rays, int64_t n, int 
   a.trace = h->trace_buf;
   a.debug_flags = h->debug_flags;
   a.comp_rgb = comp; a.depth = depth; a.opacity = opa; a.weights = wts; a.raw = raw_out; a.z_next = z_next;
+  if (S > 128) {              // MLP-only mode: tiles cut across rays, compositing afterwards with one warp per ray
+    if (!z_in) return fail(h, NSR_ERR_UNSUPPORTED, "a pass with more than 128 samples per ray needs caller-supplied z-values");
+    float* raw = raw_out ? raw_out : ws_raw;
+    a.raw = raw; a.noise = nullptr; a.comp_rgb = nullptr; a.depth = nullptr; a.opacity = nullptr; a.weights = nullptr;
+    NSR_CUDA(h, tc_pass(h, which, a, st));
+    NSR_CUDA(h, launch_composite(h, raw, z_in, noise, n, S, 0, nullptr, comp, depth, opa, wts, nullptr, st));
+    return NSR_OK;
+  }
   NSR_CUDA(h, tc_pass(h, which, a, st));
   return NSR_OK;
 }

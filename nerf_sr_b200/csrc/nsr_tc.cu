@@ -155,9 +155,15 @@ bool tc_supported(const NsrConfig& c, std::string* why) {
   auto no = [&](const char* m) { if (why) *why = m; return false; };
   if (c.D != 8 || c.W != 256 || c.skips_mask != (1u << 4)) return no("needs D=8, W=256, skips=[4]");
   if (c.deg_pos != 10 || c.deg_dir != 4 || c.no_xyz) return no("needs deg_pos=10, deg_dir=4, xyz included");
+  // coarse pass: whole rays per 128-point tile (64 or 128 samples); fine pass: the same, or 192 / 256 samples in the
+  // MLP-only mode (tiles cut across rays, compositing in k_composite); the in-kernel resampler's scratch holds
+  // 2 N_coarse + N_importance <= 320 floats per ray (640 when a tile is one ray)
   const int sc = c.n_coarse, sf = c.n_coarse + c.n_importance;
-  if (!((sc == 64 && (sf == 64 || sf == 128)) || (sc == 128 && sf == 128)))
-    return no("needs (N_coarse, N_importance) in {(64,0), (64,64), (128,0)}");
+  const bool coarse_ok = (sc == 64 || sc == 128);
+  const bool fine_ok = (sf == sc) || sf == 128 || sf == 192 || sf == 256;
+  const bool scratch_ok = c.n_importance == 0 || 2 * sc + c.n_importance <= (sc == 128 ? 640 : 320);
+  if (!(coarse_ok && fine_ok && scratch_ok))
+    return no("needs N_coarse in {64, 128} and N_coarse + N_importance in {N_coarse, 128, 192, 256}");
   return true;
 }
 
@@ -213,6 +219,10 @@ struct TcKernelArgs {
   int do_resample;
   float* comp_rgb; float* depth; float* opacity; float* weights; float* raw; float* z_next;
   long long n_tiles;
+  // loose = 1: S does not divide the 128-point tile (192 or 256 samples per ray: --N_importance 128 and friends).  Tiles
+  // then cut across rays (point p = 128 tile + row belongs to ray p / S), the kernel is the MLP only -- it writes `raw` --
+  // and compositing runs afterwards in k_composite (one warp per ray), like on the fp32 path.
+  int loose;
   long long* trace;
   int debug_flags;   // bit0: producer skips the bulk copies (timing experiment: stale weights)
   // training stash (STASH kernels only; scope row f-1): every tile's MLP inputs and activations in the
@@ -341,7 +351,7 @@ __device__ __forceinline__ void frontend_role(const TcKernelArgs& a, uint8_t* sm
                                               int first_tile, int tile_stride) {
   const int t = threadIdx.x - 32 * kFrontWarp0;   // 0..127 = tile row
   const int lane = threadIdx.x & 31;
-  const int S = a.S, RPT = kTile / S;
+  const int S = a.S, RPT = a.loose ? 2 : kTile / S;        // rays a tile can touch
   const RenderParams& rp = a.rp;
   const int fw = t >> 5;   // front-end warp index
   // Compositing (+ resampling) of tile `j`, staged in shared memory by the epilogue warps.
@@ -350,7 +360,7 @@ __device__ __forceinline__ void frontend_role(const TcKernelArgs& a, uint8_t* sm
   auto composite_tile = [&](long long j) {
     const uint32_t cbuf = (uint32_t)(j & 1);
     mbar_wait(sm_base + kSmBar + 8 * B_COMPREADY, (uint32_t)(j & 1));
-    if (fw < RPT) {
+    if (fw < RPT && !a.loose) {
       const long long tile_j = first_tile + j * (long long)tile_stride;
       const long long ray = tile_j * RPT + fw;
       if (ray < a.n_rays) {
@@ -388,8 +398,9 @@ __device__ __forceinline__ void frontend_role(const TcKernelArgs& a, uint8_t* sm
     TR_DECL(a, it - 1);     // front-end works one tile ahead: trace the work done for iteration 3 during tile 2..3
     TR(5000);
     const long long tile = first_tile + it * (long long)tile_stride;
-    const long long ray = tile * RPT + t / S;
-    const int i = t % S;
+    const long long p0 = tile * kTile;                       // first point of the tile; its first ray is p0 / S
+    const long long ray = (p0 + t) / S;
+    const int i = (int)((p0 + t) % S);
     const bool valid = ray < a.n_rays;
     float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0, near = 0, far = 0;
     if (valid) {
@@ -448,7 +459,7 @@ __device__ __forceinline__ void frontend_role(const TcKernelArgs& a, uint8_t* sm
     // dirbias[r][j] = b_dir[j] + sum_c Wdir[j][256+c] * enc_dir[r][c]   (networks.py:214-221)
     float* denc = reinterpret_cast<float*>(sm + kSmDenc);
     if (t < RPT) {
-      const long long r2 = tile * RPT + t;
+      const long long r2 = p0 / S + t;                       // slot t of the tile's rays
       float vx = 0, vy = 0, vz = 0;
       if (r2 < a.n_rays) {
         const float* rr = a.rays + r2 * a.ray_stride + rp.viewdir_offset;
@@ -563,7 +574,7 @@ __device__ __forceinline__ void epilogue_role(const TcKernelArgs& a, uint8_t* sm
   const uint32_t tlane = tmem + ((uint32_t)(32 * q) << 16);
   const uint32_t bar = sm_base + kSmBar;
   const float* cst = reinterpret_cast<const float*>(sm + kSmConst);
-  const int S = a.S, RPT = kTile / S;
+  const int S = a.S;
   const RenderParams& rp = a.rp;
   uint32_t g = 0;
   float* xch = reinterpret_cast<float*>(sm + kSmXch);
@@ -577,7 +588,7 @@ __device__ __forceinline__ void epilogue_role(const TcKernelArgs& a, uint8_t* sm
     if (hh == 1) { xch[row] = sig_p; xch[128 + row] = r0; xch[256 + row] = r1; xch[384 + row] = r2; }
     named_bar_sync(2, 32 * kWarpsEpi);
     if (hh == 0) {
-      const long long ray = tile * RPT + row / S;
+      const long long ray = (tile * kTile + row) / S;
       const bool valid = ray < a.n_rays;
       const float sigma = (sig_p + xch[row]) + cst[kcMisc];
       float col[3] = {r0 + xch[128 + row], r1 + xch[256 + row], r2 + xch[384 + row]};
@@ -635,7 +646,9 @@ __device__ __forceinline__ void epilogue_role(const TcKernelArgs& a, uint8_t* sm
       // away, so a waiter here could fall two phases behind (parity aliasing -> deadlock).
       mbar_wait(bar + 8 * (B_ACCFULL + 0), g & 1);
       tc_fence_after();
-      const uint32_t dbias_addr = sm_base + kSmDirBias + 4u * (uint32_t)(buf * 256 + (row / S) * 128);
+      const long long p0 = (first_tile + it * (long long)tile_stride) * kTile;
+      const int slot = (int)((p0 + row) / S - p0 / S);       // which of the tile's rays this row belongs to (0 or 1)
+      const uint32_t dbias_addr = sm_base + kSmDirBias + 4u * (uint32_t)(buf * 256 + slot * 128);
       const uint32_t wrgb_addr = sm_base + kSmConst + 4u * kcWrgb;
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
@@ -772,7 +785,10 @@ cudaError_t tc_init(NsrHandle_* h) {
 }
 
 cudaError_t tc_pass(NsrHandle_* h, int which, const TcPassArgs& p, cudaStream_t st) {
-  if (p.S != 64 && p.S != 128) return cudaErrorInvalidValue;
+  const bool loose = (kTile % p.S) != 0 || p.S > kTile;
+  if (p.S != 64 && p.S != 128 && p.S != 192 && p.S != 256) return cudaErrorInvalidValue;
+  // MLP-only mode: caller-provided z-values in, raw (rgb, sigma) out; no stash, no in-kernel compositing / resampling
+  if (loose && (!p.z_in || !p.raw || p.stash_enc || p.do_resample)) return cudaErrorInvalidValue;
   TcKernelArgs a{};
   a.image = h->net[which].tc_image; a.consts = h->net[which].tc_consts; a.tabs = h->d_tables; a.rp = h->rp;
   a.rays = p.rays; a.n_rays = p.n_rays; a.ray_stride = p.ray_stride; a.z_in = p.z_in; a.S = p.S;
@@ -781,8 +797,9 @@ cudaError_t tc_pass(NsrHandle_* h, int which, const TcPassArgs& p, cudaStream_t 
   a.z_next = p.z_next;
   a.trace = p.trace;
   a.debug_flags = p.debug_flags;
-  const int rpt = kTile / p.S;
-  a.n_tiles = (p.n_rays + rpt - 1) / rpt;
+  a.loose = loose ? 1 : 0;
+  if (loose) a.n_tiles = (p.n_rays * p.S + kTile - 1) / kTile;
+  else { const int rpt = kTile / p.S; a.n_tiles = (p.n_rays + rpt - 1) / rpt; }
   if (a.n_tiles == 0) return cudaSuccess;
   const int grid = (int)(a.n_tiles < h->sm_count ? a.n_tiles : h->sm_count);
   void (*kern)(const TcKernelArgs) = nullptr;

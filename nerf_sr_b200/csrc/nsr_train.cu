@@ -1529,6 +1529,8 @@ static int train_supported(NsrHandle_* h) {
   if (h->cfg.precision != NSR_PREC_BF16X3_TC)
     return tfail(h, NSR_ERR_UNSUPPORTED, "training needs the bf16 split-precision tensor-core path (precision bf16x3)");
   if (h->cfg.n_importance <= 0) return tfail(h, NSR_ERR_UNSUPPORTED, "training needs N_importance > 0 (coarse + fine)");
+  if (h->cfg.n_coarse != 64 || h->cfg.n_importance != 64)
+    return tfail(h, NSR_ERR_UNSUPPORTED, "training is built for N_coarse 64 + N_importance 64 (whole rays per 128-point tile in both passes)");
   if (h->cfg.no_dir) return tfail(h, NSR_ERR_UNSUPPORTED, "training with --no_dir is not supported");
   return NSR_OK;
 }

@@ -446,7 +446,7 @@ def patch_model(model, precision: str = "bf16x3", whole_frame: bool = True):
       backward averages the two flat gradient buffers over the DDP process group -- what DDP's reducer would have done had
       its ``forward`` been called -- so every rank steps with the same gradients.
     * Option sets the library refuses (``nsr_create`` -> NSR_ERR_UNSUPPORTED) leave the model untouched (one warning);
-      option sets only the backward does not cover (precisions other than bf16x3, N_importance == 0, --no_dir) keep the
+      option sets only the backward does not cover (precisions other than bf16x3, sample counts other than 64 + 64, --no_dir) keep the
       reference path in train mode, chunked by the ORIGINAL ``opt.ray_chunk``.
     * whole_frame: raise ``opt.ray_chunk`` so that the reference's ``chunk_batch(self.forward_rays, opt.ray_chunk, rays)``
       (models/nerf_downX_model.py:318, utils/utils.py:130-152) hands a whole frame to one call -- the chunking only exists to
@@ -469,7 +469,7 @@ def patch_model(model, precision: str = "bf16x3", whole_frame: bool = True):
     reference_forward_rays = model.forward_rays
     lazy = _install_lazy_near_far(model)
 
-    train_capable = (precision == "bf16x3" and renderer.n_importance > 0 and not renderer.cfg.no_dir)
+    train_capable = (precision == "bf16x3" and (renderer.n_coarse, renderer.n_importance) == (64, 64) and not renderer.cfg.no_dir)
 
     def reference_path(rays):
         # the PyTorch path needs its chunking back (utils/utils.py:130-152) when whole_frame lifted opt.ray_chunk

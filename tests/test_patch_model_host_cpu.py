@@ -15,7 +15,7 @@ def fake_renderer(monkeypatch):
 
     class FakeRenderer:
         def __init__(self, opt, device=None, precision="bf16x3", viewdir_offset=3):
-            self.n_importance = opt.N_importance
+            self.n_coarse, self.n_importance = opt.N_coarse, opt.N_importance
             self.cfg = types.SimpleNamespace(no_dir=int(getattr(opt, "no_dir", False)))
             self._param_versions = [None, None]
             calls.append(("init", precision, viewdir_offset))
