@@ -247,6 +247,29 @@ typedef struct NsrRayGen {
 NSR_API int nsr_generate_rays_ex(NsrHandle* h, const float* c2w_host, const NsrRayGen* spec, float* rays_out,
                                  NsrStream stream);
 
+/* Replaces: one iteration of the test sweep up to the images -- the dataset's ray generation for a pose
+ * (data/{blender,llff}_downX_dataset.py test branch; models/utils.py:98-196), forward() = chunk_batch(forward_rays)
+ * (models/nerf_downX_model.py:316-321) and comp_low_res_output's s x s box average (:337-348) -- as ONE kernel launch
+ * where the option set allows (tensor-core precision, 64 + 64 samples, s in {1, 2, 4}): the fine tiles consume the z-values
+ * the same CTA's coarse tiles produced, rays are generated in the kernel's front-end when `rays` is null, and the LR image
+ * leaves the compositing epilogue directly.  Other option sets run the same computation as separate launches; results are
+ * bit-identical either way (tests/test_gpu_fused_frame.py).
+ *   rays      : [n_rays, ray_stride] device rays, or null -> rays of pose `c2w_host` (3x4 row-major, host) on the raster
+ *               `spec` (n_rays / ray_stride are then ignored: H*W rays of 8 columns)
+ *   out       : HR outputs, any pointer null (with the fused kernel a null HR output is simply not written)
+ *   lr        : box-averaged outputs [n_rays / s^2], any pointer null; ignored when s == 1
+ *   workspace : nsr_frame_workspace_bytes(h, n_rays, rays == null) bytes */
+typedef struct NsrLrOutputs {
+  float* coarse_rgb;           /* [N/s^2,3]                                    */
+  float* coarse_depth;         /* [N/s^2]                                      */
+  float* fine_rgb;             /* [N/s^2,3]                                    */
+  float* fine_depth;           /* [N/s^2]                                      */
+} NsrLrOutputs;
+NSR_API size_t nsr_frame_workspace_bytes(const NsrHandle* h, int64_t n_rays, int from_pose);
+NSR_API int nsr_render_frame(NsrHandle* h, const float* rays, int64_t n_rays, int ray_stride, const float* c2w_host,
+                             const NsrRayGen* spec, int s, const NsrRng* rng, const NsrOutputs* out,
+                             const NsrLrOutputs* lr, void* workspace, size_t workspace_bytes, NsrStream stream);
+
 /* Replaces (scope row f-2, the LR-image + loss epilogue): comp_low_res_output's box average followed by
  * ColorMSELoss and PSNR against the LR targets (models/nerf_downX_model.py:337-340,357,380;
  * models/criterions.py:7-15,27-36).  hr_rgb: [n_lr*s*s, 3] composite colours (sub-pixels contiguous);

@@ -53,6 +53,10 @@ class NsrRayGen(C.Structure):
                 ("unified_dir", C.c_int32), ("reserved", C.c_int32 * 6)]
 
 
+class NsrLrOutputs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("coarse_rgb", "coarse_depth", "fine_rgb", "fine_depth")]
+
+
 class NsrPassOutputs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("comp_rgbs", "depth", "opacity", "weights", "raw")]
 
@@ -69,6 +73,10 @@ SIGNATURES = {
     "nsr_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64]),
     "nsr_render": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.POINTER(NsrRng),
                              C.POINTER(NsrOutputs), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "nsr_frame_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64, C.c_int]),
+    "nsr_render_frame": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_float), C.POINTER(NsrRayGen),
+                                   C.c_int, C.POINTER(NsrRng), C.POINTER(NsrOutputs), C.POINTER(NsrLrOutputs), C.c_void_p,
+                                   C.c_size_t, C.c_void_p]),
     "nsr_render_pass": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int,
                                   C.c_void_p, C.POINTER(NsrPassOutputs), C.c_void_p, C.c_size_t, C.c_void_p]),
     "nsr_sample_coarse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -199,61 +199,17 @@ __global__ void k_lr_metrics_final(const double* __restrict__ partials, int n_bl
   }
 }
 
-struct Pose { float m[12]; };
-
-__global__ void k_generate_rays(Pose c2w, int H, int W, float focal, int s, int ndc, float near_plane,
-                                float far_plane, float pixel_center, int unified_dir, float* __restrict__ rays) {
+__global__ void k_generate_rays(RayGenParams g, float* __restrict__ rays) {
   // get_ray_directions + get_rays (+ get_ndc_rays) + '(h s1) (w s2) c -> (h w) (s1 s2) c'
-  // (models/utils.py:98-196; data/blender_downX_dataset.py:207-215)
-  const int64_t total = (int64_t)H * W;
-  const int w_lr = W / s;
+  // (models/utils.py:98-196; data/blender_downX_dataset.py:207-215): generate_ray(), nsr_device.cuh
+  const int64_t total = (int64_t)g.H * g.W;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
-    // idx is the OUTPUT row: lr pixel (h, w), sub-pixel (s1, s2)
-    const int sub = (int)(idx % (s * s));
-    const int64_t lr = idx / (s * s);
-    const int hh = (int)(lr / w_lr), ww = (int)(lr % w_lr);
-    const int s1 = sub / s, s2 = sub % s;
-    const int row = hh * s + s1, col = ww * s + s2;
-    // --unified_dir (data/llff_downX_dataset.py:273-277): one camera-space direction per LR pixel, computed on the
-    // (H/s, W/s) raster with focal // s and repeated over its s x s sub-pixels; NDC below still uses H, W, focal
-    const int dcol = unified_dir ? ww : col, drow = unified_dir ? hh : row;
-    const float dW = unified_dir ? (float)(W / s) : (float)W, dH = unified_dir ? (float)(H / s) : (float)H;
-    const float dfocal = unified_dir ? floorf(__fdiv_rn(focal, (float)s)) : focal;
-    const float i = (float)dcol + pixel_center, j = (float)drow + pixel_center;
-    const float cx = __fdiv_rn(__fsub_rn(i, dW / 2.f), dfocal);
-    const float cy = -__fdiv_rn(__fsub_rn(j, dH / 2.f), dfocal);
-    const float cz = -1.f;
-    // rays_d = directions @ c2w[:, :3].T
-    float d[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k)
-      d[k] = __fadd_rn(__fadd_rn(__fmul_rn(cx, c2w.m[4 * k + 0]), __fmul_rn(cy, c2w.m[4 * k + 1])),
-                       __fmul_rn(cz, c2w.m[4 * k + 2]));
-    const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
-    d[0] = __fdiv_rn(d[0], nrm); d[1] = __fdiv_rn(d[1], nrm); d[2] = __fdiv_rn(d[2], nrm);
-    float o[3] = {c2w.m[3], c2w.m[7], c2w.m[11]};
-    float nearv = near_plane, farv = far_plane;
-    if (ndc) {   // get_ndc_rays at near = 1.0 (data/llff_downX_dataset.py:476-481)
-      const float nr = 1.0f;
-      const float t = __fdiv_rn(-__fadd_rn(nr, o[2]), d[2]);
-      o[0] = __fadd_rn(o[0], __fmul_rn(t, d[0]));
-      o[1] = __fadd_rn(o[1], __fmul_rn(t, d[1]));
-      o[2] = __fadd_rn(o[2], __fmul_rn(t, d[2]));
-      const float ox_oz = __fdiv_rn(o[0], o[2]), oy_oz = __fdiv_rn(o[1], o[2]);
-      const float kx = (float)(-1.0 / ((double)W / (2.0 * (double)focal)));
-      const float ky = (float)(-1.0 / ((double)H / (2.0 * (double)focal)));
-      const float o0 = __fmul_rn(kx, ox_oz), o1 = __fmul_rn(ky, oy_oz);
-      const float o2 = __fadd_rn(1.f, __fdiv_rn(__fmul_rn(2.f, nr), o[2]));
-      const float d0 = __fmul_rn(kx, __fsub_rn(__fdiv_rn(d[0], d[2]), ox_oz));
-      const float d1 = __fmul_rn(ky, __fsub_rn(__fdiv_rn(d[1], d[2]), oy_oz));
-      const float d2 = __fsub_rn(1.f, o2);
-      o[0] = o0; o[1] = o1; o[2] = o2; d[0] = d0; d[1] = d1; d[2] = d2;
-      nearv = 0.f; farv = 1.f;
-    }
+    float r[8];
+    generate_ray(g, idx, r);
     float* out = rays + idx * 8;
-    out[0] = o[0]; out[1] = o[1]; out[2] = o[2]; out[3] = d[0]; out[4] = d[1]; out[5] = d[2];
-    out[6] = nearv; out[7] = farv;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) out[k] = r[k];
   }
 }
 
@@ -343,6 +299,7 @@ extern "C" int nsr_create(const NsrConfig* cfg, NsrHandle** out_handle) {
   h->cfg = c;
   h->sm_count = prop.multiProcessorCount;
   if (const char* ev = getenv("NSR_TC_CLUSTER")) h->tc_cluster = atoi(ev) == 1 ? 1 : 2;
+  if (const char* ev = getenv("NSR_TC_FUSED")) h->tc_fused = atoi(ev) != 0;
   if (h->sm_count % 2) h->tc_cluster = 1;
   RenderParams& rp = h->rp;
   rp.n_coarse = c.n_coarse; rp.n_importance = c.n_importance;
@@ -564,6 +521,93 @@ static int run_pass(NsrHandle_* h, int which, const float* rays, int64_t n, int 
   return NSR_OK;
 }
 
+// LR (box-averaged) outputs of a frame render; any pointer may be null.
+struct LrOut { float* coarse_rgb = nullptr; float* coarse_depth = nullptr; float* fine_rgb = nullptr; float* fine_depth = nullptr; };
+
+static bool fused_frame_ok(const NsrHandle_* h, int s) {
+  return !(h->debug_flags & 2) && h->cfg.n_importance > 0 && tc_frame_supported(h, s) && h->net[0].packed && h->net[1].packed;
+}
+
+// Whether the box average belongs in the frame kernel's epilogue.  There a CTA's work quantum is a whole LR pixel's rays
+// (s*s rays = 1.5 s*s tiles) instead of a ray pair (3 tiles), so the busiest CTA of a SMALL batch can end up with one
+// quantum more than it would otherwise (2048 rays at s = 2: 24 tiles instead of 21, +14 %); from a few 10^4 rays on the
+// difference vanishes (a 400 x 400 frame: 1626 vs 1623 tiles).  In-kernel when it costs < 3 %; else the frame kernel writes
+// the HR composite and k_box_average follows (microseconds).
+static bool lr_in_kernel_pays(const NsrHandle_* h, int64_t n, int s) {
+  if (s <= 1 || !fused_frame_ok(h, s)) return false;
+  auto tiles_of_busiest_cta = [&](int unit) {
+    const int64_t units = (n + unit - 1) / unit;
+    int64_t grid = units < h->sm_count ? units : h->sm_count;
+    if (h->tc_cluster == 2 && units >= 2) grid = (grid + 1) & ~(int64_t)1;
+    return (units + grid - 1) / grid * (unit / 2) * 3;
+  };
+  return tiles_of_busiest_cta(s * s) * 100 <= tiles_of_busiest_cta(2) * 103;
+}
+
+// forward_rays over a ray batch (+ the s x s box average when `lr` is given).  One launch (k_tc_pass<.., FUSED>) where the
+// option set allows, else coarse pass, fine pass and one k_box_average per LR output.  `rg` != null: rays are generated from
+// the pose inside the fused kernel (callers check fused_frame_ok first).
+static int render_core(NsrHandle_* h, const float* rays, const RayGenParams* rg, int64_t n_rays, int ray_stride, int s,
+                       const NsrRng* rng, const NsrOutputs* out, const LrOut* lr, char* ws, const WsLayout& L, cudaStream_t st,
+                       int64_t rg_first = 0) {
+  const int Sc = h->cfg.n_coarse, Ni = h->cfg.n_importance;
+  float* z_f = out->z_fine ? out->z_fine : (float*)(ws + L.z_f);
+  float* ws_zc = (float*)(ws + L.z_c);
+  float* ws_raw = (float*)(ws + L.raw);
+  const NsrRng none{};
+  const NsrRng& R = rng ? *rng : none;
+  const float* noise_c = (h->cfg.noise_std > 0.f) ? R.noise_coarse : nullptr;
+  const float* noise_f = (h->cfg.noise_std > 0.f) ? R.noise_fine : nullptr;
+  const bool want_lr = lr && s > 1;
+  // box average in the kernel's epilogue: when it pays, or when the caller did not ask for the HR composite it would
+  // otherwise be computed from
+  bool lr_k = false;
+  if (want_lr && fused_frame_ok(h, s)) {
+    const bool hr_there = (!lr->coarse_rgb || out->coarse_comp_rgbs) && (!lr->coarse_depth || out->coarse_depth) &&
+                          (!lr->fine_rgb || out->fine_comp_rgbs) && (!lr->fine_depth || out->fine_depth);
+    lr_k = !hr_there || lr_in_kernel_pays(h, n_rays, s);
+  }
+  if (fused_frame_ok(h, lr_k ? s : 1)) {
+    TcFrameArgs f{};
+    f.rays = rays; f.rg = rg; f.rg_first = rg_first; f.n_rays = n_rays; f.ray_stride = ray_stride; f.s = lr_k ? s : 1;
+    f.u_jitter = R.u_coarse; f.noise_c = noise_c; f.noise_f = noise_f; f.u_resample = R.u_fine;
+    f.z_fine = z_f;
+    f.c_rgb = out->coarse_comp_rgbs; f.c_depth = out->coarse_depth; f.c_opacity = out->coarse_opacity; f.c_weights = out->coarse_weights;
+    f.f_rgb = out->fine_comp_rgbs; f.f_depth = out->fine_depth; f.f_opacity = out->fine_opacity; f.f_weights = out->fine_weights;
+    if (lr_k) { f.lr_rgb_c = lr->coarse_rgb; f.lr_depth_c = lr->coarse_depth; f.lr_rgb_f = lr->fine_rgb; f.lr_depth_f = lr->fine_depth; }
+    f.trace = h->trace_buf; f.debug_flags = h->debug_flags;
+    NSR_CUDA(h, tc_frame(h, f, st));
+    if (!want_lr || lr_k) return NSR_OK;
+  } else {
+    if (!rays) return fail(h, NSR_ERR_UNSUPPORTED, "in-kernel ray generation needs the fused frame kernel");
+    int rc = run_pass(h, 0, rays, n_rays, ray_stride, nullptr, Sc, R.u_coarse, noise_c, Ni > 0, R.u_fine,
+                      out->coarse_comp_rgbs, out->coarse_depth, out->coarse_opacity, out->coarse_weights, nullptr,
+                      Ni > 0 ? z_f : nullptr, ws_zc, ws_raw, st);
+    if (rc) return rc;
+    if (Ni > 0) {
+      rc = run_pass(h, 1, rays, n_rays, ray_stride, z_f, Sc + Ni, nullptr, noise_f, 0, nullptr, out->fine_comp_rgbs,
+                    out->fine_depth, out->fine_opacity, out->fine_weights, nullptr, nullptr, ws_zc, ws_raw, st);
+      if (rc) return rc;
+    }
+  }
+  if (want_lr) {
+    int rc = NSR_OK;
+    const int64_t n_lr = n_rays / ((int64_t)s * s);
+    auto box = [&](const float* in, int ch, float* o) -> int {
+      if (!o) return NSR_OK;
+      if (!in) return fail(h, NSR_ERR_INVALID_ARG, "an LR output needs the corresponding HR output buffer on this path");
+      return nsr_box_average(h, in, n_lr, s, ch, o, st);
+    };
+    if ((rc = box(out->coarse_comp_rgbs, 3, lr->coarse_rgb))) return rc;
+    if ((rc = box(out->coarse_depth, 1, lr->coarse_depth))) return rc;
+    if (Ni > 0) {
+      if ((rc = box(out->fine_comp_rgbs, 3, lr->fine_rgb))) return rc;
+      if ((rc = box(out->fine_depth, 1, lr->fine_depth))) return rc;
+    }
+  }
+  return NSR_OK;
+}
+
 extern "C" int nsr_render(NsrHandle* h, const float* rays, int64_t n_rays, int ray_stride, const NsrRng* rng,
                           const NsrOutputs* out, void* workspace, size_t workspace_bytes, NsrStream stream) {
   if (!h) return NSR_ERR_INVALID_ARG;
@@ -574,26 +618,63 @@ extern "C" int nsr_render(NsrHandle* h, const float* rays, int64_t n_rays, int r
   const WsLayout L = ws_layout(h, n_rays);
   if (!workspace || workspace_bytes < L.total) return fail(h, NSR_ERR_WORKSPACE, "workspace too small: need " + std::to_string(L.total));
   NSR_CUDA(h, cudaSetDevice(h->cfg.device));
-  cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-  const int Sc = h->cfg.n_coarse, Ni = h->cfg.n_importance;
-  float* z_f = out->z_fine ? out->z_fine : (float*)(ws + L.z_f);
-  float* ws_zc = (float*)(ws + L.z_c);
-  float* ws_raw = (float*)(ws + L.raw);
-  const NsrRng none{};
-  const NsrRng& R = rng ? *rng : none;
-  const float* noise_c = (h->cfg.noise_std > 0.f) ? R.noise_coarse : nullptr;
-  const float* noise_f = (h->cfg.noise_std > 0.f) ? R.noise_fine : nullptr;
-  rc = run_pass(h, 0, rays, n_rays, ray_stride, nullptr, Sc, R.u_coarse, noise_c, Ni > 0, R.u_fine,
-                out->coarse_comp_rgbs, out->coarse_depth, out->coarse_opacity, out->coarse_weights, nullptr,
-                Ni > 0 ? z_f : nullptr, ws_zc, ws_raw, st);
-  if (rc) return rc;
-  if (Ni > 0) {
-    rc = run_pass(h, 1, rays, n_rays, ray_stride, z_f, Sc + Ni, nullptr, noise_f, 0, nullptr, out->fine_comp_rgbs,
-                  out->fine_depth, out->fine_opacity, out->fine_weights, nullptr, nullptr, ws_zc, ws_raw, st);
-    if (rc) return rc;
-  }
+  return render_core(h, rays, nullptr, n_rays, ray_stride, 1, rng, out, nullptr, ws, L, (cudaStream_t)stream);
+}
+
+static int fill_raygen(NsrHandle_* h, const float* c2w_host, const NsrRayGen* spec, RayGenParams* p) {
+  if (!c2w_host || !spec || spec->struct_size != sizeof(NsrRayGen))
+    return fail(h, NSR_ERR_INVALID_ARG, "ray generation: null pose or NsrRayGen.struct_size mismatch");
+  if (spec->H <= 0 || spec->W <= 0 || spec->s < 1 || !(spec->focal > 0.f) || spec->H % spec->s || spec->W % spec->s)
+    return fail(h, NSR_ERR_INVALID_ARG, "ray generation: bad raster (H, W multiples of s; focal > 0)");
+  if (spec->unified_dir && !(floorf(spec->focal / (float)spec->s) > 0.f))
+    return fail(h, NSR_ERR_INVALID_ARG, "ray generation: unified_dir needs focal // s > 0");
+  memcpy(p->m, c2w_host, sizeof(p->m));
+  p->H = spec->H; p->W = spec->W; p->focal = spec->focal; p->s = spec->s; p->ndc = spec->ndc;
+  p->near_plane = spec->near_plane; p->far_plane = spec->far_plane;
+  p->pixel_center = spec->use_pixel_centers ? 0.5f : 0.f; p->unified_dir = spec->unified_dir;
   return NSR_OK;
+}
+
+extern "C" size_t nsr_frame_workspace_bytes(const NsrHandle* h, int64_t n_rays, int from_pose) {
+  if (!h || n_rays < 0) return 0;
+  // from a pose: room for the generated rays in case the option set needs the multi-launch path
+  return ws_layout(h, n_rays).total + (from_pose ? align_up((size_t)n_rays * 8 * sizeof(float)) : 0);
+}
+
+extern "C" int nsr_render_frame(NsrHandle* h, const float* rays, int64_t n_rays, int ray_stride, const float* c2w_host,
+                                const NsrRayGen* spec, int s, const NsrRng* rng, const NsrOutputs* out,
+                                const NsrLrOutputs* lr, void* workspace, size_t workspace_bytes, NsrStream stream) {
+  if (!h) return NSR_ERR_INVALID_ARG;
+  if (!out || !lr) return fail(h, NSR_ERR_INVALID_ARG, "nsr_render_frame: out / lr is null");
+  if (s < 1) return fail(h, NSR_ERR_INVALID_ARG, "nsr_render_frame: s < 1");
+  RayGenParams rg{};
+  const bool from_pose = rays == nullptr;
+  int rc;
+  if (from_pose) {
+    if ((rc = fill_raygen(h, c2w_host, spec, &rg))) return rc;
+    if (spec->s != s) return fail(h, NSR_ERR_INVALID_ARG, "nsr_render_frame: spec->s differs from s");
+    if (h->cfg.viewdir_offset != 3) return fail(h, NSR_ERR_UNSUPPORTED, "pose rendering produces 8-column rays (NeRFDownXModel layout)");
+    n_rays = (int64_t)spec->H * spec->W; ray_stride = 8;
+  } else if ((rc = check_render_args(h, rays, n_rays, ray_stride))) return rc;
+  if (n_rays % ((int64_t)s * s)) return fail(h, NSR_ERR_INVALID_ARG, "n_rays must be a multiple of s*s");
+  if (n_rays == 0) return NSR_OK;
+  const WsLayout L = ws_layout(h, n_rays);
+  const size_t need = nsr_frame_workspace_bytes(h, n_rays, from_pose);
+  if (!workspace || workspace_bytes < need) return fail(h, NSR_ERR_WORKSPACE, "workspace too small: need " + std::to_string(need));
+  NSR_CUDA(h, cudaSetDevice(h->cfg.device));
+  char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  cudaStream_t st = (cudaStream_t)stream;
+  LrOut l{lr->coarse_rgb, lr->coarse_depth, lr->fine_rgb, lr->fine_depth};
+  const bool want_lr = s > 1 && (l.coarse_rgb || l.coarse_depth || l.fine_rgb || l.fine_depth);
+  if (from_pose && !fused_frame_ok(h, 1)) {      // other option sets: rays through HBM, then the ordinary passes
+    float* gen = (float*)(ws + (L.total - 256));      // (L.total = 256-aligned pieces + 256 of alignment slack)
+    k_generate_rays<<<grid_for(n_rays, 256, h->sm_count * 16), 256, 0, st>>>(rg, gen);
+    h->launches += 1;
+    NSR_CUDA(h, cudaGetLastError());
+    rays = gen;
+  }
+  return render_core(h, rays, rays ? nullptr : &rg, n_rays, ray_stride, s, rng, out, want_lr ? &l : nullptr, ws, L, st);
 }
 
 extern "C" int nsr_render_pass(NsrHandle* h, int which, const float* rays, int64_t n_rays, int ray_stride,
@@ -687,10 +768,11 @@ static int generate_rays_impl(NsrHandle* h, const float* c2w_host, int H, int W,
   if (unified_dir && !(floorf(focal / (float)s) > 0.f))
     return fail(h, NSR_ERR_INVALID_ARG, "nsr_generate_rays: unified_dir needs focal // s > 0");
   NSR_CUDA(h, cudaSetDevice(h->cfg.device));
-  Pose p;
+  RayGenParams p{};
   memcpy(p.m, c2w_host, sizeof(p.m));
-  k_generate_rays<<<grid_for((int64_t)H * W, 256, h->sm_count * 16), 256, 0, (cudaStream_t)stream>>>(
-      p, H, W, focal, s, ndc, near_plane, far_plane, use_pixel_centers ? 0.5f : 0.f, unified_dir, rays_out);
+  p.H = H; p.W = W; p.focal = focal; p.s = s; p.ndc = ndc; p.near_plane = near_plane; p.far_plane = far_plane;
+  p.pixel_center = use_pixel_centers ? 0.5f : 0.f; p.unified_dir = unified_dir;
+  k_generate_rays<<<grid_for((int64_t)H * W, 256, h->sm_count * 16), 256, 0, (cudaStream_t)stream>>>(p, rays_out);
   h->launches += 1;
   NSR_CUDA(h, cudaGetLastError());
   return NSR_OK;
@@ -822,8 +904,8 @@ static constexpr int64_t kHostChunkRays = 262144;
 // Chunked, double-buffered frame render.  Rays come either from host memory (staged through pinned
 // buffers, H2D inside the pipeline) or from a device buffer the caller filled on stream hs[0]
 // (rays_dev != null: nsr_render_pose_host generates them on the device).
-static int render_frame_pipeline(NsrHandle* h, const float* rays_host, const float* rays_dev, int64_t n_rays,
-                                 int ray_stride, int s, float* rgb_host, float* depth_host) {
+static int render_frame_pipeline(NsrHandle* h, const float* rays_host, const float* rays_dev, const RayGenParams* rg,
+                                 int64_t n_rays, int ray_stride, int s, float* rgb_host, float* depth_host) {
   int rc = NSR_OK;
   const int ss = s * s;
   int64_t chunk = kHostChunkRays;
@@ -850,7 +932,9 @@ static int render_frame_pipeline(NsrHandle* h, const float* rays_host, const flo
     const int64_t r0 = k * chunk, nr = (r0 + chunk <= n_rays) ? chunk : n_rays - r0;
     cudaStream_t st = h->hs[slot];
     const float* d_rays = h->dev_in[slot];
-    if (rays_dev) {
+    if (rg) {
+      d_rays = nullptr;                 // generated in the fused kernel's front-end from (pose, r0 + row)
+    } else if (rays_dev) {
       d_rays = rays_dev + r0 * ray_stride;
     } else {
       memcpy(h->pin_in[slot], rays_host + r0 * ray_stride, (size_t)nr * ray_stride * sizeof(float));
@@ -861,19 +945,26 @@ static int render_frame_pipeline(NsrHandle* h, const float* rays_host, const flo
     float* d_dep = d_rgb + (size_t)chunk * 3;
     float* d_rgb_lr = d_dep + (size_t)chunk;
     float* d_dep_lr = d_rgb_lr + (size_t)chunk * 3;
+    // One launch per chunk on the fused path: the LR image comes straight out of the compositing epilogue and the HR
+    // composite is not written at all; other option sets: coarse pass, fine pass, two box averages.
+    const bool lr_k = lr_in_kernel_pays(h, nr, s);
     NsrOutputs o{};
-    if (fine) { o.fine_comp_rgbs = d_rgb; o.fine_depth = d_dep; }
-    else { o.coarse_comp_rgbs = d_rgb; o.coarse_depth = d_dep; }
-    rc = nsr_render(h, d_rays, nr, ray_stride, nullptr, &o, h->dev_ws[slot], h->host_ws_bytes, st);
-    if (rc) return rc;
-    const float* src_rgb = d_rgb;
-    const float* src_dep = d_dep;
-    const int64_t no = nr / ss;
-    if (s > 1) {
-      rc = nsr_box_average(h, d_rgb, no, s, 3, d_rgb_lr, st); if (rc) return rc;
-      rc = nsr_box_average(h, d_dep, no, s, 1, d_dep_lr, st); if (rc) return rc;
-      src_rgb = d_rgb_lr; src_dep = d_dep_lr;
+    LrOut l{};
+    if (!lr_k) {
+      if (fine) { o.fine_comp_rgbs = d_rgb; o.fine_depth = d_dep; }
+      else { o.coarse_comp_rgbs = d_rgb; o.coarse_depth = d_dep; }
     }
+    if (s > 1) {
+      if (fine) { l.fine_rgb = d_rgb_lr; l.fine_depth = d_dep_lr; }
+      else { l.coarse_rgb = d_rgb_lr; l.coarse_depth = d_dep_lr; }
+    }
+    const WsLayout L = ws_layout(h, nr);
+    char* ws = (char*)(((uintptr_t)h->dev_ws[slot] + 255) & ~(uintptr_t)255);
+    rc = render_core(h, d_rays, rg, nr, ray_stride, s, nullptr, &o, s > 1 ? &l : nullptr, ws, L, st, r0);
+    if (rc) return rc;
+    const float* src_rgb = s > 1 ? d_rgb_lr : d_rgb;
+    const float* src_dep = s > 1 ? d_dep_lr : d_dep;
+    const int64_t no = nr / ss;
     if (rgb_host) NSR_CUDA(h, cudaMemcpyAsync(h->pin_out[slot], src_rgb, (size_t)no * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (depth_host) NSR_CUDA(h, cudaMemcpyAsync(h->pin_out[slot] + (size_t)chunk * 3, src_dep, (size_t)no * sizeof(float), cudaMemcpyDeviceToHost, st));
     NSR_CUDA(h, cudaEventRecord(h->hev[slot], st));
@@ -891,7 +982,7 @@ extern "C" int nsr_render_host(NsrHandle* h, const float* rays_host, int64_t n_r
   if (s < 1 || n_rays % ((int64_t)s * s)) return fail(h, NSR_ERR_INVALID_ARG, "n_rays must be a multiple of s*s");
   if (n_rays == 0) return NSR_OK;
   NSR_CUDA(h, cudaSetDevice(h->cfg.device));
-  return render_frame_pipeline(h, rays_host, nullptr, n_rays, ray_stride, s, rgb_host, depth_host);
+  return render_frame_pipeline(h, rays_host, nullptr, nullptr, n_rays, ray_stride, s, rgb_host, depth_host);
 }
 
 extern "C" int nsr_render_pose_host(NsrHandle* h, const float* c2w_host, int H, int W, float focal, int s, int ndc,
@@ -907,6 +998,15 @@ extern "C" int nsr_render_pose_host(NsrHandle* h, const float* c2w_host, int H, 
   if (chunk > n_rays) chunk = n_rays;
   int rc = ensure_host_state(h, chunk, 8);      // creates the streams / events / staging
   if (rc) return rc;
+  if (fused_frame_ok(h, 1)) {       // rays never exist in HBM: the fused kernel's front-end generates them from the pose
+    NsrRayGen spec{};
+    spec.struct_size = sizeof(NsrRayGen); spec.H = H; spec.W = W; spec.s = s; spec.focal = focal; spec.ndc = ndc;
+    spec.near_plane = near_plane; spec.far_plane = far_plane; spec.use_pixel_centers = 1;
+    RayGenParams rg{};
+    if ((rc = fill_raygen(h, c2w_host, &spec, &rg))) return rc;
+    if ((rc = wait_for_packs(h))) return rc;
+    return render_frame_pipeline(h, nullptr, nullptr, &rg, n_rays, 8, s, rgb_host, depth_host);
+  }
   if (h->frame_rays_cap < (size_t)n_rays * 8) {
     cudaFree(h->frame_rays);
     h->frame_rays = nullptr; h->frame_rays_cap = 0;
@@ -920,5 +1020,5 @@ extern "C" int nsr_render_pose_host(NsrHandle* h, const float* c2w_host, int H, 
   if (!h->frame_ev) NSR_CUDA(h, cudaEventCreateWithFlags(&h->frame_ev, cudaEventDisableTiming));
   NSR_CUDA(h, cudaEventRecord(h->frame_ev, h->hs[0]));
   NSR_CUDA(h, cudaStreamWaitEvent(h->hs[1], h->frame_ev, 0));
-  return render_frame_pipeline(h, nullptr, h->frame_rays, n_rays, 8, s, rgb_host, depth_host);
+  return render_frame_pipeline(h, nullptr, h->frame_rays, nullptr, n_rays, 8, s, rgb_host, depth_host);
 }

@@ -33,6 +33,17 @@ struct RenderParams {
   float noise_std;
 };
 
+// A posed pinhole camera and its supersampling raster (nsr_generate_rays / nsr_render_pose_host)
+struct RayGenParams {
+  float m[12];                       // c2w, 3 x 4 row-major
+  int H, W;                          // HR raster
+  float focal;
+  int s, ndc;
+  float near_plane, far_plane;
+  float pixel_center;                // 0.5 (use_pixel_centers) or 0
+  int unified_dir;
+};
+
 // ----------------------------------------------------------------------------
 // a6: coarse z for sample i of a ray (models/utils.py:31-35)
 // ----------------------------------------------------------------------------
@@ -229,6 +240,59 @@ __device__ __forceinline__ void resample_ray_warp(const float* z, const float* w
     z_out[rank] = v;
   }
   __syncwarp();
+}
+
+// ----------------------------------------------------------------------------
+// a0: one ray of a posed pinhole camera: get_ray_directions + get_rays (+ get_ndc_rays) in the dataset's
+// '(h s1) (w s2) c -> (h w) (s1 s2) c' row order (models/utils.py:98-196; data/blender_downX_dataset.py:207-215).
+// `idx` is the OUTPUT row: LR pixel (h, w), sub-pixel (s1, s2).  out = (o[3], d[3], near, far).
+// Shared by k_generate_rays (nsr_api.cu) and the fused frame kernel's front-end (nsr_tc.cu): same arithmetic, same bits.
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void generate_ray(const RayGenParams& g, int64_t idx, float* out) {
+  const int s = g.s, W = g.W, H = g.H;
+  const int w_lr = W / s;
+  const int sub = (int)(idx % (s * s));
+  const int64_t lr = idx / (s * s);
+  const int hh = (int)(lr / w_lr), ww = (int)(lr % w_lr);
+  const int s1 = sub / s, s2 = sub % s;
+  const int row = hh * s + s1, col = ww * s + s2;
+  // --unified_dir (data/llff_downX_dataset.py:273-277): one camera-space direction per LR pixel, computed on the
+  // (H/s, W/s) raster with focal // s and repeated over its s x s sub-pixels; NDC below still uses H, W, focal
+  const int dcol = g.unified_dir ? ww : col, drow = g.unified_dir ? hh : row;
+  const float dW = g.unified_dir ? (float)(W / s) : (float)W, dH = g.unified_dir ? (float)(H / s) : (float)H;
+  const float dfocal = g.unified_dir ? floorf(__fdiv_rn(g.focal, (float)s)) : g.focal;
+  const float i = (float)dcol + g.pixel_center, j = (float)drow + g.pixel_center;
+  const float cx = __fdiv_rn(__fsub_rn(i, dW / 2.f), dfocal);
+  const float cy = -__fdiv_rn(__fsub_rn(j, dH / 2.f), dfocal);
+  const float cz = -1.f;
+  // rays_d = directions @ c2w[:, :3].T
+  float d[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    d[k] = __fadd_rn(__fadd_rn(__fmul_rn(cx, g.m[4 * k + 0]), __fmul_rn(cy, g.m[4 * k + 1])), __fmul_rn(cz, g.m[4 * k + 2]));
+  const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+  d[0] = __fdiv_rn(d[0], nrm); d[1] = __fdiv_rn(d[1], nrm); d[2] = __fdiv_rn(d[2], nrm);
+  float o[3] = {g.m[3], g.m[7], g.m[11]};
+  float nearv = g.near_plane, farv = g.far_plane;
+  if (g.ndc) {   // get_ndc_rays at near = 1.0 (data/llff_downX_dataset.py:476-481)
+    const float nr = 1.0f;
+    const float t = __fdiv_rn(-__fadd_rn(nr, o[2]), d[2]);
+    o[0] = __fadd_rn(o[0], __fmul_rn(t, d[0]));
+    o[1] = __fadd_rn(o[1], __fmul_rn(t, d[1]));
+    o[2] = __fadd_rn(o[2], __fmul_rn(t, d[2]));
+    const float ox_oz = __fdiv_rn(o[0], o[2]), oy_oz = __fdiv_rn(o[1], o[2]);
+    const float kx = (float)(-1.0 / ((double)W / (2.0 * (double)g.focal)));
+    const float ky = (float)(-1.0 / ((double)H / (2.0 * (double)g.focal)));
+    const float o0 = __fmul_rn(kx, ox_oz), o1 = __fmul_rn(ky, oy_oz);
+    const float o2 = __fadd_rn(1.f, __fdiv_rn(__fmul_rn(2.f, nr), o[2]));
+    const float d0 = __fmul_rn(kx, __fsub_rn(__fdiv_rn(d[0], d[2]), ox_oz));
+    const float d1 = __fmul_rn(ky, __fsub_rn(__fdiv_rn(d[1], d[2]), oy_oz));
+    const float d2 = __fsub_rn(1.f, o2);
+    o[0] = o0; o[1] = o1; o[2] = o2; d[0] = d0; d[1] = d1; d[2] = d2;
+    nearv = 0.f; farv = 1.f;
+  }
+  out[0] = o[0]; out[1] = o[1]; out[2] = o[2]; out[3] = d[0]; out[4] = d[1]; out[5] = d[2];
+  out[6] = nearv; out[7] = farv;
 }
 
 }  // namespace nsr

@@ -63,6 +63,8 @@ struct NsrHandle_ {
   int debug_flags = 0;
   int tc_cluster = 2;               // CTAs per cluster of k_tc_pass (2: the pair shares one multicast weight stream;
                                     // NSR_TC_CLUSTER=1 in the environment switches it off for A/B runs)
+  int tc_fused = 1;                 // coarse + fine pass in one launch where the option set allows (64 + 64 samples);
+                                    // NSR_TC_FUSED=0 keeps the two-launch path (A/B runs, bit-equality tests)
   std::string err;
   // nsr_render_host state (library-owned staging)
   cudaStream_t hs[2] = {nullptr, nullptr};
@@ -126,6 +128,26 @@ struct TcPassArgs {
   float* z_out = nullptr;
 };
 cudaError_t tc_pass(NsrHandle_* h, int which, const TcPassArgs& a, cudaStream_t st);
+
+// Fused frame: coarse pass + resampling + fine pass of a ray batch in ONE launch (k_tc_pass<.., FUSED>), optionally with the
+// rays generated in the front-end from a pose and with the s x s box average in the compositing epilogue.
+//   rays     : [N, ray_stride] device rays, or null -> generate_ray(*rg, idx)
+//   z_fine   : [N, 128] (required: the fine tiles read the merged z-values the coarse tiles write)
+//   c_* / f_*: HR outputs of the coarse / fine pass, any of them null
+//   lr_*     : box-averaged outputs [N / s^2], any of them null (N must then be a multiple of s^2)
+struct TcFrameArgs {
+  const float* rays = nullptr; int64_t n_rays = 0; int ray_stride = 0;
+  const RayGenParams* rg = nullptr; int64_t rg_first = 0;   // row of ray 0 within the frame's raster order
+  int s = 1;
+  const float* u_jitter = nullptr; const float* noise_c = nullptr; const float* noise_f = nullptr; const float* u_resample = nullptr;
+  float* z_fine = nullptr;
+  float* c_rgb = nullptr; float* c_depth = nullptr; float* c_opacity = nullptr; float* c_weights = nullptr;
+  float* f_rgb = nullptr; float* f_depth = nullptr; float* f_opacity = nullptr; float* f_weights = nullptr;
+  float* lr_rgb_c = nullptr; float* lr_depth_c = nullptr; float* lr_rgb_f = nullptr; float* lr_depth_f = nullptr;
+  long long* trace = nullptr; int debug_flags = 0;
+};
+bool tc_frame_supported(const NsrHandle_* h, int s);
+cudaError_t tc_frame(NsrHandle_* h, const TcFrameArgs& a, cudaStream_t st);
 
 // ---- training path (nsr_train.cu) ----
 size_t train_wt_bytes();

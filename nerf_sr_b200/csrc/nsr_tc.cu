@@ -59,18 +59,25 @@ constexpr int kMmaWarp = kProducerWarp + 1;                      // warp 13
 constexpr int kSmRing = 0;
 constexpr int kSmEnc = kSmRing + kRing * kStageBytes;            // 131072
 constexpr int kSmConst = kSmEnc + 2 * kStageBytes;               // 196608
-constexpr int kSmDirBias = kSmConst + 12544;                     // 209152
-constexpr int kSmZ = kSmDirBias + 2 * 2 * 128 * 4;               // 211200
-constexpr int kSmDenc = kSmZ + 2 * 128 * 4;                      // 212224
-constexpr int kSmSig = kSmDenc + 2 * 32 * 4;                     // 212480
+constexpr int kConstBytes = kcSmemFloats * 4;                    // 12320: one net's biases + head weights
+constexpr int kSmDirBias = kSmConst + 2 * kConstBytes;           // two nets (the fused frame kernel keeps both resident)
+constexpr int kSmZ = kSmDirBias + 2 * 2 * 128 * 4;
+constexpr int kSmDenc = kSmZ + 2 * 128 * 4;
+constexpr int kSmSig = kSmDenc + 2 * 32 * 4;
 constexpr int kSmRgb = kSmSig + 128 * 4;
 constexpr int kSmW = kSmRgb + 384 * 4;
 constexpr int kSmTmp = kSmW + 128 * 4;
 constexpr int kSmXch = kSmTmp + 128 * 4;
 constexpr int kSmScratch = kSmXch + 4 * 128 * 4;
+// fused frame kernel: per-ray (r, g, b, depth) of the current unit's rays, [2 passes][16 rays][4], box-averaged when an LR
+// pixel's last ray is composited.  It aliases the tail of the resampler scratch: the fused kernel runs 64 + 64 samples only,
+// whose scratch need is 192 floats per ray at offsets 0 and 320 -- floats [512, 640) are free.
+constexpr int kSmLrAcc = kSmScratch + 512 * 4;
 constexpr int kSmBar = kSmScratch + 2 * 320 * 4;
-constexpr int kSmTmemPtr = kSmBar + 32 * 8;
+constexpr int kSmTmemPtr = kSmBar + B_COUNT * 8;
 constexpr int kSmemTcBytes = kSmTmemPtr + 16;
+static_assert(kSmemTcBytes <= 232448, "k_tc_pass: over the 227 KB of shared memory a CTA can opt in to");
+static_assert(kConstBytes % 16 == 0 && kSmBar % 8 == 0 && kSmDirBias % 16 == 0, "alignment of the shared-memory map");
 
 // (barrier indices B_*: nsr_tc_mma.cuh)
 
@@ -236,14 +243,62 @@ struct TcKernelArgs {
   // SM-clock probe: CTA 0 stamps (clock64, globaltimer ns) at kernel entry and exit -> clk[0..3]; the ratio of the
   // deltas is the SM clock the kernel actually ran at (nsr_debug_kernel_clock; bench.py's `clocks.sm_mhz_in_kernel`)
   long long* clk;
+  // ---- fused frame (k_tc_pass<.., FUSED = true>): coarse AND fine pass of a ray batch in ONE launch -------------------------
+  // The fields above describe the coarse pass (S = 64, z_next = the merged 128 z-values per ray); these the fine pass.
+  const uint8_t* image_f; const float* consts_f; const float* noise_f;
+  float* comp_rgb_f; float* depth_f; float* opacity_f; float* weights_f;
+  // box-averaged (LR) outputs, [n_rays / ss] rows, any of them null: the compositing warp that finishes the last of an LR
+  // pixel's ss = s*s rays sums the ss staged values in ray order and divides (k_box_average's arithmetic, bit for bit)
+  float* lr_rgb_c; float* lr_depth_c; float* lr_rgb_f; float* lr_depth_f;
+  int ss;            // s * s
+  int unit_rays;     // U = lcm(2, ss): rays of one work unit (whole coarse tiles AND whole LR pixels); U <= 16
+  long long n_units; // ceil(n_rays / U); unit u belongs to CTA u % gridDim.x
+  // in-kernel ray generation (rays == null): pose -> (o, d, near, far) of ray `idx`, the arithmetic of k_generate_rays
+  RayGenParams rg; int use_rg; long long rg_first;
 };
+
+// ---------------------------------------------------------------------------
+// Work order of one CTA.
+//   two-launch kernels: trip `it` is tile blockIdx.x + it * gridDim.x of the launch's single pass.
+//   fused frame kernel: the CTA owns units (U consecutive rays) u = blockIdx.x + k * gridDim.x, i.e. P = my_units * U / 2 ray
+//   pairs; pair p is one coarse tile C_p (2 rays x 64 samples) and two fine tiles F_2p, F_2p+1 (1 ray x 128 samples, whose
+//   z-values C_p's compositing warp wrote).  The front-end encodes one tile AHEAD of the MLP and composites one tile BEHIND,
+//   so a fine tile must sit at least two trips after its coarse tile; the order is skewed by one pair:
+//        C_0 | C_1 F_0 F_1 | C_2 F_2 F_3 | ... | C_P-1 F_2P-4 F_2P-3 | F_2P-2 F_2P-1          (3 P trips)
+//   With a single pair (P = 1: C_0 F_0 F_1) the distance is one trip: F_0 `depends on its predecessor` -- the epilogue
+//   finishes C_0 at once instead of behind the next tile's first layer and the front-end composites C_0 before it
+//   encodes F_0 (one pipeline bubble; only launches of <= 2 rays per CTA take it).
+// ---------------------------------------------------------------------------
+struct Trip { long long tile; int pass; int S; };
+
+template <bool FUSED>
+__device__ __forceinline__ Trip trip_of(const TcKernelArgs& a, long long it, long long P, int first, int stride) {
+  if (!FUSED) return Trip{first + it * (long long)stride, 0, a.S};
+  int fine = 0; long long idx = 0;                 // coarse: CTA-local pair index; fine: CTA-local ray index
+  if (it > 0) {
+    const long long t = it - 1, q = t / 3;
+    const int r = (int)(t - 3 * q);
+    if (q == P - 1) { fine = 1; idx = 2 * q + r; }
+    else if (r == 0) { idx = q + 1; }
+    else { fine = 1; idx = 2 * q + r - 1; }
+  }
+  const long long pl = fine ? (idx >> 1) : idx;    // CTA-local pair
+  const int hp = a.unit_rays >> 1;                 // pairs per unit
+  const long long k = pl / hp;
+  const long long ray0 = ((long long)first + k * stride) * a.unit_rays + 2 * (pl - k * hp);
+  if (fine) return Trip{ray0 + (idx & 1), 1, 128};
+  return Trip{ray0 >> 1, 0, 64};
+}
+template <bool FUSED>
+__device__ __forceinline__ bool trip_depends_on_previous(long long it, long long P) { return FUSED && P == 1 && it == 1; }
 
 // ---------------------------------------------------------------------------
 // roles
 // ---------------------------------------------------------------------------
 // (executed by the whole warp, warp-uniformly; one elected lane issues)
-__device__ __forceinline__ void producer_role(const TcKernelArgs& a, uint32_t sm_base, long long my_tiles, uint32_t crank,
-                                              uint32_t csize) {
+template <bool FUSED>
+__device__ __forceinline__ void producer_role(const TcKernelArgs& a, uint32_t sm_base, long long my_tiles, long long P,
+                                              uint32_t crank, uint32_t csize) {
   if (!elect_one()) return;       // one elected lane runs the whole loop (uniform registers, see mma_role)
   // Cluster of 2 (CTA pair): each CTA fetches HALF of every stage (rank 0 the hi plane, rank 1 the lo plane) and the copy is
   // multicast into both CTAs' rings -- the weight stream L2 -> shared memory is halved.  (Measured, tools/l2_weight_ab.py:
@@ -254,6 +309,8 @@ __device__ __forceinline__ void producer_role(const TcKernelArgs& a, uint32_t sm
   uint32_t slot = 0, par = 0;
 #pragma unroll 1
   for (long long it = 0; it < my_tiles; ++it) {
+    // fused frame: the tile's net alternates (the schedule depends on P only, so a CTA pair streams the same image)
+    const uint8_t* image = (FUSED && trip_of<FUSED>(a, it, P, 0, 0).pass) ? a.image_f : a.image;
 #pragma unroll 1
     for (int s = 0; s < kStagesPerTile; ++s) {
       mbar_wait(sm_base + kSmBar + 8 * (B_WEMPTY + slot), par ^ 1);
@@ -262,7 +319,7 @@ __device__ __forceinline__ void producer_role(const TcKernelArgs& a, uint32_t sm
       else {
         mbar_expect_tx(full, kStageBytes);
         const uint32_t dst = sm_base + kSmRing + slot * kStageBytes;
-        const uint8_t* src = a.image + (size_t)s * kStageBytes;
+        const uint8_t* src = image + (size_t)s * kStageBytes;
         if (csize == 1) bulk_copy_g2s(dst, src, kStageBytes, full);
         else bulk_copy_g2s_mc(dst + poff, src + poff, part, full, mask);
       }
@@ -344,14 +401,14 @@ __device__ __forceinline__ void mma_role(const TcKernelArgs& a, uint8_t* sm, uin
 // instruction cache (measured: a fully inlined build was 264 KB and every role stalled on
 // instruction fetch while the front-end ran).  Hence: one out-of-line sincos, rolled loops.
 __device__ __noinline__ void sincos_shared(float x, float* s, float* c) { sincosf(x, s, c); }
+__device__ __noinline__ void generate_ray_shared(const RayGenParams& g, long long idx, float* out) { generate_ray(g, idx, out); }
 
 // ---- front-end: sample, cast, encode, split, swizzled store; per-ray dir bias ----
-template <int FMT, bool STASH>
+template <int FMT, bool STASH, bool FUSED>
 __device__ __forceinline__ void frontend_role(const TcKernelArgs& a, uint8_t* sm, uint32_t sm_base, long long my_tiles,
-                                              int first_tile, int tile_stride) {
+                                              long long P, int first_tile, int tile_stride) {
   const int t = threadIdx.x - 32 * kFrontWarp0;   // 0..127 = tile row
   const int lane = threadIdx.x & 31;
-  const int S = a.S, RPT = a.loose ? 2 : kTile / S;        // rays a tile can touch
   const RenderParams& rp = a.rp;
   const int fw = t >> 5;   // front-end warp index
   // Compositing (+ resampling) of tile `j`, staged in shared memory by the epilogue warps.
@@ -359,9 +416,17 @@ __device__ __forceinline__ void frontend_role(const TcKernelArgs& a, uint8_t* sm
   // epilogue warps go straight on to the next tile's first layer.
   auto composite_tile = [&](long long j) {
     const uint32_t cbuf = (uint32_t)(j & 1);
+    const Trip tr = trip_of<FUSED>(a, j, P, first_tile, tile_stride);
+    const int S = tr.S, RPT = a.loose ? 2 : kTile / S;        // rays a tile can touch
+    const bool fine = FUSED && tr.pass;
+    float* const o_rgb = fine ? a.comp_rgb_f : a.comp_rgb;
+    float* const o_depth = fine ? a.depth_f : a.depth;
+    float* const o_opacity = fine ? a.opacity_f : a.opacity;
+    float* const o_weights = fine ? a.weights_f : a.weights;
+    float* const lr_acc = reinterpret_cast<float*>(sm + kSmLrAcc) + (fine ? 64 : 0);     // [16 rays][4]
     mbar_wait(sm_base + kSmBar + 8 * B_COMPREADY, (uint32_t)(j & 1));
     if (fw < RPT && !a.loose) {
-      const long long tile_j = first_tile + j * (long long)tile_stride;
+      const long long tile_j = tr.tile;
       const long long ray = tile_j * RPT + fw;
       if (ray < a.n_rays) {
         const float* zt = reinterpret_cast<const float*>(sm + kSmZ) + cbuf * 128 + fw * S;
@@ -372,12 +437,16 @@ __device__ __forceinline__ void frontend_role(const TcKernelArgs& a, uint8_t* sm
         float r, gg, b, d, o;
         composite_ray_warp(zt, ssig, srgb, S, rp.white_bkgd, rp.sigma_softplus, sw, stmp, r, gg, b, d, o);
         if (lane == 0) {
-          if (a.comp_rgb) { a.comp_rgb[ray * 3] = r; a.comp_rgb[ray * 3 + 1] = gg; a.comp_rgb[ray * 3 + 2] = b; }
-          if (a.depth) a.depth[ray] = d;
-          if (a.opacity) a.opacity[ray] = o;
+          if (o_rgb) { o_rgb[ray * 3] = r; o_rgb[ray * 3 + 1] = gg; o_rgb[ray * 3 + 2] = b; }
+          if (o_depth) o_depth[ray] = d;
+          if (o_opacity) o_opacity[ray] = o;
+          if (FUSED) {       // staged for the box average below
+            float* acc = lr_acc + 4 * (int)(ray % a.unit_rays);
+            acc[0] = r; acc[1] = gg; acc[2] = b; acc[3] = d;
+          }
         }
-        if (a.weights) for (int i = lane; i < S; i += 32) a.weights[ray * S + i] = sw[i];
-        if (a.do_resample) {
+        if (o_weights) for (int i = lane; i < S; i += 32) o_weights[ray * S + i] = sw[i];
+        if (FUSED ? !fine : a.do_resample) {
           const int n_imp = rp.n_importance;
           float* scratch = reinterpret_cast<float*>(sm + kSmScratch) + fw * 320;
           resample_ray_warp(zt, sw, S, n_imp, a.u_resample ? a.u_resample + ray * n_imp : nullptr,
@@ -390,6 +459,22 @@ __device__ __forceinline__ void frontend_role(const TcKernelArgs& a, uint8_t* sm
     // all front-end warps wait here: the next encode overwrites the z / dir-bias buffers that the
     // compositing warps above are still reading
     named_bar_sync(1, 32 * kWarpsFront);
+    if (FUSED && a.ss > 1 && t < 4) {
+      // Box average (nerf_downX_model.py:337-348): a tile ends an LR pixel when its last ray is the pixel's last sub-pixel
+      // ray (U and ss are even, tiles hold 1 or 2 whole rays).  Sum in ray order, then divide -- k_box_average's arithmetic.
+      const long long last = tr.tile * RPT + RPT - 1;
+      float* const lr_rgb = fine ? a.lr_rgb_f : a.lr_rgb_c;
+      float* const lr_depth = fine ? a.lr_depth_f : a.lr_depth_c;
+      if ((last + 1) % a.ss == 0 && last < a.n_rays) {
+        const int r0 = (int)((last + 1 - a.ss) % a.unit_rays);
+        float sum = 0.f;
+        for (int k = 0; k < a.ss; ++k) sum = __fadd_rn(sum, lr_acc[4 * (r0 + k) + t]);
+        const float mean = __fdiv_rn(sum, (float)a.ss);
+        const long long px = last / a.ss;
+        if (t < 3) { if (lr_rgb) lr_rgb[px * 3 + t] = mean; }
+        else if (lr_depth) lr_depth[px] = mean;
+      }
+    }
   };
   auto encode_tile = [&](long long it) {
     const uint32_t buf = (uint32_t)(it & 1);
@@ -397,20 +482,32 @@ __device__ __forceinline__ void frontend_role(const TcKernelArgs& a, uint8_t* sm
     // previous iteration (program order + the named barrier closing composite_tile).
     TR_DECL(a, it - 1);     // front-end works one tile ahead: trace the work done for iteration 3 during tile 2..3
     TR(5000);
-    const long long tile = first_tile + it * (long long)tile_stride;
+    const Trip tr = trip_of<FUSED>(a, it, P, first_tile, tile_stride);
+    const long long tile = tr.tile;
+    const int S = tr.S, RPT = a.loose ? 2 : kTile / S;
+    const bool fine = FUSED && tr.pass;
+    const float* const consts = fine ? a.consts_f : a.consts;
     const long long p0 = tile * kTile;                       // first point of the tile; its first ray is p0 / S
     const long long ray = (p0 + t) / S;
     const int i = (int)((p0 + t) % S);
     const bool valid = ray < a.n_rays;
     float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0, near = 0, far = 0;
     if (valid) {
-      const float* rr = a.rays + ray * a.ray_stride;
-      ox = rr[0]; oy = rr[1]; oz = rr[2]; dx = rr[3]; dy = rr[4]; dz = rr[5]; near = rr[6]; far = rr[7];
+      if (FUSED && a.use_rg) {       // pose -> ray in the front-end (nsr_render_pose_host): no ray buffer in HBM
+        float r8[8];
+        generate_ray_shared(a.rg, a.rg_first + ray, r8);
+        ox = r8[0]; oy = r8[1]; oz = r8[2]; dx = r8[3]; dy = r8[4]; dz = r8[5]; near = r8[6]; far = r8[7];
+      } else {
+        const float* rr = a.rays + ray * a.ray_stride;
+        ox = rr[0]; oy = rr[1]; oz = rr[2]; dx = rr[3]; dy = rr[4]; dz = rr[5]; near = rr[6]; far = rr[7];
+      }
     }
     float zv = 0.f;
     if (valid) {
-      if (a.z_in) {
-        zv = a.z_in[ray * S + i];
+      if (FUSED ? fine : (a.z_in != nullptr)) {
+        // fused frame: the merged z-values this CTA's own compositing warp wrote >= 1 named barrier ago (L2 load: the
+        // writer may have been another warp of this SM, so no L1 line may be trusted)
+        zv = FUSED ? __ldcg(a.z_next + ray * S + i) : a.z_in[ray * S + i];
       } else {
         const float zc = coarse_z(near, far, a.tabs->t_coarse[i], a.tabs->one_minus_t[i], rp.lindisp);
         zv = zc;
@@ -462,8 +559,14 @@ __device__ __forceinline__ void frontend_role(const TcKernelArgs& a, uint8_t* sm
       const long long r2 = p0 / S + t;                       // slot t of the tile's rays
       float vx = 0, vy = 0, vz = 0;
       if (r2 < a.n_rays) {
-        const float* rr = a.rays + r2 * a.ray_stride + rp.viewdir_offset;
-        vx = rr[0]; vy = rr[1]; vz = rr[2];
+        if (FUSED && a.use_rg) {     // 8-column rays: the view direction is the (normalised) ray direction
+          float r8[8];
+          generate_ray_shared(a.rg, a.rg_first + r2, r8);
+          vx = r8[3]; vy = r8[4]; vz = r8[5];
+        } else {
+          const float* rr = a.rays + r2 * a.ray_stride + rp.viewdir_offset;
+          vx = rr[0]; vy = rr[1]; vz = rr[2];
+        }
       }
       float* o = denc + t * 32;
       o[0] = vx; o[1] = vy; o[2] = vz;
@@ -480,9 +583,9 @@ __device__ __forceinline__ void frontend_role(const TcKernelArgs& a, uint8_t* sm
     float* dbias = reinterpret_cast<float*>(sm + kSmDirBias) + buf * 256;
     for (int idx = t; idx < RPT * 128; idx += 128) {
       const int r = idx >> 7, j = idx & 127;
-      float s = a.consts[kcBiasDir + j];
+      float s = consts[kcBiasDir + j];
       if (!rp.no_dir) {
-        const float* w = a.consts + kcWdd + j * 28;
+        const float* w = consts + kcWdd + j * 28;
         const float* de = denc + r * 32;
 #pragma unroll
         for (int c = 0; c < 27; ++c) s = fmaf(__ldg(w + c), de[c], s);
@@ -497,10 +600,14 @@ __device__ __forceinline__ void frontend_role(const TcKernelArgs& a, uint8_t* sm
   };
   // encode(it) runs one tile ahead of the MLP; composite(it-1) follows it (single call sites keep
   // the instruction footprint small); one extra trip composites the last tile.
+  // Order: e0 e1 c0 e2 c1 ... (encode at most one tile ahead of the last composited one); a tile that depends on its
+  // predecessor (fused frame, P = 1) is encoded only after the predecessor's compositing.
+  long long e = 0, c = 0;
 #pragma unroll 1
-  for (long long it = 0; it <= my_tiles; ++it) {
-    if (it < my_tiles) encode_tile(it);
-    if (it >= 1) composite_tile(it - 1);
+  while (c < my_tiles) {
+    const bool enc = e < my_tiles && (e == c || (e == c + 1 && !trip_depends_on_previous<FUSED>(e, P)));
+    if (enc) encode_tile(e++);
+    else composite_tile(c++);
   }
 }
 
@@ -563,9 +670,9 @@ __device__ __forceinline__ void epi_layer(int L, float relu_floor, uint32_t g, u
 }
 
 // ---- epilogue + compositing ----
-template <int FMT, int PASSES, bool STASH>
+template <int FMT, int PASSES, bool STASH, bool FUSED>
 __device__ __forceinline__ void epilogue_role(const TcKernelArgs& a, uint8_t* sm, uint32_t sm_base, uint32_t tmem,
-                                              long long my_tiles, int first_tile, int tile_stride) {
+                                              long long my_tiles, long long P, int first_tile, int tile_stride) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ew = warp - kEpiWarp0;          // 0..7
   const int q = warp & 3;                   // TMEM lane quarter this warp may access
@@ -573,8 +680,6 @@ __device__ __forceinline__ void epilogue_role(const TcKernelArgs& a, uint8_t* sm
   const int row = 32 * q + lane;            // tile row == TMEM lane
   const uint32_t tlane = tmem + ((uint32_t)(32 * q) << 16);
   const uint32_t bar = sm_base + kSmBar;
-  const float* cst = reinterpret_cast<const float*>(sm + kSmConst);
-  const int S = a.S;
   const RenderParams& rp = a.rp;
   uint32_t g = 0;
   float* xch = reinterpret_cast<float*>(sm + kSmXch);
@@ -584,7 +689,11 @@ __device__ __forceinline__ void epilogue_role(const TcKernelArgs& a, uint8_t* sm
   // per-point (rgb, sigma) for the compositing done by the front-end warps.  It is NOT on the MMA
   // critical path, so it runs after the NEXT tile's first-layer epilogue (see the loop below).
   auto tile_tail = [&](long long j, float sig_p, float r0, float r1, float r2) {
-    const long long tile = first_tile + j * (long long)tile_stride;
+    const Trip tr = trip_of<FUSED>(a, j, P, first_tile, tile_stride);
+    const long long tile = tr.tile;
+    const int S = tr.S;
+    const float* cst = reinterpret_cast<const float*>(sm + kSmConst + ((FUSED && tr.pass) ? kConstBytes : 0));
+    const float* noise = (FUSED && tr.pass) ? a.noise_f : a.noise;
     if (hh == 1) { xch[row] = sig_p; xch[128 + row] = r0; xch[256 + row] = r1; xch[384 + row] = r2; }
     named_bar_sync(2, 32 * kWarpsEpi);
     if (hh == 0) {
@@ -605,7 +714,7 @@ __device__ __forceinline__ void epilogue_role(const TcKernelArgs& a, uint8_t* sm
         for (int c = 0; c < 3; ++c) col[c] = powf(col[c], 1.f / 2.2f);        // nerf_downX_model.py:271
       }
       float sg = sigma;
-      if (a.noise && valid) sg = __fadd_rn(sg, __fmul_rn(a.noise[gp], rp.noise_std));   // utils.py:210
+      if (noise && valid) sg = __fadd_rn(sg, __fmul_rn(noise[gp], rp.noise_std));   // utils.py:210
       // the staging buffers are single: wait until the previous tile has been composited
       if (j >= 1) mbar_wait(bar + 8 * B_COMPDONE, (uint32_t)((j - 1) & 1));
       ssig[row] = sg; srgb[3 * row] = col[0]; srgb[3 * row + 1] = col[1]; srgb[3 * row + 2] = col[2];
@@ -614,10 +723,14 @@ __device__ __forceinline__ void epilogue_role(const TcKernelArgs& a, uint8_t* sm
     if (lane == 0) mbar_arrive(bar + 8 * B_COMPREADY);
   };
   float sig_prev = 0.f, rgb_prev[3] = {0.f, 0.f, 0.f};
+  bool tail_pending = false;              // the previous tile's tail has not run yet
 #pragma unroll 1
   for (long long it = 0; it < my_tiles; ++it) {
     const uint32_t buf = (uint32_t)(it & 1);
     float sig_p = 0.f;
+    const Trip tr = trip_of<FUSED>(a, it, P, first_tile, tile_stride);
+    const int S = tr.S;
+    const uint32_t cst_addr = sm_base + kSmConst + ((FUSED && tr.pass) ? kConstBytes : 0);
     TR_DECL(a, it);
     // ---- layers 1..9: bias (+ReLU) -> hi/lo split -> next A operand ----
     // (two code variants only -- the I-cache is shared by four roles: the ReLU floor is a runtime
@@ -626,16 +739,16 @@ __device__ __forceinline__ void epilogue_role(const TcKernelArgs& a, uint8_t* sm
     for (int L = 1; L <= 9; ++L, ++g) {
       // the previous tile's tail goes here, behind this tile's first layer: the MMA lane is already
       // busy with L2 while the heads' activations are finished and staged
-      if (L == 2 && it >= 1) tile_tail(it - 1, sig_prev, rgb_prev[0], rgb_prev[1], rgb_prev[2]);
+      if (L == 2 && tail_pending) { tile_tail(it - 1, sig_prev, rgb_prev[0], rgb_prev[1], rgb_prev[2]); tail_pending = false; }
       uint8_t* stash_chunks = nullptr;
       uint32_t* mask_row = nullptr;
-      if (STASH && first_tile + it * (long long)tile_stride < a.n_tiles) {      // (a cluster's dummy tile stores nothing)
-        const size_t lt = (size_t)(L - 1) * (size_t)a.n_tiles + (size_t)(first_tile + it * (long long)tile_stride);
+      if (STASH && tr.tile < a.n_tiles) {      // (a cluster's dummy tile stores nothing)
+        const size_t lt = (size_t)(L - 1) * (size_t)a.n_tiles + (size_t)tr.tile;
         stash_chunks = a.stash_h + lt * (size_t)(4 * kStageBytes);
         if (L <= 8) mask_row = a.stash_mask + (lt * 128 + (size_t)row) * 8;
       }
-      if (L == 8) epi_layer<FMT, PASSES, true, STASH>(L, 0.f, g, bar, tlane, sm_base + kSmConst, hh, lane, sig_p, row, stash_chunks, mask_row TR_ARGS);   // + sigma head
-      else epi_layer<FMT, PASSES, false, STASH>(L, L <= 8 ? 0.f : -INFINITY, g, bar, tlane, sm_base + kSmConst, hh, lane, sig_p, row, stash_chunks, mask_row TR_ARGS);
+      if (L == 8) epi_layer<FMT, PASSES, true, STASH>(L, 0.f, g, bar, tlane, cst_addr, hh, lane, sig_p, row, stash_chunks, mask_row TR_ARGS);   // + sigma head
+      else epi_layer<FMT, PASSES, false, STASH>(L, L <= 8 ? 0.f : -INFINITY, g, bar, tlane, cst_addr, hh, lane, sig_p, row, stash_chunks, mask_row TR_ARGS);
     }
     // ---- layer 10: dir layer (N=128, accumulator half 0) + rgb head ----
     float rgb_p[3] = {0.f, 0.f, 0.f};
@@ -646,10 +759,10 @@ __device__ __forceinline__ void epilogue_role(const TcKernelArgs& a, uint8_t* sm
       // away, so a waiter here could fall two phases behind (parity aliasing -> deadlock).
       mbar_wait(bar + 8 * (B_ACCFULL + 0), g & 1);
       tc_fence_after();
-      const long long p0 = (first_tile + it * (long long)tile_stride) * kTile;
+      const long long p0 = tr.tile * kTile;
       const int slot = (int)((p0 + row) / S - p0 / S);       // which of the tile's rays this row belongs to (0 or 1)
       const uint32_t dbias_addr = sm_base + kSmDirBias + 4u * (uint32_t)(buf * 256 + slot * 128);
-      const uint32_t wrgb_addr = sm_base + kSmConst + 4u * kcWrgb;
+      const uint32_t wrgb_addr = cst_addr + 4u * kcWrgb;
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
         const int col0 = 64 * hh + 32 * c;
@@ -673,8 +786,8 @@ __device__ __forceinline__ void epilogue_role(const TcKernelArgs& a, uint8_t* sm
             Split<FMT>::apply(v2, v3, dhi[j / 2 + 1], dlo[j / 2 + 1]);
           }
         }
-        if (STASH && first_tile + it * (long long)tile_stride < a.n_tiles) {   // dir layer activations (post-ReLU) -> tile image, chunk hh, pieces j = 4c .. 4c+3
-          uint8_t* gp = a.stash_dir + ((size_t)(first_tile + it * (long long)tile_stride) * 2 + (size_t)hh) * (size_t)kStageBytes + img2_off(row, 4 * c);
+        if (STASH && tr.tile < a.n_tiles) {   // dir layer activations (post-ReLU) -> tile image, chunk hh, pieces j = 4c .. 4c+3
+          uint8_t* gp = a.stash_dir + ((size_t)tr.tile * 2 + (size_t)hh) * (size_t)kStageBytes + img2_off(row, 4 * c);
 #pragma unroll
           for (int t2 = 0; t2 < 4; ++t2) {
             stg128(gp + 1024 * t2, dhi[4 * t2], dhi[4 * t2 + 1], dhi[4 * t2 + 2], dhi[4 * t2 + 3]);
@@ -691,11 +804,17 @@ __device__ __forceinline__ void epilogue_role(const TcKernelArgs& a, uint8_t* sm
       ++g;
     }
     sig_prev = sig_p; rgb_prev[0] = rgb_p[0]; rgb_prev[1] = rgb_p[1]; rgb_prev[2] = rgb_p[2];
+    // The tail normally runs behind the NEXT tile's first layer; the last tile's, and that of a tile the next one depends
+    // on (fused frame, P = 1), runs at once.
+    tail_pending = true;
+    if (it + 1 == my_tiles || trip_depends_on_previous<FUSED>(it + 1, P)) {
+      tile_tail(it, sig_prev, rgb_prev[0], rgb_prev[1], rgb_prev[2]);
+      tail_pending = false;
+    }
   }
-  if (my_tiles > 0) tile_tail(my_tiles - 1, sig_prev, rgb_prev[0], rgb_prev[1], rgb_prev[2]);
 }
-template <int FMT, int PASSES, bool STASH>
-__global__ void __launch_bounds__(kThreadsTc, 1) k_tc_pass(const TcKernelArgs a) {
+template <int FMT, int PASSES, bool STASH, bool FUSED = false>
+__global__ void __launch_bounds__(kThreadsTc, 1) k_tc_pass(const __grid_constant__ TcKernelArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];   // SWIZZLE_128B operands need 1024-B alignment
   uint8_t* sm = smem_raw;                                 // (keeps the __shared__ address space: LDS/STS)
   const uint32_t sm_base = smem_u32(sm);
@@ -704,8 +823,12 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_tc_pass(const TcKernelArgs a)
   // In a cluster the CTAs share the weight ring stage by stage, so all of them run the SAME number of tiles; a tile index
   // past the end is a dummy (no valid ray: nothing is read or written for it).
   const uint32_t csize = cluster_nctarank(), crank = cluster_ctarank();
-  const long long my_tiles = (csize > 1) ? (a.n_tiles + gridDim.x - 1) / gridDim.x
-                                         : ((a.n_tiles > blockIdx.x) ? (a.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
+  // (fused frame: the same rule over work units; P ray pairs = 3 P trips, see trip_of)
+  const long long n_work = FUSED ? a.n_units : a.n_tiles;
+  const long long my_work = (csize > 1) ? (n_work + gridDim.x - 1) / gridDim.x
+                                        : ((n_work > blockIdx.x) ? (n_work - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
+  const long long P = FUSED ? my_work * (a.unit_rays >> 1) : 0;
+  const long long my_tiles = FUSED ? 3 * P : my_work;
   if (a.clk && blockIdx.x == 0 && threadIdx.x == 0) {
     unsigned long long ns;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
@@ -726,6 +849,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_tc_pass(const TcKernelArgs a)
   {
     float* cst = reinterpret_cast<float*>(sm + kSmConst);
     for (int i = threadIdx.x; i < kcSmemFloats; i += kThreadsTc) cst[i] = a.consts[i];
+    if (FUSED) for (int i = threadIdx.x; i < kcSmemFloats; i += kThreadsTc) cst[kcSmemFloats + i] = a.consts_f[i];
   }
   if (warp == kMmaWarp) {   // TMEM: all 512 columns (one CTA per SM)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sm_base + kSmTmemPtr), "r"(512));
@@ -744,15 +868,15 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_tc_pass(const TcKernelArgs a)
   const uint32_t tmem = 0u;
 
   if (warp == kProducerWarp) {
-    producer_role(a, sm_base, my_tiles, crank, csize);
+    producer_role<FUSED>(a, sm_base, my_tiles, P, crank, csize);
     __syncwarp();
   } else if (warp == kMmaWarp) {
     mma_role<PASSES>(a, sm, sm_base, tmem, umma_idesc(FMT, 128, 128), my_tiles, csize);
     __syncwarp();
   } else if (warp < kEpiWarp0) {
-    frontend_role<FMT, STASH>(a, sm, sm_base, my_tiles, blockIdx.x, gridDim.x);
+    frontend_role<FMT, STASH, FUSED>(a, sm, sm_base, my_tiles, P, blockIdx.x, gridDim.x);
   } else {
-    epilogue_role<FMT, PASSES, STASH>(a, sm, sm_base, tmem, my_tiles, blockIdx.x, gridDim.x);
+    epilogue_role<FMT, PASSES, STASH, FUSED>(a, sm, sm_base, tmem, my_tiles, P, blockIdx.x, gridDim.x);
   }
 
   tc_fence_before();
@@ -776,9 +900,9 @@ cudaError_t tc_init(NsrHandle_* h) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTcBytes);
   };
   switch (h->cfg.precision) {
-    case NSR_PREC_BF16X3_TC: set(k_tc_pass<1, 3, true>); set(k_tc_pass<1, 3, false>); break;
-    case NSR_PREC_FP16X3_TC: set(k_tc_pass<0, 3, true>); set(k_tc_pass<0, 3, false>); break;
-    case NSR_PREC_BF16_TC: set(k_tc_pass<1, 1, false>); break;
+    case NSR_PREC_BF16X3_TC: set(k_tc_pass<1, 3, true>); set(k_tc_pass<1, 3, false>); set(k_tc_pass<1, 3, false, true>); break;
+    case NSR_PREC_FP16X3_TC: set(k_tc_pass<0, 3, true>); set(k_tc_pass<0, 3, false>); set(k_tc_pass<0, 3, false, true>); break;
+    case NSR_PREC_BF16_TC: set(k_tc_pass<1, 1, false>); set(k_tc_pass<1, 1, false, true>); break;
     default: break;
   }
   return e;
@@ -813,6 +937,62 @@ cudaError_t tc_pass(NsrHandle_* h, int which, const TcPassArgs& p, cudaStream_t 
   }
   a.clk = h->d_clk;
   const int csize = (h->tc_cluster == 2 && a.n_tiles >= 2) ? 2 : 1;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(csize == 2 ? (grid + 1) & ~1 : grid));
+  cfg.blockDim = dim3(kThreadsTc);
+  cfg.dynamicSmemBytes = kSmemTcBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a);
+  if (e != cudaSuccess) return e;
+  h->launches += 1;
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// fused frame: coarse + fine pass (+ ray generation, + box average) of a ray batch in one launch
+// ---------------------------------------------------------------------------
+bool tc_frame_supported(const NsrHandle_* h, int s) {
+  if (!h->tc_fused) return false;
+  const int p = h->cfg.precision;
+  if (p != NSR_PREC_BF16X3_TC && p != NSR_PREC_FP16X3_TC && p != NSR_PREC_BF16_TC) return false;
+  if (h->cfg.n_coarse != 64 || h->cfg.n_importance != 64) return false;      // coarse tile = 2 rays, fine tile = 1 ray
+  return s == 1 || s == 2 || s == 4;                                         // unit = lcm(2, s*s) <= 16 rays
+}
+
+cudaError_t tc_frame(NsrHandle_* h, const TcFrameArgs& p, cudaStream_t st) {
+  if (!tc_frame_supported(h, p.s) || !p.z_fine || (!p.rays && !p.rg)) return cudaErrorInvalidValue;
+  const int ss = p.s * p.s;
+  const bool lr = p.lr_rgb_c || p.lr_depth_c || p.lr_rgb_f || p.lr_depth_f;
+  if (lr && (p.n_rays % ss)) return cudaErrorInvalidValue;
+  if (p.n_rays == 0) return cudaSuccess;
+  TcKernelArgs a{};
+  a.image = h->net[0].tc_image; a.consts = h->net[0].tc_consts; a.image_f = h->net[1].tc_image; a.consts_f = h->net[1].tc_consts;
+  a.tabs = h->d_tables; a.rp = h->rp;
+  a.rays = p.rays; a.n_rays = p.n_rays; a.ray_stride = p.ray_stride; a.S = 64;
+  if (!p.rays) { a.rg = *p.rg; a.use_rg = 1; a.rg_first = p.rg_first; }
+  a.u_jitter = p.u_jitter; a.noise = p.noise_c; a.noise_f = p.noise_f; a.u_resample = p.u_resample; a.do_resample = 1;
+  a.comp_rgb = p.c_rgb; a.depth = p.c_depth; a.opacity = p.c_opacity; a.weights = p.c_weights;
+  a.comp_rgb_f = p.f_rgb; a.depth_f = p.f_depth; a.opacity_f = p.f_opacity; a.weights_f = p.f_weights;
+  a.z_next = p.z_fine;
+  a.lr_rgb_c = p.lr_rgb_c; a.lr_depth_c = p.lr_depth_c; a.lr_rgb_f = p.lr_rgb_f; a.lr_depth_f = p.lr_depth_f;
+  a.ss = lr ? ss : 1;
+  a.unit_rays = (a.ss == 1) ? 2 : a.ss;            // lcm(2, ss) for ss in {1, 4, 16}
+  a.n_units = (p.n_rays + a.unit_rays - 1) / a.unit_rays;
+  a.n_tiles = 0;
+  a.trace = p.trace; a.debug_flags = p.debug_flags; a.clk = h->d_clk;
+  void (*kern)(const TcKernelArgs) = nullptr;
+  switch (h->cfg.precision) {
+    case NSR_PREC_BF16X3_TC: kern = k_tc_pass<1, 3, false, true>; break;
+    case NSR_PREC_FP16X3_TC: kern = k_tc_pass<0, 3, false, true>; break;
+    case NSR_PREC_BF16_TC: kern = k_tc_pass<1, 1, false, true>; break;
+    default: return cudaErrorInvalidValue;
+  }
+  const int grid = (int)(a.n_units < h->sm_count ? a.n_units : h->sm_count);
+  const int csize = (h->tc_cluster == 2 && a.n_units >= 2) ? 2 : 1;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(csize == 2 ? (grid + 1) & ~1 : grid));
   cfg.blockDim = dim3(kThreadsTc);

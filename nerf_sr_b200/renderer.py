@@ -22,7 +22,7 @@ from typing import Dict, Mapping, Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import NsrConfig, NsrError, NsrOutputs, NsrPassOutputs, NsrRayGen, NsrRng, PRECISIONS
+from ._lib import NsrConfig, NsrError, NsrLrOutputs, NsrOutputs, NsrPassOutputs, NsrRayGen, NsrRng, PRECISIONS
 from .train_seams import TrainSeams
 
 
@@ -200,6 +200,69 @@ class Renderer(TrainSeams):
                                         C.byref(o), ws, ws_bytes, self._stream()))
         return out
 
+    def set_debug_flags(self, flags: int) -> None:
+        """nsr_debug_set_flags: bit 0 = the weight producer skips its copies (timing experiment, wrong results);
+        bit 1 = keep the separate coarse / fine / box-average launches where the one-launch frame kernel would run
+        (A/B runs and the bit-equality tests)."""
+        self._check(self.lib.nsr_debug_set_flags(self._h, int(flags)))
+
+    def render_frame(self, rays: Optional[torch.Tensor] = None, s: int = 1, pose=None, H: int = 0, W: int = 0,
+                     focal: float = 0.0, ndc: bool = False, near: float = 2.0, far: float = 6.0,
+                     use_pixel_centers: bool = True, unified_dir: bool = False, want_hr: bool = True,
+                     rng: Optional[Mapping[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+        """One frame through nsr_render_frame: forward() + comp_low_res_output (models/nerf_downX_model.py:316-348) and,
+        with `pose` instead of `rays`, the dataset's ray generation too -- ONE kernel launch where the option set allows
+        (tensor-core precision, 64 + 64 samples, s in {1, 2, 4}), the same results from separate launches otherwise.
+        Returns device tensors: {coarse,fine}_comp_rgbs / _depth / _opacity (HR, when want_hr) and, for s > 1,
+        {coarse,fine}_lr_rgb [N/s^2, 3] / _lr_depth [N/s^2]."""
+        dev, f32 = self.device, torch.float32
+        spec, arr = None, None
+        if rays is not None:
+            rays = self._f32(rays)
+            n, stride = rays.shape
+        else:
+            c = torch.as_tensor(pose, dtype=torch.float32).reshape(12).cpu()
+            arr = (C.c_float * 12)(*c.tolist())
+            spec = NsrRayGen()
+            spec.struct_size = C.sizeof(NsrRayGen)
+            spec.H, spec.W, spec.s, spec.focal, spec.ndc = H, W, s, float(focal), int(ndc)
+            spec.near_plane, spec.far_plane = float(near), float(far)
+            spec.use_pixel_centers, spec.unified_dir = int(use_pixel_centers), int(unified_dir)
+            n, stride = H * W, 8
+        if n % (s * s):
+            raise NsrError(1, f"{n} rays are not a multiple of s*s = {s * s}")
+        names = ("coarse", "fine") if self.n_importance > 0 else ("coarse",)
+        out: Dict[str, torch.Tensor] = {}
+        o, l = NsrOutputs(), NsrLrOutputs()
+        for name in names:
+            if want_hr or s == 1:
+                out[f"{name}_comp_rgbs"] = torch.empty(n, 3, device=dev, dtype=f32)
+                out[f"{name}_depth"] = torch.empty(n, device=dev, dtype=f32)
+                out[f"{name}_opacity"] = torch.empty(n, device=dev, dtype=f32)
+                for k in ("comp_rgbs", "depth", "opacity"):
+                    setattr(o, f"{name}_{k}", out[f"{name}_{k}"].data_ptr())
+            if s > 1:
+                out[f"{name}_lr_rgb"] = torch.empty(n // (s * s), 3, device=dev, dtype=f32)
+                out[f"{name}_lr_depth"] = torch.empty(n // (s * s), device=dev, dtype=f32)
+                setattr(l, f"{name}_rgb", out[f"{name}_lr_rgb"].data_ptr())
+                setattr(l, f"{name}_depth", out[f"{name}_lr_depth"].data_ptr())
+        r = NsrRng()
+        keep = []
+        if rng is not None:
+            for k in ("u_coarse", "noise_coarse", "u_fine", "noise_fine"):
+                t = rng.get(k) if isinstance(rng, Mapping) else getattr(rng, k, None)
+                if t is not None:
+                    t = self._f32(t.to(dev))
+                    keep.append(t)
+                    setattr(r, k, t.data_ptr())
+        need = self.lib.nsr_frame_workspace_bytes(self._h, n, int(rays is None))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        self._check(self.lib.nsr_render_frame(self._h, _ptr(rays), n, stride, arr, C.byref(spec) if spec is not None else None,
+                                              s, C.byref(r) if rng is not None else None, C.byref(o), C.byref(l),
+                                              self._ws.data_ptr(), self._ws.numel(), self._stream()))
+        return out
+
     def render_pass(self, which: int, rays: torch.Tensor, z_vals: torch.Tensor,
                     noise: Optional[torch.Tensor] = None, want_raw: bool = False) -> Dict[str, torch.Tensor]:
         """One network over caller-supplied z-values: (comp_rgbs, depth, opacity, weights[, raw])."""
@@ -331,14 +394,14 @@ class Renderer(TrainSeams):
         {coarse,fine}_pred_ori  uint8 [H, 2W, 3]      HR [pred | depth] frames
         {coarse,fine}_pred      uint8 [H/s, 2W/s, 3]  LR (box-averaged) frames
         {coarse,fine}_depth_mat_ori [H, W], {coarse,fine}_depth_mat [H/s, W/s]   fp32 depth matrices (the *.npz payloads)"""
-        rays = self.generate_rays(c2w, H, W, focal, s=s, ndc=ndc, near=near, far=far)
         nr, fr = (0.0, 1.0) if ndc else (near, far)              # self.near / self.far = rays[0, 6:8]
-        out = self.forward_rays(rays, want_weights=False)
+        # rays, both passes and the box averages: one launch on the tensor-core path (nsr_render_frame)
+        out = self.render_frame(None, s, pose=c2w, H=H, W=W, focal=focal, ndc=ndc, near=near, far=far)
         res: Dict[str, torch.Tensor] = {}
         for name in ("coarse", "fine") if self.n_importance > 0 else ("coarse",):
             rgb, depth = out[f"{name}_comp_rgbs"], out[f"{name}_depth"]
             res[f"{name}_pred_ori"], res[f"{name}_depth_mat_ori"] = self.assemble_frame(rgb, depth, H, W, s, nr, fr)
-            lr_rgb, lr_depth = self.box_average(rgb, s), self.box_average(depth, s)
+            lr_rgb, lr_depth = (out[f"{name}_lr_rgb"], out[f"{name}_lr_depth"]) if s > 1 else (rgb, depth)
             res[f"{name}_pred"], res[f"{name}_depth_mat"] = self.assemble_frame(lr_rgb, lr_depth, H // s, W // s, 1, nr, fr)
         return res
 

@@ -48,7 +48,7 @@ def test_header_is_plain_c_and_struct_sizes_match_the_binding(tmp_path):
     if gcc is None:
         pytest.skip("gcc not available")
     structs = {"NsrConfig": _lib.NsrConfig, "NsrRng": _lib.NsrRng, "NsrOutputs": _lib.NsrOutputs, "NsrPassOutputs": _lib.NsrPassOutputs,
-               "NsrOutGrads": _lib.NsrOutGrads, "NsrLossTerms": _lib.NsrLossTerms, "NsrRayGen": _lib.NsrRayGen}
+               "NsrOutGrads": _lib.NsrOutGrads, "NsrLossTerms": _lib.NsrLossTerms, "NsrRayGen": _lib.NsrRayGen, "NsrLrOutputs": _lib.NsrLrOutputs}
     lines = ['#include "nsr.h"', "#include <stdio.h>", "#include <stddef.h>", "int main(void) {"]
     for name, cls in structs.items():
         lines.append(f'  printf("{name} %zu", sizeof({name}));')
