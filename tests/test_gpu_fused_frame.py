@@ -78,7 +78,7 @@ def test_train_mode_draws_in_one_launch_are_bit_identical(kind, white):
 # would (nsr_api.cu: lr_in_kernel_pays) -- always for frames, and here for the batch sizes that divide evenly over the 148 SMs
 # (1184 LR pixels at s = 2, 296 at s = 4) -- or when the caller does not want the HR composite at all; otherwise the frame
 # kernel is followed by k_box_average launches.  Either way the results are the same bits.
-@pytest.mark.parametrize("s,n_lr,in_kernel", [(2, 1, False), (2, 75, False), (2, 1184, True), (2, 1201, False), (4, 1, False),
+@pytest.mark.parametrize("s,n_lr,in_kernel", [(2, 1, False), (2, 75, True), (2, 1184, True), (2, 1201, False), (4, 1, False),
                                               (4, 37, False), (4, 296, True)])
 def test_box_average_in_the_compositing_epilogue_is_bit_identical(s, n_lr, in_kernel):
     r = _renderer("bf16x3")
