@@ -421,16 +421,18 @@ def train_roofline(n: int, steps: int, dev_ms: float, pk: dict, pk_kind: str) ->
     }
 
 
-def render_roofline(precision: str, n: int, steps: int, dev_ms: float, fine_ms: float, pk: dict, pk_kind: str) -> dict:
+def render_roofline(precision: str, n: int, steps: int, dev_ms: float, fine_ms: float, pk: dict, pk_kind: str,
+                    launches_per_step: float = 1.0) -> dict:
     """The `roofline` object of the render line (pure: unit-tested on CPU).
 
-    Dominant kernel = k_tc_pass, launched twice per step (coarse pass S=64, fine pass S=128; 99.9 % of the step's device
-    time, profiles/r01_launch_list.md).  `achieved` = the algorithmic FLOP of those two launches (1 186 816 FLOP
-    per point x (64 + 128) points per ray) over the step time measured with CUDA events INSIDE the timed region, so the
-    denominator is the SUSTAINED measured peak (a kernel timed inside a long step).  The fine pass timed ALONE (its own
-    event pair per launch) is reported next to it, against both the sustained and the burst peak.
-    n: rays per step per GPU; dev_ms: device time of all `steps` steps (max over ranks; it also holds the step's two
-    k_box_average launches, < 0.1 %); fine_ms: one fine-pass launch."""
+    Dominant kernel = k_tc_pass.  On the tensor-core path a step is ONE launch of its frame variant (coarse S=64 tiles, the
+    resampling, fine S=128 tiles and the box average; profiles/r02_launch_list.md) -- `launches_per_step` is what the
+    library counted in the timed region (6 with NSR_TC_FUSED=0: coarse, fine, 4 box averages; the fp32 path has more).
+    `achieved` = the algorithmic FLOP of the step (1 186 816 FLOP per point x (64 + 128) points per ray) over
+    the step time measured with CUDA events INSIDE the timed region, so the denominator is the SUSTAINED measured peak (a
+    kernel timed inside a long step).  The fine pass timed ALONE as its own launch (nsr_render_pass; its own event pair) is
+    reported next to it, against both the sustained and the burst peak.
+    n: rays per step per GPU; dev_ms: device time of all `steps` steps (max over ranks); fine_ms: one fine-pass launch."""
     step_flops = n * (N_COARSE + N_COARSE + N_IMPORTANCE) * FLOP_PER_POINT
     achieved = step_flops * steps / (dev_ms / 1e3) / 1e12
     fine_flops = n * (N_COARSE + N_IMPORTANCE) * FLOP_PER_POINT
@@ -439,18 +441,21 @@ def render_roofline(precision: str, n: int, steps: int, dev_ms: float, fine_ms: 
     split = 3 if "x3" in precision else 1
     tc = precision != "fp32_simt"
     return {
-        "bound": "tensor", "kernel": "k_tc_pass (coarse S=64 + fine S=128 launches of one step)" if tc else "k_simt_mlp",
+        "bound": "tensor", "kernel": ("k_tc_pass, frame variant: coarse S=64 + fine S=128 tiles of one frame in one launch" if launches_per_step == 1
+                                      else "k_tc_pass (coarse S=64 + fine S=128 launches of one step)") if tc else "k_simt_mlp",
         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
         "peak_kind": f"{pk_kind} cuBLAS bf16 sustained (kernel timed inside the timed region of back-to-back steps)",
         "issued_frac": split * achieved / peak,
-        "flop_per_launch": step_flops / 2, "ms_per_launch": dev_ms / steps / 2,
-        "launches_per_step": 2,
+        "flop_per_launch": step_flops / (1 if launches_per_step == 1 else 2),
+        "ms_per_launch": dev_ms / steps / (1 if launches_per_step == 1 else 2),
+        "launches_per_step": launches_per_step,
         # dram__bytes_read.sum + dram__bytes_write.sum per launch: NOT measurable inside this process (it needs ncu
         # replays); taken from this round's committed `ncu --set full` capture when it exists, with its provenance
-        "traffic": ncu_traffic("k_tc_pass", "mean_bytes_per_launch") if tc else None,
+        "traffic": ncu_traffic("k_tc_pass", "frame_bytes_per_launch" if launches_per_step == 1 else "mean_bytes_per_launch") if tc else None,
         "traffic_source": ncu_traffic("k_tc_pass", "source") if tc else None,
-        # per ray: coarse launch 32 B rays in + 20 B results + 512 B fine z-values out; fine launch 32 B + 512 B in + 20 B out
-        "algorithmic_bytes_per_launch": n * (32 + 4 * (N_COARSE + N_IMPORTANCE) + 20),
+        # frame variant, per ray: 32 B rays in + 2 x 20 B HR results + 2 x 16 B / s^2 LR results out (the 512 B of fine
+        # z-values per ray are an L2-resident intermediate); separate launches: 32 B + 512 B + 20 B per ray and launch
+        "algorithmic_bytes_per_launch": n * (32 + 40 + 32 // (SS * SS)) if launches_per_step == 1 else n * (32 + 4 * (N_COARSE + N_IMPORTANCE) + 20),
         "fine_pass_alone": {"achieved": fine_achieved, "flop_per_launch": fine_flops, "ms_per_launch": fine_ms,
                             "frac_vs_sustained_peak": fine_achieved / peak, "burst_peak": pk["bf16_tflops"],
                             "frac_vs_burst_peak": fine_achieved / pk["bf16_tflops"],
@@ -661,10 +666,9 @@ def main():
     n = rays.shape[0]
 
     def step_device():
-        out = r.forward_rays(rays, want_weights=False)
-        lr_rgb = r.box_average(out["fine_comp_rgbs"], SS)
-        lr_depth = r.box_average(out["fine_depth"], SS)
-        return out, lr_rgb, lr_depth
+        # forward() + comp_low_res_output of one frame (models/nerf_downX_model.py:316-348): HR composites / depths / opacities
+        # and the LR (box-averaged) images of both nets -- ONE kernel launch on the tensor-core path (nsr_render_frame)
+        return r.render_frame(rays, SS)
 
     def barrier():
         if world > 1:
@@ -693,13 +697,12 @@ def main():
 
     def step_e2e_full():
         rays_stage.copy_(rays_pinned, non_blocking=True)
-        o = r.forward_rays(rays_stage, want_weights=False)
+        o = r.render_frame(rays_stage, SS)
         for net in ("coarse", "fine"):
-            rgb, dep = o[f"{net}_comp_rgbs"], o[f"{net}_depth"]
-            full_pin[f"{net}_rgb_ori"].copy_(rgb, non_blocking=True)
-            full_pin[f"{net}_depth_ori"].copy_(dep.view(-1, 1), non_blocking=True)
-            full_pin[f"{net}_rgb"].copy_(r.box_average(rgb, SS), non_blocking=True)
-            full_pin[f"{net}_depth"].copy_(r.box_average(dep, SS), non_blocking=True)
+            full_pin[f"{net}_rgb_ori"].copy_(o[f"{net}_comp_rgbs"], non_blocking=True)
+            full_pin[f"{net}_depth_ori"].copy_(o[f"{net}_depth"].view(-1, 1), non_blocking=True)
+            full_pin[f"{net}_rgb"].copy_(o[f"{net}_lr_rgb"], non_blocking=True)
+            full_pin[f"{net}_depth"].copy_(o[f"{net}_lr_depth"].view(-1, 1), non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
     for _ in range(args.warmup):
@@ -803,7 +806,7 @@ def main():
             "e2e": {"value": total_rays / (e2e_ms / 1e3), "unit": "rays/s", "h2d_bytes_per_step": n * rays.shape[1] * 4,
                     "d2h_bytes_per_step": (n // (SS * SS)) * 4 * 4, "api": "nsr_render_host (pinned host rays in, LR rgb+depth out)"},
             "gpu_launches": int(launches),
-            "roofline": render_roofline(args.precision, n, args.steps, dev_ms, fine_ms, pk, pk_kind),
+            "roofline": render_roofline(args.precision, n, args.steps, dev_ms, fine_ms, pk, pk_kind, launches / args.steps),
             "clocks": {**sampler.summary(), "sm_mhz_in_kernel": sm_mhz_in_kernel,
                        "sm_mhz_in_kernel_how": "clock64 / globaltimer deltas stamped by CTA 0 of the last fine-pass launch"},
         }

@@ -525,7 +525,7 @@ static int run_pass(NsrHandle_* h, int which, const float* rays, int64_t n, int 
 struct LrOut { float* coarse_rgb = nullptr; float* coarse_depth = nullptr; float* fine_rgb = nullptr; float* fine_depth = nullptr; };
 
 static bool fused_frame_ok(const NsrHandle_* h, int s) {
-  return !(h->debug_flags & 2) && h->cfg.n_importance > 0 && tc_frame_supported(h, s) && h->net[0].packed && h->net[1].packed;
+  return !(h->debug_flags & 64) && h->cfg.n_importance > 0 && tc_frame_supported(h, s) && h->net[0].packed && h->net[1].packed;
 }
 
 // Whether the box average belongs in the frame kernel's epilogue.  There a CTA's work quantum is a whole LR pixel's rays

@@ -202,7 +202,7 @@ class Renderer(TrainSeams):
 
     def set_debug_flags(self, flags: int) -> None:
         """nsr_debug_set_flags: bit 0 = the weight producer skips its copies (timing experiment, wrong results);
-        bit 1 = keep the separate coarse / fine / box-average launches where the one-launch frame kernel would run
+        bit 6 (64) = keep the separate coarse / fine / box-average launches where the one-launch frame kernel would run
         (A/B runs and the bit-equality tests)."""
         self._check(self.lib.nsr_debug_set_flags(self._h, int(flags)))
 

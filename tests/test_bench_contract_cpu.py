@@ -59,7 +59,7 @@ def test_render_roofline_object():
     b = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(b)
     pk = {"bf16_tflops": 1652.1, "bf16_tflops_sustained": 1386.6, "hbm_gbs": 6550.7}
-    r = b.render_roofline("bf16x3", 160000, 10, 708.297, 47.049, pk, "measured")     # the numbers of profiles/r01_bench_bf16x3.json
+    r = b.render_roofline("bf16x3", 160000, 10, 708.297, 47.049, pk, "measured", 2.0)   # the numbers of profiles/r01_bench_bf16x3.json
     assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and r["peak"] == 1386.6 and r["launches_per_step"] == 2
     assert r["flop_per_launch"] * 2 == 160000 * 192 * 1186816                          # 227.87 MFLOP per ray
     assert r["achieved"] == pytest.approx(r["flop_per_launch"] / (r["ms_per_launch"] / 1e3) / 1e12)
@@ -71,7 +71,12 @@ def test_render_roofline_object():
     f = r["fine_pass_alone"]
     assert f["flop_per_launch"] == 160000 * 128 * 1186816 and f["achieved"] == pytest.approx(516.6, rel=1e-3)
     assert f["frac_vs_burst_peak"] == pytest.approx(f["achieved"] / 1652.1) and f["frac_vs_sustained_peak"] == pytest.approx(f["achieved"] / 1386.6)
-    s = b.render_roofline("fp32_simt", 160000, 2, 2400.0, 800.0, {"bf16_tflops": 1590.0}, "fallback")   # no sustained figure
+    # one launch per frame (round 2): the same step FLOP in one launch; traffic from the frame variant's capture
+    o = b.render_roofline("bf16x3", 160000, 10, 708.297, 47.049, pk, "measured", 1.0)
+    assert o["launches_per_step"] == 1 and o["flop_per_launch"] == 160000 * 192 * 1186816 and o["ms_per_launch"] == pytest.approx(70.8297)
+    assert o["achieved"] == pytest.approx(r["achieved"]) and "one launch" in o["kernel"]
+    assert o["traffic"] == b.ncu_traffic("k_tc_pass", "frame_bytes_per_launch") and o["algorithmic_bytes_per_launch"] == 160000 * 80
+    s = b.render_roofline("fp32_simt", 160000, 2, 2400.0, 800.0, {"bf16_tflops": 1590.0}, "fallback", 7.0)   # no sustained figure
     assert s["kernel"] == "k_simt_mlp" and s["traffic"] is None and s["peak"] == 1590.0 and s["issued_frac"] == pytest.approx(s["frac"])
     import json
     json.dumps(r), json.dumps(s)

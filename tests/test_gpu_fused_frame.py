@@ -5,7 +5,7 @@ against the separate launches it replaces (coarse k_tc_pass, fine k_tc_pass, k_b
 Both paths run the same device functions in the same order per ray, so the comparison is BIT-EXACT (torch.equal) on every
 output -- composites, depths, opacities, per-sample weights, merged z-values, LR images.  Parity of either path against the
 oracle / the reference is the rest of the GPU suite's job (it runs on the one-launch path wherever the option set allows).
-`set_debug_flags(2)` keeps the separate launches on the same handle."""
+`set_debug_flags(64)` keeps the separate launches on the same handle."""
 import pytest
 import torch
 
@@ -31,7 +31,7 @@ def _both(r, fn):
     l0 = r.launch_count
     a = fn()
     l1 = r.launch_count
-    r.set_debug_flags(2)
+    r.set_debug_flags(64)
     b = fn()
     l2 = r.launch_count
     r.set_debug_flags(0)
@@ -112,7 +112,7 @@ def test_rays_generated_in_the_front_end_are_bit_identical(H, W, s, ndc):
     _assert_identical(a, b)
     # ... and equal to the public pieces called one by one
     rays = r.generate_rays(c2w, H, W, 0.9 * W, s=s, ndc=ndc, near=2.0, far=6.0)
-    r.set_debug_flags(2)
+    r.set_debug_flags(64)
     ref = r.forward_rays(rays, want_weights=False)
     r.set_debug_flags(0)
     for k in ("coarse_comp_rgbs", "coarse_depth", "fine_comp_rgbs", "fine_depth", "fine_opacity"):

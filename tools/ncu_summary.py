@@ -56,7 +56,12 @@ def full(rep, dst, title, traffic_name=None):
         per = [to_bytes(r[rd], units[rd]) + to_bytes(r[wr], units[wr]) for r in rows]
         p = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
         d = json.load(open(p)) if os.path.exists(p) else {}
-        d[traffic_name] = {"mean_bytes_per_launch": int(sum(per) / len(per)), "fine_bytes_per_launch": int(per[-1]),
+        # k_tc_pass<FMT, PASSES, STASH, FUSED>: the one-launch frame variant has FUSED = 1; the others are the separate coarse and
+        # fine launches (in that order) of the same frame
+        frame = [b for b, r in zip(per, rows) if r[kcol].split("(")[0].rstrip().endswith(", 1>")]
+        sep = [b for b, r in zip(per, rows) if not r[kcol].split("(")[0].rstrip().endswith(", 1>")] or per
+        d[traffic_name] = {"frame_bytes_per_launch": int(frame[-1]) if frame else None,
+                           "mean_bytes_per_launch": int(sum(sep) / len(sep)), "fine_bytes_per_launch": int(sep[-1]),
                            "bytes_per_launch": [int(x) for x in per],
                            "source": f"{os.path.relpath(dst, ROOT)} (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)"}
         json.dump(d, open(p, "w"), indent=1)

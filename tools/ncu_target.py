@@ -1,4 +1,5 @@
-"""Short single-GPU target for ncu captures: two full-frame forwards (first = warm-up)."""
+"""Short single-GPU target for ncu captures: two full frames through the one-launch kernel (first = warm-up), then the same
+frame as separate coarse / fine launches (debug flag 64)."""
 import os
 import sys
 
@@ -15,5 +16,7 @@ r.load_state_dict(0, pc)
 r.load_state_dict(1, pf)
 rays = rays.cuda()
 for _ in range(2):
-    r.forward_rays(rays, want_weights=False)
+    r.render_frame(rays, bench.SS)
+r.set_debug_flags(64)
+r.forward_rays(rays, want_weights=False)
 torch.cuda.synchronize()
