@@ -58,11 +58,12 @@ def full(rep, dst, title, traffic_name=None):
         d = json.load(open(p)) if os.path.exists(p) else {}
         # k_tc_pass<FMT, PASSES, STASH, FUSED>: the one-launch frame variant has FUSED = 1; the others are the separate coarse and
         # fine launches (in that order) of the same frame
-        frame = [b for b, r in zip(per, rows) if r[kcol].split("(")[0].rstrip().endswith(", 1>")]
-        sep = [b for b, r in zip(per, rows) if not r[kcol].split("(")[0].rstrip().endswith(", 1>")] or per
+        ok = [(b, r) for b, r in zip(per, rows) if b == b]          # (a launch ncu failed to collect reads as NaN: left out)
+        frame = [b for b, r in ok if r[kcol].split("(")[0].rstrip().endswith(", 1>")]
+        sep = [b for b, r in ok if not r[kcol].split("(")[0].rstrip().endswith(", 1>")] or [b for b, _ in ok]
         d[traffic_name] = {"frame_bytes_per_launch": int(frame[-1]) if frame else None,
                            "mean_bytes_per_launch": int(sum(sep) / len(sep)), "fine_bytes_per_launch": int(sep[-1]),
-                           "bytes_per_launch": [int(x) for x in per],
+                           "bytes_per_launch": [int(x) if x == x else None for x in per],
                            "source": f"{os.path.relpath(dst, ROOT)} (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)"}
         json.dump(d, open(p, "w"), indent=1)
     print("\n".join(lines[:12]))
