@@ -819,7 +819,7 @@ def main():
             line["e2e_full"] = {
                 "value": total_rays / (full_ms / 1e3), "unit": "rays/s", "h2d_bytes_per_step": n * rays.shape[1] * 4,
                 "d2h_bytes_per_step": 2 * (n * 16 + n_lr * 16),
-                "api": "Renderer.forward_rays + box_average, pinned host rays in; HR `_ori` rgb+depth and LR rgb+depth of the "
+                "api": "Renderer.render_frame (nsr_render_frame, one kernel launch per frame), pinned host rays in; HR `_ori` rgb+depth and LR rgb+depth of the "
                        "coarse AND the fine net out (what the reference's test() consumes, models/nerf_downX_model.py:326-353)"}
         if strong is not None:
             line["strong"] = strong
