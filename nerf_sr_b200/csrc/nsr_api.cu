@@ -441,7 +441,8 @@ extern "C" int nsr_pack_weights(NsrHandle* h, int which, const float* const* par
   if (h->cfg.precision != NSR_PREC_FP32_SIMT) {
     NSR_CUDA(h, tc_pack(h, which, param_ptrs, st));
     // the device-side pointer table tc_pack staged behind the consts blob also feeds the backward's images
-    NSR_CUDA(h, train_pack_wt(h, which, reinterpret_cast<const float* const*>(h->net[which].tc_consts + 8192), st));
+    if (h->cfg.W == 256)        // (training is built for the 256-wide net)
+      NSR_CUDA(h, train_pack_wt(h, which, reinterpret_cast<const float* const*>(h->net[which].tc_consts + 8192), st));
   }
   h->net[which].packed = true;
   // The host-buffer pipeline (nsr_render_host / nsr_render_pose_host) runs on library-owned non-blocking streams: order it

@@ -91,31 +91,38 @@ struct StageDesc {
   int16_t col0;      // first input column of this 64-wide k chunk
   int16_t kvalid;    // valid columns (63 for the encoding chunk, else 64)
   int16_t ld;        // row length (in_features) of the weight tensor
+  int16_t rows;      // valid output rows of this 128-row half (128 at W = 256; fewer / none for narrower nets: zero-padded)
 };
 struct StageTable { StageDesc s[kStagesPerTile]; };
 
-static StageTable build_stage_table(int ch_dir, bool no_dir) {
+// Nets narrower than the kernel's 256 features (--W 128 ..., models/networks.py:125) run on the same schedule with their weights, biases and
+// head weights ZERO-PADDED to 256 / 128: a padded activation is relu(0 + 0) = 0 and contributes exact zeros to every fp32
+// accumulation, so the result is what a 128-wide evaluation with the same split arithmetic would give (at the MMA cost of
+// the 256-wide net -- still several times the fp32 CUDA-core path's rate).
+static StageTable build_stage_table(int ch_dir, bool no_dir, int W) {
   StageTable T{};
   int n = 0;
-  auto push = [&](int param, int half, int col0, int kvalid, int ld) {
-    T.s[n++] = StageDesc{(int16_t)param, (int16_t)half, (int16_t)col0, (int16_t)kvalid, (int16_t)ld};
+  auto clampi = [](int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); };
+  auto rows_of = [&](int n_out, int half) { return clampi(n_out - 128 * half, 0, 128); };
+  auto push = [&](int param, int half, int col0, int kvalid, int ld, int rows) {
+    T.s[n++] = StageDesc{(int16_t)param, (int16_t)half, (int16_t)col0, (int16_t)kvalid, (int16_t)ld, (int16_t)rows};
   };
   // L1 (xyz_encoding_1, K=63): half 1 first, then half 0 (lets the next tile start while the
   // previous tile's last epilogue still owns accumulator half 0)
-  push(0, 1, 0, 63, 63);
-  push(0, 0, 0, 63, 63);
+  push(0, 1, 0, 63, 63, rows_of(W, 1));
+  push(0, 0, 0, 63, 63, rows_of(W, 0));
   for (int L = 2; L <= 9; ++L) {
     const int param = 2 * (L - 1);                 // L9 = xyz_encoding_final (state_dict index 16)
     const bool skip = (L == 5);
-    const int ld = skip ? 319 : 256;
-    const int off = skip ? 63 : 0;                 // cat([input_xyz(63), h(256)])  networks.py:204
+    const int ld = skip ? 63 + W : W;
+    const int off = skip ? 63 : 0;                 // cat([input_xyz(63), h(W)])  networks.py:204
     for (int h = 0; h < 2; ++h) {
-      if (skip) push(param, h, 0, 63, ld);
-      for (int c = 0; c < 4; ++c) push(param, h, off + 64 * c, 64, ld);
+      if (skip) push(param, h, 0, 63, ld, rows_of(W, h));
+      for (int c = 0; c < 4; ++c) push(param, h, off + 64 * c, clampi(W - 64 * c, 0, 64), ld, rows_of(W, h));
     }
   }
-  const int ld_dir = no_dir ? 256 : 256 + ch_dir;   // cat([feat(256), enc_dir]) networks.py:214
-  for (int c = 0; c < 4; ++c) push(18, 0, 64 * c, 64, ld_dir);
+  const int ld_dir = no_dir ? W : W + ch_dir;       // cat([feat(W), enc_dir]) networks.py:214
+  for (int c = 0; c < 4; ++c) push(18, 0, 64 * c, clampi(W - 64 * c, 0, 64), ld_dir, rows_of(W / 2, 0));
   return T;
 }
 
@@ -133,7 +140,7 @@ __global__ void k_tc_pack_image(StageTable T, const float* const* __restrict__ p
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int kl = 8 * j + e;
-      const float v = (kl < d.kvalid) ? W[(int64_t)n * d.ld + d.col0 + kl] : 0.f;
+      const float v = (kl < d.kvalid && r < d.rows) ? W[(int64_t)n * d.ld + d.col0 + kl] : 0.f;
       Split<FMT>::apply1(v, hi[e], lo[e]);
     }
     const size_t off = (size_t)s * kStageBytes + (size_t)r * 128 + (size_t)((j ^ (r & 7)) << 4);
@@ -142,25 +149,28 @@ __global__ void k_tc_pack_image(StageTable T, const float* const* __restrict__ p
   }
 }
 
-__global__ void k_tc_pack_consts(const float* const* __restrict__ p, float* __restrict__ c, int ch_dir, int no_dir) {
+__global__ void k_tc_pack_consts(const float* const* __restrict__ p, float* __restrict__ c, int ch_dir, int no_dir, int W) {
+  // (zero padding from the net's width W / W/2 to the kernel's 256 / 128: see build_stage_table)
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int nt = gridDim.x * blockDim.x;
-  for (int i = t; i < 8 * 256; i += nt) c[kcBias + i] = p[2 * (i / 256) + 1][i % 256];
-  for (int i = t; i < 256; i += nt) c[kcBiasFinal + i] = p[17][i];
-  for (int i = t; i < 128; i += nt) c[kcBiasDir + i] = p[19][i];
-  for (int i = t; i < 256; i += nt) c[kcWsig + i] = p[20][i];
-  for (int i = t; i < 384; i += nt) c[kcWrgb + i] = p[22][i];
+  const int Wd = W / 2;
+  for (int i = t; i < 8 * 256; i += nt) c[kcBias + i] = (i % 256 < W) ? p[2 * (i / 256) + 1][i % 256] : 0.f;
+  for (int i = t; i < 256; i += nt) c[kcBiasFinal + i] = (i < W) ? p[17][i] : 0.f;
+  for (int i = t; i < 128; i += nt) c[kcBiasDir + i] = (i < Wd) ? p[19][i] : 0.f;
+  for (int i = t; i < 256; i += nt) c[kcWsig + i] = (i < W) ? p[20][i] : 0.f;
+  for (int i = t; i < 384; i += nt) c[kcWrgb + i] = (i % 128 < Wd) ? p[22][(i / 128) * Wd + i % 128] : 0.f;
   if (t == 0) { c[kcMisc] = p[21][0]; c[kcMisc + 1] = p[23][0]; c[kcMisc + 2] = p[23][1]; c[kcMisc + 3] = p[23][2]; }
-  const int ld = no_dir ? 256 : 256 + ch_dir;
+  const int ld = no_dir ? W : W + ch_dir;
   for (int i = t; i < 128 * 28; i += nt) {
     const int j = i / 28, k = i % 28;
-    c[kcWdd + i] = (!no_dir && k < ch_dir) ? p[18][(int64_t)j * ld + 256 + k] : 0.f;
+    c[kcWdd + i] = (!no_dir && k < ch_dir && j < Wd) ? p[18][(int64_t)j * ld + W + k] : 0.f;
   }
 }
 
 bool tc_supported(const NsrConfig& c, std::string* why) {
   auto no = [&](const char* m) { if (why) *why = m; return false; };
-  if (c.D != 8 || c.W != 256 || c.skips_mask != (1u << 4)) return no("needs D=8, W=256, skips=[4]");
+  if (c.D != 8 || c.skips_mask != (1u << 4)) return no("needs D=8, skips=[4]");
+  if (c.W != 256 && c.W != 128 && c.W != 64) return no("needs a net width W of 64, 128 or 256 (narrower nets run zero-padded)");
   if (c.deg_pos != 10 || c.deg_dir != 4 || c.no_xyz) return no("needs deg_pos=10, deg_dir=4, xyz included");
   // coarse pass: whole rays per 128-point tile (64 or 128 samples); fine pass: the same, or 192 / 256 samples in the
   // MLP-only mode (tiles cut across rays, compositing in k_composite); the in-kernel resampler's scratch holds
@@ -183,11 +193,11 @@ cudaError_t tc_pack(NsrHandle_* h, int which, const float* const* params, cudaSt
   const float** d_ptrs = reinterpret_cast<const float**>(net.tc_consts + 8192);
   cudaError_t e = cudaMemcpyAsync(d_ptrs, params, np * sizeof(float*), cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return e;
-  const StageTable T = build_stage_table(h->rp.ch_dir, h->cfg.no_dir != 0);
+  const StageTable T = build_stage_table(h->rp.ch_dir, h->cfg.no_dir != 0, h->cfg.W);
   const int fmt = (h->cfg.precision == NSR_PREC_FP16X3_TC) ? 0 : 1;
   if (fmt == 1) k_tc_pack_image<1><<<144, 256, 0, st>>>(T, d_ptrs, net.tc_image);
   else k_tc_pack_image<0><<<144, 256, 0, st>>>(T, d_ptrs, net.tc_image);
-  k_tc_pack_consts<<<8, 256, 0, st>>>(d_ptrs, net.tc_consts, h->rp.ch_dir, h->cfg.no_dir);
+  k_tc_pack_consts<<<8, 256, 0, st>>>(d_ptrs, net.tc_consts, h->rp.ch_dir, h->cfg.no_dir, h->cfg.W);
   h->launches += 2;
   return cudaGetLastError();
 }

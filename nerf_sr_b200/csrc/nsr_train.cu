@@ -1532,6 +1532,7 @@ static int train_supported(NsrHandle_* h) {
   if (h->cfg.n_coarse != 64 || h->cfg.n_importance != 64)
     return tfail(h, NSR_ERR_UNSUPPORTED, "training is built for N_coarse 64 + N_importance 64 (whole rays per 128-point tile in both passes)");
   if (h->cfg.no_dir) return tfail(h, NSR_ERR_UNSUPPORTED, "training with --no_dir is not supported");
+  if (h->cfg.W != 256) return tfail(h, NSR_ERR_UNSUPPORTED, "training is built for the 256-wide net (narrower nets render zero-padded, inference only)");
   return NSR_OK;
 }
 

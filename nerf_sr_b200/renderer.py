@@ -532,7 +532,8 @@ def patch_model(model, precision: str = "bf16x3", whole_frame: bool = True):
     reference_forward_rays = model.forward_rays
     lazy = _install_lazy_near_far(model)
 
-    train_capable = (precision == "bf16x3" and (renderer.n_coarse, renderer.n_importance) == (64, 64) and not renderer.cfg.no_dir)
+    train_capable = (precision == "bf16x3" and (renderer.n_coarse, renderer.n_importance) == (64, 64) and not renderer.cfg.no_dir
+                     and renderer.cfg.W == 256)
 
     def reference_path(rays):
         # the PyTorch path needs its chunking back (utils/utils.py:130-152) when whole_frame lifted opt.ray_chunk

@@ -472,6 +472,54 @@ def test_against_oracle_run_on_the_gpu(prec, load_fixture):
     r.close()
 
 
+@pytest.mark.parametrize("W", [128, 64])
+@pytest.mark.parametrize("prec", ["bf16x3", "fp16x3"])
+def test_narrower_nets_run_zero_padded_on_the_tensor_core_path(W, prec):
+    """--W 128 and friends (models/networks.py:125): weights, biases and head weights are zero-padded to the kernel's 256 /
+    128 features, which is exact (a padded activation is relu(0) = 0 and adds exact zeros).  Same acceptance rules as the
+    256-wide net, against the oracle's ATen op sequence on the GPU; one launch per call proves it is the tcgen05 frame kernel
+    and not the fp32 CUDA-core path."""
+    from conftest import e2e_bounds
+    from nerf_sr_b200 import Renderer
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = O.RenderConfig(W=W, white_bkgd=True)
+    pc, pf = O.make_mlp_params(cfg, 4), O.make_mlp_params(cfg, 17)
+    assert pc["xyz_encoding_2.0.weight"].shape == (W, W) and pc["dir_encoding.0.weight"].shape == (W // 2, W + 27)
+    rays = O.synthetic_rays(4096, 60 + W, "blender").cuda()
+    pcd, pfd = {k: v.cuda() for k, v in pc.items()}, {k: v.cuda() for k, v in pf.items()}
+    ex = {}
+    with torch.no_grad():
+        ref = O.forward_rays(pcd, pfd, rays, cfg, extras=ex)
+        d = lambda p: {k: v.double() for k, v in p.items()}
+        ref64 = O.forward_rays(d(pcd), d(pfd), rays.double(), cfg)
+    r = Renderer(cfg, torch.device("cuda:0"), precision=prec)
+    r.load_state_dict(0, pc)
+    r.load_state_dict(1, pf)
+    l0 = r.launch_count
+    out = r.forward_rays(rays)
+    assert r.launch_count - l0 == 1
+    for k in COARSE_KEYS:
+        mx, viol = O.tolerance_violations(out[k], ref[k])
+        assert viol == 0.0, (k, mx, viol)
+    tf = r.render_pass(1, rays, ex["z_fine"], want_raw=True)
+    for kl, kr in (("comp_rgbs", "fine_comp_rgbs"), ("depth", "fine_depth"), ("opacity", "fine_opacity"), ("weights", "fine_weights")):
+        mx, viol = O.tolerance_violations(tf[kl], ref[kr])
+        assert viol == 0.0, (kl, mx, viol)
+    mx, viol = O.tolerance_violations(tf["raw"], ex["raw_fine"])
+    assert viol == 0.0, ("raw", mx, viol)
+    for k in ("fine_comp_rgbs", "fine_depth", "fine_weights"):
+        _, viol = O.tolerance_violations(out[k], ref[k])
+        _, floor = O.tolerance_violations(ref[k], ref64[k])
+        _, v64 = O.tolerance_violations(out[k], ref64[k])
+        _report(test="narrow_net", W=W, prec=prec, key=k, viol_vs_ref32=viol, viol_vs_fp64=v64, floor=floor)
+        b64, b32 = e2e_bounds(floor, rays.shape[0], prec)
+        assert v64 <= b64 and viol <= b32, (k, viol, v64, floor)
+    with pytest.raises(Exception):                       # training stays with the 256-wide net
+        from nerf_sr_b200 import Trainer
+        Trainer(r, pc, pf, downscale=2).optimize_parameters(rays[:64], torch.rand(16, 3, device="cuda"), None)
+    r.close()
+
+
 def test_single_pass_bf16_fast_mode_is_close_but_not_parity_grade(load_fixture):
     """NSR_PREC_BF16_TC: one bf16 MMA per product.  Documented as NOT parity grade; it must
     still be a faithful render: high PSNR against the reference, finite, same shapes."""

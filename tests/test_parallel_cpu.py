@@ -127,7 +127,7 @@ class _RecordingRenderer:
 
     def __init__(self, opt, device=None, precision="bf16x3", viewdir_offset=3):
         import types
-        self.n_coarse, self.n_importance, self.cfg = opt.N_coarse, opt.N_importance, types.SimpleNamespace(no_dir=0)
+        self.n_coarse, self.n_importance, self.cfg = opt.N_coarse, opt.N_importance, types.SimpleNamespace(no_dir=0, W=256)
         self._param_versions = [None, None]
         self.numel = None
 

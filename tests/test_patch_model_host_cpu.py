@@ -16,7 +16,7 @@ def fake_renderer(monkeypatch):
     class FakeRenderer:
         def __init__(self, opt, device=None, precision="bf16x3", viewdir_offset=3):
             self.n_coarse, self.n_importance = opt.N_coarse, opt.N_importance
-            self.cfg = types.SimpleNamespace(no_dir=int(getattr(opt, "no_dir", False)))
+            self.cfg = types.SimpleNamespace(no_dir=int(getattr(opt, "no_dir", False)), W=int(getattr(opt, "W", 256)))
             self._param_versions = [None, None]
             calls.append(("init", precision, viewdir_offset))
 
@@ -73,7 +73,8 @@ def test_randomized_draws_follow_the_reference_order(fake_renderer):
     assert list(fake_renderer[-1][1]) == ["u_coarse"]
 
 
-@pytest.mark.parametrize("precision,opt", [("fp32_simt", {}), ("fp16x3", {}), ("bf16x3", {"N_importance": 0}), ("bf16x3", {"no_dir": True})])
+@pytest.mark.parametrize("precision,opt", [("fp32_simt", {}), ("fp16x3", {}), ("bf16x3", {"N_importance": 0}), ("bf16x3", {"no_dir": True}),
+                                           ("bf16x3", {"W": 128})])
 def test_option_sets_without_a_cuda_backward_keep_the_reference_path_under_autograd(fake_renderer, precision, opt):
     m = R.patch_model(_model(**opt), precision=precision)
     assert m.forward_rays(torch.rand(4, 8)) == "reference path"          # grad enabled, parameters require grad
