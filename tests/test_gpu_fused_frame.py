@@ -135,6 +135,20 @@ def test_host_frame_pipeline_in_one_launch_per_chunk_is_bit_identical():
     r.close()
 
 
+def test_pose_frames_larger_than_one_host_chunk_are_bit_identical():
+    """A frame of more than 262 144 rays goes through the host pipeline in several chunks; with in-kernel ray generation
+    every chunk passes its first row (`rg_first`) to the kernel.  600 x 600 at s = 2 = 360 000 rays = two chunks."""
+    r = _renderer("bf16x3")
+    c2w = torch.tensor([[0.96, -0.10, 0.26, 1.1], [0.05, 0.98, 0.19, 0.7], [-0.27, -0.17, 0.95, 3.6]])
+    a, la, b, lb = _both(r, lambda: dict(zip(("rgb", "depth"), r.render_pose_host(c2w, 600, 600, 540.0, s=2))))
+    assert la == 2 and lb == 1 + 2 * 4                           # one launch per chunk | rays + (coarse, fine, 2 box averages) per chunk
+    _assert_identical(a, b)
+    # the device-side entry point on the same pose: one launch for the whole frame, the same LR image
+    o = r.render_frame(None, 2, pose=c2w, H=600, W=600, focal=540.0, want_hr=False)
+    assert torch.equal(o["fine_lr_rgb"].cpu(), a["rgb"]) and torch.equal(o["fine_lr_depth"].cpu(), a["depth"])
+    r.close()
+
+
 def test_option_sets_outside_the_one_launch_kernel_still_render_frames():
     """nsr_render_frame is a complete entry point: 64 + 128 samples (MLP-only fine pass) and the fp32 path fall back to the
     separate launches inside the library and give the same answers as the public pieces."""
