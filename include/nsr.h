@@ -439,6 +439,16 @@ NSR_API int nsr_comm_connect_ipc(NsrComm* c, const void* handles64, int n_handle
 NSR_API int nsr_comm_connect_ptrs(NsrComm* c, void* const* peer_buffers, int n);      /* same-process peers */
 NSR_API int nsr_comm_allreduce_mean(NsrComm* c, NsrStream stream);
 
+/* Debug / test seam (no GPU needed): the order in which one CTA of the one-launch frame kernel visits its tiles, computed on
+ * the host by the function the kernel itself uses.  The CTA owns `pairs` ray pairs (a multiple of unit_rays / 2) in work units
+ * first_unit, first_unit + unit_stride, ... of unit_rays (2, 4 or 16) consecutive rays.  out: int64[3 * pairs][3] =
+ * (pass: 0 coarse / 1 fine, tile index within that pass: coarse tile t = rays 2t, 2t+1; fine tile t = ray t,
+ *  1 if the trip depends on the one right before it). */
+NSR_API int nsr_debug_frame_schedule(int64_t pairs, int unit_rays, int first_unit, int unit_stride, int64_t* out);
+/* Debug: 1 if nsr_render_frame / nsr_render_host would run the s x s box average of an n_rays batch inside the frame kernel
+ * (it does when that costs the busiest CTA < 3 % more tiles than ray-pair granularity), else 0. */
+NSR_API int nsr_debug_frame_lr_in_kernel(const NsrHandle* h, int64_t n_rays, int s);
+
 /* Debug: (clock64, globaltimer ns) stamped by CTA 0 at entry and at exit of the most recent fused-pass kernel
  * (k_tc_pass) of this handle -> out4_host = {clk0, ns0, clk1, ns1}; (clk1-clk0)/(ns1-ns0) GHz is the SM clock the
  * kernel actually ran at.  Synchronises `stream` (a measurement aid, not part of the render path). */

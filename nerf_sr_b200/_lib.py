@@ -126,6 +126,8 @@ SIGNATURES = {
     "nsr_comm_connect_ipc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "nsr_comm_connect_ptrs": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int]),
     "nsr_comm_allreduce_mean": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "nsr_debug_frame_schedule": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64)]),
+    "nsr_debug_frame_lr_in_kernel": (C.c_int, [C.c_void_p, C.c_int64, C.c_int]),
     "nsr_debug_kernel_clock": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
 }
 

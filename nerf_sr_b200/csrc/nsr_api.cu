@@ -415,6 +415,11 @@ extern "C" int nsr_debug_set_flags(NsrHandle* h, int flags) {
   return NSR_OK;
 }
 extern "C" int64_t nsr_launch_count(const NsrHandle* h) { return h ? h->launches.load() : 0; }
+extern "C" int nsr_debug_frame_schedule(int64_t pairs, int unit_rays, int first_unit, int unit_stride, int64_t* out) {
+  static_assert(sizeof(long long) == sizeof(int64_t), "int64_t is long long here");
+  return frame_schedule((long long)pairs, unit_rays, first_unit, unit_stride, reinterpret_cast<long long*>(out)) ? NSR_ERR_INVALID_ARG : NSR_OK;
+}
+
 extern "C" int nsr_debug_kernel_clock(NsrHandle* h, int64_t* out4_host, NsrStream stream) {
   if (!h || !out4_host) return NSR_ERR_INVALID_ARG;
   NSR_CUDA(h, cudaSetDevice(h->cfg.device));
@@ -543,6 +548,10 @@ static bool lr_in_kernel_pays(const NsrHandle_* h, int64_t n, int s) {
     return (units + grid - 1) / grid * (unit / 2) * 3;
   };
   return tiles_of_busiest_cta(s * s) * 100 <= tiles_of_busiest_cta(2) * 103;
+}
+
+extern "C" int nsr_debug_frame_lr_in_kernel(const NsrHandle* h, int64_t n_rays, int s) {
+  return (h && lr_in_kernel_pays(h, n_rays, s)) ? 1 : 0;
 }
 
 // forward_rays over a ray batch (+ the s x s box average when `lr` is given).  One launch (k_tc_pass<.., FUSED>) where the

@@ -148,6 +148,7 @@ struct TcFrameArgs {
 };
 bool tc_frame_supported(const NsrHandle_* h, int s);
 cudaError_t tc_frame(NsrHandle_* h, const TcFrameArgs& a, cudaStream_t st);
+int frame_schedule(long long pairs, int unit_rays, int first, int stride, long long* out);
 
 // ---- training path (nsr_train.cu) ----
 size_t train_wt_bytes();

@@ -281,9 +281,8 @@ struct TcKernelArgs {
 // ---------------------------------------------------------------------------
 struct Trip { long long tile; int pass; int S; };
 
-template <bool FUSED>
-__device__ __forceinline__ Trip trip_of(const TcKernelArgs& a, long long it, long long P, int first, int stride) {
-  if (!FUSED) return Trip{first + it * (long long)stride, 0, a.S};
+// (host + device: nsr_debug_frame_schedule exposes the order to the CPU tests)
+__host__ __device__ __forceinline__ Trip frame_trip(int unit_rays, long long it, long long P, int first, int stride) {
   int fine = 0; long long idx = 0;                 // coarse: CTA-local pair index; fine: CTA-local ray index
   if (it > 0) {
     const long long t = it - 1, q = t / 3;
@@ -293,14 +292,19 @@ __device__ __forceinline__ Trip trip_of(const TcKernelArgs& a, long long it, lon
     else { fine = 1; idx = 2 * q + r - 1; }
   }
   const long long pl = fine ? (idx >> 1) : idx;    // CTA-local pair
-  const int hp = a.unit_rays >> 1;                 // pairs per unit
+  const int hp = unit_rays >> 1;                   // pairs per unit
   const long long k = pl / hp;
-  const long long ray0 = ((long long)first + k * stride) * a.unit_rays + 2 * (pl - k * hp);
+  const long long ray0 = ((long long)first + k * stride) * unit_rays + 2 * (pl - k * hp);
   if (fine) return Trip{ray0 + (idx & 1), 1, 128};
   return Trip{ray0 >> 1, 0, 64};
 }
 template <bool FUSED>
-__device__ __forceinline__ bool trip_depends_on_previous(long long it, long long P) { return FUSED && P == 1 && it == 1; }
+__device__ __forceinline__ Trip trip_of(const TcKernelArgs& a, long long it, long long P, int first, int stride) {
+  if (!FUSED) return Trip{first + it * (long long)stride, 0, a.S};
+  return frame_trip(a.unit_rays, it, P, first, stride);
+}
+template <bool FUSED>
+__host__ __device__ __forceinline__ bool trip_depends_on_previous(long long it, long long P) { return FUSED && P == 1 && it == 1; }
 
 // ---------------------------------------------------------------------------
 // roles
@@ -971,6 +975,17 @@ bool tc_frame_supported(const NsrHandle_* h, int s) {
   if (p != NSR_PREC_BF16X3_TC && p != NSR_PREC_FP16X3_TC && p != NSR_PREC_BF16_TC) return false;
   if (h->cfg.n_coarse != 64 || h->cfg.n_importance != 64) return false;      // coarse tile = 2 rays, fine tile = 1 ray
   return s == 1 || s == 2 || s == 4;                                         // unit = lcm(2, s*s) <= 16 rays
+}
+
+// Debug / test seam: the tile order of one CTA of the frame kernel, computed on the host by the function the kernel uses.
+// out[3 * trip + {0, 1, 2}] = pass (0 coarse, 1 fine), tile index within that pass, 1 if the trip depends on its predecessor.
+int frame_schedule(long long pairs, int unit_rays, int first, int stride, long long* out) {
+  if (pairs < 0 || (unit_rays != 2 && unit_rays != 4 && unit_rays != 16) || (pairs % (unit_rays / 2)) || !out) return 1;
+  for (long long it = 0; it < 3 * pairs; ++it) {
+    const Trip t = frame_trip(unit_rays, it, pairs, first, stride);
+    out[3 * it] = t.pass; out[3 * it + 1] = t.tile; out[3 * it + 2] = trip_depends_on_previous<true>(it, pairs) ? 1 : 0;
+  }
+  return 0;
 }
 
 cudaError_t tc_frame(NsrHandle_* h, const TcFrameArgs& p, cudaStream_t st) {
