@@ -38,6 +38,13 @@ __device__ __forceinline__ void ring_release(const MmaCtx& c, int slot) {
   else tc_commit(c.bar + 8 * (B_WEMPTY + slot));
 }
 
+// Order of the three split terms of one k-step (timing experiment, tools/gpu_mma_order_ab.sh; the sum is the same up to
+// fp32 rounding order): 0 = hi.hi, lo.hi, hi.lo (B repeats); 1 = hi.hi, hi.lo, lo.hi (A repeats); 2 = all four k-steps of a
+// term before the next term (each operand plane is walked contiguously)
+#ifndef NSR_MMA_ORDER
+#define NSR_MMA_ORDER 0
+#endif
+
 // 12 (or 4) MMAs of one weight stage with A from TMEM.  N8 = stage index mod 8 (compile time).
 template <int PASSES, int N8>
 __device__ __forceinline__ void mma_stage_ts(const MmaCtx& c, int half, int chunk, bool first, bool wait_next) {
@@ -47,11 +54,28 @@ __device__ __forceinline__ void mma_stage_ts(const MmaCtx& c, int half, int chun
   const uint32_t wlo = ((c.ring + slot * kStageBytes) >> 4) | (1u << 16);
   const uint32_t d = 128u * half;
   const uint32_t a_hi = 256u + 32u * chunk;
+#if NSR_MMA_ORDER == 2
+  if (PASSES == 3) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) mma_ts(d, a_hi + 8u * k, HI | (uint64_t)(wlo + 2u * k), c.idesc, (k == 0 && first) ? 0u : 1u);
+    if (wait_next) { mbar_wait(c.bar + 8 * (B_WFULL + nslot), npar); tc_fence_after(); }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) mma_ts(d, a_hi + 128u + 8u * k, HI | (uint64_t)(wlo + 2u * k), c.idesc, 1u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) mma_ts(d, a_hi + 8u * k, HI | (uint64_t)(wlo + 1024u + 2u * k), c.idesc, 1u);
+    ring_release(c, slot);
+    return;
+  }
+#endif
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const uint64_t bh = HI | (uint64_t)(wlo + 2u * k), bl = HI | (uint64_t)(wlo + 1024u + 2u * k);
     mma_ts(d, a_hi + 8u * k, bh, c.idesc, (k == 0 && first) ? 0u : 1u);
+#if NSR_MMA_ORDER == 1
+    if (PASSES == 3) { mma_ts(d, a_hi + 8u * k, bl, c.idesc, 1u); mma_ts(d, a_hi + 128u + 8u * k, bh, c.idesc, 1u); }
+#else
     if (PASSES == 3) { mma_ts(d, a_hi + 128u + 8u * k, bh, c.idesc, 1u); mma_ts(d, a_hi + 8u * k, bl, c.idesc, 1u); }
+#endif
     // the NEXT stage's weights are waited for here, hidden behind this stage's queued MMAs
     if (k == 1 && wait_next) { mbar_wait(c.bar + 8 * (B_WFULL + nslot), npar); tc_fence_after(); }
   }
