@@ -1035,13 +1035,19 @@ __global__ void __launch_bounds__(256) k_grad_reduce(const RedArgs a) {
     const int r = idx % J.rows, c = idx / J.rows;                  // partials are [split][n][m]: lanes walk the rows m
     const float* p = J.part + (size_t)c * 128 + J.row0 + r;
     const size_t stride = (size_t)128 * J.N;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;       // four independent chains (fixed order: deterministic)
+    // eight independent chains (fixed order: deterministic); the eight loads of a trip are issued before the first add, which
+    // is what keeps enough bytes in flight for a kernel that only streams 0.2 GB of partials
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     int k = 0;
-    for (; k + 4 <= J.n_split; k += 4) {
-      s0 += p[(size_t)k * stride]; s1 += p[(size_t)(k + 1) * stride]; s2 += p[(size_t)(k + 2) * stride]; s3 += p[(size_t)(k + 3) * stride];
+    for (; k + 8 <= J.n_split; k += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldcs(p + (size_t)(k + u) * stride);      // read once: streaming
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s[u] += v[u];
     }
-    for (; k < J.n_split; ++k) s0 += p[(size_t)k * stride];
-    a.grad[J.dst + (long long)r * J.ld + J.col0 + c] = (s0 + s1) + (s2 + s3);
+    for (; k < J.n_split; ++k) s[k & 7] += __ldcs(p + (size_t)k * stride);
+    a.grad[J.dst + (long long)r * J.ld + J.col0 + c] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
   }
   if (J.bias_dst >= 0) {
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < J.rows; r += gridDim.x * blockDim.x) {
