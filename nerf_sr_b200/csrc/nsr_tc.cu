@@ -19,6 +19,13 @@
 //                     resampling + sort-merge for the fine pass, output stores.
 // Encoded features, activations and per-sample (rgb, sigma) never reach HBM.
 //
+// Two launch shapes share this code (template parameter FUSED):
+//   one pass  : the CTA walks tiles blockIdx.x, + gridDim.x, ... of ONE net (coarse or fine; the training forward with its
+//               activation stash, the teacher-forced seam nsr_render_pass, option sets outside the frame variant);
+//   one frame : coarse tiles, resampling, fine tiles -- plus ray generation in the front-end and the s x s box average in
+//               the compositing epilogue -- of a whole ray batch in ONE launch; the fine tiles read the z-values the same
+//               CTA's coarse tiles wrote two trips earlier (trip_of / frame_trip below).  Bit-identical to the passes.
+//
 // TMEM map (512 columns x 128 lanes x 32 bit):
 //   [  0,256) fp32 accumulator, two N-halves of 128 columns
 //   [256,384) A operand, hi plane (256 k-values, 2 per column)
