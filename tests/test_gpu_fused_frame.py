@@ -151,6 +151,20 @@ def test_pose_frames_larger_than_one_host_chunk_are_bit_identical():
     r.close()
 
 
+def test_single_cta_launches_of_the_frame_kernel_are_bit_identical_too():
+    """NSR_TC_CLUSTER=1 (the A/B switch that launches single CTAs instead of CTA pairs: CTAs then run different numbers of
+    units and nobody multicasts) is read at nsr_create, so the check runs in a child process."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, NSR_TC_CLUSTER="1")
+    cmd = [sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", os.path.abspath(__file__), "-k",
+           "(forward_rays_in_one_launch and bf16x3) or (box_average and 1184) or larger_than_one_host_chunk"]
+    p = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-3000:]
+    assert " passed" in p.stdout and "failed" not in p.stdout, p.stdout[-1000:]
+
+
 def test_option_sets_outside_the_one_launch_kernel_still_render_frames():
     """nsr_render_frame is a complete entry point: 64 + 128 samples (MLP-only fine pass) and the fp32 path fall back to the
     separate launches inside the library and give the same answers as the public pieces."""
