@@ -258,7 +258,8 @@ NSR_API int nsr_generate_rays_ex(NsrHandle* h, const float* c2w_host, const NsrR
  *               `spec` (n_rays / ray_stride are then ignored: H*W rays of 8 columns)
  *   out       : HR outputs, any pointer null (with the fused kernel a null HR output is simply not written)
  *   lr        : box-averaged outputs [n_rays / s^2], any pointer null; ignored when s == 1
- *   workspace : nsr_frame_workspace_bytes(h, n_rays, rays == null) bytes */
+ *   workspace : nsr_frame_workspace_bytes(h, n_rays, rays == null) bytes (fine z-values; on option sets that take
+ *               separate launches also the generated rays and any HR composite the box average needs but `out` omits) */
 typedef struct NsrLrOutputs {
   float* coarse_rgb;           /* [N/s^2,3]                                    */
   float* coarse_depth;         /* [N/s^2]                                      */

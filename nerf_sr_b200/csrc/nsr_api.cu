@@ -648,8 +648,10 @@ static int fill_raygen(NsrHandle_* h, const float* c2w_host, const NsrRayGen* sp
 
 extern "C" size_t nsr_frame_workspace_bytes(const NsrHandle* h, int64_t n_rays, int from_pose) {
   if (!h || n_rays < 0) return 0;
-  // from a pose: room for the generated rays in case the option set needs the multi-launch path
-  return ws_layout(h, n_rays).total + (from_pose ? align_up((size_t)n_rays * 8 * sizeof(float)) : 0);
+  // + room for what an option set on the multi-launch path needs: the generated rays (from a pose) and HR composites /
+  // depths the caller did not ask for but the box average is computed from (8 floats per ray: rgb + depth of both nets)
+  return ws_layout(h, n_rays).total + (from_pose ? align_up((size_t)n_rays * 8 * sizeof(float)) : 0) +
+         align_up((size_t)n_rays * 8 * sizeof(float));
 }
 
 extern "C" int nsr_render_frame(NsrHandle* h, const float* rays, int64_t n_rays, int ray_stride, const float* c2w_host,
@@ -677,14 +679,25 @@ extern "C" int nsr_render_frame(NsrHandle* h, const float* rays, int64_t n_rays,
   cudaStream_t st = (cudaStream_t)stream;
   LrOut l{lr->coarse_rgb, lr->coarse_depth, lr->fine_rgb, lr->fine_depth};
   const bool want_lr = s > 1 && (l.coarse_rgb || l.coarse_depth || l.fine_rgb || l.fine_depth);
+  char* extra = ws + (L.total - 256);               // (L.total = 256-aligned pieces + 256 of alignment slack)
   if (from_pose && !fused_frame_ok(h, 1)) {      // other option sets: rays through HBM, then the ordinary passes
-    float* gen = (float*)(ws + (L.total - 256));      // (L.total = 256-aligned pieces + 256 of alignment slack)
+    float* gen = (float*)extra;
     k_generate_rays<<<grid_for(n_rays, 256, h->sm_count * 16), 256, 0, st>>>(rg, gen);
     h->launches += 1;
     NSR_CUDA(h, cudaGetLastError());
     rays = gen;
   }
-  return render_core(h, rays, rays ? nullptr : &rg, n_rays, ray_stride, s, rng, out, want_lr ? &l : nullptr, ws, L, st);
+  if (from_pose) extra += align_up((size_t)n_rays * 8 * sizeof(float));
+  NsrOutputs o = *out;
+  if (want_lr && !fused_frame_ok(h, s)) {
+    // the box average runs as its own launches here and reads the HR composites: lend workspace to those the caller left out
+    float* tmp = (float*)extra;
+    if (l.coarse_rgb && !o.coarse_comp_rgbs) o.coarse_comp_rgbs = tmp;
+    if (l.coarse_depth && !o.coarse_depth) o.coarse_depth = tmp + 3 * n_rays;
+    if (l.fine_rgb && !o.fine_comp_rgbs) o.fine_comp_rgbs = tmp + 4 * n_rays;
+    if (l.fine_depth && !o.fine_depth) o.fine_depth = tmp + 7 * n_rays;
+  }
+  return render_core(h, rays, rays ? nullptr : &rg, n_rays, ray_stride, s, rng, &o, want_lr ? &l : nullptr, ws, L, st);
 }
 
 extern "C" int nsr_render_pass(NsrHandle* h, int which, const float* rays, int64_t n_rays, int ray_stride,

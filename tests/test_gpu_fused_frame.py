@@ -181,4 +181,7 @@ def test_option_sets_outside_the_one_launch_kernel_still_render_frames():
         for k in ("coarse_comp_rgbs", "fine_comp_rgbs", "fine_depth"):
             assert torch.equal(out[k], ref[k]), (prec, k)
         assert torch.equal(out["fine_lr_rgb"], r.box_average(ref["fine_comp_rgbs"], 2)), prec
+        lr_only = r.render_frame(rays, 2, want_hr=False)            # HR composites not requested: the library lends workspace
+        assert set(lr_only) == {"coarse_lr_rgb", "coarse_lr_depth", "fine_lr_rgb", "fine_lr_depth"}
+        assert torch.equal(lr_only["fine_lr_rgb"], out["fine_lr_rgb"]) and torch.equal(lr_only["coarse_lr_depth"], out["coarse_lr_depth"]), prec
         r.close()
